@@ -1,0 +1,199 @@
+"""The reference's own known-answer tests, restated 1:1, run against BOTH the CPU oracle
+(oracle/clg_oracle.c) and the product's host mirror (complogic_b200, C++ behind the C ABI).
+
+These are what pins the oracle (the Rust reference cannot be run in this image). Each test cites
+the reference test it restates.
+"""
+import pytest
+
+
+# ---- complogic/src/simulation.rs:42-94 ---------------------------------------------------------
+def test_op_set(api):  # simulation.rs:42-59
+    sim = api.Simulation(registers=[False, False, False],
+                         ops=[api.Set_op(0, False), api.Set_op(1, True), api.Set_op(2, False)])
+    sim.run([False, False])
+    assert not sim.registers[0] and not sim.registers[1] and not sim.registers[2]
+    sim.run([True, True])
+    assert sim.registers[0] and sim.registers[1] and not sim.registers[2]
+
+
+def test_op_set_no_immediate(api):  # simulation.rs:61-73
+    sim = api.Simulation(registers=[False, False, False],
+                         ops=[api.Set_op(0, False), api.Set_op(1, True), api.Set_op(2, False)])
+    sim.run([])
+    assert not sim.registers[0] and sim.registers[1] and not sim.registers[2]
+
+
+def test_op_nand(api):  # simulation.rs:75-94
+    sim = api.Simulation(registers=[False, False, False],
+                         ops=[api.Set_op(0, False), api.Set_op(1, False), api.Nand_op(0, 1, 2)])
+    for imm, want in (([False, False], True), ([True, False], True), ([False, True], True), ([True, True], False)):
+        sim.run(imm)
+        assert sim.registers[2] is want
+        assert sim.register(2) is want  # simulation.rs:33-35
+
+
+def test_run_out_of_bounds_panics(api):  # simulation.rs:20-26 index panics
+    sim = api.Simulation(registers=[False], ops=[api.Nand_op(0, 0, 3)])
+    with pytest.raises(api.ReferencePanic):
+        sim.run([])
+
+
+# ---- complogic/src/compile.rs:211-294 ----------------------------------------------------------
+def test_alloc_lazy_increment(api):  # compile.rs:211-218
+    c = api.Compiler(0)
+    assert [c.alloc(), c.alloc(), c.alloc()] == [0, 1, 2]
+
+
+def test_alloc_plus_immediates(api):  # compile.rs:220-227
+    c = api.Compiler(2)
+    assert [c.alloc(), c.alloc(), c.alloc()] == [2, 3, 4]
+
+
+def test_alloc_all_on_compile(api):  # compile.rs:229-245
+    c = api.Compiler(2)
+    assert len(c.compile([]).registers) == 2
+    assert c.alloc() == 2 and c.alloc() == 3
+    sim = c.compile([])
+    assert len(sim.registers) == 2 and sim.ops == []
+
+
+def test_keep_incrementer_on_compile(api):  # compile.rs:247-266
+    c = api.Compiler(2)
+    and_ = api.And(0, 1, c.alloc())
+    c.compile([and_])
+    c.compile([and_])
+    sim = c.compile([and_])
+    assert len(sim.registers) == 4
+    assert c.incrementer.val == 3
+
+
+def _rs_sequence(sim, q):
+    sim.run([False, False]); assert not sim.registers[q]
+    sim.run([True, False]); assert sim.registers[q]
+    sim.run([False, True]); assert not sim.registers[q]
+    sim.run([True, True]); assert not sim.registers[q]
+
+
+def test_non_sorted_gates_should_sort(api):  # compile.rs:268-294
+    c = api.Compiler(2)
+    rs = api.RSLatchTest(0, 1, c.alloc())
+    _rs_sequence(c.compile([rs]), rs.q)
+
+
+# ---- complogic/src/gates.rs:464-645 ------------------------------------------------------------
+def test_and_gate(api):  # gates.rs:464-482
+    c = api.Compiler(2)
+    g = api.And(0, 1, c.alloc())
+    sim = c.compile([g])
+    sim.run([True, True]); assert sim.registers[g.out]
+    sim.run([True, False]); assert not sim.registers[g.out]
+
+
+def test_or_gate(api):  # gates.rs:484-508
+    c = api.Compiler(2)
+    g = api.Or(0, 1, c.alloc())
+    sim = c.compile([g])
+    for imm, want in (([False, False], False), ([False, True], True), ([True, False], True), ([True, True], True)):
+        sim.run(imm)
+        assert sim.registers[g.out] is want
+
+
+def test_rs_nor_latch(api):  # gates.rs:510-535
+    c = api.Compiler(2)
+    rs = api.RSLatch(0, 1, c.alloc())
+    _rs_sequence(c.compile([rs]), rs.q)
+
+
+def test_dlatch(api):  # gates.rs:537-571 (the last input needs two runs: FIXME at :559-567)
+    c = api.Compiler(2)
+    g = api.DLatch(0, 1, c.alloc())
+    sim = c.compile([g])
+    sim.run([False, False]); assert not sim.registers[g.q]
+    sim.run([False, True]); assert not sim.registers[g.q]
+    sim.run([True, False]); assert not sim.registers[g.q]
+    sim.run([True, True])
+    sim.run([True, True])
+    assert sim.registers[g.q]
+
+
+def test_half_adder(api):  # gates.rs:573-600
+    c = api.Compiler(2)
+    s, cy = c.alloc(), c.alloc()
+    g = api.HalfAdder(0, 1, s, cy)
+    sim = c.compile([g])
+    for a in (False, True):
+        for b in (False, True):
+            sim.run([a, b])
+            assert sim.registers[g.s] is (a != b) and sim.registers[g.c] is (a and b)
+
+
+def test_full_adder(api):  # gates.rs:602-645
+    c = api.Compiler(3)
+    s, cout = c.alloc(), c.alloc()
+    g = api.FullAdder(0, 1, 2, s, cout)
+    sim = c.compile([g])
+    for a in (0, 1):
+        for b in (0, 1):
+            for cin in (0, 1):
+                sim.run([bool(a), bool(b), bool(cin)])
+                assert sim.registers[g.s] is bool((a + b + cin) & 1)
+                assert sim.registers[g.cout] is bool((a + b + cin) >> 1)
+
+
+def test_four_bit_adder_panics_like_the_reference(api):
+    """gates.rs:663-707 is commented out as broken: FourBitAdder's cin (gates.rs:421) is a register no
+    op writes, so #registers > #ops and compile.rs:137 indexes the graph out of bounds."""
+    c = api.Compiler(8)
+    c.incrementer.skip(5)
+    g = api.FourBitAdder(3, 2, 1, 0, 7, 6, 5, 4, 12, 11, 10, 9, 8)
+    with pytest.raises(api.ReferencePanic):
+        c.compile([g])
+
+
+# ---- graph.dot:1-37 (the committed Dot dump of RSLatch{s:0,r:1,q:2} under Compiler::new(2)) -------
+GRAPH_DOT_LABELS = ["Set(0, false)", "Set(1, false)", "Nand(11, 12, 2)", "Nand(5, 5, 3)", "Nand(8, 8, 4)",
+                    "Nand(6, 7, 5)", "Nand(0, 0, 6)", "Nand(4, 4, 7)", "Nand(9, 10, 8)", "Nand(1, 1, 9)",
+                    "Nand(3, 3, 10)", "Nand(4, 4, 11)", "Nand(4, 4, 12)"]
+GRAPH_DOT_EDGES = [(0, 6), (0, 6), (4, 7), (4, 7), (6, 5), (7, 5), (5, 3), (5, 3), (1, 9), (1, 9), (3, 10),
+                   (3, 10), (9, 8), (10, 8), (8, 4), (8, 4), (4, 11), (4, 11), (4, 12), (4, 12), (11, 2), (12, 2)]
+
+
+def expected_graph_dot() -> str:
+    lines = ["digraph {"]
+    lines += ['    %d [ label = "%s" ]' % (i, l) for i, l in enumerate(GRAPH_DOT_LABELS)]
+    lines += ['    %d -> %d [ label = "()" ]' % e for e in GRAPH_DOT_EDGES]
+    return "\n".join(lines + ["}"]) + "\n"
+
+
+def test_graph_dot_golden(api):
+    c = api.Compiler(2)
+    rs = api.RSLatch(0, 1, c.alloc())
+    c.compile([rs])
+    assert c.last_dot == expected_graph_dot()
+
+
+# ---- emission order of compile(): unpinned by reference tests; derived by hand from compile.rs:154-196
+def test_compile_emission_order(api):
+    c = api.Compiler(2)
+    sim = c.compile([api.And(0, 1, c.alloc())])
+    assert sim.ops == [api.Set_op(0, False), api.Set_op(1, False), api.Nand_op(0, 1, 3), api.Nand_op(3, 3, 2)]
+    c = api.Compiler(2)
+    sim = c.compile([api.RSLatch(0, 1, c.alloc())])
+    N, S = api.Nand_op, api.Set_op
+    assert sim.ops == [S(0, False), S(1, False), N(0, 0, 6), N(1, 1, 9), N(6, 7, 5), N(9, 10, 8), N(5, 5, 3),
+                       N(8, 8, 4), N(4, 4, 7), N(3, 3, 10), N(4, 4, 11), N(4, 4, 12), N(11, 12, 2)]
+    assert len(sim.registers) == 13
+    c = api.Compiler(3)
+    sim = c.compile([api.FullAdder(0, 1, 2, c.alloc(), c.alloc())])
+    assert len(sim.ops) == 3 + 19 and len(sim.registers) == 22
+
+
+def test_gate_nand_counts(api):  # gates.rs:193-456: 1/1/2/3/4/6/11/16/8/19/76
+    want = [(api.Nand(0, 1, 2), 1), (api.Not(0, 1), 1), (api.And(0, 1, 2), 2), (api.Or(0, 1, 2), 3),
+            (api.Nor(0, 1, 2), 4), (api.Xor(0, 1, 2), 6), (api.RSLatch(0, 1, 2), 11), (api.DLatch(0, 1, 2), 16),
+            (api.HalfAdder(0, 1, 2, 3), 8), (api.FullAdder(0, 1, 2, 3, 4), 19),
+            (api.FourBitAdder(*range(13)), 76)]
+    for gate, n in want:
+        ops = gate.create(api.Incrementer(100))
+        assert len(ops) == n and all(o[0] == "Nand" for o in ops)
