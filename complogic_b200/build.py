@@ -1,0 +1,74 @@
+"""In-tree build of libcomplogic_cuda.so (host C++ + embedded sm_100a cubin).
+
+    python -m complogic_b200.build [--force]
+
+nvcc cross-compiles the kernels for sm_100a without a GPU; the resulting cubin is embedded in the
+shared library as a byte array, so the .so is the only artefact that has to travel to the GPU box.
+The library has no link-time dependency on CUDA: libcuda.so.1 is dlopen'ed when a context is made.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(CSRC, "_build")
+SO = os.path.join(HERE, "libcomplogic_cuda.so")
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+
+HOST_SOURCES = ["compiler.cpp", "lower.cpp", "json.cpp", "spec.cpp", "backend.cpp", "capi.cpp"]
+HEADERS = ["host.hpp", "flat.hpp", "device.hpp", os.path.join("..", "..", "include", "complogic_cuda.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"]
+
+
+def _tool(name: str) -> str:
+    p = os.path.join(CUDA_HOME, "bin", name)
+    return p if os.path.exists(p) else (shutil.which(name) or name)
+
+
+def _newer(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    cu = os.path.join(CSRC, "kernels.cu")
+    cubin = os.path.join(BUILD, "kernels.cubin")
+    inc = os.path.join(BUILD, "kernels_cubin.inc")
+    if force or _newer(cubin, [cu, os.path.join(CSRC, "flat.hpp")]):
+        cmd = [_tool("nvcc"), "-cubin", *NVCC_FLAGS, "-Xptxas", "-v", "-o", cubin, cu]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed")
+        with open(os.path.join(BUILD, "ptxas_info.txt"), "w") as f:
+            f.write(r.stderr)
+    if force or _newer(inc, [cubin]):
+        with open(inc, "w") as f:
+            subprocess.check_call([_tool("bin2c"), "--name", "clg_cubin", "--const", "--static", cubin], stdout=f)
+    srcs = [os.path.join(CSRC, s) for s in HOST_SOURCES]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [inc]
+    if force or _newer(SO, deps):
+        objs = []
+        procs = []
+        for s in srcs:
+            o = os.path.join(BUILD, os.path.basename(s) + ".o")
+            objs.append(o)
+            if force or _newer(o, [s, inc] + [os.path.join(CSRC, h) for h in HEADERS]):
+                procs.append(subprocess.Popen(["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-fvisibility=hidden",
+                                               "-I" + os.path.join(CUDA_HOME, "include"), "-I" + BUILD, "-c", s, "-o", o]))
+        if any(p.wait() for p in procs):
+            raise RuntimeError("g++ failed")
+        subprocess.check_call(["g++", "-shared", "-o", SO, *objs, "-ldl", "-lpthread"])
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,349 @@
+// CUDA driver binding, contexts, resident programs, launches. See device.hpp.
+#include <cuda.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+#include "device.hpp"
+
+#include "kernels_cubin.inc"  // static const unsigned char clg_cubin[] (nvcc -cubin of kernels.cu, sm_100a)
+
+namespace clg {
+
+namespace {
+
+// ---- libcuda.so.1, bound at run time ---------------------------------------------------------------
+#define CU_FNS(X)                                                                                                      \
+  X(cuInit) X(cuDeviceGet) X(cuDeviceGetCount) X(cuDeviceGetName) X(cuDeviceGetAttribute) X(cuDevicePrimaryCtxRetain)  \
+  X(cuDevicePrimaryCtxRelease) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuModuleLoadData) X(cuModuleLoadDataEx)        \
+  X(cuModuleGetFunction) X(cuModuleUnload) X(cuFuncSetAttribute) X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree)          \
+  X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuMemsetD8Async) X(cuMemAllocHost) X(cuMemFreeHost) X(cuStreamSynchronize) \
+  X(cuStreamCreate) X(cuStreamDestroy) X(cuEventCreate) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime)   \
+  X(cuEventDestroy) X(cuGetErrorString)
+
+struct Driver {
+#define X(name) decltype(&::name) name = nullptr;
+  CU_FNS(X)
+#undef X
+  bool ok = false;
+  std::string why;
+};
+
+Driver &driver() {
+  static Driver d;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      d.why = std::string("cannot load the CUDA driver (libcuda.so.1): ") + dlerror();
+      return;
+    }
+    // cuda.h maps the unsuffixed names onto the current ABI (_v2 ...); stringify after expansion
+#define STR2(x) #x
+#define STR(x) STR2(x)
+#define X(name)                                                     \
+  d.name = reinterpret_cast<decltype(d.name)>(dlsym(h, STR(name))); \
+  if (!d.name) {                                                    \
+    d.why = "CUDA driver lacks " STR(name);                         \
+    return;                                                         \
+  }
+    CU_FNS(X)
+#undef X
+    CUresult r = d.cuInit(0);
+    if (r != CUDA_SUCCESS) {
+      d.why = "cuInit failed (" + std::to_string((int)r) + "): no usable CUDA device";
+      return;
+    }
+    d.ok = true;
+  });
+  return d;
+}
+
+void cu_check(CUresult r, const char *what) {
+  if (r == CUDA_SUCCESS) return;
+  const char *s = nullptr;
+  driver().cuGetErrorString(r, &s);
+  fail(CLG_E_CUDA, std::string(what) + ": " + (s ? s : "unknown CUDA error") + " (" + std::to_string((int)r) + ")");
+}
+#define CU(call) cu_check(driver().call, #call)
+
+}  // namespace
+
+// ---- context ---------------------------------------------------------------------------------------
+struct Ctx {
+  CUdevice dev = 0;
+  CUcontext cu = nullptr;
+  CUmodule mod = nullptr;
+  int sm_count = 0;
+  CUfunction lane[3] = {}, coop[3] = {}, slice = nullptr, unslice = nullptr, fill = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  std::string name;
+
+  explicit Ctx(int device) {
+    Driver &d = driver();
+    if (!d.ok) fail(CLG_E_NO_DRIVER, d.why + " -- this backend has no CPU execution path");
+    int n = 0;
+    CU(cuDeviceGetCount(&n));
+    if (device < 0 || device >= n) fail(CLG_E_INVALID, "no CUDA device " + std::to_string(device));
+    CU(cuDeviceGet(&dev, device));
+    char nm[128] = {0};
+    CU(cuDeviceGetName(nm, sizeof nm, dev));
+    name = nm;
+    int major = 0, minor = 0;
+    CU(cuDeviceGetAttribute(&major, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, dev));
+    CU(cuDeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, dev));
+    if (major != 10 || minor != 0)
+      fail(CLG_E_UNSUPPORTED, "device " + name + " is sm_" + std::to_string(major) + std::to_string(minor) +
+                                  "; this backend is built for sm_100a (B200) only");
+    CU(cuDeviceGetAttribute(&sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+    CU(cuDevicePrimaryCtxRetain(&cu, dev));
+    bind();
+    CU(cuModuleLoadData(&mod, clg_cubin));
+    static const char *ks[3] = {"1", "2", "4"};
+    for (int i = 0; i < 3; i++) {
+      CU(cuModuleGetFunction(&lane[i], mod, (std::string("clg_lane_k") + ks[i]).c_str()));
+      CU(cuModuleGetFunction(&coop[i], mod, (std::string("clg_coop_k") + ks[i]).c_str()));
+      CU(cuFuncSetAttribute(lane[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
+      CU(cuFuncSetAttribute(coop[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
+    }
+    CU(cuModuleGetFunction(&slice, mod, "clg_slice"));
+    CU(cuModuleGetFunction(&unslice, mod, "clg_unslice"));
+    CU(cuModuleGetFunction(&fill, mod, "clg_fill_random"));
+  }
+  ~Ctx() {
+    Driver &d = driver();
+    if (cu) {
+      d.cuCtxSetCurrent(cu);
+      if (mod) d.cuModuleUnload(mod);
+      d.cuDevicePrimaryCtxRelease(dev);
+    }
+  }
+  void bind() const { CU(cuCtxSetCurrent(cu)); }
+};
+
+static int kidx(int K) { return K == 4 ? 2 : K == 2 ? 1 : 0; }
+
+// ---- resident program --------------------------------------------------------------------------------
+struct Exec {
+  Ctx *ctx;
+  Flat flat;  // own copy: the caller may destroy its clg_flat
+  int mode = 0, K = 4;
+  CUdeviceptr d_instr = 0, d_levels = 0;
+  uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0;
+  size_t smem = 0;
+  CUmodule spec_mod = nullptr;
+  CUfunction spec_fn = nullptr;
+  std::string ptx;
+
+  Exec(Ctx *c, const Flat &f, int want) : ctx(c), flat(f) {
+    ctx->bind();
+    const FlatHeader &h = flat.header();
+    const FlatStream &lv = h.stream[STREAM_LEVEL], &ln = h.stream[STREAM_LANE];
+    auto spec_k = [&]() -> int {
+      if (ln.n_instr == 0 || ln.n_instr > 400000) return 0;
+      for (int k : {4, 2, 1})
+        if ((uint64_t)ln.n_slots * k <= 200) return k;
+      return ln.n_slots <= 240 ? 1 : 0;
+    };
+    auto lane_k = [&]() -> int {
+      if (ln.n_instr == 0) return 0;
+      // prefer the widest vector that still leaves >= 3 CTAs (12 consumer warps) per SM
+      for (int pass = 0; pass < 2; pass++)
+        for (int k : {4, 2, 1}) {
+          size_t need = LANE_RING_BYTES + (size_t)ln.n_slots * LANE_THREADS * k * 4;
+          if (need * (pass == 0 ? 3 : 1) <= SMEM_MAX) return k;
+        }
+      return 0;
+    };
+    auto coop_k = [&]() -> int {
+      if (lv.n_instr == 0) return 0;
+      for (int k : {4, 2, 1})
+        if ((size_t)lv.n_slots * k * 4 <= SMEM_MAX) return k;
+      return 0;
+    };
+    mode = want;
+    if (mode == CLG_MODE_AUTO) mode = spec_k() ? CLG_MODE_SPEC : lane_k() ? CLG_MODE_LANE : CLG_MODE_COOP;
+    const FlatStream *st = nullptr;
+    int sidx = STREAM_LANE;
+    switch (mode) {
+      case CLG_MODE_SPEC:
+        K = spec_k();
+        if (!K) fail(CLG_E_UNSUPPORTED, "program does not fit the specialised mode (no lane stream, too long, or too many live registers)");
+        break;
+      case CLG_MODE_LANE:
+        K = lane_k();
+        if (!K) fail(CLG_E_UNSUPPORTED, "live register set does not fit a per-thread shared-memory stack; use the cooperative mode");
+        st = &ln;
+        smem = LANE_RING_BYTES + (size_t)ln.n_slots * LANE_THREADS * K * 4;
+        break;
+      case CLG_MODE_COOP:
+        K = coop_k();
+        if (!K) fail(CLG_E_UNSUPPORTED, "live register set exceeds one SM's shared memory even at one word per register");
+        st = &lv, sidx = STREAM_LEVEL;
+        smem = std::max<size_t>((size_t)lv.n_slots * K * 4, 16);
+        coop_threads = std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (lv.max_level_width + 31u) / 32u * 32u));
+        break;
+      default: fail(CLG_E_INVALID, "unknown execution mode");
+    }
+    if (st) {
+      n_instr = st->n_instr, n_levels = st->n_levels, n_slots = st->n_slots;
+      CU(cuMemAlloc(&d_instr, std::max<size_t>(16, (size_t)n_instr * 16)));
+      CU(cuMemcpyHtoDAsync(d_instr, flat.instrs(sidx), (size_t)n_instr * 16, nullptr));
+      CU(cuMemAlloc(&d_levels, ((size_t)n_levels + 1) * 4));
+      CU(cuMemcpyHtoDAsync(d_levels, flat.levels(sidx), ((size_t)n_levels + 1) * 4, nullptr));
+      CU(cuStreamSynchronize(nullptr));
+    } else {
+      ptx = emit_spec_ptx(flat, K);
+      char log[8192] = {0}, info[4096] = {0};
+      CUjit_option opt[] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES, CU_JIT_INFO_LOG_BUFFER,
+                            CU_JIT_INFO_LOG_BUFFER_SIZE_BYTES};
+      void *val[] = {log, (void *)(uintptr_t)sizeof log, info, (void *)(uintptr_t)sizeof info};
+      CUresult r = driver().cuModuleLoadDataEx(&spec_mod, ptx.c_str(), 4, opt, val);
+      if (r != CUDA_SUCCESS) fail(CLG_E_PTX, std::string("assembling the specialised kernel failed: ") + log);
+      CU(cuModuleGetFunction(&spec_fn, spec_mod, "clg_spec"));
+    }
+  }
+  ~Exec() {
+    Driver &d = driver();
+    d.cuCtxSetCurrent(ctx->cu);
+    if (d_instr) d.cuMemFree(d_instr);
+    if (d_levels) d.cuMemFree(d_levels);
+    if (spec_mod) d.cuModuleUnload(spec_mod);
+  }
+
+  void run(const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, CUstream stream) {
+    const FlatHeader &h = flat.header();
+    if (stride % 4 != 0) fail(CLG_E_INVALID, "stride must be a multiple of 4 words (16-byte aligned rows)");
+    const size_t words = (n_vectors + 31) / 32;
+    if (words > stride) fail(CLG_E_INVALID, "n_vectors does not fit in stride words");
+    if (stride > 0xFFFFFFFFull) fail(CLG_E_INVALID, "stride too large");
+    if (h.n_inputs && !imm) fail(CLG_E_INVALID, "imm is null");
+    if (h.n_outputs && !out) fail(CLG_E_INVALID, "out is null");
+    if (h.n_state && !state) fail(CLG_E_INVALID, "state is null for a stateful program");
+    if (((uintptr_t)imm | (uintptr_t)out | (uintptr_t)state) & 15) fail(CLG_E_INVALID, "buffers must be 16-byte aligned");
+    if (n_vectors == 0) return;
+    ctx->bind();
+    const uint32_t groups = (uint32_t)((words + K - 1) / K);
+    if (mode == CLG_MODE_SPEC) {
+      uint32_t stride32 = (uint32_t)stride, g = groups;
+      void *args[] = {&imm, &out, &state, &stride32, &g};
+      const uint32_t nt = 128;
+      CU(cuLaunchKernel(spec_fn, (groups + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, args, nullptr));
+      return;
+    }
+    RunParams p{};
+    p.instr = (const void *)d_instr, p.levels = (const uint32_t *)d_levels;
+    p.imm = imm, p.out = out, p.state = state;
+    p.n_inputs = h.n_inputs, p.n_outputs = h.n_outputs;
+    p.n_instr = n_instr, p.n_levels = n_levels, p.n_slots = n_slots;
+    p.stride = (uint32_t)stride, p.n_groups = groups;
+    void *args[] = {&p};
+    if (mode == CLG_MODE_LANE) {
+      const uint32_t grid = (groups + LANE_THREADS - 1) / LANE_THREADS;
+      CU(cuLaunchKernel(ctx->lane[kidx(K)], grid, 1, 1, LANE_THREADS + 32, 1, 1, (unsigned)smem, stream, args, nullptr));
+    } else {
+      const uint32_t grid = std::min<uint32_t>(groups, (uint32_t)ctx->sm_count * (uint32_t)std::max<size_t>(1, std::min<size_t>(SMEM_MAX / (smem + 1024), 2048 / coop_threads)));
+      CU(cuLaunchKernel(ctx->coop[kidx(K)], grid, 1, 1, coop_threads, 1, 1, (unsigned)smem, stream, args, nullptr));
+    }
+  }
+};
+
+// ---- helpers used by the C ABI -------------------------------------------------------------------------
+Ctx *ctx_create(int device) { return new Ctx(device); }
+void ctx_destroy(Ctx *c) { delete c; }
+const std::string &ctx_name(Ctx *c) { return c->name; }
+int ctx_sm_count(Ctx *c) { return c->sm_count; }
+void ctx_sync(Ctx *c) {
+  c->bind();
+  CU(cuCtxSynchronize());
+}
+void *dev_alloc(Ctx *c, size_t bytes) {
+  c->bind();
+  CUdeviceptr p = 0;
+  CU(cuMemAlloc(&p, std::max<size_t>(bytes, 16)));
+  return (void *)p;
+}
+void dev_free(Ctx *c, void *p) {
+  c->bind();
+  CU(cuMemFree((CUdeviceptr)p));
+}
+void dev_memset(Ctx *c, void *p, int byte, size_t bytes, void *stream) {
+  c->bind();
+  CU(cuMemsetD8Async((CUdeviceptr)p, (unsigned char)byte, bytes, (CUstream)stream));
+}
+void h2d(Ctx *c, void *dst, const void *src, size_t bytes, void *stream) {
+  c->bind();
+  CU(cuMemcpyHtoDAsync((CUdeviceptr)dst, src, bytes, (CUstream)stream));
+}
+void d2h(Ctx *c, void *dst, const void *src, size_t bytes, void *stream) {
+  c->bind();
+  CU(cuMemcpyDtoHAsync(dst, (CUdeviceptr)src, bytes, (CUstream)stream));
+}
+void *host_alloc(Ctx *c, size_t bytes) {
+  c->bind();
+  void *p = nullptr;
+  CU(cuMemAllocHost(&p, std::max<size_t>(bytes, 16)));
+  return p;
+}
+void host_free(Ctx *c, void *p) {
+  c->bind();
+  CU(cuMemFreeHost(p));
+}
+void stream_sync(Ctx *c, void *stream) {
+  c->bind();
+  CU(cuStreamSynchronize((CUstream)stream));
+}
+
+Exec *exec_create(Ctx *c, const Flat &f, int mode) { return new Exec(c, f, mode); }
+void exec_destroy(Exec *e) { delete e; }
+int exec_mode(const Exec *e) { return e->mode; }
+int exec_k(const Exec *e) { return e->K; }
+const std::string &exec_ptx(const Exec *e) { return e->ptx; }
+const Flat &exec_flat(const Exec *e) { return e->flat; }
+Ctx *exec_ctx(const Exec *e) { return e->ctx; }
+void exec_run(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, void *stream) {
+  e->run(imm, out, state, n_vectors, stride, (CUstream)stream);
+}
+
+void launch_slice(Ctx *c, bool unslice, const void *src, void *dst, size_t n_vectors, size_t n_rows, size_t stride, void *stream) {
+  if (n_vectors == 0 || n_rows == 0) return;
+  if (n_vectors > 0xFFFFFFFFull || n_rows > 0xFFFFFFFFull || stride > 0xFFFFFFFFull) fail(CLG_E_INVALID, "transpose dimensions too large");
+  if ((n_vectors + 31) / 32 > stride) fail(CLG_E_INVALID, "n_vectors does not fit in stride words");
+  c->bind();
+  uint32_t nv = (uint32_t)n_vectors, nr = (uint32_t)n_rows, st = (uint32_t)stride;
+  uint64_t warps = (uint64_t)((n_rows + 31) / 32) * ((n_vectors + 31) / 32);
+  uint64_t blocks = (warps * 32 + 255) / 256;
+  if (blocks > 0x7FFFFFFFull) fail(CLG_E_INVALID, "transpose too large for one launch");
+  void *args[] = {&src, &dst, &nv, &nr, &st};
+  CU(cuLaunchKernel(unslice ? c->unslice : c->slice, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr));
+}
+
+void launch_fill(Ctx *c, uint32_t *dst, size_t n_rows, size_t stride, uint64_t seed, void *stream) {
+  if (n_rows == 0 || stride == 0) return;
+  if (n_rows > 0xFFFFFFFFull || stride > 0xFFFFFFFFull) fail(CLG_E_INVALID, "fill dimensions too large");
+  c->bind();
+  uint32_t nr = (uint32_t)n_rows, st = (uint32_t)stride;
+  void *args[] = {&dst, &nr, &st, &seed};
+  CU(cuLaunchKernel(c->fill, (unsigned)(c->sm_count * 8), 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr));
+}
+
+// event-timed run used by the sharded driver
+double timed_run(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride) {
+  e->ctx->bind();
+  CUevent a, b;
+  CU(cuEventCreate(&a, CU_EVENT_DEFAULT));
+  CU(cuEventCreate(&b, CU_EVENT_DEFAULT));
+  CU(cuEventRecord(a, nullptr));
+  e->run(imm, out, state, n_vectors, stride, nullptr);
+  CU(cuEventRecord(b, nullptr));
+  CU(cuEventSynchronize(b));
+  float ms = 0;
+  CU(cuEventElapsedTime(&ms, a, b));
+  driver().cuEventDestroy(a), driver().cuEventDestroy(b);
+  return ms * 1e-3;
+}
+
+}  // namespace clg

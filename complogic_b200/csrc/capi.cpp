@@ -1,0 +1,530 @@
+// extern "C" surface (include/complogic_cuda.h). Exceptions never cross it: every entry point
+// catches clg::Error and turns it into a status code + thread-local message.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <thread>
+
+#include "device.hpp"
+
+namespace clg {
+struct Ctx;
+struct Exec;
+Ctx *ctx_create(int device);
+void ctx_destroy(Ctx *);
+const std::string &ctx_name(Ctx *);
+int ctx_sm_count(Ctx *);
+void ctx_sync(Ctx *);
+void *dev_alloc(Ctx *, size_t);
+void dev_free(Ctx *, void *);
+void dev_memset(Ctx *, void *, int, size_t, void *);
+void h2d(Ctx *, void *, const void *, size_t, void *);
+void d2h(Ctx *, void *, const void *, size_t, void *);
+void *host_alloc(Ctx *, size_t);
+void host_free(Ctx *, void *);
+void stream_sync(Ctx *, void *);
+Exec *exec_create(Ctx *, const Flat &, int);
+void exec_destroy(Exec *);
+int exec_mode(const Exec *);
+int exec_k(const Exec *);
+const std::string &exec_ptx(const Exec *);
+const Flat &exec_flat(const Exec *);
+Ctx *exec_ctx(const Exec *);
+void exec_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t, void *);
+void launch_slice(Ctx *, bool, const void *, void *, size_t, size_t, size_t, void *);
+void launch_fill(Ctx *, uint32_t *, size_t, size_t, uint64_t, void *);
+double timed_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t);
+
+static thread_local std::string g_err;
+void fail(int code, const std::string &msg) { throw Error{code, msg}; }
+}  // namespace clg
+
+using namespace clg;
+
+struct clg_ctx {
+  Ctx *c;
+};
+struct clg_exec {
+  Exec *e;
+};
+
+#define CLG_TRY try {
+#define CLG_CATCH                                   \
+  }                                                 \
+  catch (const clg::Error &e) {                     \
+    clg::g_err = e.msg;                             \
+    return e.code;                                  \
+  }                                                 \
+  catch (const std::bad_alloc &) {                  \
+    clg::g_err = "out of memory";                   \
+    return CLG_E_NOMEM;                             \
+  }                                                 \
+  catch (const std::exception &e) {                 \
+    clg::g_err = std::string("internal: ") + e.what(); \
+    return CLG_E_INVALID;                           \
+  }                                                 \
+  return CLG_OK;
+#define NEED(p) ((p) ? (void)0 : fail(CLG_E_INVALID, "null argument: " #p))
+
+extern "C" {
+
+const char *clg_last_error(void) { return g_err.c_str(); }
+uint32_t clg_abi_version(void) { return CLG_ABI_VERSION; }
+void clg_free(void *p) { std::free(p); }
+
+int clg_gate_create(const clg_gate *gate, uint64_t *incrementer_val, clg_op **ops_out, size_t *n_ops_out) {
+  CLG_TRY
+  NEED(gate), NEED(incrementer_val), NEED(ops_out), NEED(n_ops_out);
+  std::vector<Op> ops;
+  gate_create(*gate, *incrementer_val, ops);
+  clg_op *o = (clg_op *)std::malloc(std::max<size_t>(1, ops.size()) * sizeof(clg_op));
+  if (!o) throw std::bad_alloc();
+  std::memcpy(o, ops.data(), ops.size() * sizeof(clg_op));
+  *ops_out = o, *n_ops_out = ops.size();
+  CLG_CATCH
+}
+
+// ---- Simulation ----------------------------------------------------------------------------------------
+int clg_simulation_new(const clg_op *ops, size_t n_ops, const uint8_t *registers, size_t n_registers, clg_simulation **out) {
+  CLG_TRY
+  NEED(out);
+  if (n_ops) NEED(ops);
+  auto *s = new clg_simulation();
+  s->sim.ops.assign(ops, ops + n_ops);
+  for (Op &op : s->sim.ops) op.reserved = 0;
+  if (registers) s->sim.registers.assign(registers, registers + n_registers);
+  else s->sim.registers.assign(n_registers, 0);
+  *out = s;
+  CLG_CATCH
+}
+void clg_simulation_destroy(clg_simulation *sim) { delete sim; }
+const clg_op *clg_simulation_ops(const clg_simulation *sim, size_t *n_ops) {
+  if (n_ops) *n_ops = sim->sim.ops.size();
+  return sim->sim.ops.data();
+}
+uint8_t *clg_simulation_registers(clg_simulation *sim, size_t *n_registers) {
+  if (n_registers) *n_registers = sim->sim.registers.size();
+  return sim->sim.registers.data();
+}
+int clg_simulation_register(const clg_simulation *sim, size_t id, int *value_out) {
+  CLG_TRY
+  NEED(sim), NEED(value_out);
+  if (id >= sim->sim.registers.size()) fail(CLG_E_BAD_REGISTER, "register index out of range (the reference panics at simulation.rs:34)");
+  *value_out = sim->sim.registers[id] != 0;
+  CLG_CATCH
+}
+uint64_t clg_simulation_nand_count(const clg_simulation *sim) {
+  uint64_t n = 0;
+  for (const Op &op : sim->sim.ops) n += op.tag == CLG_OP_NAND;
+  return n;
+}
+
+// ---- Compiler --------------------------------------------------------------------------------------------
+int clg_compiler_new(uint64_t immediate_count, clg_compiler **out) {
+  CLG_TRY
+  NEED(out);
+  *out = new clg_compiler(immediate_count);
+  CLG_CATCH
+}
+void clg_compiler_destroy(clg_compiler *c) { delete c; }
+void clg_compiler_reset_ops(clg_compiler *c) { c->c.reset_ops(); }
+void clg_compiler_reset_incrementer(clg_compiler *c) { c->c.reset_incrementer(); }
+uint64_t clg_compiler_alloc(clg_compiler *c) { return c->c.alloc(); }
+uint64_t clg_compiler_immediate_count(const clg_compiler *c) { return c->c.immediate_count; }
+void clg_compiler_set_immediate_count(clg_compiler *c, uint64_t v) { c->c.immediate_count = v; }
+uint64_t clg_compiler_incrementer(const clg_compiler *c) { return c->c.incrementer; }
+void clg_compiler_set_incrementer(clg_compiler *c, uint64_t v) { c->c.incrementer = v; }
+const clg_op *clg_compiler_ops(const clg_compiler *c, size_t *n_ops) {
+  if (n_ops) *n_ops = c->c.ops.size();
+  return c->c.ops.data();
+}
+int clg_compiler_compile(clg_compiler *c, const clg_gate *gates, size_t n_gates, clg_simulation **out) {
+  CLG_TRY
+  NEED(c), NEED(out);
+  if (n_gates) NEED(gates);
+  auto *s = new clg_simulation();
+  try {
+    s->sim = c->c.compile(gates, n_gates);
+  } catch (...) {
+    delete s;
+    throw;
+  }
+  *out = s;
+  CLG_CATCH
+}
+const char *clg_compiler_graph_dot(const clg_compiler *c) { return c->c.graph_dot.c_str(); }
+
+// ---- levelize / flat ---------------------------------------------------------------------------------------
+int clg_levelize(const clg_simulation *sim, size_t n_immediates, const uint64_t *out_regs, size_t n_out, uint32_t flags,
+                 clg_flat **out) {
+  CLG_TRY
+  NEED(sim), NEED(out);
+  auto *f = new clg_flat();
+  try {
+    f->f = levelize(sim->sim, n_immediates, out_regs, n_out, flags);
+    validate_flat(f->f);
+  } catch (...) {
+    delete f;
+    throw;
+  }
+  *out = f;
+  CLG_CATCH
+}
+void clg_flat_destroy(clg_flat *f) { delete f; }
+int clg_flat_bytes(const clg_flat *f, const void **data, size_t *len) {
+  CLG_TRY
+  NEED(f), NEED(data), NEED(len);
+  *data = f->f.bytes.data(), *len = f->f.bytes.size();
+  CLG_CATCH
+}
+int clg_flat_from_bytes(const void *data, size_t len, clg_flat **out) {
+  CLG_TRY
+  NEED(data), NEED(out);
+  auto *f = new clg_flat();
+  try {
+    f->f.bytes.assign((const uint8_t *)data, (const uint8_t *)data + len);
+    validate_flat(f->f);
+  } catch (...) {
+    delete f;
+    throw;
+  }
+  *out = f;
+  CLG_CATCH
+}
+int clg_flat_get_info(const clg_flat *f, clg_flat_info *info) {
+  CLG_TRY
+  NEED(f), NEED(info);
+  const FlatHeader &h = f->f.header();
+  info->ref_nand_count = h.ref_nand_count, info->ref_set_count = h.ref_set_count;
+  info->n_inputs = h.n_inputs, info->n_outputs = h.n_outputs, info->n_state = h.n_state, info->n_luts = h.n_luts;
+  info->n_levels = h.stream[STREAM_LEVEL].n_levels, info->max_level_width = h.stream[STREAM_LEVEL].max_level_width;
+  info->level_slots = h.stream[STREAM_LEVEL].n_slots, info->lane_slots = h.stream[STREAM_LANE].n_slots;
+  info->level_instrs = h.stream[STREAM_LEVEL].n_instr, info->lane_instrs = h.stream[STREAM_LANE].n_instr;
+  CLG_CATCH
+}
+int clg_flat_state_regs(const clg_flat *f, const uint64_t **regs, size_t *n) {
+  CLG_TRY
+  NEED(f), NEED(regs), NEED(n);
+  *regs = f->f.state_regs(), *n = f->f.header().n_state;
+  CLG_CATCH
+}
+int clg_flat_spec_ptx(const clg_flat *f, int k, char **ptx_out) {
+  CLG_TRY
+  NEED(f), NEED(ptx_out);
+  std::string s = emit_spec_ptx(f->f, k);
+  char *p = (char *)std::malloc(s.size() + 1);
+  if (!p) throw std::bad_alloc();
+  std::memcpy(p, s.c_str(), s.size() + 1);
+  *ptx_out = p;
+  CLG_CATCH
+}
+
+// ---- device -------------------------------------------------------------------------------------------------
+int clg_ctx_create(int device, clg_ctx **out) {
+  CLG_TRY
+  NEED(out);
+  *out = new clg_ctx{ctx_create(device)};
+  CLG_CATCH
+}
+void clg_ctx_destroy(clg_ctx *ctx) {
+  if (!ctx) return;
+  try {
+    ctx_destroy(ctx->c);
+  } catch (...) {
+  }
+  delete ctx;
+}
+int clg_ctx_device_name(clg_ctx *ctx, char *buf, size_t cap) {
+  CLG_TRY
+  NEED(ctx), NEED(buf);
+  std::snprintf(buf, cap, "%s", ctx_name(ctx->c).c_str());
+  CLG_CATCH
+}
+int clg_ctx_sm_count(clg_ctx *ctx) { return ctx ? ctx_sm_count(ctx->c) : 0; }
+int clg_ctx_synchronize(clg_ctx *ctx) {
+  CLG_TRY
+  NEED(ctx);
+  ctx_sync(ctx->c);
+  CLG_CATCH
+}
+int clg_dev_alloc(clg_ctx *ctx, size_t bytes, void **dptr) {
+  CLG_TRY
+  NEED(ctx), NEED(dptr);
+  *dptr = dev_alloc(ctx->c, bytes);
+  CLG_CATCH
+}
+int clg_dev_free(clg_ctx *ctx, void *dptr) {
+  CLG_TRY
+  NEED(ctx);
+  if (dptr) dev_free(ctx->c, dptr);
+  CLG_CATCH
+}
+int clg_dev_memset(clg_ctx *ctx, void *dptr, int byte, size_t bytes, void *stream) {
+  CLG_TRY
+  NEED(ctx), NEED(dptr);
+  dev_memset(ctx->c, dptr, byte, bytes, stream);
+  CLG_CATCH
+}
+int clg_memcpy_h2d(clg_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream) {
+  CLG_TRY
+  NEED(ctx), NEED(dst), NEED(src);
+  h2d(ctx->c, dst, src, bytes, stream);
+  CLG_CATCH
+}
+int clg_memcpy_d2h(clg_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream) {
+  CLG_TRY
+  NEED(ctx), NEED(dst), NEED(src);
+  d2h(ctx->c, dst, src, bytes, stream);
+  CLG_CATCH
+}
+int clg_host_alloc_pinned(clg_ctx *ctx, size_t bytes, void **hptr) {
+  CLG_TRY
+  NEED(ctx), NEED(hptr);
+  *hptr = host_alloc(ctx->c, bytes);
+  CLG_CATCH
+}
+int clg_host_free_pinned(clg_ctx *ctx, void *hptr) {
+  CLG_TRY
+  NEED(ctx);
+  if (hptr) host_free(ctx->c, hptr);
+  CLG_CATCH
+}
+
+int clg_exec_create(clg_ctx *ctx, const clg_flat *flat, int mode, clg_exec **out) {
+  CLG_TRY
+  NEED(ctx), NEED(flat), NEED(out);
+  *out = new clg_exec{exec_create(ctx->c, flat->f, mode)};
+  CLG_CATCH
+}
+void clg_exec_destroy(clg_exec *ex) {
+  if (!ex) return;
+  try {
+    exec_destroy(ex->e);
+  } catch (...) {
+  }
+  delete ex;
+}
+int clg_exec_mode(const clg_exec *ex) { return ex ? exec_mode(ex->e) : 0; }
+int clg_exec_words_per_thread(const clg_exec *ex) { return ex ? exec_k(ex->e) : 0; }
+int clg_exec_launches_per_run(const clg_exec *) { return 1; }
+const char *clg_exec_ptx(const clg_exec *ex) { return ex ? exec_ptx(ex->e).c_str() : ""; }
+
+int clg_exec_run(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, void *stream) {
+  CLG_TRY
+  NEED(ex);
+  exec_run(ex->e, imm, out, state, n_vectors, stride, stream);
+  CLG_CATCH
+}
+
+namespace {
+struct DevBuf {
+  Ctx *c;
+  void *p = nullptr;
+  DevBuf(Ctx *c_, size_t bytes) : c(c_) { p = dev_alloc(c, bytes); }
+  ~DevBuf() {
+    try {
+      if (p) dev_free(c, p);
+    } catch (...) {
+    }
+  }
+};
+}  // namespace
+
+int clg_exec_run_host(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride) {
+  CLG_TRY
+  NEED(ex);
+  Ctx *c = exec_ctx(ex->e);
+  const FlatHeader &h = exec_flat(ex->e).header();
+  const size_t row = stride * 4;
+  DevBuf di(c, h.n_inputs * row), dout(c, h.n_outputs * row), ds(c, h.n_state * row);
+  if (h.n_inputs) {
+    NEED(imm);
+    h2d(c, di.p, imm, h.n_inputs * row, nullptr);
+  }
+  if (h.n_state) {
+    NEED(state);
+    h2d(c, ds.p, state, h.n_state * row, nullptr);
+  }
+  exec_run(ex->e, (const uint32_t *)di.p, (uint32_t *)dout.p, h.n_state ? (uint32_t *)ds.p : nullptr, n_vectors, stride, nullptr);
+  if (h.n_outputs) {
+    NEED(out);
+    d2h(c, out, dout.p, h.n_outputs * row, nullptr);
+  }
+  if (h.n_state) d2h(c, state, ds.p, h.n_state * row, nullptr);
+  stream_sync(c, nullptr);
+  CLG_CATCH
+}
+
+int clg_exec_run_bools_host(clg_exec *ex, const uint8_t *imm, uint8_t *out, size_t n_vectors) {
+  CLG_TRY
+  NEED(ex);
+  Ctx *c = exec_ctx(ex->e);
+  const FlatHeader &h = exec_flat(ex->e).header();
+  if (h.n_state) fail(CLG_E_UNSUPPORTED, "run_bools_host is for stateless programs; use clg_sim_runner for carried state");
+  const size_t stride = ((n_vectors + 31) / 32 + 3) / 4 * 4, row = stride * 4;
+  DevBuf bi(c, n_vectors * h.n_inputs), bo(c, n_vectors * h.n_outputs), di(c, h.n_inputs * row), dout(c, h.n_outputs * row);
+  if (h.n_inputs && n_vectors) {
+    NEED(imm);
+    h2d(c, bi.p, imm, n_vectors * h.n_inputs, nullptr);
+    dev_memset(c, di.p, 0, h.n_inputs * row, nullptr);
+    launch_slice(c, false, bi.p, di.p, n_vectors, h.n_inputs, stride, nullptr);
+  }
+  exec_run(ex->e, (const uint32_t *)di.p, (uint32_t *)dout.p, nullptr, n_vectors, stride, nullptr);
+  if (h.n_outputs && n_vectors) {
+    NEED(out);
+    launch_slice(c, true, dout.p, bo.p, n_vectors, h.n_outputs, stride, nullptr);
+    d2h(c, out, bo.p, n_vectors * h.n_outputs, nullptr);
+  }
+  stream_sync(c, nullptr);
+  CLG_CATCH
+}
+
+int clg_slice_bools(clg_ctx *ctx, const uint8_t *bools, uint32_t *sliced, size_t n_vectors, size_t n_rows, size_t stride, void *stream) {
+  CLG_TRY
+  NEED(ctx), NEED(bools), NEED(sliced);
+  launch_slice(ctx->c, false, bools, sliced, n_vectors, n_rows, stride, stream);
+  CLG_CATCH
+}
+int clg_unslice_bools(clg_ctx *ctx, const uint32_t *sliced, uint8_t *bools, size_t n_vectors, size_t n_rows, size_t stride, void *stream) {
+  CLG_TRY
+  NEED(ctx), NEED(bools), NEED(sliced);
+  launch_slice(ctx->c, true, sliced, bools, n_vectors, n_rows, stride, stream);
+  CLG_CATCH
+}
+int clg_fill_random(clg_ctx *ctx, uint32_t *sliced, size_t n_rows, size_t stride, uint64_t seed, void *stream) {
+  CLG_TRY
+  NEED(ctx), NEED(sliced);
+  launch_fill(ctx->c, sliced, n_rows, stride, seed, stream);
+  CLG_CATCH
+}
+
+// ---- Simulation::run for one vector, carried registers, on the device -----------------------------------------
+struct clg_sim_runner {
+  Ctx *c;
+  clg_simulation *sim;
+  Exec *e = nullptr;
+  size_t n_imm;
+  void *d_imm = nullptr, *d_out = nullptr, *d_state = nullptr;
+  std::vector<uint32_t> h_imm, h_out, h_state;
+  clg_sim_runner(Ctx *c_, clg_simulation *s_, size_t n) : c(c_), sim(s_), n_imm(n) {}
+  ~clg_sim_runner() {
+    try {
+      if (e) exec_destroy(e);
+      if (d_imm) dev_free(c, d_imm);
+      if (d_out) dev_free(c, d_out);
+      if (d_state) dev_free(c, d_state);
+    } catch (...) {
+    }
+  }
+};
+
+int clg_sim_runner_create(clg_ctx *ctx, clg_simulation *sim, size_t n_immediates, int mode, clg_sim_runner **out) {
+  CLG_TRY
+  NEED(ctx), NEED(sim), NEED(out);
+  Flat f = levelize(sim->sim, n_immediates, nullptr, 0, CLG_LV_STATEFUL);
+  validate_flat(f);
+  auto *r = new clg_sim_runner(ctx->c, sim, n_immediates);
+  try {
+    r->e = exec_create(ctx->c, f, mode);
+    const FlatHeader &h = f.header();
+    r->h_imm.assign((size_t)h.n_inputs * 4, 0), r->h_out.assign((size_t)h.n_outputs * 4, 0), r->h_state.assign((size_t)h.n_state * 4, 0);
+    r->d_imm = dev_alloc(ctx->c, r->h_imm.size() * 4), r->d_out = dev_alloc(ctx->c, r->h_out.size() * 4);
+    r->d_state = dev_alloc(ctx->c, r->h_state.size() * 4);
+  } catch (...) {
+    delete r;
+    throw;
+  }
+  *out = r;
+  CLG_CATCH
+}
+void clg_sim_runner_destroy(clg_sim_runner *r) { delete r; }
+
+int clg_sim_runner_run(clg_sim_runner *r, const uint8_t *immediates, size_t n_immediates) {
+  CLG_TRY
+  NEED(r);
+  if (n_immediates != r->n_imm) fail(CLG_E_INVALID, "runner was built for a different immediates length");
+  if (n_immediates) NEED(immediates);
+  const Flat &f = exec_flat(r->e);
+  const FlatHeader &h = f.header();
+  std::vector<uint8_t> &regs = r->sim->sim.registers;
+  if (regs.size() != h.n_registers) fail(CLG_E_INVALID, "Simulation::registers was resized after the runner was created");
+  for (size_t i = 0; i < h.n_inputs; i++) r->h_imm[i * 4] = immediates[i] ? 1u : 0u;
+  const uint64_t *sr = f.state_regs();
+  for (size_t k = 0; k < h.n_state; k++) r->h_state[k * 4] = regs[sr[k]] ? 1u : 0u;  // registers are public and writable
+  if (h.n_inputs) h2d(r->c, r->d_imm, r->h_imm.data(), r->h_imm.size() * 4, nullptr);
+  if (h.n_state) h2d(r->c, r->d_state, r->h_state.data(), r->h_state.size() * 4, nullptr);
+  exec_run(r->e, (const uint32_t *)r->d_imm, (uint32_t *)r->d_out, h.n_state ? (uint32_t *)r->d_state : nullptr, 1, 4, nullptr);
+  if (h.n_outputs) d2h(r->c, r->h_out.data(), r->d_out, r->h_out.size() * 4, nullptr);
+  stream_sync(r->c, nullptr);
+  for (size_t i = 0; i < h.n_outputs; i++) regs[i] = (uint8_t)(r->h_out[i * 4] & 1u);  // outputs == every register, in order
+  CLG_CATCH
+}
+
+// ---- single-process multi-GPU sharding --------------------------------------------------------------------------
+int clg_run_sharded_host(const clg_flat *flat, int mode, const int *devices, int n_devices, const uint32_t *imm, uint32_t *out,
+                         size_t n_vectors, size_t stride, double *seconds_out) {
+  CLG_TRY
+  NEED(flat), NEED(devices);
+  if (n_devices < 1) fail(CLG_E_INVALID, "need at least one device");
+  const FlatHeader &h = flat->f.header();
+  if (h.n_state) fail(CLG_E_UNSUPPORTED, "sharded runs are for stateless programs");
+  if (stride % 4) fail(CLG_E_INVALID, "stride must be a multiple of 4 words");
+  const size_t words = (n_vectors + 31) / 32, quads = (words + 3) / 4;
+  std::vector<Error> errs(n_devices, Error{CLG_OK, ""});
+  std::vector<std::thread> th;
+  for (int d = 0; d < n_devices; d++)
+    th.emplace_back([&, d] {
+      try {
+        // contiguous ranges of 4-word quads: rows stay 16-byte aligned on every shard
+        const size_t w0 = quads * d / n_devices * 4, w1 = std::min(words, quads * (d + 1) / n_devices * 4);
+        if (seconds_out) seconds_out[d] = 0;
+        if (w1 <= w0) return;
+        const size_t sw = (w1 - w0 + 3) / 4 * 4, nv = std::min(n_vectors, w1 * 32) - w0 * 32;
+        std::unique_ptr<Ctx, void (*)(Ctx *)> c(ctx_create(devices[d]), ctx_destroy);
+        std::unique_ptr<Exec, void (*)(Exec *)> e(exec_create(c.get(), flat->f, mode), exec_destroy);
+        DevBuf di(c.get(), h.n_inputs * sw * 4), dout(c.get(), h.n_outputs * sw * 4);
+        for (size_t r = 0; r < h.n_inputs; r++)
+          h2d(c.get(), (char *)di.p + r * sw * 4, imm + r * stride + w0, (w1 - w0) * 4, nullptr);
+        double t = timed_run(e.get(), (const uint32_t *)di.p, (uint32_t *)dout.p, nullptr, nv, sw);
+        if (seconds_out) seconds_out[d] = t;
+        for (size_t r = 0; r < h.n_outputs; r++)
+          d2h(c.get(), out + r * stride + w0, (char *)dout.p + r * sw * 4, (w1 - w0) * 4, nullptr);
+        stream_sync(c.get(), nullptr);
+      } catch (const Error &e) {
+        errs[d] = e;
+      } catch (const std::exception &e) {
+        errs[d] = Error{CLG_E_INVALID, e.what()};
+      }
+    });
+  for (auto &t : th) t.join();
+  for (const Error &e : errs)
+    if (e.code != CLG_OK) throw e;
+  CLG_CATCH
+}
+
+// ---- JSON ---------------------------------------------------------------------------------------------------------
+int clg_simulation_to_json(const clg_simulation *sim, char **json_out) {
+  CLG_TRY
+  NEED(sim), NEED(json_out);
+  std::string s = simulation_to_json(sim->sim);
+  char *p = (char *)std::malloc(s.size() + 1);
+  if (!p) throw std::bad_alloc();
+  std::memcpy(p, s.c_str(), s.size() + 1);
+  *json_out = p;
+  CLG_CATCH
+}
+int clg_simulation_from_json(const char *json, clg_simulation **out) {
+  CLG_TRY
+  NEED(json), NEED(out);
+  auto *s = new clg_simulation();
+  try {
+    s->sim = simulation_from_json(json);
+  } catch (...) {
+    delete s;
+    throw;
+  }
+  *out = s;
+  CLG_CATCH
+}
+
+}  // extern "C"

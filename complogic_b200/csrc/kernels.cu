@@ -1,0 +1,346 @@
+// sm_100a kernels of the NAND-VM backend. Compiled to a cubin (nvcc -cubin -arch=sm_100a) that is
+// embedded in libcomplogic_cuda.so and loaded through the driver API.
+//
+// What is evaluated is `Simulation::run` (complogic/src/simulation.rs:16-30) for many independent
+// input vectors at once: bit-sliced, so one 32-bit lane word carries 32 circuit instances and
+// `!(a && b)` over 32 instances is one LOP3. The program is the flat stream of flat.hpp (NAND cones
+// already fused into 3-input LUTs, one LOP3 each, physical registers already allocated).
+//
+//   clg_lane<K>  lane-parallel interpreter. One thread owns K consecutive words of every row
+//                (32*K vectors) and runs the whole lane-ordered stream on them. The live register
+//                stack sits in shared memory as [slot][thread] (bank = thread: conflict free, K*4-byte
+//                vector accesses). A producer warp streams the instruction stream into a shared-memory
+//                ring with cp.async.bulk + mbarrier (full/empty pipeline); consumer warps run freely,
+//                never synchronising with each other. Instructions are warp-uniform: one broadcast
+//                128-bit LDS fetches them, the LUT immediate is dispatched through a uniform branch.
+//   clg_coop<K>  cooperative intra-level interpreter for programs whose live set cannot be held per
+//                thread (10^4..10^5 live values): one CTA shares ONE register stack for K words
+//                (32*K vectors) in shared memory as [slot][K]; the instructions of a level are
+//                independent, so the CTA's threads split them and meet at a barrier per level.
+//   clg_slice / clg_unslice / clg_fill_random  layout helpers (vector-major <-> bit-sliced).
+//
+// Global memory is touched only for the algorithmic traffic: each input row word is read once
+// (ld.global.nc, K*4-byte vectors, coalesced across the warp in lane mode), each output word is
+// written once.
+#include <cstdint>
+
+#include "flat.hpp"
+
+namespace clg {
+
+struct RunParams {
+  const uint4 *instr;      // FlatInstr stream on the device
+  const uint32_t *levels;  // level offsets (coop)
+  const uint32_t *imm;     // [n_inputs][stride]
+  uint32_t *out;           // [n_outputs][stride]
+  uint32_t *state;         // [n_state][stride], updated in place
+  uint32_t n_inputs, n_outputs;
+  uint32_t n_instr, n_levels, n_slots;
+  uint32_t stride;    // words between rows
+  uint32_t n_groups;  // K-word column groups to evaluate
+};
+
+// ---- LOP3 with a compile-time immediate, dispatched on the instruction's truth table --------------
+template <int TT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(TT));
+  return d;
+}
+
+template <int K>
+struct Vec;
+template <>
+struct Vec<1> {
+  uint32_t w[1];
+};
+template <>
+struct __align__(8) Vec<2> {
+  uint32_t w[2];
+};
+template <>
+struct __align__(16) Vec<4> {
+  uint32_t w[4];
+};
+
+#define CLG_C1(n)                                                           \
+  case (n):                                                                 \
+    _Pragma("unroll") for (int k = 0; k < K; k++) r.w[k] = lop3<(n)>(a.w[k], b.w[k], c.w[k]); \
+    break;
+#define CLG_C4(n) CLG_C1(n) CLG_C1((n) + 1) CLG_C1((n) + 2) CLG_C1((n) + 3)
+#define CLG_C16(n) CLG_C4(n) CLG_C4((n) + 4) CLG_C4((n) + 8) CLG_C4((n) + 12)
+#define CLG_C64(n) CLG_C16(n) CLG_C16((n) + 16) CLG_C16((n) + 32) CLG_C16((n) + 48)
+
+template <int K>
+__device__ __forceinline__ Vec<K> lut3(uint32_t tt, const Vec<K> &a, const Vec<K> &b, const Vec<K> &c) {
+  Vec<K> r;
+  switch (tt) {
+    CLG_C64(0)
+    CLG_C64(64)
+    CLG_C64(128)
+    CLG_C64(192)
+    default:
+      _Pragma("unroll") for (int k = 0; k < K; k++) r.w[k] = 0;
+  }
+  return r;
+}
+
+// ---- global memory: read-once / write-once vectors -------------------------------------------------
+template <int K>
+__device__ __forceinline__ Vec<K> ld_row(const uint32_t *p) {
+  Vec<K> v;
+  if constexpr (K == 4)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3])
+                 : "l"(p));
+  else if constexpr (K == 2)
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.w[0]), "=r"(v.w[1]) : "l"(p));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v.w[0]) : "l"(p));
+  return v;
+}
+template <int K>
+__device__ __forceinline__ void st_row(uint32_t *p, const Vec<K> &v) {
+  if constexpr (K == 4)
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]),
+                 "r"(v.w[3])
+                 : "memory");
+  else if constexpr (K == 2)
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]) : "memory");
+  else
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v.w[0]) : "memory");
+}
+
+__device__ __forceinline__ const uint32_t *in_row(const RunParams &p, uint32_t row) {
+  return row < p.n_inputs ? p.imm + (size_t)row * p.stride : p.state + (size_t)(row - p.n_inputs) * p.stride;
+}
+__device__ __forceinline__ uint32_t *out_row(const RunParams &p, uint32_t row) {
+  return row < p.n_outputs ? p.out + (size_t)row * p.stride : p.state + (size_t)(row - p.n_outputs) * p.stride;
+}
+
+// ---- mbarrier / bulk-copy primitives (PTX) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA engine, 1-D), completion signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- lane-parallel interpreter -----------------------------------------------------------------------
+constexpr int LANE_THREADS = 128;  // consumer threads per CTA (+ one producer warp)
+constexpr int RING_STAGES = 4;
+constexpr int RING_CHUNK = 256;  // instructions per stage (4 KiB)
+
+template <int K>
+__device__ __forceinline__ void lane_body(const RunParams &p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint4 *ring = reinterpret_cast<uint4 *>(smem);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + RING_STAGES * RING_CHUNK * 16);
+  uint64_t *empty = full + RING_STAGES;
+  Vec<K> *slots = reinterpret_cast<Vec<K> *>(smem + RING_STAGES * RING_CHUNK * 16 + 128);
+
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < RING_STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], LANE_THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint32_t n_chunks = (p.n_instr + RING_CHUNK - 1) / RING_CHUNK;
+
+  if (tid >= LANE_THREADS) {
+    // ---- producer warp: one elected lane feeds the ring ----
+    if (tid == LANE_THREADS) {
+      for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t s = c % RING_STAGES, use = c / RING_STAGES;
+        if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+        const uint32_t n = min((uint32_t)RING_CHUNK, p.n_instr - c * RING_CHUNK);
+        mbar_expect_tx(&full[s], n * 16);
+        bulk_g2s(ring + s * RING_CHUNK, p.instr + (size_t)c * RING_CHUNK, n * 16, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warps ----
+  const uint32_t gid = blockIdx.x * LANE_THREADS + tid;
+  const bool active = gid < p.n_groups;
+  const size_t col = (size_t)(active ? gid : 0) * K;
+  Vec<K> *my = slots + tid;  // slot s lives at my[s * LANE_THREADS]
+
+  for (uint32_t c = 0; c < n_chunks; c++) {
+    const uint32_t s = c % RING_STAGES, use = c / RING_STAGES;
+    mbar_wait(&full[s], use & 1);
+    const uint32_t n = min((uint32_t)RING_CHUNK, p.n_instr - c * RING_CHUNK);
+    const uint4 *code = ring + s * RING_CHUNK;
+    for (uint32_t i = 0; i < n; i++) {
+      const uint4 ins = code[i];  // warp-uniform address: one broadcast LDS.128
+      const uint32_t dst = ins.x & 0xFFFFu, sa = ins.x >> 16, sb = ins.y & 0xFFFFu, sc = ins.y >> 16;
+      const uint32_t tt = ins.z & 0xFFu, kind = (ins.z >> 8) & 0xFFu, inv = (ins.z >> 16) & 1u;
+      if (kind == K_LUT) {
+        const Vec<K> a = my[sa * LANE_THREADS], b = my[sb * LANE_THREADS], cc = my[sc * LANE_THREADS];
+        my[dst * LANE_THREADS] = lut3<K>(tt, a, b, cc);
+      } else if (kind == K_LDIN) {
+        Vec<K> v;
+#pragma unroll
+        for (int k = 0; k < K; k++) v.w[k] = 0;
+        if (active) v = ld_row<K>(in_row(p, ins.w) + col);
+        my[dst * LANE_THREADS] = v;
+      } else {
+        Vec<K> v;
+        const uint32_t m = inv ? 0xFFFFFFFFu : 0u;
+        if (kind == K_STOUT) {
+          v = my[sa * LANE_THREADS];
+#pragma unroll
+          for (int k = 0; k < K; k++) v.w[k] ^= m;
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; k++) v.w[k] = m;
+        }
+        if (active) st_row<K>(out_row(p, ins.w) + col, v);
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+  }
+}
+
+// ---- cooperative intra-level interpreter ---------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_instr(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+template <int K>
+__device__ __forceinline__ void coop_body(const RunParams &p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  Vec<K> *slots = reinterpret_cast<Vec<K> *>(smem);
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+
+  for (uint32_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+    const size_t col = (size_t)g * K;
+    uint32_t lb = __ldg(p.levels);
+    for (uint32_t l = 0; l < p.n_levels; l++) {
+      const uint32_t le = __ldg(p.levels + l + 1);
+      uint32_t i = lb + tid;
+      uint4 ins = make_uint4(0, 0, 0, 0);
+      if (i < le) ins = ld_instr(p.instr + i);
+      while (i < le) {
+        const uint32_t nexti = i + nt;
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (nexti < le) nxt = ld_instr(p.instr + nexti);  // software prefetch of the next instruction
+        const uint32_t dst = ins.x & 0xFFFFu, sa = ins.x >> 16, sb = ins.y & 0xFFFFu, sc = ins.y >> 16;
+        const uint32_t tt = ins.z & 0xFFu, kind = (ins.z >> 8) & 0xFFu, inv = (ins.z >> 16) & 1u;
+        if (kind == K_LUT) {
+          const Vec<K> a = slots[sa], b = slots[sb], cc = slots[sc];
+          slots[dst] = lut3<K>(tt, a, b, cc);
+        } else if (kind == K_LDIN) {
+          slots[dst] = ld_row<K>(in_row(p, ins.w) + col);
+        } else {
+          Vec<K> v;
+          const uint32_t m = inv ? 0xFFFFFFFFu : 0u;
+          if (kind == K_STOUT) {
+            v = slots[sa];
+#pragma unroll
+            for (int k = 0; k < K; k++) v.w[k] ^= m;
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) v.w[k] = m;
+          }
+          st_row<K>(out_row(p, ins.w) + col, v);
+        }
+        ins = nxt;
+        i = nexti;
+      }
+      lb = le;
+      __syncthreads();  // level boundary: every slot written in this level is visible to the next
+    }
+  }
+}
+
+// ---- layout helpers ----------------------------------------------------------------------------------
+// bools [n_vectors][n_rows] bytes (one run()'s `&[bool]` per vector)  ->  sliced [n_rows][stride] words
+extern "C" __global__ void __launch_bounds__(256) clg_slice(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows,
+                                                  uint32_t stride) {
+  const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t row_tiles = (n_rows + 31) / 32, words = (n_vectors + 31) / 32;
+  if (warp >= row_tiles * words) return;
+  const uint32_t w = warp / row_tiles, r0 = (warp % row_tiles) * 32;
+  const uint32_t v = w * 32 + lane;
+  uint32_t mine = 0;
+  for (uint32_t r = 0; r < 32; r++) {
+    uint32_t bit = 0;
+    if (v < n_vectors && r0 + r < n_rows) bit = bools[(size_t)v * n_rows + r0 + r] != 0;
+    const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
+    if (lane == r) mine = word;
+  }
+  if (r0 + lane < n_rows) sliced[(size_t)(r0 + lane) * stride + w] = mine;
+}
+
+extern "C" __global__ void __launch_bounds__(256) clg_unslice(const uint32_t *sliced, uint8_t *bools, uint32_t n_vectors, uint32_t n_rows,
+                                                    uint32_t stride) {
+  const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t row_tiles = (n_rows + 31) / 32, words = (n_vectors + 31) / 32;
+  if (warp >= row_tiles * words) return;
+  const uint32_t w = warp / row_tiles, r0 = (warp % row_tiles) * 32;
+  uint32_t word = 0;
+  if (r0 + lane < n_rows) word = sliced[(size_t)(r0 + lane) * stride + w];
+  for (uint32_t k = 0; k < 32; k++) {
+    const uint32_t v = w * 32 + k;
+    if (v < n_vectors && r0 + lane < n_rows) bools[(size_t)v * n_rows + r0 + lane] = (word >> k) & 1u;
+  }
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+
+extern "C" __global__ void __launch_bounds__(256) clg_fill_random(uint32_t *sliced, uint32_t n_rows, uint32_t stride, uint64_t seed) {
+  const size_t total = (size_t)n_rows * stride;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const uint64_t row = i / stride, w = i % stride;
+    sliced[i] = (uint32_t)(splitmix64(seed ^ (row << 40) ^ w) >> 32);
+  }
+}
+
+}  // namespace clg
+
+// C-named entry points the host looks up in the cubin (one per words-per-thread variant)
+#define CLG_ENTRY(K)                                                                                           \
+  extern "C" __global__ void __launch_bounds__(clg::LANE_THREADS + 32) clg_lane_k##K(const clg::RunParams p) { \
+    clg::lane_body<K>(p);                                                                                      \
+  }                                                                                                            \
+  extern "C" __global__ void __launch_bounds__(1024) clg_coop_k##K(const clg::RunParams p) { clg::coop_body<K>(p); }
+CLG_ENTRY(1)
+CLG_ENTRY(2)
+CLG_ENTRY(4)

@@ -1,0 +1,845 @@
+// The compiler pass the north-star adds in front of the device: take the reference's in-order
+// NAND program (`Simulation::ops`, executed by simulation.rs:16-30) and produce the flat,
+// level-ordered, register-allocated device buffer (flat.hpp).
+//
+//   1. SSA rename.  Ops execute strictly in list order, registers may be written more than once
+//      and read before they are written (simulation.rs:16-30). Walking the
+//      list with a "current value of register r" table turns that into a pure dataflow graph.
+//      The graph is an and-inverter graph with complemented edges, so `Nand(a,a,out)` (more than
+//      half of what gates.rs emits) costs nothing, and structural hashing shares duplicates.
+//   2. Set handling (simulation.rs:26): id < n_immediates reads input row id, otherwise the
+//      literal. Reads of a never-written register see `false` (fresh Simulation, compile.rs:199)
+//      or, in stateful mode, the carried value of that register.
+//   3. LUT3 mapping: priority-cut enumeration (k = 3) + area-flow selection. One LUT3 is one LOP3.
+//   4. Two schedules of the same LUT network, each with its own physical register allocation:
+//      level order (instructions of a level are independent; the cooperative kernel splits them
+//      across the threads of a CTA) and lane order (depth-first, small live set; the lane-parallel
+//      kernels run it sequentially per thread).
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <queue>
+
+#include "host.hpp"
+
+namespace clg {
+
+namespace {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+// ---- and-inverter graph ---------------------------------------------------------------------
+// literal = 2 * node + complement; node 0 is constant false (literal 0 = false, 1 = true).
+struct Aig {
+  std::vector<uint32_t> f0, f1;  // AND fanin literals; inputs: f0 = NONE, f1 = input row
+  std::vector<uint32_t> table;   // open-addressing structural hash: node ids, NONE = empty
+  size_t used = 0;
+
+  Aig() {
+    f0.push_back(NONE), f1.push_back(NONE);
+    table.assign(1u << 12, NONE);
+  }
+  size_t size() const { return f0.size(); }
+  bool is_and(uint32_t n) const { return f0[n] != NONE; }
+  bool is_input(uint32_t n) const { return n != 0 && f0[n] == NONE; }
+  uint32_t input(uint32_t row) {
+    f0.push_back(NONE), f1.push_back(row);
+    return (uint32_t)(f0.size() - 1) << 1;
+  }
+  static uint64_t mix(uint32_t a, uint32_t b) {
+    uint64_t x = ((uint64_t)a << 32) | b;
+    x ^= x >> 33, x *= 0xff51afd7ed558ccdULL, x ^= x >> 33, x *= 0xc4ceb9fe1a85ec53ULL, x ^= x >> 33;
+    return x;
+  }
+  void grow() {
+    std::vector<uint32_t> old;
+    old.swap(table);
+    table.assign(old.size() * 2, NONE);
+    for (uint32_t n : old)
+      if (n != NONE) {
+        size_t h = mix(f0[n], f1[n]) & (table.size() - 1);
+        while (table[h] != NONE) h = (h + 1) & (table.size() - 1);
+        table[h] = n;
+      }
+  }
+  uint32_t and_(uint32_t a, uint32_t b) {
+    if (a > b) std::swap(a, b);
+    if (a == 0) return 0;
+    if (a == 1) return b;
+    if (a == b) return a;
+    if ((a ^ 1u) == b) return 0;
+    size_t h = mix(a, b) & (table.size() - 1);
+    while (table[h] != NONE) {
+      uint32_t n = table[h];
+      if (f0[n] == a && f1[n] == b) return n << 1;
+      h = (h + 1) & (table.size() - 1);
+    }
+    if (f0.size() >= 0x7FFFFFF0u) fail(CLG_E_UNSUPPORTED, "program too large (2^31 graph nodes)");
+    f0.push_back(a), f1.push_back(b);
+    uint32_t n = (uint32_t)(f0.size() - 1);
+    table[h] = n;
+    if (++used * 2 > table.size()) grow();
+    return n << 1;
+  }
+};
+
+// ---- truth tables over <= 3 ordered leaves -----------------------------------------------------
+// Bit ((v0 << 2) | (v1 << 1) | v2) of a table is the function value; leaf i is LOP3 operand a/b/c.
+constexpr uint8_t VAR[3] = {0xF0, 0xCC, 0xAA};
+
+// Re-express table `tt` (over leaves placed at positions 0..2) with leaf i moved to position p[i].
+inline uint8_t remap(uint8_t tt, const uint8_t p[3]) {
+  uint8_t r = 0;
+  for (int m = 0; m < 8; m++) {
+    int idx = ((((m >> (2 - p[0])) & 1) << 2) | (((m >> (2 - p[1])) & 1) << 1) | ((m >> (2 - p[2])) & 1));
+    r |= (uint8_t)(((tt >> idx) & 1) << m);
+  }
+  return r;
+}
+
+struct RemapTable {
+  uint8_t t[27][256];
+  RemapTable() {
+    for (int q = 0; q < 27; q++) {
+      uint8_t p[3] = {(uint8_t)(q / 9), (uint8_t)((q / 3) % 3), (uint8_t)(q % 3)};
+      for (int tt = 0; tt < 256; tt++) t[q][tt] = remap((uint8_t)tt, p);
+    }
+  }
+};
+const RemapTable &remap_table() {
+  static RemapTable T;
+  return T;
+}
+
+struct Cut {
+  uint32_t leaf[3];
+  uint8_t n;
+  uint8_t tt;
+  uint16_t depth;
+  float flow;
+};
+
+// The mapped network handed to the schedulers.
+struct Val {
+  uint8_t is_lut;  // 0: input row
+  uint8_t tt;
+  uint8_t nfan;
+  uint32_t fan[3];
+  uint32_t row;  // input row for is_lut == 0
+};
+struct OutRef {
+  uint32_t row;
+  uint32_t val;  // NONE: constant
+  bool inv;      // invert on store / constant value
+};
+
+struct Network {
+  std::vector<Val> vals;  // topological: every fanin index < own index
+  std::vector<OutRef> outs;
+  uint32_t n_inputs = 0, n_state = 0, n_outputs = 0;
+};
+
+// ---- LUT3 mapping ------------------------------------------------------------------------------
+struct Mapper {
+  const Aig &g;
+  const std::vector<uint32_t> &out_lits;
+  bool fuse;
+  int P;  // cuts kept per node
+
+  std::vector<uint8_t> live;
+  std::vector<uint32_t> refs;      // AIG fanout counts (reachable part)
+  std::vector<float> flow;         // best area flow per node
+  std::vector<uint16_t> depth;     // best depth per node
+  std::vector<Cut> best;           // chosen cut per AND node
+  std::vector<Cut> pool;           // all kept cuts
+  std::vector<uint32_t> pool_off;  // per node
+  std::vector<uint8_t> pool_cnt;
+
+  Mapper(const Aig &g_, const std::vector<uint32_t> &o, bool fuse_) : g(g_), out_lits(o), fuse(fuse_), P(6) {}
+
+  void mark_live() {
+    size_t N = g.size();
+    live.assign(N, 0);
+    refs.assign(N, 0);
+    for (uint32_t l : out_lits) live[l >> 1] = 1, refs[l >> 1]++;
+    for (size_t n = N; n-- > 1;)
+      if (live[n] && g.is_and((uint32_t)n)) {
+        live[g.f0[n] >> 1] = 1, refs[g.f0[n] >> 1]++;
+        live[g.f1[n] >> 1] = 1, refs[g.f1[n] >> 1]++;
+      }
+  }
+
+  static int merge(const Cut &x, const Cut &y, uint32_t out[3]) {
+    int i = 0, j = 0, k = 0;
+    while (i < x.n || j < y.n) {
+      uint32_t v;
+      if (j >= y.n || (i < x.n && x.leaf[i] < y.leaf[j])) v = x.leaf[i++];
+      else if (i >= x.n || y.leaf[j] < x.leaf[i]) v = y.leaf[j++];
+      else v = x.leaf[i], i++, j++;
+      if (k == 3) return -1;
+      out[k++] = v;
+    }
+    return k;
+  }
+  static uint8_t expand(const Cut &c, const uint32_t *leaf, int n) {
+    uint8_t p[3] = {0, 0, 0};
+    for (int i = 0; i < c.n; i++)
+      for (int j = 0; j < n; j++)
+        if (leaf[j] == c.leaf[i]) p[i] = (uint8_t)j;
+    return remap_table().t[p[0] * 9 + p[1] * 3 + p[2]][c.tt];
+  }
+
+  void eval_cut(Cut &c, uint32_t node) const {
+    float f = 1.0f;
+    uint16_t d = 0;
+    for (int i = 0; i < c.n; i++) f += flow[c.leaf[i]], d = std::max(d, depth[c.leaf[i]]);
+    c.flow = f / (float)std::max<uint32_t>(1u, refs[node]);
+    c.depth = (uint16_t)std::min<int>(65535, d + 1);
+  }
+  static bool better(const Cut &a, const Cut &b) {
+    if (a.flow != b.flow) return a.flow < b.flow;
+    if (a.depth != b.depth) return a.depth < b.depth;
+    return a.n < b.n;
+  }
+
+  void enumerate() {
+    size_t N = g.size();
+    flow.assign(N, 0.f), depth.assign(N, 0);
+    best.assign(N, Cut{});
+    pool_off.assign(N, 0), pool_cnt.assign(N, 0);
+    pool.clear();
+    std::vector<Cut> cand, sx, sy;
+    for (uint32_t n = 1; n < N; n++) {
+      if (!live[n] || !g.is_and(n)) continue;
+      uint32_t x = g.f0[n] >> 1, y = g.f1[n] >> 1;
+      uint8_t nx = (g.f0[n] & 1) ? 0xFF : 0, ny = (g.f1[n] & 1) ? 0xFF : 0;
+      auto gather = [&](uint32_t v, std::vector<Cut> &s) {
+        s.clear();
+        Cut t{};
+        t.leaf[0] = v, t.n = 1, t.tt = VAR[0];
+        s.push_back(t);
+        if (fuse)
+          for (int i = 0; i < pool_cnt[v]; i++) s.push_back(pool[pool_off[v] + i]);
+      };
+      gather(x, sx), gather(y, sy);
+      cand.clear();
+      for (const Cut &cx : sx)
+        for (const Cut &cy : sy) {
+          Cut c{};
+          int k = merge(cx, cy, c.leaf);
+          if (k < 0) continue;
+          c.n = (uint8_t)k;
+          bool dup = false;
+          for (const Cut &o : cand)
+            if (o.n == c.n && o.leaf[0] == c.leaf[0] && (c.n < 2 || o.leaf[1] == c.leaf[1]) &&
+                (c.n < 3 || o.leaf[2] == c.leaf[2])) {
+              dup = true;
+              break;
+            }
+          if (dup) continue;
+          c.tt = (uint8_t)((expand(cx, c.leaf, k) ^ nx) & (expand(cy, c.leaf, k) ^ ny));
+          eval_cut(c, n);
+          cand.push_back(c);
+        }
+      std::sort(cand.begin(), cand.end(), better);
+      if ((int)cand.size() > P) cand.resize(P);
+      best[n] = cand[0];
+      flow[n] = cand[0].flow, depth[n] = cand[0].depth;
+      pool_off[n] = (uint32_t)pool.size(), pool_cnt[n] = (uint8_t)cand.size();
+      pool.insert(pool.end(), cand.begin(), cand.end());
+    }
+  }
+
+  // Re-pick best cuts with fanout estimates taken from the current cover (area recovery).
+  std::vector<uint32_t> cover_refs() const {
+    size_t N = g.size();
+    std::vector<uint32_t> r(N, 0);
+    for (uint32_t l : out_lits) r[l >> 1]++;
+    for (size_t n = N; n-- > 1;)
+      if (r[n] && g.is_and((uint32_t)n))
+        for (int i = 0; i < best[n].n; i++) r[best[n].leaf[i]]++;
+    return r;
+  }
+  size_t cover_size() const {
+    std::vector<uint32_t> r = cover_refs();
+    size_t c = 0;
+    for (size_t n = 1; n < g.size(); n++) c += (r[n] && g.is_and((uint32_t)n));
+    return c;
+  }
+  void reselect() {
+    std::vector<uint32_t> cr = cover_refs();
+    size_t N = g.size();
+    for (size_t n = 1; n < N; n++) refs[n] = std::max<uint32_t>(1u, (uint32_t)((cr[n] * 2 + refs[n] + 1) / 3));
+    for (uint32_t n = 1; n < N; n++) {
+      if (!live[n] || !g.is_and(n)) continue;
+      Cut *c = &pool[pool_off[n]];
+      int bi = 0;
+      for (int i = 0; i < pool_cnt[n]; i++) {
+        eval_cut(c[i], n);
+        if (better(c[i], c[bi])) bi = i;
+      }
+      best[n] = c[bi];
+      flow[n] = c[bi].flow, depth[n] = c[bi].depth;
+    }
+  }
+
+  // Exact-area local refinement: for every node in the cover try each of its cuts and keep the
+  // one that minimises the number of LUTs that would become (or stay) referenced.
+  struct Exact {
+    Mapper &m;
+    std::vector<uint32_t> r;
+    explicit Exact(Mapper &m_) : m(m_), r(m_.cover_refs()) {}
+    uint32_t deref(uint32_t n) {
+      uint32_t a = 1;
+      for (int i = 0; i < m.best[n].n; i++) {
+        uint32_t l = m.best[n].leaf[i];
+        if (--r[l] == 0 && m.g.is_and(l)) a += deref(l);
+      }
+      return a;
+    }
+    uint32_t ref(uint32_t n) {
+      uint32_t a = 1;
+      for (int i = 0; i < m.best[n].n; i++) {
+        uint32_t l = m.best[n].leaf[i];
+        if (r[l]++ == 0 && m.g.is_and(l)) a += ref(l);
+      }
+      return a;
+    }
+    void run() {
+      size_t N = m.g.size();
+      for (uint32_t n = 1; n < N; n++) {
+        if (!r[n] || !m.g.is_and(n)) continue;
+        deref(n);
+        Cut keep = m.best[n];
+        uint32_t best_area = NONE;
+        Cut best_cut = keep;
+        Cut *c = &m.pool[m.pool_off[n]];
+        for (int i = 0; i < m.pool_cnt[n]; i++) {
+          m.best[n] = c[i];
+          uint32_t a = ref(n);
+          deref(n);
+          if (a < best_area || (a == best_area && c[i].depth < best_cut.depth)) best_area = a, best_cut = c[i];
+        }
+        m.best[n] = best_cut;
+        ref(n);
+      }
+    }
+  };
+
+  void run() {
+    mark_live();
+    enumerate();
+    if (!fuse) return;
+    for (int it = 0; it < 2; it++) reselect();
+    // deep recursion in Exact is bounded by cone size, not graph depth, but guard huge graphs
+    if (g.size() < (1u << 24))
+      for (int it = 0; it < 2; it++) Exact(*this).run();
+  }
+};
+
+// ---- schedules + register allocation -----------------------------------------------------------
+struct Sched {
+  std::vector<FlatInstr> instr;
+  std::vector<uint32_t> levels;
+  uint32_t n_slots = 0, max_width = 0;
+  bool ok = true;
+};
+
+struct SlotPool {
+  std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<uint32_t>> free_;
+  uint32_t high = 0;
+  uint32_t get() {
+    if (!free_.empty()) {
+      uint32_t s = free_.top();
+      free_.pop();
+      return s;
+    }
+    return high++;
+  }
+  void put(uint32_t s) { free_.push(s); }
+};
+
+FlatInstr make_lut(const Val &v) {
+  FlatInstr in{};
+  in.kind = K_LUT, in.tt = v.tt;
+  return in;
+}
+
+// Lane order: depth-first from the outputs (taller operand first), inputs loaded at first use,
+// outputs stored as soon as they exist. Slots are recycled the moment their last reader is done.
+Sched schedule_lane(const Network &net) {
+  const size_t V = net.vals.size();
+  std::vector<uint32_t> height(V, 0);
+  for (size_t v = 0; v < V; v++)
+    if (net.vals[v].is_lut) {
+      uint32_t h = 0;
+      for (int i = 0; i < net.vals[v].nfan; i++) h = std::max(h, height[net.vals[v].fan[i]]);
+      height[v] = h + 1;
+    }
+  std::vector<std::vector<uint32_t>> outs_of(V);
+  std::vector<uint32_t> state_in_val(net.n_state, NONE);  // value that loads state row k
+  for (size_t v = 0; v < V; v++)
+    if (!net.vals[v].is_lut && net.vals[v].row >= net.n_inputs) state_in_val[net.vals[v].row - net.n_inputs] = (uint32_t)v;
+  for (size_t o = 0; o < net.outs.size(); o++)
+    if (net.outs[o].val != NONE) outs_of[net.outs[o].val].push_back((uint32_t)o);
+
+  // order: positive = value id (LDIN or LUT), stores as (V + out index)
+  std::vector<uint32_t> order;
+  order.reserve(V + net.outs.size());
+  std::vector<uint8_t> done(V, 0), stored(net.outs.size(), 0);
+  std::function<void(uint32_t)> emit_value;
+  auto emit_store = [&](uint32_t o) {
+    if (stored[o]) return;
+    uint32_t row = net.outs[o].row;
+    if (row >= net.n_outputs) {  // in-place state row: its old value must have been read first
+      uint32_t sv = state_in_val[row - net.n_outputs];
+      if (sv != NONE && !done[sv]) emit_value(sv);
+    }
+    stored[o] = 1;
+    order.push_back((uint32_t)V + o);
+  };
+  emit_value = [&](uint32_t v) {
+    done[v] = 1;
+    order.push_back(v);
+    for (uint32_t o : outs_of[v]) emit_store(o);
+  };
+  struct Frame {
+    uint32_t v;
+    uint8_t next;
+    uint32_t kid[3];
+    uint8_t nk;
+  };
+  std::vector<Frame> stack;
+  auto visit = [&](uint32_t root) {
+    if (done[root]) return;
+    auto open = [&](uint32_t v) {
+      Frame f{v, 0, {0, 0, 0}, 0};
+      const Val &val = net.vals[v];
+      if (val.is_lut) {
+        f.nk = val.nfan;
+        for (int i = 0; i < val.nfan; i++) f.kid[i] = val.fan[i];
+        std::stable_sort(f.kid, f.kid + f.nk, [&](uint32_t a, uint32_t b) { return height[a] > height[b]; });
+      }
+      stack.push_back(f);
+    };
+    open(root);
+    while (!stack.empty()) {
+      Frame &f = stack.back();
+      if (done[f.v]) {
+        stack.pop_back();
+        continue;
+      }
+      if (f.next < f.nk) {
+        uint32_t k = f.kid[f.next++];
+        if (!done[k]) open(k);
+        continue;
+      }
+      uint32_t v = f.v;
+      stack.pop_back();
+      emit_value(v);
+    }
+  };
+  for (size_t o = 0; o < net.outs.size(); o++) {
+    if (net.outs[o].val == NONE) {
+      stored[o] = 1;
+      order.push_back((uint32_t)V + (uint32_t)o);
+      continue;
+    }
+    visit(net.outs[o].val);
+    emit_store((uint32_t)o);
+  }
+
+  // last use positions
+  std::vector<uint32_t> last(V, 0);
+  for (size_t i = 0; i < order.size(); i++) {
+    uint32_t x = order[i];
+    if (x >= V) {
+      const OutRef &o = net.outs[x - V];
+      if (o.val != NONE) last[o.val] = (uint32_t)i;
+    } else if (net.vals[x].is_lut)
+      for (int k = 0; k < net.vals[x].nfan; k++) last[net.vals[x].fan[k]] = (uint32_t)i;
+  }
+  Sched s;
+  SlotPool pool;
+  std::vector<uint32_t> slot(V, NONE);
+  for (size_t i = 0; i < order.size(); i++) {
+    uint32_t x = order[i];
+    FlatInstr in{};
+    if (x >= V) {
+      const OutRef &o = net.outs[x - V];
+      in.row = o.row, in.flags = o.inv ? 1 : 0;
+      if (o.val == NONE) in.kind = K_STCONST;
+      else {
+        in.kind = K_STOUT, in.a = (uint16_t)slot[o.val];
+        if (last[o.val] == i) pool.put(slot[o.val]);
+      }
+    } else {
+      const Val &v = net.vals[x];
+      if (v.is_lut) {
+        in = make_lut(v);
+        uint32_t sl[3] = {0, 0, 0};
+        for (int k = 0; k < v.nfan; k++) sl[k] = slot[v.fan[k]];
+        for (int k = v.nfan; k < 3; k++) sl[k] = sl[0];  // unused operands alias operand a
+        in.a = (uint16_t)sl[0], in.b = (uint16_t)sl[1], in.c = (uint16_t)sl[2];
+        for (int k = 0; k < v.nfan; k++) {
+          uint32_t fv = v.fan[k];
+          bool seen = false;
+          for (int j = 0; j < k; j++) seen |= (v.fan[j] == fv);
+          if (!seen && last[fv] == i) pool.put(slot[fv]);
+        }
+      } else {
+        in.kind = K_LDIN, in.row = v.row;
+      }
+      slot[x] = pool.get();
+      if (slot[x] > 0xFFFF) {
+        s.ok = false;
+        return s;
+      }
+      in.dst = (uint16_t)slot[x];
+    }
+    s.instr.push_back(in);
+  }
+  s.n_slots = pool.high;
+  s.levels = {0, (uint32_t)s.instr.size()};
+  s.max_width = (uint32_t)s.instr.size();
+  return s;
+}
+
+// Level order. LUT levels are as late as the consumers allow (short live ranges), loads sit one
+// level before their first reader, stores one level after their producer. A slot freed by its
+// last reader in level L is handed out again from level L + 1 on: within a level other threads may
+// still be reading it.
+Sched schedule_level(const Network &net) {
+  const size_t V = net.vals.size(), O = net.outs.size();
+  std::vector<uint32_t> lev(V, 0);
+  for (size_t v = 0; v < V; v++)
+    if (net.vals[v].is_lut) {
+      uint32_t h = 0;
+      for (int i = 0; i < net.vals[v].nfan; i++) h = std::max(h, lev[net.vals[v].fan[i]]);
+      lev[v] = h + 1;  // ASAP; inputs count as level 0
+    }
+  std::vector<uint32_t> ub(V, NONE);
+  for (size_t v = V; v-- > 0;) {
+    if (net.vals[v].is_lut) {
+      if (ub[v] != NONE) lev[v] = ub[v];
+      for (int i = 0; i < net.vals[v].nfan; i++) {
+        uint32_t f = net.vals[v].fan[i];
+        ub[f] = std::min(ub[f], lev[v] - 1);
+      }
+    }
+  }
+  // loads: one level before the first reader (a load read only by a store sits at level 0)
+  for (size_t v = 0; v < V; v++)
+    if (!net.vals[v].is_lut) lev[v] = (ub[v] == NONE) ? 0 : ub[v];
+  std::vector<uint32_t> state_in_lev(net.n_state, NONE);
+  for (size_t v = 0; v < V; v++)
+    if (!net.vals[v].is_lut && net.vals[v].row >= net.n_inputs) state_in_lev[net.vals[v].row - net.n_inputs] = lev[v];
+  std::vector<uint32_t> olev(O, 0);
+  uint32_t n_levels = 1;
+  for (size_t o = 0; o < O; o++) {
+    const OutRef &r = net.outs[o];
+    uint32_t l = (r.val == NONE) ? 0 : lev[r.val] + 1;
+    if (r.row >= net.n_outputs) {
+      uint32_t sl = state_in_lev[r.row - net.n_outputs];
+      if (sl != NONE) l = std::max(l, sl + 1);
+    }
+    olev[o] = l;
+    n_levels = std::max(n_levels, l + 1);
+  }
+  for (size_t v = 0; v < V; v++) n_levels = std::max(n_levels, lev[v] + 1);
+
+  std::vector<uint32_t> last(V, 0);
+  for (size_t v = 0; v < V; v++) {
+    last[v] = std::max(last[v], lev[v]);
+    if (net.vals[v].is_lut)
+      for (int i = 0; i < net.vals[v].nfan; i++) last[net.vals[v].fan[i]] = std::max(last[net.vals[v].fan[i]], lev[v]);
+  }
+  for (size_t o = 0; o < O; o++)
+    if (net.outs[o].val != NONE) last[net.outs[o].val] = std::max(last[net.outs[o].val], olev[o]);
+
+  // bucket by level
+  std::vector<uint32_t> cnt(n_levels + 1, 0);
+  for (size_t v = 0; v < V; v++) cnt[lev[v] + 1]++;
+  for (size_t o = 0; o < O; o++) cnt[olev[o] + 1]++;
+  for (uint32_t l = 0; l < n_levels; l++) cnt[l + 1] += cnt[l];
+  std::vector<uint32_t> items(V + O), fill(cnt.begin(), cnt.end() - 1);
+  for (size_t v = 0; v < V; v++) items[fill[lev[v]]++] = (uint32_t)v;
+  for (size_t o = 0; o < O; o++) items[fill[olev[o]]++] = (uint32_t)(V + o);
+
+  Sched s;
+  s.instr.resize(V + O);
+  s.levels.assign(cnt.begin(), cnt.end());
+  SlotPool pool;
+  std::vector<uint32_t> slot(V, NONE);
+  std::vector<std::vector<uint32_t>> release(n_levels + 1);
+  auto key = [&](uint32_t x) -> uint32_t {  // (kind, tt) so that warps mostly run one LOP3 immediate
+    if (x >= V) return (net.outs[x - V].val == NONE ? (3u << 8) : (2u << 8)) | (net.outs[x - V].inv ? 1u : 0u);
+    return net.vals[x].is_lut ? net.vals[x].tt : (1u << 8);
+  };
+  for (uint32_t l = 0; l < n_levels; l++) {
+    if (l > 0) {
+      for (uint32_t sl : release[l - 1]) pool.put(sl);
+      release[l - 1].clear(), release[l - 1].shrink_to_fit();
+    }
+    uint32_t b = cnt[l], e = cnt[l + 1];
+    s.max_width = std::max(s.max_width, e - b);
+    std::stable_sort(items.begin() + b, items.begin() + e, [&](uint32_t x, uint32_t y) { return key(x) < key(y); });
+    for (uint32_t i = b; i < e; i++) {
+      uint32_t x = items[i];
+      FlatInstr in{};
+      if (x >= V) {
+        const OutRef &o = net.outs[x - V];
+        in.row = o.row, in.flags = o.inv ? 1 : 0;
+        if (o.val == NONE) in.kind = K_STCONST;
+        else in.kind = K_STOUT, in.a = (uint16_t)slot[o.val];
+      } else {
+        const Val &v = net.vals[x];
+        if (v.is_lut) {
+          in = make_lut(v);
+          uint32_t sl[3] = {0, 0, 0};
+          for (int k = 0; k < v.nfan; k++) sl[k] = slot[v.fan[k]];
+          for (int k = v.nfan; k < 3; k++) sl[k] = sl[0];
+          in.a = (uint16_t)sl[0], in.b = (uint16_t)sl[1], in.c = (uint16_t)sl[2];
+        } else {
+          in.kind = K_LDIN, in.row = v.row;
+        }
+        slot[x] = pool.get();
+        if (slot[x] > 0xFFFF) {
+          s.ok = false;
+          return s;
+        }
+        in.dst = (uint16_t)slot[x];
+        release[last[x]].push_back(slot[x]);
+      }
+      s.instr[i] = in;
+    }
+  }
+  s.n_slots = pool.high;
+  return s;
+}
+
+size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+}  // namespace
+
+Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_regs, size_t n_out, uint32_t flags) {
+  const size_t R = sim.registers.size();
+  const bool stateful = flags & CLG_LV_STATEFUL;
+  if (R >= 0x7FFFFFFFu || sim.ops.size() >= 0x7FFFFFFFu) fail(CLG_E_UNSUPPORTED, "program too large");
+  uint64_t n_nand = 0, n_set = 0;
+  for (const Op &op : sim.ops) {
+    if (op.tag == CLG_OP_NAND) {
+      n_nand++;
+      if (op.a >= R || op.b >= R || op.c >= R)
+        fail(CLG_E_BAD_REGISTER, "Nand register out of range (the reference panics at simulation.rs:20-23)");
+    } else if (op.tag == CLG_OP_SET) {
+      n_set++;
+      if (op.a >= R) fail(CLG_E_BAD_REGISTER, "Set register out of range (the reference panics at simulation.rs:26)");
+    } else
+      fail(CLG_E_INVALID, "unknown op tag");
+  }
+  std::vector<uint64_t> outs;
+  if (out_regs == nullptr && n_out == 0) {
+    outs.resize(R);
+    for (size_t r = 0; r < R; r++) outs[r] = r;
+  } else {
+    outs.assign(out_regs, out_regs + n_out);
+    for (uint64_t r : outs)
+      if (r >= R) fail(CLG_E_BAD_REGISTER, "output register out of range (simulation.rs:34)");
+  }
+  if (n_immediates > 0x7FFFFFFFu) fail(CLG_E_INVALID, "too many immediates");
+
+  // carried registers: first access in program order is a read (or an output nobody writes)
+  std::vector<uint64_t> state_regs;
+  if (stateful) {
+    std::vector<uint8_t> first(R, 0);  // 1 = read first, 2 = written first
+    for (const Op &op : sim.ops) {
+      if (op.tag == CLG_OP_NAND) {
+        if (!first[op.a]) first[op.a] = 1;
+        if (!first[op.b]) first[op.b] = 1;
+        if (!first[op.c]) first[op.c] = 2;
+      } else if (!first[op.a])
+        first[op.a] = 2;
+    }
+    for (uint64_t r : outs)
+      if (!first[r]) first[r] = 1;
+    for (size_t r = 0; r < R; r++)
+      if (first[r] == 1) state_regs.push_back(r);
+  }
+
+  Aig g;
+  std::vector<uint32_t> imm_lit(n_immediates);
+  for (size_t i = 0; i < n_immediates; i++) imm_lit[i] = g.input((uint32_t)i);
+  std::vector<uint32_t> cur(R, 0);
+  for (size_t k = 0; k < state_regs.size(); k++) cur[state_regs[k]] = g.input((uint32_t)(n_immediates + k));
+  for (const Op &op : sim.ops) {
+    if (op.tag == CLG_OP_NAND) cur[op.c] = g.and_(cur[op.a], cur[op.b]) ^ 1u;
+    else cur[op.a] = (op.a < n_immediates) ? imm_lit[op.a] : (op.b ? 1u : 0u);
+  }
+  std::vector<uint32_t> out_lits;
+  for (uint64_t r : outs) out_lits.push_back(cur[r]);
+  for (uint64_t r : state_regs) out_lits.push_back(cur[r]);
+
+  Mapper m(g, out_lits, !(flags & CLG_LV_NO_FUSE));
+  m.run();
+
+  // build the value network: used input rows first, then LUT roots in topological order
+  Network net;
+  net.n_inputs = (uint32_t)n_immediates, net.n_state = (uint32_t)state_regs.size(), net.n_outputs = (uint32_t)outs.size();
+  std::vector<uint32_t> cref = m.cover_refs();
+  std::vector<uint32_t> val_of(g.size(), NONE);
+  for (uint32_t n = 1; n < g.size(); n++)
+    if (cref[n] && g.is_input(n)) {
+      Val v{};
+      v.row = g.f1[n];
+      val_of[n] = (uint32_t)net.vals.size();
+      net.vals.push_back(v);
+    }
+  uint32_t n_luts = 0;
+  for (uint32_t n = 1; n < g.size(); n++)
+    if (cref[n] && g.is_and(n)) {
+      const Cut &c = m.best[n];
+      Val v{};
+      v.is_lut = 1, v.tt = c.tt, v.nfan = c.n;
+      for (int i = 0; i < c.n; i++) v.fan[i] = val_of[c.leaf[i]];
+      val_of[n] = (uint32_t)net.vals.size();
+      net.vals.push_back(v);
+      n_luts++;
+    }
+  for (size_t o = 0; o < out_lits.size(); o++) {
+    uint32_t l = out_lits[o];
+    OutRef r{(uint32_t)o, NONE, (bool)(l & 1)};
+    if ((l >> 1) != 0) r.val = val_of[l >> 1];
+    // a carried register whose value is unchanged needs no store at all
+    if (o >= outs.size() && r.val != NONE && !r.inv && !net.vals[r.val].is_lut &&
+        net.vals[r.val].row == n_immediates + (o - outs.size()))
+      continue;
+    net.outs.push_back(r);
+  }
+
+  Sched level = schedule_level(net);
+  if (!level.ok) fail(CLG_E_UNSUPPORTED, "level-ordered stream needs more than 65536 physical registers");
+  Sched lane;
+  lane.ok = false;
+  if (!(flags & CLG_LV_NO_LANE_STREAM)) lane = schedule_lane(net);
+
+  // serialise
+  Flat f;
+  size_t off = align16(sizeof(FlatHeader));
+  FlatHeader h{};
+  h.magic = FLAT_MAGIC, h.version = FLAT_VERSION, h.header_bytes = (uint32_t)sizeof(FlatHeader);
+  h.n_inputs = net.n_inputs, h.n_outputs = net.n_outputs, h.n_state = net.n_state, h.n_luts = n_luts;
+  h.ref_nand_count = n_nand, h.ref_set_count = n_set, h.flags = flags, h.n_registers = (uint32_t)R;
+  h.off_state_regs = (uint32_t)off, off = align16(off + state_regs.size() * 8);
+  h.off_out_regs = (uint32_t)off, off = align16(off + outs.size() * 8);
+  const Sched *ss[2] = {&level, &lane};
+  for (int i = 0; i < 2; i++) {
+    if (!ss[i]->ok) continue;
+    FlatStream &st = h.stream[i];
+    st.n_slots = ss[i]->n_slots, st.n_instr = (uint32_t)ss[i]->instr.size();
+    st.n_levels = (uint32_t)ss[i]->levels.size() - 1, st.max_level_width = ss[i]->max_width;
+    st.off_levels = (uint32_t)off, off = align16(off + ss[i]->levels.size() * 4);
+    st.off_instr = (uint32_t)off, off = align16(off + ss[i]->instr.size() * sizeof(FlatInstr));
+  }
+  if (off >= 0xFFFFFFFFull) fail(CLG_E_UNSUPPORTED, "flat buffer exceeds 4 GiB");
+  h.total_bytes = (uint32_t)off;
+  f.bytes.assign(off, 0);
+  std::memcpy(f.bytes.data(), &h, sizeof h);
+  std::memcpy(f.bytes.data() + h.off_state_regs, state_regs.data(), state_regs.size() * 8);
+  std::memcpy(f.bytes.data() + h.off_out_regs, outs.data(), outs.size() * 8);
+  for (int i = 0; i < 2; i++) {
+    if (!ss[i]->ok) continue;
+    std::memcpy(f.bytes.data() + h.stream[i].off_levels, ss[i]->levels.data(), ss[i]->levels.size() * 4);
+    std::memcpy(f.bytes.data() + h.stream[i].off_instr, ss[i]->instr.data(), ss[i]->instr.size() * sizeof(FlatInstr));
+  }
+  return f;
+}
+
+// Everything a kernel relies on is checked here once, so the device code carries no bounds checks:
+// index ranges, definition-before-use, and the hazards each execution order must be free of.
+void validate_flat(const Flat &f) {
+  auto bad = [](const std::string &m) { fail(CLG_E_FORMAT, "flat buffer: " + m); };
+  if (f.bytes.size() < sizeof(FlatHeader)) bad("truncated header");
+  const FlatHeader &h = f.header();
+  if (h.magic != FLAT_MAGIC) bad("bad magic");
+  if (h.version != FLAT_VERSION) bad("unsupported version");
+  if (h.total_bytes != f.bytes.size()) bad("size mismatch");
+  auto span_ok = [&](uint32_t off, uint64_t bytes) { return off % 16 == 0 && (uint64_t)off + bytes <= f.bytes.size(); };
+  if (!span_ok(h.off_state_regs, (uint64_t)h.n_state * 8) || !span_ok(h.off_out_regs, (uint64_t)h.n_outputs * 8))
+    bad("register tables out of range");
+  const uint32_t n_in_rows = h.n_inputs + h.n_state, n_out_rows = h.n_outputs + h.n_state;
+  for (int s = 0; s < 2; s++) {
+    const FlatStream &st = h.stream[s];
+    if (st.n_instr == 0) continue;
+    if (!span_ok(st.off_levels, ((uint64_t)st.n_levels + 1) * 4) || !span_ok(st.off_instr, (uint64_t)st.n_instr * 16))
+      bad("stream out of range");
+    if (st.n_slots > 65536) bad("too many slots");
+    const uint32_t *lv = f.levels(s);
+    const FlatInstr *in = f.instrs(s);
+    if (st.n_levels == 0 || lv[0] != 0 || lv[st.n_levels] != st.n_instr) bad("level table does not cover the stream");
+    // a level is one hazard window; the lane stream is sequential, i.e. every instruction is its own window
+    const bool seq = (s == STREAM_LANE);
+    std::vector<uint8_t> defined(st.n_slots, 0);
+    std::vector<uint32_t> written_in(st.n_slots, NONE);
+    std::vector<uint32_t> loaded_in(h.n_state, NONE), stored_in(h.n_state, NONE);
+    uint32_t window = 0;
+    for (uint32_t l = 0; l < st.n_levels; l++) {
+      if (lv[l] > lv[l + 1] || lv[l + 1] > st.n_instr) bad("level table not monotone");
+      if (lv[l + 1] - lv[l] > st.max_level_width) bad("max_level_width too small");
+      for (uint32_t pass = 0; pass < (seq ? 1u : 2u); pass++)
+        for (uint32_t i = lv[l]; i < lv[l + 1]; i++) {
+          const FlatInstr &x = in[i];
+          if (seq) window = i;
+          else window = l;
+          const bool reads = seq || pass == 0, writes = seq || pass == 1;
+          auto rd = [&](uint16_t sl) {
+            if (sl >= st.n_slots) bad("slot out of range");
+            if (!defined[sl]) bad("slot read before it is written");
+          };
+          if (x.kind > K_STCONST) bad("unknown instruction kind");
+          if (reads) {
+            if (x.kind == K_LUT) rd(x.a), rd(x.b), rd(x.c);
+            if (x.kind == K_STOUT) rd(x.a);
+            if (x.kind == K_LDIN) {
+              if (x.row >= n_in_rows) bad("input row out of range");
+              if (x.row >= h.n_inputs) {
+                uint32_t k = x.row - h.n_inputs;
+                if (stored_in[k] != NONE) bad("state row loaded after it was stored");
+                loaded_in[k] = window;
+              }
+            }
+            if (x.kind == K_STOUT || x.kind == K_STCONST) {
+              if (x.row >= n_out_rows) bad("output row out of range");
+              if (x.row >= h.n_outputs) {
+                uint32_t k = x.row - h.n_outputs;
+                if (!seq && loaded_in[k] == window) bad("state row loaded and stored in the same level");
+                if (stored_in[k] != NONE) bad("state row stored twice");
+              }
+            }
+          }
+          if (writes) {
+            if (x.kind == K_LUT || x.kind == K_LDIN) {
+              if (x.dst >= st.n_slots) bad("slot out of range");
+              if (!seq && written_in[x.dst] == window) bad("slot written twice in one level");
+              written_in[x.dst] = window;
+              defined[x.dst] = 1;
+            }
+            if ((x.kind == K_STOUT || x.kind == K_STCONST) && x.row >= h.n_outputs) stored_in[x.row - h.n_outputs] = window;
+          }
+        }
+      if (!seq) {
+        // nothing read in this level may also be written in it (other threads are still reading)
+        for (uint32_t i = lv[l]; i < lv[l + 1]; i++) {
+          const FlatInstr &x = in[i];
+          auto chk = [&](uint16_t sl) {
+            if (written_in[sl] == l) bad("slot read and written in the same level");
+          };
+          if (x.kind == K_LUT) chk(x.a), chk(x.b), chk(x.c);
+          if (x.kind == K_STOUT) chk(x.a);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace clg

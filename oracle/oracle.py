@@ -163,12 +163,27 @@ class ReferencePanic(Exception):
 class Simulation:
     """simulation.rs:5-36 -- public `ops` and `registers`."""
 
-    def __init__(self, ops: Sequence[Op] = (), registers: Sequence[bool] = ()):
-        self.ops = list(ops)
+    def __init__(self, ops: Sequence[Op] = (), registers: Sequence[bool] = (), _ops_array=None):
+        self._ops_arr = _ops_array if _ops_array is not None else ops_to_array(list(ops))
+        self._ops_list = None if _ops_array is not None else list(ops)
         self.registers = [bool(r) for r in registers]
 
+    @property
+    def ops(self) -> List[Op]:
+        if self._ops_list is None:
+            self._ops_list = array_to_ops(self._ops_arr)
+        return self._ops_list
+
+    @property
+    def ops_array(self) -> np.ndarray:
+        return self._ops_arr
+
+    @property
+    def nand_count(self) -> int:
+        return int((self._ops_arr["tag"] == 0).sum())
+
     def run(self, immediates: Sequence[bool]) -> None:
-        ops = ops_to_array(self.ops)
+        ops = self._ops_arr
         regs = np.array(self.registers, dtype=np.uint8)
         imm = np.array([1 if x else 0 for x in immediates], dtype=np.uint8)
         rc = lib().orc_run(ops.ctypes.data, len(ops), regs.ctypes.data, len(regs), imm.ctypes.data, len(imm))
@@ -177,6 +192,8 @@ class Simulation:
         self.registers = [bool(x) for x in regs]
 
     def register(self, id: int) -> bool:
+        if id >= len(self.registers):
+            raise ReferencePanic("index out of bounds (simulation.rs:34)")
         return self.registers[id]
 
 
@@ -210,13 +227,24 @@ class Compiler:
         if dot.value is not None:
             self.last_dot = dot.value.decode()
             lib().orc_free(C.cast(dot, C.c_void_p))
-        ops = array_to_ops(_take_ops(ptr, n.value))
-        return Simulation(ops, [False] * nreg.value)
+        return Simulation(registers=[False] * nreg.value, _ops_array=_take_ops(ptr, n.value))
+
+
+def _as_orc_ops(ops) -> np.ndarray:
+    """Accept tuple ops, the oracle's array, or the product's 32-byte array (same bytes: u32 tag + u32 zero)."""
+    if hasattr(ops, "ops_array"):  # a Simulation (oracle's or the product mirror's)
+        ops = ops.ops_array
+    if not isinstance(ops, np.ndarray):
+        return ops_to_array(ops)
+    if ops.dtype != OP_DTYPE:
+        assert ops.dtype.itemsize == 32
+        ops = np.ascontiguousarray(ops).view(OP_DTYPE)
+    return np.ascontiguousarray(ops)
 
 
 # ---- batch drivers (bit-sliced [row][stride] uint32, SURVEY.md 8b) -----------------------------
 def _batch(fn, ops, n_regs, imm, n_vectors, out_regs, steps, all_steps, *extra):
-    ops = ops if isinstance(ops, np.ndarray) else ops_to_array(ops)
+    ops = _as_orc_ops(ops)
     imm = np.ascontiguousarray(imm, dtype=np.uint32)
     if imm.ndim == 2:
         imm = imm[None]

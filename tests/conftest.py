@@ -22,8 +22,15 @@ def _oracle_api():
     return api
 
 
-@pytest.fixture(params=["oracle", "host"])
+@pytest.fixture(params=["oracle", pytest.param("host", marks=pytest.mark.gpu)])
 def api(request):
-    """The reference's public API surface (Compiler, Simulation, gates), once as the CPU oracle and
-    once as the product's host mirror -- the same reference tests run against both."""
+    """The reference's public API surface (Compiler, Simulation, gates) for tests that RUN programs: once as
+    the CPU oracle, once as the product's host mirror -- whose Simulation.run executes on the GPU (there is
+    no CPU execution path in the product), hence the gpu mark on that leg."""
+    return _oracle_api() if request.param == "oracle" else _host_api()
+
+
+@pytest.fixture(params=["oracle", "host"])
+def capi(request):
+    """Same surface for tests that only lower/compile (host logic; both legs run on the CPU)."""
     return _oracle_api() if request.param == "oracle" else _host_api()

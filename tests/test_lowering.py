@@ -1,0 +1,189 @@
+"""The levelize / LUT-map / register-allocate pass, checked on the CPU: the flat buffer it produces is
+interpreted with numpy (tests/flat_interp.py) and compared, bit for bit, with the oracle VM
+(scalar tier L0 and bit-sliced tier L1) and with arithmetic ground truth."""
+import numpy as np
+import pytest
+
+import complogic_b200 as host
+from complogic_b200 import circuits
+from oracle import oracle
+from tests import flat_interp
+from tests.helpers import exhaustive_sliced, mask_tail, random_sliced, stride_for, unslice_int
+
+
+def both_streams(fp, imm, n_vectors, state=None, seed=0):
+    flat = flat_interp.Flat(fp.to_bytes())
+    outs = []
+    for s in (flat_interp.STREAM_LEVEL, flat_interp.STREAM_LANE):
+        if flat.streams[s]["n_instr"] == 0:
+            continue
+        st = None if state is None else state.copy()
+        outs.append((mask_tail(flat_interp.run(flat, s, imm, st, rng=np.random.default_rng(seed)), n_vectors), st))
+    return outs
+
+
+def test_adder8_exhaustive_three_ways():
+    """BASELINE config 1: 8-bit ripple adder, all 2^17 input vectors; scalar VM == sliced VM == a+b+cin == flat."""
+    circ_o = circuits.ripple_adder(8, api=oracle)
+    circ_h = circuits.ripple_adder(8, api=host)
+    assert circ_o.sim.ops == circ_h.sim.ops and len(circ_o.sim.registers) == len(circ_h.sim.registers) == 169
+    assert circ_h.sim.nand_count == 152
+    n = 1 << 17
+    imm = exhaustive_sliced(17)
+    scalar = oracle.run_batch_scalar(circ_o.sim, 169, imm, n, circ_o.out_regs, threads=4)
+    sliced = oracle.run_batch_sliced(circ_o.sim, 169, imm, n, circ_o.out_regs)
+    assert np.array_equal(scalar, sliced)
+    v = np.arange(n, dtype=np.uint64)
+    want = (v & np.uint64(0xFF)) + ((v >> np.uint64(8)) & np.uint64(0xFF)) + (v >> np.uint64(16))
+    assert np.array_equal(unslice_int(sliced, n), want)
+    fp = host.FlatProgram.levelize(circ_h.sim, 17, circ_h.out_regs)
+    assert fp.info["ref_nand_count"] == 152 and fp.info["n_luts"] <= 2 * 8 + 2
+    for got, _ in both_streams(fp, imm, n):
+        assert np.array_equal(got, sliced)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 32])
+def test_ripple_adder_random(n):
+    circ = circuits.ripple_adder(n, api=host)
+    assert circ.sim.nand_count == 19 * n and len(circ.sim.registers) == 21 * n + 1
+    nv = 1000
+    imm = random_sliced(2 * n + 1, stride_for(nv), seed=0xC0FFEE)
+    want = mask_tail(oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs), nv)
+    a, b = unslice_int(imm[:n], nv), unslice_int(imm[n:2 * n], nv)
+    cin = unslice_int(imm[2 * n:], nv)
+    assert np.array_equal(unslice_int(want, nv), a + b + cin)
+    fp = host.FlatProgram.levelize(circ.sim, 2 * n + 1, circ.out_regs)
+    for got, _ in both_streams(fp, imm, nv):
+        assert np.array_equal(got, want)
+
+
+def test_mul4_exhaustive():
+    circ = circuits.array_multiplier(4, api=host)
+    assert circ.sim.nand_count == 216
+    n = 256
+    imm = exhaustive_sliced(8)
+    want = oracle.run_batch_scalar(circ.sim, len(circ.sim.registers), imm, n, circ.out_regs)
+    v = np.arange(n, dtype=np.uint64)
+    assert np.array_equal(unslice_int(want, n), (v & np.uint64(15)) * (v >> np.uint64(4)))
+    fp = host.FlatProgram.levelize(circ.sim, 8, circ.out_regs)
+    for got, _ in both_streams(fp, imm, n):
+        assert np.array_equal(got, mask_tail(want, n))
+
+
+def test_mul16_random():
+    """BASELINE config 3's circuit: 4 896 NANDs (reference expansions), checked against a*b."""
+    circ = circuits.array_multiplier(16, api=host)
+    circ_o = circuits.array_multiplier(16, api=oracle)
+    assert circ.sim.ops == circ_o.sim.ops
+    assert circ.sim.nand_count == 4896 and len(circ.sim.registers) == 4928
+    nv = 2048
+    imm = random_sliced(32, stride_for(nv), seed=0xC0FFEF)
+    want = oracle.run_batch_sliced(circ.sim, 4928, imm, nv, circ.out_regs)
+    a, b = unslice_int(imm[:16], nv), unslice_int(imm[16:], nv)
+    assert np.array_equal(unslice_int(want, nv), a * b)
+    scalar = oracle.run_batch_scalar(circ.sim, 4928, imm, 256, circ.out_regs)
+    assert np.array_equal(mask_tail(scalar, 256), mask_tail(want, 256))
+    fp = host.FlatProgram.levelize(circ.sim, 32, circ.out_regs)
+    assert fp.info["n_luts"] < 1000  # ~6.6 reference NANDs per LOP3
+    for got, _ in both_streams(fp, imm, nv):
+        assert np.array_equal(got, mask_tail(want, nv))
+
+
+@pytest.mark.parametrize("window", [2, 0])
+def test_random_dag_small(window):
+    circ = circuits.random_dag(levels=24, width=96, n_immediates=40, window=window, seed=7, api=host)
+    circ_o = circuits.random_dag(levels=24, width=96, n_immediates=40, window=window, seed=7, api=oracle)
+    assert np.array_equal(circ.sim.ops_array["a"], circ_o.sim.ops_array["a"])
+    nv = 300
+    imm = random_sliced(40, stride_for(nv), seed=3)
+    R = len(circ.sim.registers)
+    want = oracle.run_batch_sliced(circ_o.sim, R, imm, nv, circ.out_regs)
+    scalar = oracle.run_batch_scalar(circ_o.sim, R, imm, nv, circ.out_regs)
+    assert np.array_equal(mask_tail(want, nv), mask_tail(scalar, nv))
+    for flags in (0, host.LV_NO_FUSE):
+        fp = host.FlatProgram.levelize(circ.sim, 40, circ.out_regs, flags=flags)
+        for got, _ in both_streams(fp, imm, nv):
+            assert np.array_equal(got, mask_tail(want, nv))
+
+
+def test_flatten_instances():
+    base = circuits.array_multiplier(4, api=host)
+    flat3 = circuits.flatten_instances(base, 3, api=host)
+    assert flat3.sim.nand_count == 3 * 216 and flat3.n_immediates == 24
+    nv = 64
+    imm = random_sliced(24, stride_for(nv), seed=11)
+    want = oracle.run_batch_sliced(flat3.sim, len(flat3.sim.registers), imm, nv, flat3.out_regs)
+    for m in range(3):
+        a, b = unslice_int(imm[8 * m:8 * m + 4], nv), unslice_int(imm[8 * m + 4:8 * m + 8], nv)
+        assert np.array_equal(unslice_int(want[8 * m:8 * m + 8], nv), a * b)
+    fp = host.FlatProgram.levelize(flat3.sim, 24, flat3.out_regs)
+    for got, _ in both_streams(fp, imm, nv):
+        assert np.array_equal(got, mask_tail(want, nv))
+
+
+def test_all_registers_observable_by_default():
+    """out_regs=None: every register is read back (Simulation::registers is public, simulation.rs:11)."""
+    c = host.Compiler(3)
+    sim = c.compile([host.FullAdder(0, 1, 2, c.alloc(), c.alloc())])
+    imm = exhaustive_sliced(3)
+    want = oracle.run_batch_scalar(sim, 22, imm, 8, list(range(22)))
+    fp = host.FlatProgram.levelize(sim, 3)
+    assert fp.info["n_outputs"] == 22
+    for got, _ in both_streams(fp, imm, 8):
+        assert np.array_equal(got, mask_tail(want, 8))
+
+
+def test_short_immediates_fall_back_to_literals():
+    """simulation.rs:26 `immediates.get(id).copied().unwrap_or(val)`; op_set / op_set_no_immediate batch-wise."""
+    sim = host.Simulation(ops=[host.Set_op(0, False), host.Set_op(1, True), host.Set_op(2, True), host.Nand_op(1, 2, 3),
+                               host.Nand_op(0, 3, 4)], registers=[False] * 5)
+    for n_imm in (0, 1, 2, 3):
+        imm = exhaustive_sliced(n_imm) if n_imm else np.zeros((0, 4), np.uint32)
+        nv = 1 << n_imm
+        want = oracle.run_batch_scalar(sim, 5, imm, nv, list(range(5)))
+        fp = host.FlatProgram.levelize(sim, n_imm)
+        for got, _ in both_streams(fp, imm, nv):
+            assert np.array_equal(got, mask_tail(want, nv))
+
+
+def test_out_of_range_registers_are_errors_not_ub():
+    sim = host.Simulation(ops=[host.Nand_op(0, 0, 9)], registers=[False])
+    with pytest.raises(host.ReferencePanic):
+        host.FlatProgram.levelize(sim, 0)
+    sim = host.Simulation(ops=[host.Set_op(0, False)], registers=[False])
+    with pytest.raises(host.ReferencePanic):
+        host.FlatProgram.levelize(sim, 1, out_regs=[5])
+
+
+def test_flat_roundtrip_and_validation():
+    circ = circuits.ripple_adder(4, api=host)
+    fp = host.FlatProgram.levelize(circ.sim, 9, circ.out_regs)
+    data = fp.to_bytes()
+    again = host.FlatProgram.from_bytes(data)
+    assert again.to_bytes() == data and again.info == fp.info
+    with pytest.raises(host.ClgError):
+        host.FlatProgram.from_bytes(data[:-16])
+    flat = flat_interp.Flat(data)
+    off = int.from_bytes(data[64 + 16:64 + 20], "little")  # level stream: off_instr
+    first_lut = int(np.flatnonzero(flat.streams[0]["instr"]["kind"] == flat_interp.K_LUT)[0])
+    bad = bytearray(data)
+    bad[off + 16 * first_lut + 2:off + 16 * first_lut + 4] = b"\xff\xff"  # operand slot a -> out of range
+    with pytest.raises(host.ClgError):
+        host.FlatProgram.from_bytes(bytes(bad))
+    bad = bytearray(data)
+    bad[off + 16 * first_lut + 9] = 7  # unknown instruction kind
+    with pytest.raises(host.ClgError):
+        host.FlatProgram.from_bytes(bytes(bad))
+    assert flat.n_inputs == 9
+
+
+def test_json_roundtrip():
+    c = host.Compiler(2)
+    sim = c.compile([host.And(0, 1, c.alloc())])
+    text = sim.to_json()
+    assert text == ('{"ops":[{"Set":[0,false]},{"Set":[1,false]},{"Nand":[0,1,3]},{"Nand":[3,3,2]}],'
+                    '"registers":[false,false,false,false]}')
+    back = host.Simulation.from_json(text)
+    assert back.ops == sim.ops and back.registers == sim.registers
+    with pytest.raises(host.ClgError):
+        host.Simulation.from_json('{"ops":[{"Nor":[0,1,2]}],"registers":[]}')

@@ -40,27 +40,27 @@ def test_run_out_of_bounds_panics(api):  # simulation.rs:20-26 index panics
 
 
 # ---- complogic/src/compile.rs:211-294 ----------------------------------------------------------
-def test_alloc_lazy_increment(api):  # compile.rs:211-218
-    c = api.Compiler(0)
+def test_alloc_lazy_increment(capi):  # compile.rs:211-218
+    c = capi.Compiler(0)
     assert [c.alloc(), c.alloc(), c.alloc()] == [0, 1, 2]
 
 
-def test_alloc_plus_immediates(api):  # compile.rs:220-227
-    c = api.Compiler(2)
+def test_alloc_plus_immediates(capi):  # compile.rs:220-227
+    c = capi.Compiler(2)
     assert [c.alloc(), c.alloc(), c.alloc()] == [2, 3, 4]
 
 
-def test_alloc_all_on_compile(api):  # compile.rs:229-245
-    c = api.Compiler(2)
+def test_alloc_all_on_compile(capi):  # compile.rs:229-245
+    c = capi.Compiler(2)
     assert len(c.compile([]).registers) == 2
     assert c.alloc() == 2 and c.alloc() == 3
     sim = c.compile([])
     assert len(sim.registers) == 2 and sim.ops == []
 
 
-def test_keep_incrementer_on_compile(api):  # compile.rs:247-266
-    c = api.Compiler(2)
-    and_ = api.And(0, 1, c.alloc())
+def test_keep_incrementer_on_compile(capi):  # compile.rs:247-266
+    c = capi.Compiler(2)
+    and_ = capi.And(0, 1, c.alloc())
     c.compile([and_])
     c.compile([and_])
     sim = c.compile([and_])
@@ -141,13 +141,13 @@ def test_full_adder(api):  # gates.rs:602-645
                 assert sim.registers[g.cout] is bool((a + b + cin) >> 1)
 
 
-def test_four_bit_adder_panics_like_the_reference(api):
+def test_four_bit_adder_panics_like_the_reference(capi):
     """gates.rs:663-707 is commented out as broken: FourBitAdder's cin (gates.rs:421) is a register no
     op writes, so #registers > #ops and compile.rs:137 indexes the graph out of bounds."""
-    c = api.Compiler(8)
+    c = capi.Compiler(8)
     c.incrementer.skip(5)
-    g = api.FourBitAdder(3, 2, 1, 0, 7, 6, 5, 4, 12, 11, 10, 9, 8)
-    with pytest.raises(api.ReferencePanic):
+    g = capi.FourBitAdder(3, 2, 1, 0, 7, 6, 5, 4, 12, 11, 10, 9, 8)
+    with pytest.raises(capi.ReferencePanic):
         c.compile([g])
 
 
@@ -166,34 +166,34 @@ def expected_graph_dot() -> str:
     return "\n".join(lines + ["}"]) + "\n"
 
 
-def test_graph_dot_golden(api):
-    c = api.Compiler(2)
-    rs = api.RSLatch(0, 1, c.alloc())
+def test_graph_dot_golden(capi):
+    c = capi.Compiler(2)
+    rs = capi.RSLatch(0, 1, c.alloc())
     c.compile([rs])
     assert c.last_dot == expected_graph_dot()
 
 
 # ---- emission order of compile(): unpinned by reference tests; derived by hand from compile.rs:154-196
-def test_compile_emission_order(api):
-    c = api.Compiler(2)
-    sim = c.compile([api.And(0, 1, c.alloc())])
-    assert sim.ops == [api.Set_op(0, False), api.Set_op(1, False), api.Nand_op(0, 1, 3), api.Nand_op(3, 3, 2)]
-    c = api.Compiler(2)
-    sim = c.compile([api.RSLatch(0, 1, c.alloc())])
-    N, S = api.Nand_op, api.Set_op
+def test_compile_emission_order(capi):
+    c = capi.Compiler(2)
+    sim = c.compile([capi.And(0, 1, c.alloc())])
+    assert sim.ops == [capi.Set_op(0, False), capi.Set_op(1, False), capi.Nand_op(0, 1, 3), capi.Nand_op(3, 3, 2)]
+    c = capi.Compiler(2)
+    sim = c.compile([capi.RSLatch(0, 1, c.alloc())])
+    N, S = capi.Nand_op, capi.Set_op
     assert sim.ops == [S(0, False), S(1, False), N(0, 0, 6), N(1, 1, 9), N(6, 7, 5), N(9, 10, 8), N(5, 5, 3),
                        N(8, 8, 4), N(4, 4, 7), N(3, 3, 10), N(4, 4, 11), N(4, 4, 12), N(11, 12, 2)]
     assert len(sim.registers) == 13
-    c = api.Compiler(3)
-    sim = c.compile([api.FullAdder(0, 1, 2, c.alloc(), c.alloc())])
+    c = capi.Compiler(3)
+    sim = c.compile([capi.FullAdder(0, 1, 2, c.alloc(), c.alloc())])
     assert len(sim.ops) == 3 + 19 and len(sim.registers) == 22
 
 
-def test_gate_nand_counts(api):  # gates.rs:193-456: 1/1/2/3/4/6/11/16/8/19/76
-    want = [(api.Nand(0, 1, 2), 1), (api.Not(0, 1), 1), (api.And(0, 1, 2), 2), (api.Or(0, 1, 2), 3),
-            (api.Nor(0, 1, 2), 4), (api.Xor(0, 1, 2), 6), (api.RSLatch(0, 1, 2), 11), (api.DLatch(0, 1, 2), 16),
-            (api.HalfAdder(0, 1, 2, 3), 8), (api.FullAdder(0, 1, 2, 3, 4), 19),
-            (api.FourBitAdder(*range(13)), 76)]
+def test_gate_nand_counts(capi):  # gates.rs:193-456: 1/1/2/3/4/6/11/16/8/19/76
+    want = [(capi.Nand(0, 1, 2), 1), (capi.Not(0, 1), 1), (capi.And(0, 1, 2), 2), (capi.Or(0, 1, 2), 3),
+            (capi.Nor(0, 1, 2), 4), (capi.Xor(0, 1, 2), 6), (capi.RSLatch(0, 1, 2), 11), (capi.DLatch(0, 1, 2), 16),
+            (capi.HalfAdder(0, 1, 2, 3), 8), (capi.FullAdder(0, 1, 2, 3, 4), 19),
+            (capi.FourBitAdder(*range(13)), 76)]
     for gate, n in want:
-        ops = gate.create(api.Incrementer(100))
+        ops = gate.create(capi.Incrementer(100))
         assert len(ops) == n and all(o[0] == "Nand" for o in ops)
