@@ -87,6 +87,7 @@ PROTOTYPES = {
     "clg_slice_bools": (i32, [vp, vp, vp, sz, sz, sz, vp]),
     "clg_unslice_bools": (i32, [vp, vp, vp, sz, sz, sz, vp]),
     "clg_fill_random": (i32, [vp, vp, sz, sz, u64, vp]),
+    "clg_measure_lop3_peak": (i32, [vp, P(C.c_double)]),
     "clg_sim_runner_create": (i32, [vp, vp, sz, i32, P(vp)]),
     "clg_sim_runner_destroy": (None, [vp]),
     "clg_sim_runner_run": (i32, [vp, vp, sz]),

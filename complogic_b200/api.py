@@ -157,6 +157,12 @@ class Context:
     def synchronize(self) -> None:
         check(lib().clg_ctx_synchronize(self._h))
 
+    def measure_lop3_peak(self) -> float:
+        """32-bit LOP3 lane-ops per second of a pure-LOP3 kernel on this device (measured roofline denominator)."""
+        v = C.c_double()
+        check(lib().clg_measure_lop3_peak(self._h, C.byref(v)))
+        return v.value
+
     def fill_random(self, dptr: int, n_rows: int, stride: int, seed: int, stream: int = 0) -> None:
         check(lib().clg_fill_random(self._h, dptr, n_rows, stride, seed, stream))
 

@@ -79,7 +79,7 @@ struct Ctx {
   CUcontext cu = nullptr;
   CUmodule mod = nullptr;
   int sm_count = 0;
-  CUfunction lane[3] = {}, coop[3] = {}, slice = nullptr, unslice = nullptr, fill = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  CUfunction lane[3] = {}, coop[3] = {}, slice = nullptr, unslice = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
   std::string name;
 
   explicit Ctx(int device) {
@@ -112,6 +112,7 @@ struct Ctx {
     CU(cuModuleGetFunction(&slice, mod, "clg_slice"));
     CU(cuModuleGetFunction(&unslice, mod, "clg_unslice"));
     CU(cuModuleGetFunction(&fill, mod, "clg_fill_random"));
+    CU(cuModuleGetFunction(&lop3_peak, mod, "clg_lop3_peak"));
   }
   ~Ctx() {
     Driver &d = driver();
@@ -328,6 +329,35 @@ void launch_fill(Ctx *c, uint32_t *dst, size_t n_rows, size_t stride, uint64_t s
   uint32_t nr = (uint32_t)n_rows, st = (uint32_t)stride;
   void *args[] = {&dst, &nr, &st, &seed};
   CU(cuLaunchKernel(c->fill, (unsigned)(c->sm_count * 8), 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr));
+}
+
+// pure-LOP3 microbenchmark: returns lane-ops (32-bit LOP3 results) per second
+double measure_lop3_peak(Ctx *c, int reps) {
+  c->bind();
+  CUdeviceptr seed = 0, sink = 0;
+  const uint32_t threads = 512, blocks = (uint32_t)c->sm_count * 4, iters = 64;
+  CU(cuMemAlloc(&seed, 4096));
+  CU(cuMemAlloc(&sink, (size_t)threads * blocks * 4));
+  CU(cuMemsetD8Async(seed, 0x5A, 4096, nullptr));
+  CUevent a, b;
+  CU(cuEventCreate(&a, CU_EVENT_DEFAULT));
+  CU(cuEventCreate(&b, CU_EVENT_DEFAULT));
+  uint32_t it = iters;
+  void *args[] = {&seed, &sink, &it};
+  double best = 0;
+  for (int r = 0; r < reps + 2; r++) {
+    CU(cuEventRecord(a, nullptr));
+    CU(cuLaunchKernel(c->lop3_peak, blocks, 1, 1, threads, 1, 1, 0, nullptr, args, nullptr));
+    CU(cuEventRecord(b, nullptr));
+    CU(cuEventSynchronize(b));
+    float ms = 0;
+    CU(cuEventElapsedTime(&ms, a, b));
+    const double ops = (double)threads * blocks * 8.0 * 64.0 * iters;
+    if (r >= 2) best = std::max(best, ops / (ms * 1e-3));
+  }
+  driver().cuEventDestroy(a), driver().cuEventDestroy(b);
+  driver().cuMemFree(seed), driver().cuMemFree(sink);
+  return best;
 }
 
 // event-timed run used by the sharded driver

@@ -34,6 +34,7 @@ void exec_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t, 
 void launch_slice(Ctx *, bool, const void *, void *, size_t, size_t, size_t, void *);
 void launch_fill(Ctx *, uint32_t *, size_t, size_t, uint64_t, void *);
 double timed_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t);
+double measure_lop3_peak(Ctx *, int);
 
 static thread_local std::string g_err;
 void fail(int code, const std::string &msg) { throw Error{code, msg}; }
@@ -389,6 +390,12 @@ int clg_unslice_bools(clg_ctx *ctx, const uint32_t *sliced, uint8_t *bools, size
   CLG_TRY
   NEED(ctx), NEED(bools), NEED(sliced);
   launch_slice(ctx->c, true, sliced, bools, n_vectors, n_rows, stride, stream);
+  CLG_CATCH
+}
+int clg_measure_lop3_peak(clg_ctx *ctx, double *lane_ops_per_second) {
+  CLG_TRY
+  NEED(ctx), NEED(lane_ops_per_second);
+  *lane_ops_per_second = measure_lop3_peak(ctx->c, 5);
   CLG_CATCH
 }
 int clg_fill_random(clg_ctx *ctx, uint32_t *sliced, size_t n_rows, size_t stride, uint64_t seed, void *stream) {

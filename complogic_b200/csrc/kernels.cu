@@ -335,6 +335,28 @@ extern "C" __global__ void __launch_bounds__(256) clg_fill_random(uint32_t *slic
 
 }  // namespace clg
 
+// Measured denominator for the LOP3 roofline: nothing but dependent LOP3 chains (8 independent chains per
+// thread so the 4-cycle ALU latency is covered), 8 * 64 * iters LOP3 per thread. The chains are seeded from
+// memory and folded into one store so nothing is optimised away.
+extern "C" __global__ void __launch_bounds__(512) clg_lop3_peak(const uint32_t *seed, uint32_t *sink, uint32_t iters) {
+  uint32_t v[8];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = seed[(t + j) & 1023] + j;
+  const uint32_t k0 = seed[t & 1023], k1 = seed[(t * 7) & 1023];
+  for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+    for (int r = 0; r < 64; r++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = clg::lop3<0x3F>(v[j], k0, k1);  // the NAND immediate; opaque to the compiler
+    }
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc ^= v[j];
+  if (acc == 0xDEADBEEFu) sink[t] = acc;
+}
+
 // C-named entry points the host looks up in the cubin (one per words-per-thread variant)
 #define CLG_ENTRY(K)                                                                                           \
   extern "C" __global__ void __launch_bounds__(clg::LANE_THREADS + 32) clg_lane_k##K(const clg::RunParams p) { \

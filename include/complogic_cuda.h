@@ -255,6 +255,10 @@ int clg_unslice_bools(clg_ctx *ctx, const uint32_t *sliced, uint8_t *bools, size
  * hi32(splitmix64(seed ^ (row << 40) ^ w)); fills rows x stride words on the device. */
 int clg_fill_random(clg_ctx *ctx, uint32_t *sliced, size_t n_rows, size_t stride, uint64_t seed, void *stream);
 
+/* Measured denominator of the integer-ALU roofline: a kernel of nothing but dependent LOP3 chains; returns
+ * 32-bit LOP3 lane-operations per second on this device (nominal: 148 SM x 64 lanes/clk x SM clock). */
+int clg_measure_lop3_peak(clg_ctx *ctx, double *lane_ops_per_second);
+
 /* Simulation::run for ONE vector, on the device, with the reference's carried-register
  * semantics: binds `sim` to a 1-lane stateful program (all registers observable), and every
  * call evaluates one run(immediates) and writes sim.registers back. This is what lets the

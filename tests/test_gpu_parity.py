@@ -1,0 +1,220 @@
+"""GPU parity tests (run on a B200 with `-m gpu`): every execution mode of the CUDA path, called through
+the C ABI, must reproduce the oracle VM bit for bit on the same seeded inputs.
+
+(The reference's own unit tests also run on the GPU path: tests/test_reference_golden.py, `host` leg.)
+"""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import complogic_b200 as host
+from complogic_b200 import circuits
+from oracle import oracle
+from tests.helpers import exhaustive_sliced, mask_tail, random_sliced, stride_for, unslice_int
+
+pytestmark = pytest.mark.gpu
+
+MODES = [host.MODE_SPEC, host.MODE_LANE, host.MODE_COOP]
+
+
+def oracle_out(circ, imm, nv):
+    return mask_tail(oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs), nv)
+
+
+def gpu_out(circ, imm, nv, mode, flags=0):
+    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, flags=flags, mode=mode)
+    assert cs.mode == mode
+    return mask_tail(cs.run_batch(imm, nv), nv)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_config1_adder8_exhaustive(mode):
+    """BASELINE config 1: 8-bit ripple adder, exhaustive 2^17 vectors: GPU == scalar VM == sliced VM == a+b+cin."""
+    circ = circuits.ripple_adder(8)
+    n = 1 << 17
+    imm = exhaustive_sliced(17)
+    got = gpu_out(circ, imm, n, mode)
+    scalar = oracle.run_batch_scalar(circ.sim, 169, imm, n, circ.out_regs, threads=8)
+    assert np.array_equal(got, mask_tail(scalar, n))
+    v = np.arange(n, dtype=np.uint64)
+    want = (v & np.uint64(0xFF)) + ((v >> np.uint64(8)) & np.uint64(0xFF)) + (v >> np.uint64(16))
+    assert np.array_equal(unslice_int(got, n), want)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("nv", [1, 31, 33, 127, 4097, 1 << 16])
+def test_adder32_ragged_sizes(mode, nv):
+    circ = circuits.ripple_adder(32)
+    imm = random_sliced(65, stride_for(nv), seed=0xC0FFEE)
+    assert np.array_equal(gpu_out(circ, imm, nv, mode), oracle_out(circ, imm, nv))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_mul16(mode):
+    circ = circuits.array_multiplier(16)
+    nv = 1 << 15
+    imm = random_sliced(32, stride_for(nv), seed=0xC0FFEF)
+    got = gpu_out(circ, imm, nv, mode)
+    assert np.array_equal(got, oracle_out(circ, imm, nv))
+    a, b = unslice_int(imm[:16], nv), unslice_int(imm[16:], nv)
+    assert np.array_equal(unslice_int(got, nv), a * b)
+
+
+@pytest.mark.parametrize("mode", [host.MODE_COOP, host.MODE_LANE])
+@pytest.mark.parametrize("window", [2, 0])
+def test_small_dag(mode, window):
+    width = 200 if mode == host.MODE_COOP else 60  # the per-thread stack of the lane mode holds ~440 live values
+    circ = circuits.random_dag(levels=40, width=width, n_immediates=64, window=window, seed=9)
+    nv = 5000
+    imm = random_sliced(64, stride_for(nv), seed=21)
+    for flags in (0, host.LV_NO_FUSE):
+        assert np.array_equal(gpu_out(circ, imm, nv, mode, flags), oracle_out(circ, imm, nv))
+
+
+def test_dag_1m_gates_prefix():
+    """BASELINE config 4's circuit (1 048 576 gates, depth 256, K=2) on a 2^12-vector batch."""
+    circ = circuits.random_dag()
+    nv = 1 << 12
+    imm = random_sliced(1024, stride_for(nv), seed=0xD46)
+    got = gpu_out(circ, imm, nv, host.MODE_COOP)
+    assert np.array_equal(got, oracle_out(circ, imm, nv))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_flattened_instances_single_vector(mode):
+    """config 5 in miniature: independent multiplier instances flattened, ONE input vector."""
+    base = circuits.array_multiplier(8)
+    circ = circuits.flatten_instances(base, 6)
+    for nv in (1, 40):
+        imm = random_sliced(circ.n_immediates, stride_for(nv), seed=77)
+        assert np.array_equal(gpu_out(circ, imm, nv, mode), oracle_out(circ, imm, nv))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("gate", ["RSLatch", "RSLatchTest", "DLatch"])
+def test_latch_sequences_per_lane(mode, gate):
+    """Carried registers (simulation.rs never clears them): 6 steps x 300 lanes, every register, every step."""
+    c = host.Compiler(2)
+    sim = c.compile([getattr(host, gate)(0, 1, c.alloc())])
+    nv, steps, R = 300, 6, len(sim.registers)
+    stride = stride_for(nv)
+    imm = np.stack([random_sliced(2, stride, 5 + 97 * s) for s in range(steps)])
+    want = oracle.run_batch_scalar(sim, R, imm, nv, list(range(R)), steps=steps, all_steps=True)
+    cs = host.CudaSimulation.from_simulation(sim, 2, None, flags=host.LV_STATEFUL, mode=mode)
+    state = np.zeros((cs.info["n_state"], stride), np.uint32)
+    for s in range(steps):
+        got = cs.run_batch(imm[s], nv, state=state)
+        assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv)), f"step {s}"
+
+
+@st.composite
+def programs(draw):
+    n_regs = draw(st.integers(1, 10))
+    ops = []
+    for _ in range(draw(st.integers(0, 30))):
+        if draw(st.integers(0, 4)) == 0:
+            ops.append(host.Set_op(draw(st.integers(0, n_regs - 1)), draw(st.booleans())))
+        else:
+            ops.append(host.Nand_op(*[draw(st.integers(0, n_regs - 1)) for _ in range(3)]))
+    return ops, n_regs, draw(st.integers(0, n_regs + 1)), draw(st.sampled_from(MODES))
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(programs(), st.integers(0, 2 ** 31))
+def test_random_programs(prog, seed):
+    ops, n_regs, n_imm, mode = prog
+    sim = host.Simulation(ops=ops, registers=[False] * n_regs)
+    nv, steps = 70, 2
+    stride = stride_for(nv)
+    imm = np.stack([random_sliced(n_imm, stride, seed + s) for s in range(steps)]) if n_imm else \
+        np.zeros((steps, 0, stride), np.uint32)
+    want = oracle.run_batch_scalar(ops, n_regs, imm, nv, list(range(n_regs)), steps=steps, all_steps=True)
+    cs = host.CudaSimulation.from_simulation(sim, n_imm, None, flags=host.LV_STATEFUL, mode=mode)
+    state = np.zeros((cs.info["n_state"], stride), np.uint32)
+    for s in range(steps):
+        got = cs.run_batch(imm[s], nv, state=state)
+        assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv))
+
+
+def test_bools_api_and_transposes():
+    """`&[bool]`-shaped entry point (one run()'s immediates per row) through the device transposes."""
+    circ = circuits.array_multiplier(8)
+    cs = host.CudaSimulation.from_simulation(circ.sim, 16, circ.out_regs)
+    rng = np.random.default_rng(3)
+    for nv in (1, 33, 1000):
+        imm = rng.integers(0, 2, size=(nv, 16), dtype=np.uint8)
+        out = cs.run_bools(imm)
+        a = (imm[:, :8].astype(np.uint64) << np.arange(8, dtype=np.uint64)).sum(axis=1)
+        b = (imm[:, 8:].astype(np.uint64) << np.arange(8, dtype=np.uint64)).sum(axis=1)
+        p = (out.astype(np.uint64) << np.arange(16, dtype=np.uint64)).sum(axis=1)
+        assert np.array_equal(p, a * b)
+
+
+def test_torch_buffers_and_stream_and_fill():
+    """Device pointers from torch, torch's current stream, and the on-device input generator."""
+    import torch
+
+    circ = circuits.ripple_adder(32)
+    nv = (1 << 18) + 5
+    stride = stride_for(nv)
+    ctx = host.Context.default()
+    cs = host.CudaSimulation.from_simulation(circ.sim, 65, circ.out_regs, ctx=ctx)
+    imm = torch.empty((65, stride), dtype=torch.int32, device="cuda:0")
+    out = torch.zeros((33, stride), dtype=torch.int32, device="cuda:0")
+    s = torch.cuda.current_stream().cuda_stream
+    ctx.fill_random(imm.data_ptr(), 65, stride, 0xC0FFEE, s)
+    cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride, stream=s)
+    torch.cuda.synchronize()
+    imm_h = imm.cpu().numpy().view(np.uint32)
+    assert np.array_equal(imm_h, random_sliced(65, stride, 0xC0FFEE))
+    got = mask_tail(out.cpu().numpy().view(np.uint32), nv)
+    assert np.array_equal(got, oracle_out(circ, imm_h, nv))
+
+
+def test_full_size_adder32_2p24():
+    """BASELINE config 2 at full size (2^24 vectors): a + b + cin for every lane, and a checksum of the words."""
+    import torch
+
+    circ = circuits.ripple_adder(32)
+    nv = 1 << 24
+    stride = stride_for(nv)
+    ctx = host.Context.default()
+    cs = host.CudaSimulation.from_simulation(circ.sim, 65, circ.out_regs, ctx=ctx)
+    imm = torch.empty((65, stride), dtype=torch.int32, device="cuda:0")
+    out = torch.zeros((33, stride), dtype=torch.int32, device="cuda:0")
+    ctx.fill_random(imm.data_ptr(), 65, stride, 0xC0FFEE, 0)
+    cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    imm_h, out_h = imm.cpu().numpy().view(np.uint32), out.cpu().numpy().view(np.uint32)
+    want = oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm_h, nv, circ.out_regs)
+    assert np.array_equal(out_h, want)
+    sample = slice(0, 1 << 12)  # 2^17 lanes through the arithmetic identity
+    n = 1 << 17
+    a, b, cin = (unslice_int(imm_h[:32, sample], n), unslice_int(imm_h[32:64, sample], n), unslice_int(imm_h[64:, sample], n))
+    assert np.array_equal(unslice_int(out_h[:, sample], n), a + b + cin)
+
+
+def test_modes_agree_at_scale_mul16():
+    """Size-independent property at 2^22 vectors: the three execution modes produce identical buffers, and they
+    equal a*b on a strided sample."""
+    circ = circuits.array_multiplier(16)
+    nv = 1 << 22
+    imm = random_sliced(32, stride_for(nv), seed=0xC0FFEF)
+    outs = [host.CudaSimulation.from_simulation(circ.sim, 32, circ.out_regs, mode=m).run_batch(imm, nv) for m in MODES]
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    cols = np.arange(0, imm.shape[1], 257)
+    n = len(cols) * 32
+    a, b = unslice_int(imm[:16][:, cols], n), unslice_int(imm[16:][:, cols], n)
+    assert np.array_equal(unslice_int(outs[0][:, cols], n), a * b)
+
+
+def test_errors_are_status_codes():
+    circ = circuits.ripple_adder(4)
+    cs = host.CudaSimulation.from_simulation(circ.sim, 9, circ.out_regs)
+    with pytest.raises(host.ClgError):  # stride not a multiple of 4 words
+        cs.run_device(16, 16, 32, 3)
+    with pytest.raises(host.ClgError):  # lanes do not fit
+        cs.run_device(16, 16, 32 * 5, 4)
+    big = circuits.random_dag(levels=6, width=3000, n_immediates=3000, window=0, seed=2)
+    with pytest.raises(host.ClgError):  # live set too large for the per-thread modes
+        host.CudaSimulation.from_simulation(big.sim, 3000, big.out_regs, mode=host.MODE_LANE)
