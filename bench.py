@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline metric on B200: NAND gate-evals/s (gates x vectors / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload dag1m|mul16|adder32]
+
+One "step" is one pass of the hot path (`Simulation::run` for every vector of the batch,
+complogic/src/simulation.rs:16-30) over one batch of synthetic random input vectors.
+Default workload = the configuration BASELINE.json's target is quoted on ("1M-gate circuit x 2^24
+vectors", configs[3]): the synthetic random levelized NAND DAG, 1 048 576 gates, depth 256, 2^24 vectors
+PER GPU (weak scaling: every rank evaluates its own shard, no data-path collective).
+
+Prints ONE JSON line (rank 0). Contract keys: metric/value/unit/n_gpus/steps/warmup/ms_per_step/
+higher_is_better/scaling/vs_baseline/dtype/data/config/clocks/e2e/gpu_launches + roofline + cpu_baseline.
+`--impl reference` times the reference's CPU VM (the oracle's literal restatement, all host threads) on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "NAND gate-evals/sec (gates x vectors / s)"
+UNIT = "gate-evals/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+def build_workload(name: str, api=None):
+    """-> (Circuit, default log2 vectors per GPU, seed)"""
+    from complogic_b200 import circuits
+
+    if name == "dag1m":
+        return circuits.random_dag(256, 4096, 1024, 2, 1, api=api), 24, 0xDA6
+    if name == "mul16":
+        return circuits.array_multiplier(16, api=api), 26, 0xC0FFEF
+    if name == "adder32":
+        return circuits.ripple_adder(32, api=api), 24, 0xC0FFEE
+    if name == "adder8":
+        return circuits.ripple_adder(8, api=api), 17, 0xC0FFED
+    raise SystemExit(f"unknown workload {name}")
+
+
+WORKLOAD_DESC = {
+    "dag1m": "synthetic random levelized NAND DAG, 1 048 576 gates (256 levels x 4096), 1024 immediates, window K=2, "
+             "4096 outputs (BASELINE configs[3])",
+    "mul16": "16x16 array multiplier, 4 896 NANDs with the reference's gate expansions (BASELINE configs[2])",
+    "adder32": "32-bit ripple-carry adder, 608 NANDs (BASELINE configs[1])",
+    "adder8": "8-bit ripple-carry adder, 152 NANDs (BASELINE configs[0])",
+}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            inside = t0 - 0.05 <= ts <= t1 + 0.15
+            try:
+                if inside:
+                    sm.append(float(parts[0]))
+                    power.append(float(parts[2]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            if inside:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: fall back to every sample taken
+            for ts, line in self.rows:
+                try:
+                    sm.append(float(line.split(",")[0]))
+                except ValueError:
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def cpu_reference_throughput(circ, seed: int, threads: int, target_s: float):
+    """The reference VM on the host cores: literal restatement of simulation.rs:16-30 (32-byte ops, one byte per
+    register, bounds checks, one run() per vector), `threads` pthreads each on its own slice of vectors."""
+    from oracle import oracle
+    from tests.helpers import random_sliced, stride_for
+
+    gates = circ.sim.nand_count
+    R = len(circ.sim.registers)
+    ops = oracle._as_orc_ops(circ.sim)
+    # calibrate on one word per thread, then size the sample for ~target_s
+    nv = 32 * threads
+    imm = random_sliced(circ.n_immediates, stride_for(nv), seed)
+    t0 = time.perf_counter()
+    oracle.run_batch_scalar(ops, R, imm, nv, circ.out_regs, threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    scale = max(1, int(target_s / dt))
+    nv = 32 * threads * min(scale, 1 << 16)
+    imm = random_sliced(circ.n_immediates, stride_for(nv), seed)
+    t0 = time.perf_counter()
+    oracle.run_batch_scalar(ops, R, imm, nv, circ.out_regs, threads=threads)
+    dt = time.perf_counter() - t0
+    return gates * nv / dt, nv, dt
+
+
+def run_reference(args):
+    """--impl reference: rank 0 only; every step is a bounded sample of the same workload on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    from tests.helpers import random_sliced, stride_for
+
+    oracle.build()
+    circ, lg, seed = build_workload(args.workload, api=None)
+    threads = os.cpu_count() or 1
+    gates = circ.sim.nand_count
+    R = len(circ.sim.registers)
+    ops = oracle._as_orc_ops(circ.sim)
+    # size a step for ~ (budget / (steps + warmup)) seconds
+    per_step = max(0.5, min(20.0, 120.0 / (args.steps + args.warmup)))
+    _, nv_cal, dt_cal = cpu_reference_throughput(circ, seed, threads, 1.0)
+    nv = max(32 * threads, int(nv_cal * per_step / max(dt_cal, 1e-6)) // (32 * threads) * (32 * threads))
+    imm = random_sliced(circ.n_immediates, stride_for(nv), seed)
+    times = []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        oracle.run_batch_scalar(ops, R, imm, nv, circ.out_regs, threads=threads)
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = gates * nv / (ms * 1e-3)
+    sample = f"{nv} vectors per step ({threads} threads x {nv // threads} lanes) of {args.workload}, {gates} NANDs"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bool (u8 per register)", "data": "synthetic",
+        "config": {"workload": args.workload, "description": WORKLOAD_DESC[args.workload], "gates": gates,
+                   "vectors_per_step": nv, "note": "reference CPU VM: C restatement of simulation.rs:16-30 (the Rust "
+                   "reference cannot be built in this image: no cargo/rustc), all host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dag1m", choices=list(WORKLOAD_DESC))
+    ap.add_argument("--log2-vectors", type=int, default=None, help="vectors per GPU (log2); default = the config's")
+    ap.add_argument("--mode", default="auto", choices=["auto", "lane", "coop", "spec"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time the other BASELINE configs (device-resident only)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: >= 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import complogic_b200 as host
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    hbm_peak, sm_max_mhz, peak_kind = load_peaks()
+    ctx = host.Context(local)
+    mode = {"auto": host.MODE_AUTO, "lane": host.MODE_LANE, "coop": host.MODE_COOP, "spec": host.MODE_SPEC}[args.mode]
+
+    def prepare(workload, lg2):
+        circ, lg_default, seed = build_workload(workload)
+        lg2 = lg_default if lg2 is None else lg2
+        t0 = time.perf_counter()
+        cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=mode)
+        compile_s = time.perf_counter() - t0
+        nv = 1 << lg2
+        stride = host.round_stride(nv)
+        n_in, n_out = cs.info["n_inputs"], cs.info["n_outputs"]
+        io_bytes = (n_in + n_out) * stride * 4
+        # inputs larger than L2, or rotate enough buffer sets that a step never finds its rows in L2
+        sets = 1 if n_in * stride * 4 > 2 * L2_BYTES else max(2, int(np.ceil(3 * L2_BYTES / max(1, io_bytes))))
+        bufs = []
+        for b in range(sets):
+            imm = torch.empty((n_in, stride), dtype=torch.int32, device=dev)
+            out = torch.zeros((n_out, stride), dtype=torch.int32, device=dev)
+            ctx.fill_random(imm.data_ptr(), n_in, stride, seed + 1000 * rank + b, torch.cuda.current_stream().cuda_stream)
+            bufs.append((imm, out))
+        torch.cuda.synchronize()
+        return dict(circ=circ, cs=cs, nv=nv, stride=stride, bufs=bufs, seed=seed, compile_s=compile_s, io_bytes=io_bytes,
+                    gates=cs.info["ref_nand_count"], name=workload)
+
+    def timed_steps(w, steps, warmup, sample_clocks=False):
+        cs, bufs, nv, stride = w["cs"], w["bufs"], w["nv"], w["stride"]
+        stream = torch.cuda.current_stream().cuda_stream
+        for s in range(warmup):
+            imm, out = bufs[s % len(bufs)]
+            cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride, stream=stream)
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            time.sleep(0.25)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for s in range(steps):
+            imm, out = bufs[s % len(bufs)]
+            cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        clocks = sampler.stop(t0, t1) if sampler else None
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+        return ms, clocks
+
+    w = prepare(args.workload, args.log2_vectors)
+    cs = w["cs"]
+    ms, clocks = timed_steps(w, args.steps, args.warmup, sample_clocks=True)
+    total_vectors = w["nv"] * world
+    value = w["gates"] * total_vectors / (ms * 1e-3)
+
+    # ---- roofline of the dominant (only) kernel -----------------------------------------------------------
+    lop3_measured = ctx.measure_lop3_peak() if rank == 0 else 0.0  # lane-ops/s of a pure-LOP3 kernel, this device
+    lop3_nominal = 148 * 64 * sm_max_mhz * 1e6
+    lane_ops = w["gates"] * w["nv"] / 32.0  # algorithmic: 1 LOP3 lane-op per 32 gate-evals
+    issued_lane_ops = cs.info["n_luts"] * w["nv"] / 32.0  # what the kernel really issues after LUT3 fusion
+    per_gpu_s = ms * 1e-3
+    hbm_achieved = w["io_bytes"] / per_gpu_s / 1e9
+    gates_per_byte = w["gates"] * w["nv"] / w["io_bytes"]
+    io_bound = gates_per_byte < 91.0 or (hbm_achieved / hbm_peak) > (lane_ops / per_gpu_s / lop3_nominal)
+    if io_bound:
+        roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                    "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"}
+    else:
+        roofline = {"bound": "lop3 (integer ALU pipe; not a tensor-core path)", "achieved": lane_ops / per_gpu_s / 1e12,
+                    "peak": lop3_nominal / 1e12, "unit": "T lane-op/s", "frac": lane_ops / per_gpu_s / lop3_nominal,
+                    "traffic": None,
+                    "peak_source": f"nominal 148 SM x 64 LOP3 lanes/clk x {sm_max_mhz:.0f} MHz; measured pure-LOP3 kernel: "
+                                   f"{lop3_measured / 1e12:.2f} T lane-op/s"}
+    roofline.update({
+        "kernel": f"clg_{cs.mode_name}" + (f"_k{cs.words_per_thread}" if cs.mode_name != "spec" else f" (K={cs.words_per_thread})"),
+        "algorithmic_lane_ops_per_launch": lane_ops, "issued_lop3_lane_ops_per_launch": issued_lane_ops,
+        "frac_of_measured_lop3": (lane_ops / per_gpu_s / lop3_measured) if lop3_measured else None,
+        "frac_issued_of_nominal_lop3": issued_lane_ops / per_gpu_s / lop3_nominal,
+        "hbm_GBps": hbm_achieved, "hbm_frac": hbm_achieved / hbm_peak, "algorithmic_bytes_per_launch": w["io_bytes"],
+        "gates_per_io_byte": gates_per_byte,
+        "smem_interpreter_bound_frac": None if cs.mode_name == "spec" else 1.0 / 6.0,
+    })
+
+    # ---- e2e: the C-ABI call with HOST buffers, H2D + kernel + D2H inside the timed region ----------------------
+    e2e = None
+    if not args.no_e2e:
+        n_in, n_out, stride, nv = cs.info["n_inputs"], cs.info["n_outputs"], w["stride"], w["nv"]
+        h_imm = torch.empty((n_in, stride), dtype=torch.int32, pin_memory=True)
+        h_out = torch.empty((n_out, stride), dtype=torch.int32, pin_memory=True)
+        h_imm.copy_(w["bufs"][0][0])
+        torch.cuda.synchronize()
+        d_imm, d_out = w["bufs"][0]
+        stream = torch.cuda.current_stream().cuda_stream
+        lib = host._lib.lib()
+
+        def e2e_step():
+            host._lib.check(lib.clg_memcpy_h2d(ctx._h, d_imm.data_ptr(), h_imm.data_ptr(), n_in * stride * 4, stream))
+            cs.run_device(d_imm.data_ptr(), d_out.data_ptr(), nv, stride, stream=stream)
+            host._lib.check(lib.clg_memcpy_d2h(ctx._h, h_out.data_ptr(), d_out.data_ptr(), n_out * stride * 4, stream))
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e_steps = max(2, min(args.steps, 5))
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+        checksum = int(h_out.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFFFFFF  # the result is really on the host
+        e2e = {"value": w["gates"] * total_vectors / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_in * stride * 4,
+               "d2h_bytes_per_step": n_out * stride * 4, "ms_per_step": e_ms, "steps": e2e_steps,
+               "api": "clg_memcpy_h2d + clg_exec_run + clg_memcpy_d2h (pinned host buffers, one stream)",
+               "out_checksum": f"{checksum:016x}"}
+        del h_imm, h_out
+
+    main_gates, main_compile_s = w["gates"], w["compile_s"]
+    l2_note = ("inputs larger than 2x L2 (no flush needed)" if len(w["bufs"]) == 1
+               else f"rotating {len(w['bufs'])} buffer sets, together larger than 3x L2")
+    extras = None
+    if args.extras and rank == 0 and world == 1:
+        extras = {}
+        for name in ("adder32", "mul16", "dag1m"):
+            if name == args.workload:
+                continue
+            del w
+            torch.cuda.empty_cache()
+            w = prepare(name, None)
+            ms_x, _ = timed_steps(w, 10, 3)
+            extras[name] = {"ms_per_step": ms_x, "value": w["gates"] * w["nv"] / (ms_x * 1e-3), "vectors": w["nv"],
+                            "mode": w["cs"].mode_name, "K": w["cs"].words_per_thread, "n_luts": w["cs"].info["n_luts"],
+                            "gates": w["gates"], "hbm_GBps": w["io_bytes"] / (ms_x * 1e-3) / 1e9,
+                            "hbm_frac": w["io_bytes"] / (ms_x * 1e-3) / 1e9 / hbm_peak,
+                            "lop3_frac_algorithmic": w["gates"] * w["nv"] / 32 / (ms_x * 1e-3) / lop3_nominal,
+                            "lop3_frac_issued": w["cs"].info["n_luts"] * w["nv"] / 32 / (ms_x * 1e-3) / lop3_nominal}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+
+        oracle.build()
+        circ, _, seed = build_workload(args.workload)
+        threads = os.cpu_count() or 1
+        v, nv_s, dt = cpu_reference_throughput(circ, seed, threads, args.cpu_seconds)
+        v1, nv1, dt1 = cpu_reference_throughput(circ, seed, 1, min(3.0, args.cpu_seconds))
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{nv_s} vectors of {args.workload} in {dt:.1f} s on {threads} threads (scalar VM restating "
+                         f"simulation.rs:16-30; 32-byte ops, byte registers, bounds checks)",
+               "single_thread_value": v1, "single_thread_sample": f"{nv1} vectors in {dt1:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (bit-sliced: 32 circuit instances per lane word)", "data": "synthetic",
+            "config": {"workload": args.workload, "description": WORKLOAD_DESC[args.workload], "gates": main_gates,
+                       "vectors_per_gpu": 1 << (args.log2_vectors or build_workload(args.workload)[1]), "total_vectors": total_vectors,
+                       "mode": cs.mode_name, "words_per_thread_or_cta": cs.words_per_thread, "fused_lop3_instructions": cs.info["n_luts"],
+                       "levels": cs.info["n_levels"], "slots": cs.info["level_slots"] if cs.mode_name == "coop" else cs.info["lane_slots"],
+                       "l2": l2_note, "sharding": "independent vector shards per rank, no collective",
+                       "compile_seconds": main_compile_s},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * cs.launches_per_run,
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        if extras:
+            line["other_configs"] = extras
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
