@@ -91,6 +91,7 @@ PROTOTYPES = {
     "clg_sim_runner_create": (i32, [vp, vp, sz, i32, P(vp)]),
     "clg_sim_runner_destroy": (None, [vp]),
     "clg_sim_runner_run": (i32, [vp, vp, sz]),
+    "clg_shard_range": (i32, [sz, i32, i32, P(sz), P(sz)]),
     "clg_run_sharded_host": (i32, [vp, i32, P(i32), i32, vp, vp, sz, sz, P(C.c_double)]),
     "clg_simulation_to_json": (i32, [vp, P(vp)]),
     "clg_simulation_from_json": (i32, [C.c_char_p, P(vp)]),

@@ -497,6 +497,13 @@ class CudaSimulation:
             pass
 
 
+def shard_range(n_vectors: int, n_shards: int, shard: int):
+    """clg_shard_range: the word range [w0, w1) of every row that `shard` of `n_shards` owns."""
+    w0, w1 = C.c_size_t(), C.c_size_t()
+    check(lib().clg_shard_range(n_vectors, n_shards, shard, C.byref(w0), C.byref(w1)))
+    return w0.value, w1.value
+
+
 def run_sharded(flat: FlatProgram, imm: np.ndarray, n_vectors: int, devices: Sequence[int], mode: int = MODE_AUTO):
     """clg_run_sharded_host: one process, one host thread + context per device, no collective."""
     imm = np.ascontiguousarray(imm, dtype=np.uint32)

@@ -468,6 +468,20 @@ int clg_sim_runner_run(clg_sim_runner *r, const uint8_t *immediates, size_t n_im
 }
 
 // ---- single-process multi-GPU sharding --------------------------------------------------------------------------
+static void shard_range(size_t n_vectors, int n_shards, int shard, size_t &w0, size_t &w1) {
+  const size_t words = (n_vectors + 31) / 32, quads = (words + 3) / 4;
+  w0 = std::min(words, quads * (size_t)shard / (size_t)n_shards * 4);
+  w1 = std::min(words, quads * (size_t)(shard + 1) / (size_t)n_shards * 4);
+}
+
+int clg_shard_range(size_t n_vectors, int n_shards, int shard, size_t *w0, size_t *w1) {
+  CLG_TRY
+  NEED(w0), NEED(w1);
+  if (n_shards < 1 || shard < 0 || shard >= n_shards) fail(CLG_E_INVALID, "shard index out of range");
+  shard_range(n_vectors, n_shards, shard, *w0, *w1);
+  CLG_CATCH
+}
+
 int clg_run_sharded_host(const clg_flat *flat, int mode, const int *devices, int n_devices, const uint32_t *imm, uint32_t *out,
                          size_t n_vectors, size_t stride, double *seconds_out) {
   CLG_TRY
@@ -476,14 +490,13 @@ int clg_run_sharded_host(const clg_flat *flat, int mode, const int *devices, int
   const FlatHeader &h = flat->f.header();
   if (h.n_state) fail(CLG_E_UNSUPPORTED, "sharded runs are for stateless programs");
   if (stride % 4) fail(CLG_E_INVALID, "stride must be a multiple of 4 words");
-  const size_t words = (n_vectors + 31) / 32, quads = (words + 3) / 4;
   std::vector<Error> errs(n_devices, Error{CLG_OK, ""});
   std::vector<std::thread> th;
   for (int d = 0; d < n_devices; d++)
     th.emplace_back([&, d] {
       try {
-        // contiguous ranges of 4-word quads: rows stay 16-byte aligned on every shard
-        const size_t w0 = quads * d / n_devices * 4, w1 = std::min(words, quads * (d + 1) / n_devices * 4);
+        size_t w0, w1;  // contiguous ranges of 4-word quads: rows stay 16-byte aligned on every shard
+        shard_range(n_vectors, n_devices, d, w0, w1);
         if (seconds_out) seconds_out[d] = 0;
         if (w1 <= w0) return;
         const size_t sw = (w1 - w0 + 3) / 4 * 4, nv = std::min(n_vectors, w1 * 32) - w0 * 32;

@@ -268,6 +268,11 @@ int clg_sim_runner_create(clg_ctx *ctx, clg_simulation *sim, size_t n_immediates
 void clg_sim_runner_destroy(clg_sim_runner *r);
 int clg_sim_runner_run(clg_sim_runner *r, const uint8_t *immediates, size_t n_immediates);
 
+/* Shard arithmetic used by every multi-GPU driver: the words [*w0, *w1) of each row that shard `shard` of
+ * `n_shards` owns. Ranges are contiguous, cover ceil(n_vectors/32) words exactly once, and start on multiples
+ * of 4 words so that a shard's rows stay 16-byte aligned. Pure host logic (no device needed). */
+int clg_shard_range(size_t n_vectors, int n_shards, int shard, size_t *w0, size_t *w1);
+
 /* Single-process multi-GPU driver (north-star: the vector batch shards independently across the
  * GPUs of one box, per-GPU device-side result buffers copied back by the host; no collective).
  * HOST pointers; words are split into contiguous multiples-of-4 ranges, one host thread, context
