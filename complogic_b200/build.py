@@ -36,13 +36,32 @@ def _newer(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _gen_dispatch() -> None:
+    """PTX text of the 256-entry LOP3 jump table (see kernels.cu, lut3): one file per (K, uniform?)."""
+    for K in (1, 2, 4):
+        for uni in (True, False):
+            path = os.path.join(BUILD, f"lut_dispatch_k{K}{'u' if uni else 'd'}.inc")
+            u = ".uni" if uni else ""
+            lines = ['"{\\n"', '"TBL_%=: .branchtargets ' + ", ".join(f"L{n}_%=" for n in range(256)) + ';\\n"',
+                     f'"brx.idx{u} %{4 * K}, TBL_%=;\\n"']
+            for n in range(256):
+                body = " ".join(f"lop3.b32 %{k}, %{K + k}, %{2 * K + k}, %{3 * K + k}, {n};" for k in range(K))
+                lines.append(f'"L{n}_%=: {body} bra{u} DONE_%=;\\n"')
+            lines += ['"DONE_%=:\\n"', '"}\\n"']
+            text = "\n".join(lines) + "\n"
+            if not os.path.exists(path) or open(path).read() != text:
+                with open(path, "w") as f:
+                    f.write(text)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
+    _gen_dispatch()
     cu = os.path.join(CSRC, "kernels.cu")
     cubin = os.path.join(BUILD, "kernels.cubin")
     inc = os.path.join(BUILD, "kernels_cubin.inc")
-    if force or _newer(cubin, [cu, os.path.join(CSRC, "flat.hpp")]):
-        cmd = [_tool("nvcc"), "-cubin", *NVCC_FLAGS, "-Xptxas", "-v", "-o", cubin, cu]
+    if force or _newer(cubin, [cu, os.path.join(CSRC, "flat.hpp"), os.path.abspath(__file__)]):
+        cmd = [_tool("nvcc"), "-cubin", *NVCC_FLAGS, "-I" + BUILD, "-Xptxas", "-v", "-o", cubin, cu]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

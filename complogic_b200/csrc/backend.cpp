@@ -191,8 +191,31 @@ struct Exec {
     }
     if (st) {
       n_instr = st->n_instr, n_levels = st->n_levels, n_slots = st->n_slots;
+      // device encoding (kernels.cu): byte offsets pre-scaled for this mode's register-stack layout
+      const uint32_t slot_bytes = (mode == CLG_MODE_LANE ? LANE_THREADS : 1) * K * 4;
+      if ((uint64_t)n_slots * slot_bytes >= (1u << 24)) fail(CLG_E_UNSUPPORTED, "register stack exceeds the 24-bit offset field");
+      std::vector<uint32_t> enc((size_t)n_instr * 4);
+      const FlatInstr *src = flat.instrs(sidx);
+      for (uint32_t i = 0; i < n_instr; i++) {
+        const FlatInstr &x = src[i];
+        uint32_t *e = &enc[(size_t)i * 4];
+        switch (x.kind) {
+          case K_LUT: {
+            const int nf = lut_nfan(x);
+            const uint32_t kind = nf >= 3 ? 0u : nf == 2 ? 1u : 2u;  // D_LUT3 / D_LUT2 / D_LUT1
+            e[0] = x.a * slot_bytes | (uint32_t)x.tt << 24;
+            e[1] = x.b * slot_bytes | kind << 28;
+            e[2] = x.c * slot_bytes;
+            e[3] = x.dst * slot_bytes;
+            break;
+          }
+          case K_LDIN: e[0] = 0, e[1] = 3u << 28, e[2] = x.row, e[3] = x.dst * slot_bytes; break;
+          case K_STOUT: e[0] = x.a * slot_bytes, e[1] = 4u << 28 | (uint32_t)(x.flags & 1) << 24, e[2] = x.row, e[3] = 0; break;
+          default: e[0] = 0, e[1] = 5u << 28 | (uint32_t)(x.flags & 1) << 24, e[2] = x.row, e[3] = 0; break;
+        }
+      }
       CU(cuMemAlloc(&d_instr, std::max<size_t>(16, (size_t)n_instr * 16)));
-      CU(cuMemcpyHtoDAsync(d_instr, flat.instrs(sidx), (size_t)n_instr * 16, nullptr));
+      CU(cuMemcpyHtoDAsync(d_instr, enc.data(), (size_t)n_instr * 16, nullptr));
       CU(cuMemAlloc(&d_levels, ((size_t)n_levels + 1) * 4));
       CU(cuMemcpyHtoDAsync(d_levels, flat.levels(sidx), ((size_t)n_levels + 1) * 4, nullptr));
       CU(cuStreamSynchronize(nullptr));

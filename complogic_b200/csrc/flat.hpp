@@ -7,7 +7,7 @@
 namespace clg {
 
 constexpr uint32_t FLAT_MAGIC = 0x46474C43u;  // "CLGF"
-constexpr uint32_t FLAT_VERSION = 2u;
+constexpr uint32_t FLAT_VERSION = 3u;
 
 enum InstrKind : uint8_t {
   K_LUT = 0,      // slot[dst] = LUT3(tt; slot[a], slot[b], slot[c])      (one LOP3 per 32 lanes)
@@ -21,9 +21,12 @@ struct FlatInstr {
   uint16_t dst, a, b, c;
   uint8_t tt;    // LOP3 immediate: bit ((va << 2) | (vb << 1) | vc) of tt is the result
   uint8_t kind;  // InstrKind
-  uint16_t flags;
+  uint16_t flags;  // bit 0: invert (STOUT) / value (STCONST); bits 8-9: number of operands a LUT really reads (1..3)
   uint32_t row;
 };
+constexpr uint16_t FLAG_INV = 1;
+constexpr int NFAN_SHIFT = 8;
+inline int lut_nfan(const FlatInstr &x) { return (x.flags >> NFAN_SHIFT) & 3; }
 static_assert(sizeof(FlatInstr) == 16, "FlatInstr must be 16 bytes");
 
 constexpr uint32_t STREAM_LEVEL = 0;  // level-ordered: instructions of one level are independent

@@ -28,8 +28,17 @@
 
 namespace clg {
 
+// Device encoding of one instruction (16 bytes, produced by the host from the flat stream for the execution
+// mode and K it was made resident with; byte offsets are pre-scaled so the kernels do no address arithmetic):
+//   LUT3/2/1  x = a_off | tt << 24    y = b_off | kind << 28          z = c_off   w = dst_off
+//   LDIN                              y = kind << 28                  z = row     w = dst_off
+//   STOUT     x = a_off               y = kind << 28 | inv << 24      z = row
+//   STCONST                           y = kind << 28 | value << 24    z = row
+// *_off are byte offsets into the register stack: slot * K * 4 (cooperative) or slot * threads * K * 4 (lane).
+enum DevKind : uint32_t { D_LUT3 = 0, D_LUT2 = 1, D_LUT1 = 2, D_LDIN = 3, D_STOUT = 4, D_STCONST = 5 };
+
 struct RunParams {
-  const uint4 *instr;      // FlatInstr stream on the device
+  const uint4 *instr;      // device-encoded instruction stream
   const uint32_t *levels;  // level offsets (coop)
   const uint32_t *imm;     // [n_inputs][stride]
   uint32_t *out;           // [n_outputs][stride]
@@ -63,24 +72,49 @@ struct __align__(16) Vec<4> {
   uint32_t w[4];
 };
 
-#define CLG_C1(n)                                                           \
-  case (n):                                                                 \
-    _Pragma("unroll") for (int k = 0; k < K; k++) r.w[k] = lop3<(n)>(a.w[k], b.w[k], c.w[k]); \
-    break;
-#define CLG_C4(n) CLG_C1(n) CLG_C1((n) + 1) CLG_C1((n) + 2) CLG_C1((n) + 3)
-#define CLG_C16(n) CLG_C4(n) CLG_C4((n) + 4) CLG_C4((n) + 8) CLG_C4((n) + 12)
-#define CLG_C64(n) CLG_C16(n) CLG_C16((n) + 16) CLG_C16((n) + 32) CLG_C16((n) + 48)
-
-template <int K>
+// The LUT immediate must be a compile-time constant of the SASS instruction, so a run-time truth table means
+// a dispatch. A C++ switch compiles to a 7-deep compare/branch tree plus both arms of a predicated leaf; the
+// PTX below is a real jump table instead: `brx.idx` (SASS: LDC from the table + BRX) into one of 256 stubs of
+// K LOP3s. The stub text is generated at build time (complogic_b200/build.py -> _build/lut_dispatch_*.inc):
+// "u" variants assert a warp-uniform index (lane kernel), "d" variants may diverge (cooperative kernel).
+template <int K, bool UNIFORM>
 __device__ __forceinline__ Vec<K> lut3(uint32_t tt, const Vec<K> &a, const Vec<K> &b, const Vec<K> &c) {
   Vec<K> r;
-  switch (tt) {
-    CLG_C64(0)
-    CLG_C64(64)
-    CLG_C64(128)
-    CLG_C64(192)
-    default:
-      _Pragma("unroll") for (int k = 0; k < K; k++) r.w[k] = 0;
+  if constexpr (K == 4) {
+    if constexpr (UNIFORM)
+      asm volatile(
+#include "lut_dispatch_k4u.inc"
+          : "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3])
+          : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(b.w[0]), "r"(b.w[1]), "r"(b.w[2]), "r"(b.w[3]),
+            "r"(c.w[0]), "r"(c.w[1]), "r"(c.w[2]), "r"(c.w[3]), "r"(tt));
+    else
+      asm volatile(
+#include "lut_dispatch_k4d.inc"
+          : "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3])
+          : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(b.w[0]), "r"(b.w[1]), "r"(b.w[2]), "r"(b.w[3]),
+            "r"(c.w[0]), "r"(c.w[1]), "r"(c.w[2]), "r"(c.w[3]), "r"(tt));
+  } else if constexpr (K == 2) {
+    if constexpr (UNIFORM)
+      asm volatile(
+#include "lut_dispatch_k2u.inc"
+          : "=&r"(r.w[0]), "=&r"(r.w[1])
+          : "r"(a.w[0]), "r"(a.w[1]), "r"(b.w[0]), "r"(b.w[1]), "r"(c.w[0]), "r"(c.w[1]), "r"(tt));
+    else
+      asm volatile(
+#include "lut_dispatch_k2d.inc"
+          : "=&r"(r.w[0]), "=&r"(r.w[1])
+          : "r"(a.w[0]), "r"(a.w[1]), "r"(b.w[0]), "r"(b.w[1]), "r"(c.w[0]), "r"(c.w[1]), "r"(tt));
+  } else {
+    if constexpr (UNIFORM)
+      asm volatile(
+#include "lut_dispatch_k1u.inc"
+          : "=&r"(r.w[0])
+          : "r"(a.w[0]), "r"(b.w[0]), "r"(c.w[0]), "r"(tt));
+    else
+      asm volatile(
+#include "lut_dispatch_k1d.inc"
+          : "=&r"(r.w[0])
+          : "r"(a.w[0]), "r"(b.w[0]), "r"(c.w[0]), "r"(tt));
   }
   return r;
 }
@@ -109,6 +143,37 @@ __device__ __forceinline__ void st_row(uint32_t *p, const Vec<K> &v) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]) : "memory");
   else
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v.w[0]) : "memory");
+}
+
+// register-stack access by 32-bit shared-space address (base computed once per thread, offsets come pre-scaled
+// from the instruction): LDS/STS of K words
+template <int K>
+__device__ __forceinline__ Vec<K> lds(uint32_t addr) {
+  Vec<K> v;
+  if constexpr (K == 4)
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "r"(addr));
+  else if constexpr (K == 2)
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.w[0]), "=r"(v.w[1]) : "r"(addr));
+  else
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.w[0]) : "r"(addr));
+  return v;
+}
+template <int K>
+__device__ __forceinline__ void sts(uint32_t addr, const Vec<K> &v) {
+  if constexpr (K == 4)
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]) : "memory");
+  else if constexpr (K == 2)
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(v.w[0]), "r"(v.w[1]) : "memory");
+  else
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v.w[0]) : "memory");
+}
+// a register value that is "defined" for the compiler but costs no instruction: operands a LUT does not read
+template <int K>
+__device__ __forceinline__ Vec<K> dont_care() {
+  Vec<K> v;
+#pragma unroll
+  for (int k = 0; k < K; k++) asm volatile("" : "=r"(v.w[k]));
+  return v;
 }
 
 __device__ __forceinline__ const uint32_t *in_row(const RunParams &p, uint32_t row) {
@@ -192,7 +257,8 @@ __device__ __forceinline__ void lane_body(const RunParams &p) {
   const uint32_t gid = blockIdx.x * LANE_THREADS + tid;
   const bool active = gid < p.n_groups;
   const size_t col = (size_t)(active ? gid : 0) * K;
-  Vec<K> *my = slots + tid;  // slot s lives at my[s * LANE_THREADS]
+  uint32_t my = smem_u32(slots + tid);  // slot s lives at my + s * LANE_THREADS * K * 4 (shared-space address)
+  asm volatile("" : "+r"(my));
 
   for (uint32_t c = 0; c < n_chunks; c++) {
     const uint32_t s = c % RING_STAGES, use = c / RING_STAGES;
@@ -201,29 +267,31 @@ __device__ __forceinline__ void lane_body(const RunParams &p) {
     const uint4 *code = ring + s * RING_CHUNK;
     for (uint32_t i = 0; i < n; i++) {
       const uint4 ins = code[i];  // warp-uniform address: one broadcast LDS.128
-      const uint32_t dst = ins.x & 0xFFFFu, sa = ins.x >> 16, sb = ins.y & 0xFFFFu, sc = ins.y >> 16;
-      const uint32_t tt = ins.z & 0xFFu, kind = (ins.z >> 8) & 0xFFu, inv = (ins.z >> 16) & 1u;
-      if (kind == K_LUT) {
-        const Vec<K> a = my[sa * LANE_THREADS], b = my[sb * LANE_THREADS], cc = my[sc * LANE_THREADS];
-        my[dst * LANE_THREADS] = lut3<K>(tt, a, b, cc);
-      } else if (kind == K_LDIN) {
+      const uint32_t kind = ins.y >> 28;
+      if (kind <= D_LUT1) {
+        const Vec<K> a = lds<K>(my + (ins.x & 0xFFFFFFu));
+        Vec<K> b = dont_care<K>(), cc = dont_care<K>();
+        if (kind <= D_LUT2) b = lds<K>(my + (ins.y & 0xFFFFFFu));
+        if (kind == D_LUT3) cc = lds<K>(my + ins.z);
+        sts<K>(my + ins.w, lut3<K, true>(ins.x >> 24, a, b, cc));
+      } else if (kind == D_LDIN) {
         Vec<K> v;
 #pragma unroll
         for (int k = 0; k < K; k++) v.w[k] = 0;
-        if (active) v = ld_row<K>(in_row(p, ins.w) + col);
-        my[dst * LANE_THREADS] = v;
+        if (active) v = ld_row<K>(in_row(p, ins.z) + col);
+        sts<K>(my + ins.w, v);
       } else {
         Vec<K> v;
-        const uint32_t m = inv ? 0xFFFFFFFFu : 0u;
-        if (kind == K_STOUT) {
-          v = my[sa * LANE_THREADS];
+        const uint32_t m = (ins.y & (1u << 24)) ? 0xFFFFFFFFu : 0u;
+        if (kind == D_STOUT) {
+          v = lds<K>(my + (ins.x & 0xFFFFFFu));
 #pragma unroll
           for (int k = 0; k < K; k++) v.w[k] ^= m;
         } else {
 #pragma unroll
           for (int k = 0; k < K; k++) v.w[k] = m;
         }
-        if (active) st_row<K>(out_row(p, ins.w) + col, v);
+        if (active) st_row<K>(out_row(p, ins.z) + col, v);
       }
     }
     __syncwarp();
@@ -241,8 +309,9 @@ __device__ __forceinline__ uint4 ld_instr(const uint4 *p) {
 template <int K>
 __device__ __forceinline__ void coop_body(const RunParams &p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  Vec<K> *slots = reinterpret_cast<Vec<K> *>(smem);
   const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  uint32_t sb = smem_u32(smem);  // register stack [slot][K] starts here (shared-space address)
+  asm volatile("" : "+r"(sb));     // opaque: keep it in a register instead of re-deriving it in the loop
 
   for (uint32_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
     const size_t col = (size_t)g * K;
@@ -256,25 +325,27 @@ __device__ __forceinline__ void coop_body(const RunParams &p) {
         const uint32_t nexti = i + nt;
         uint4 nxt = make_uint4(0, 0, 0, 0);
         if (nexti < le) nxt = ld_instr(p.instr + nexti);  // software prefetch of the next instruction
-        const uint32_t dst = ins.x & 0xFFFFu, sa = ins.x >> 16, sb = ins.y & 0xFFFFu, sc = ins.y >> 16;
-        const uint32_t tt = ins.z & 0xFFu, kind = (ins.z >> 8) & 0xFFu, inv = (ins.z >> 16) & 1u;
-        if (kind == K_LUT) {
-          const Vec<K> a = slots[sa], b = slots[sb], cc = slots[sc];
-          slots[dst] = lut3<K>(tt, a, b, cc);
-        } else if (kind == K_LDIN) {
-          slots[dst] = ld_row<K>(in_row(p, ins.w) + col);
+        const uint32_t kind = ins.y >> 28;
+        if (kind <= D_LUT1) {
+          const Vec<K> a = lds<K>(sb + (ins.x & 0xFFFFFFu));
+          Vec<K> b = dont_care<K>(), cc = dont_care<K>();
+          if (kind <= D_LUT2) b = lds<K>(sb + (ins.y & 0xFFFFFFu));
+          if (kind == D_LUT3) cc = lds<K>(sb + ins.z);
+          sts<K>(sb + ins.w, lut3<K, false>(ins.x >> 24, a, b, cc));
+        } else if (kind == D_LDIN) {
+          sts<K>(sb + ins.w, ld_row<K>(in_row(p, ins.z) + col));
         } else {
           Vec<K> v;
-          const uint32_t m = inv ? 0xFFFFFFFFu : 0u;
-          if (kind == K_STOUT) {
-            v = slots[sa];
+          const uint32_t m = (ins.y & (1u << 24)) ? 0xFFFFFFFFu : 0u;
+          if (kind == D_STOUT) {
+            v = lds<K>(sb + (ins.x & 0xFFFFFFu));
 #pragma unroll
             for (int k = 0; k < K; k++) v.w[k] ^= m;
           } else {
 #pragma unroll
             for (int k = 0; k < K; k++) v.w[k] = m;
           }
-          st_row<K>(out_row(p, ins.w) + col, v);
+          st_row<K>(out_row(p, ins.z) + col, v);
         }
         ins = nxt;
         i = nexti;

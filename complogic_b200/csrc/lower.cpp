@@ -362,6 +362,7 @@ struct SlotPool {
 FlatInstr make_lut(const Val &v) {
   FlatInstr in{};
   in.kind = K_LUT, in.tt = v.tt;
+  in.flags = (uint16_t)(v.nfan << NFAN_SHIFT);
   return in;
 }
 
@@ -573,8 +574,9 @@ Sched schedule_level(const Network &net) {
   std::vector<uint32_t> slot(V, NONE);
   std::vector<std::vector<uint32_t>> release(n_levels + 1);
   auto key = [&](uint32_t x) -> uint32_t {  // (kind, tt) so that warps mostly run one LOP3 immediate
-    if (x >= V) return (net.outs[x - V].val == NONE ? (3u << 8) : (2u << 8)) | (net.outs[x - V].inv ? 1u : 0u);
-    return net.vals[x].is_lut ? net.vals[x].tt : (1u << 8);
+    if (x >= V) return (net.outs[x - V].val == NONE ? (6u << 8) : (5u << 8)) | (net.outs[x - V].inv ? 1u : 0u);
+    // LUTs first, widest first (the kernel skips the operand loads a LUT does not need), then by truth table
+    return net.vals[x].is_lut ? ((uint32_t)(3 - net.vals[x].nfan) << 8) | net.vals[x].tt : (4u << 8);
   };
   for (uint32_t l = 0; l < n_levels; l++) {
     if (l > 0) {
@@ -798,7 +800,13 @@ void validate_flat(const Flat &f) {
           };
           if (x.kind > K_STCONST) bad("unknown instruction kind");
           if (reads) {
-            if (x.kind == K_LUT) rd(x.a), rd(x.b), rd(x.c);
+            if (x.kind == K_LUT) {
+              const int nf = lut_nfan(x);
+              if (nf < 1) bad("LUT without operands");
+              rd(x.a);
+              if (nf >= 2) rd(x.b);
+              if (nf >= 3) rd(x.c);
+            }
             if (x.kind == K_STOUT) rd(x.a);
             if (x.kind == K_LDIN) {
               if (x.row >= n_in_rows) bad("input row out of range");
@@ -834,7 +842,11 @@ void validate_flat(const Flat &f) {
           auto chk = [&](uint16_t sl) {
             if (written_in[sl] == l) bad("slot read and written in the same level");
           };
-          if (x.kind == K_LUT) chk(x.a), chk(x.b), chk(x.c);
+          if (x.kind == K_LUT) {
+            chk(x.a);
+            if (lut_nfan(x) >= 2) chk(x.b);
+            if (lut_nfan(x) >= 3) chk(x.c);
+          }
           if (x.kind == K_STOUT) chk(x.a);
         }
       }
