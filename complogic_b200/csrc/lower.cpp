@@ -567,27 +567,104 @@ Sched schedule_level(const Network &net) {
   for (size_t v = 0; v < V; v++) items[fill[lev[v]]++] = (uint32_t)v;
   for (size_t o = 0; o < O; o++) items[fill[olev[o]]++] = (uint32_t)(V + o);
 
+  // ---- emission: bank-aware order, operand placement and slot choice -------------------------------------
+  // The cooperative kernel keeps the stack as [slot][4 words]: a slot is 16 bytes, 8 consecutive slots span
+  // the 32 banks, and an LDS.128/STS.128 is served one quarter-warp (8 lanes = 8 consecutive instructions of
+  // the level) at a time. A quarter is conflict-free iff its 8 addresses fall in 8 different 16-byte bank
+  // groups, i.e. slot % 8 all different -- separately for operand a, b, c and the destination, since each is
+  // its own LDS/STS. Three degrees of freedom are used: which 8 instructions share a quarter (greedy packing
+  // from a window of candidates), which operand sits in which position (LUT inputs commute if the truth table
+  // is permuted with them), and which free slot a result takes (one bank group per quarter member).
+  constexpr uint32_t BANKS = 8, WINDOW = 512;
   Sched s;
   s.instr.resize(V + O);
   s.levels.assign(cnt.begin(), cnt.end());
-  SlotPool pool;
+  struct BankPool {
+    std::vector<uint32_t> free_[BANKS];
+    uint32_t fresh[BANKS];
+    uint32_t high = 0;
+    BankPool() {
+      for (uint32_t b = 0; b < BANKS; b++) fresh[b] = b;
+    }
+    bool has_free(uint32_t b) const { return !free_[b].empty(); }
+    uint32_t get(uint32_t b) {
+      uint32_t sl;
+      if (!free_[b].empty()) sl = free_[b].back(), free_[b].pop_back();
+      else sl = fresh[b], fresh[b] += BANKS;
+      high = std::max(high, sl + 1);
+      return sl;
+    }
+    void put(uint32_t sl) { free_[sl % BANKS].push_back(sl); }
+  } pool;
   std::vector<uint32_t> slot(V, NONE);
   std::vector<std::vector<uint32_t>> release(n_levels + 1);
-  auto key = [&](uint32_t x) -> uint32_t {  // (kind, tt) so that warps mostly run one LOP3 immediate
-    if (x >= V) return (net.outs[x - V].val == NONE ? (6u << 8) : (5u << 8)) | (net.outs[x - V].inv ? 1u : 0u);
-    // LUTs first, widest first (the kernel skips the operand loads a LUT does not need), then by truth table
-    return net.vals[x].is_lut ? ((uint32_t)(3 - net.vals[x].nfan) << 8) | net.vals[x].tt : (4u << 8);
+  auto klass = [&](uint32_t x) -> uint32_t {  // widest LUTs first (the kernel skips loads a LUT does not need)
+    if (x >= V) return net.outs[x - V].val == NONE ? 5u : 4u;
+    return net.vals[x].is_lut ? (uint32_t)(3 - net.vals[x].nfan) : 3u;
   };
+  auto key = [&](uint32_t x) -> uint32_t {
+    uint32_t sub = x >= V ? (net.outs[x - V].inv ? 1u : 0u) : net.vals[x].is_lut ? net.vals[x].tt : 0u;
+    return klass(x) << 8 | sub;
+  };
+  static const uint8_t PERM[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+  struct Placed {
+    uint32_t x;
+    uint8_t perm;  // operand k of the value goes to position PERM[perm][k]
+  };
+  std::vector<Placed> order;
+  std::vector<uint8_t> taken;
   for (uint32_t l = 0; l < n_levels; l++) {
     if (l > 0) {
       for (uint32_t sl : release[l - 1]) pool.put(sl);
       release[l - 1].clear(), release[l - 1].shrink_to_fit();
     }
-    uint32_t b = cnt[l], e = cnt[l + 1];
-    s.max_width = std::max(s.max_width, e - b);
+    const uint32_t b = cnt[l], e = cnt[l + 1], n = e - b;
+    s.max_width = std::max(s.max_width, n);
     std::stable_sort(items.begin() + b, items.begin() + e, [&](uint32_t x, uint32_t y) { return key(x) < key(y); });
-    for (uint32_t i = b; i < e; i++) {
-      uint32_t x = items[i];
+    // -- pack quarters
+    order.clear();
+    taken.assign(n, 0);
+    uint32_t head = 0, placed = 0;
+    auto n_ops = [&](uint32_t x) -> int { return x >= V ? (net.outs[x - V].val == NONE ? 0 : 1) : net.vals[x].is_lut ? net.vals[x].nfan : 0; };
+    auto op_slot = [&](uint32_t x, int k) -> uint32_t { return x >= V ? slot[net.outs[x - V].val] : slot[net.vals[x].fan[k]]; };
+    while (placed < n) {
+      uint32_t mask[3] = {0, 0, 0};
+      uint32_t members = 0;
+      while (head < n && taken[head]) head++;
+      uint32_t scanned = 0;
+      for (uint32_t c = head; c < n && members < BANKS && scanned < WINDOW; c++) {
+        if (taken[c]) continue;
+        scanned++;
+        const uint32_t x = items[b + c];
+        const int no = n_ops(x);
+        int pick = -1;
+        const int nperm = (x < V && no >= 2) ? 6 : 1;
+        for (int q = 0; q < nperm && pick < 0; q++) {
+          bool ok = true;
+          for (int k = 0; k < no && ok; k++) {
+            const uint8_t pos = PERM[q][k];
+            if (pos >= no) ok = false;  // a 2-input LUT only has positions a, b
+            else if (mask[pos] >> (op_slot(x, k) % BANKS) & 1u) ok = false;
+          }
+          if (ok) pick = q;
+        }
+        if (pick < 0) continue;
+        for (int k = 0; k < no; k++) mask[PERM[pick][k]] |= 1u << (op_slot(x, k) % BANKS);
+        taken[c] = 1, members++, placed++;
+        order.push_back({x, (uint8_t)pick});
+      }
+      // nothing else in the window fits without a conflict: fill the quarter in order, conflicts accepted
+      for (uint32_t c = head; c < n && members < BANKS; c++) {
+        if (taken[c]) continue;
+        taken[c] = 1, members++, placed++;
+        order.push_back({items[b + c], 0});
+      }
+    }
+    // -- emit, choosing destination bank groups quarter by quarter
+    uint32_t dmask = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      if (i % BANKS == 0) dmask = 0;
+      const uint32_t x = order[i].x;
       FlatInstr in{};
       if (x >= V) {
         const OutRef &o = net.outs[x - V];
@@ -598,14 +675,32 @@ Sched schedule_level(const Network &net) {
         const Val &v = net.vals[x];
         if (v.is_lut) {
           in = make_lut(v);
-          uint32_t sl[3] = {0, 0, 0};
-          for (int k = 0; k < v.nfan; k++) sl[k] = slot[v.fan[k]];
-          for (int k = v.nfan; k < 3; k++) sl[k] = sl[0];
+          const uint8_t *pm = PERM[order[i].perm];
+          uint32_t sl[3] = {NONE, NONE, NONE};
+          uint8_t where[3] = {0, 1, 2};
+          for (int k = 0; k < v.nfan; k++) sl[pm[k]] = slot[v.fan[k]], where[k] = pm[k];
+          for (int k = 0; k < 3; k++)
+            if (sl[k] == NONE) sl[k] = sl[where[0]];  // positions the LUT does not read alias a read one
+          if (order[i].perm != 0) {
+            uint8_t p3[3] = {where[0], where[1], where[2]};
+            if (v.nfan == 2) p3[2] = 2;
+            in.tt = remap(v.tt, p3);
+          }
           in.a = (uint16_t)sl[0], in.b = (uint16_t)sl[1], in.c = (uint16_t)sl[2];
         } else {
           in.kind = K_LDIN, in.row = v.row;
         }
-        slot[x] = pool.get();
+        uint32_t bank = NONE;
+        for (uint32_t t = 0; t < BANKS && bank == NONE; t++) {
+          const uint32_t cand = (i + t) % BANKS;
+          if (!(dmask >> cand & 1u) && pool.has_free(cand)) bank = cand;
+        }
+        for (uint32_t t = 0; t < BANKS && bank == NONE; t++) {
+          const uint32_t cand = (i + t) % BANKS;
+          if (!(dmask >> cand & 1u)) bank = cand;
+        }
+        dmask |= 1u << bank;
+        slot[x] = pool.get(bank);
         if (slot[x] > 0xFFFF) {
           s.ok = false;
           return s;
@@ -613,7 +708,7 @@ Sched schedule_level(const Network &net) {
         in.dst = (uint16_t)slot[x];
         release[last[x]].push_back(slot[x]);
       }
-      s.instr[i] = in;
+      s.instr[b + i] = in;
     }
   }
   s.n_slots = pool.high;
