@@ -176,8 +176,21 @@ __device__ __forceinline__ Vec<K> dont_care() {
   return v;
 }
 
-__device__ __forceinline__ const uint32_t *in_row(const RunParams &p, uint32_t row) {
-  return row < p.n_inputs ? p.imm + (size_t)row * p.stride : p.state + (size_t)(row - p.n_inputs) * p.stride;
+// Input row `row` for column `col`: immediates are read-only for the whole launch (ld.global.nc); carried
+// state rows are rewritten in place later by this same thread, so they are read with ordinary coherent loads
+// that stay ordered before those stores.
+template <int K>
+__device__ __forceinline__ Vec<K> ld_input(const RunParams &p, uint32_t row, size_t col) {
+  if (row < p.n_inputs) return ld_row<K>(p.imm + (size_t)row * p.stride + col);
+  const uint32_t *q = p.state + (size_t)(row - p.n_inputs) * p.stride + col;
+  Vec<K> v;
+  if constexpr (K == 4)
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(q) : "memory");
+  else if constexpr (K == 2)
+    asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.w[0]), "=r"(v.w[1]) : "l"(q) : "memory");
+  else
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v.w[0]) : "l"(q) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t *out_row(const RunParams &p, uint32_t row) {
   return row < p.n_outputs ? p.out + (size_t)row * p.stride : p.state + (size_t)(row - p.n_outputs) * p.stride;
@@ -278,7 +291,7 @@ __device__ __forceinline__ void lane_body(const RunParams &p) {
         Vec<K> v;
 #pragma unroll
         for (int k = 0; k < K; k++) v.w[k] = 0;
-        if (active) v = ld_row<K>(in_row(p, ins.z) + col);
+        if (active) v = ld_input<K>(p, ins.z, col);
         sts<K>(my + ins.w, v);
       } else {
         Vec<K> v;
@@ -315,12 +328,16 @@ __device__ __forceinline__ void coop_body(const RunParams &p) {
 
   for (uint32_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
     const size_t col = (size_t)g * K;
-    uint32_t lb = __ldg(p.levels);
+    uint32_t lb = __ldg(p.levels), le = __ldg(p.levels + 1);
+    uint4 ins = make_uint4(0, 0, 0, 0);
+    if (lb + tid < le) ins = ld_instr(p.instr + lb + tid);
     for (uint32_t l = 0; l < p.n_levels; l++) {
-      const uint32_t le = __ldg(p.levels + l + 1);
+      // this thread's first instruction of the NEXT level is requested now, so its L2 latency is hidden behind
+      // this level's work and the barrier instead of being paid after it
+      const uint32_t le2 = __ldg(p.levels + min(l + 2, p.n_levels));
+      uint4 first_next = make_uint4(0, 0, 0, 0);
+      if (le + tid < le2) first_next = ld_instr(p.instr + le + tid);
       uint32_t i = lb + tid;
-      uint4 ins = make_uint4(0, 0, 0, 0);
-      if (i < le) ins = ld_instr(p.instr + i);
       while (i < le) {
         const uint32_t nexti = i + nt;
         uint4 nxt = make_uint4(0, 0, 0, 0);
@@ -333,7 +350,7 @@ __device__ __forceinline__ void coop_body(const RunParams &p) {
           if (kind == D_LUT3) cc = lds<K>(sb + ins.z);
           sts<K>(sb + ins.w, lut3<K, false>(ins.x >> 24, a, b, cc));
         } else if (kind == D_LDIN) {
-          sts<K>(sb + ins.w, ld_row<K>(in_row(p, ins.z) + col));
+          sts<K>(sb + ins.w, ld_input<K>(p, ins.z, col));
         } else {
           Vec<K> v;
           const uint32_t m = (ins.y & (1u << 24)) ? 0xFFFFFFFFu : 0u;
@@ -350,7 +367,8 @@ __device__ __forceinline__ void coop_body(const RunParams &p) {
         ins = nxt;
         i = nexti;
       }
-      lb = le;
+      lb = le, le = le2;
+      ins = first_next;
       __syncthreads();  // level boundary: every slot written in this level is visible to the next
     }
   }

@@ -139,6 +139,26 @@ struct Network {
   uint32_t n_inputs = 0, n_state = 0, n_outputs = 0;
 };
 
+// LUT inputs commute if the truth table is permuted with them. Put every LUT into the operand order with the
+// smallest table: functions that differ only by operand order (e.g. the three placements of the odd input of
+// NAND(NAND(p,q),y)) collapse onto one LOP3 immediate, which keeps warps of the cooperative kernel on one
+// dispatch target.
+void canonical_operand_order(Val &v) {
+  static const uint8_t P3[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+  if (v.nfan < 2) return;
+  uint8_t best_tt = v.tt;
+  int best = 0;
+  for (int q = 1; q < 6; q++) {
+    if (v.nfan == 2 && P3[q][2] != 2) continue;
+    uint8_t t = remap(v.tt, P3[q]);
+    if (t < best_tt) best_tt = t, best = q;
+  }
+  if (!best) return;
+  uint32_t f[3] = {v.fan[0], v.fan[1], v.fan[2]};
+  for (int k = 0; k < v.nfan; k++) v.fan[P3[best][k]] = f[k];
+  v.tt = best_tt;
+}
+
 // ---- LUT3 mapping ------------------------------------------------------------------------------
 struct Mapper {
   const Aig &g;
@@ -640,6 +660,8 @@ Sched schedule_level(const Network &net) {
         int pick = -1;
         const int nperm = (x < V && no >= 2) ? 6 : 1;
         for (int q = 0; q < nperm && pick < 0; q++) {
+          // only operand orders that leave the truth table unchanged (the function's own symmetries)
+          if (q && remap(net.vals[x].tt, PERM[q]) != net.vals[x].tt) continue;
           bool ok = true;
           for (int k = 0; k < no && ok; k++) {
             const uint8_t pos = PERM[q][k];
@@ -681,11 +703,7 @@ Sched schedule_level(const Network &net) {
           for (int k = 0; k < v.nfan; k++) sl[pm[k]] = slot[v.fan[k]], where[k] = pm[k];
           for (int k = 0; k < 3; k++)
             if (sl[k] == NONE) sl[k] = sl[where[0]];  // positions the LUT does not read alias a read one
-          if (order[i].perm != 0) {
-            uint8_t p3[3] = {where[0], where[1], where[2]};
-            if (v.nfan == 2) p3[2] = 2;
-            in.tt = remap(v.tt, p3);
-          }
+          // (the permutation is one of the function's symmetries, so the table is unchanged)
           in.a = (uint16_t)sl[0], in.b = (uint16_t)sl[1], in.c = (uint16_t)sl[2];
         } else {
           in.kind = K_LDIN, in.row = v.row;
@@ -799,6 +817,7 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
       Val v{};
       v.is_lut = 1, v.tt = c.tt, v.nfan = c.n;
       for (int i = 0; i < c.n; i++) v.fan[i] = val_of[c.leaf[i]];
+      canonical_operand_order(v);
       val_of[n] = (uint32_t)net.vals.size();
       net.vals.push_back(v);
       n_luts++;

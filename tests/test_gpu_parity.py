@@ -119,7 +119,8 @@ def programs(draw):
     return ops, n_regs, draw(st.integers(0, n_regs + 1)), draw(st.sampled_from(MODES))
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=int(__import__("os").environ.get("CLG_HYPOTHESIS_EXAMPLES", "60")), deadline=None,
+          suppress_health_check=[HealthCheck.too_slow])
 @given(programs(), st.integers(0, 2 ** 31))
 def test_random_programs(prog, seed):
     ops, n_regs, n_imm, mode = prog
