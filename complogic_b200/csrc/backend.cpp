@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -20,7 +21,7 @@ namespace {
   X(cuInit) X(cuDeviceGet) X(cuDeviceGetCount) X(cuDeviceGetName) X(cuDeviceGetAttribute) X(cuDevicePrimaryCtxRetain)  \
   X(cuDevicePrimaryCtxRelease) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuModuleLoadData) X(cuModuleLoadDataEx)        \
   X(cuModuleGetFunction) X(cuModuleUnload) X(cuFuncSetAttribute) X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree)          \
-  X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuMemsetD8Async) X(cuMemAllocHost) X(cuMemFreeHost) X(cuStreamSynchronize) \
+  X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuMemcpy2DAsync) X(cuStreamWaitEvent) X(cuMemsetD8Async) X(cuMemAllocHost) X(cuMemFreeHost) X(cuStreamSynchronize) \
   X(cuStreamCreate) X(cuStreamDestroy) X(cuEventCreate) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime)   \
   X(cuEventDestroy) X(cuGetErrorString)
 
@@ -236,6 +237,104 @@ struct Exec {
     if (d_instr) d.cuMemFree(d_instr);
     if (d_levels) d.cuMemFree(d_levels);
     if (spec_mod) d.cuModuleUnload(spec_mod);
+    for (int b = 0; b < NBUF; b++) {
+      if (stage_in[b]) d.cuMemFree(stage_in[b]);
+      if (stage_out[b]) d.cuMemFree(stage_out[b]);
+      if (stage_state[b]) d.cuMemFree(stage_state[b]);
+      if (ev_in[b]) d.cuEventDestroy(ev_in[b]);
+      if (ev_run[b]) d.cuEventDestroy(ev_run[b]);
+      if (ev_out[b]) d.cuEventDestroy(ev_out[b]);
+    }
+    if (s_in) d.cuStreamDestroy(s_in);
+    if (s_run) d.cuStreamDestroy(s_run);
+    if (s_out) d.cuStreamDestroy(s_out);
+  }
+
+  // ---- host-buffer path: column chunks pipelined over three streams (H2D | kernel | D2H) -----------------
+  static constexpr int NBUF = 3;
+  CUstream s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  CUevent ev_in[NBUF] = {}, ev_run[NBUF] = {}, ev_out[NBUF] = {};
+  CUdeviceptr stage_in[NBUF] = {}, stage_out[NBUF] = {}, stage_state[NBUF] = {};
+  size_t stage_words = 0;
+
+  void copy2d(bool to_device, CUdeviceptr dev, size_t dev_pitch, const void *host, size_t host_pitch, size_t width, size_t rows,
+              CUstream st) {
+    if (!width || !rows) return;
+    CUDA_MEMCPY2D c{};
+    if (to_device) {
+      c.srcMemoryType = CU_MEMORYTYPE_HOST, c.srcHost = host, c.srcPitch = host_pitch;
+      c.dstMemoryType = CU_MEMORYTYPE_DEVICE, c.dstDevice = dev, c.dstPitch = dev_pitch;
+    } else {
+      c.srcMemoryType = CU_MEMORYTYPE_DEVICE, c.srcDevice = dev, c.srcPitch = dev_pitch;
+      c.dstMemoryType = CU_MEMORYTYPE_HOST, c.dstHost = const_cast<void *>(host), c.dstPitch = host_pitch;
+    }
+    c.WidthInBytes = width, c.Height = rows;
+    CU(cuMemcpy2DAsync(&c, st));
+  }
+
+  void run_host(const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride) {
+    const FlatHeader &h = flat.header();
+    if (stride % 4 != 0) fail(CLG_E_INVALID, "stride must be a multiple of 4 words (16-byte aligned rows)");
+    const size_t words = (n_vectors + 31) / 32;
+    if (words > stride) fail(CLG_E_INVALID, "n_vectors does not fit in stride words");
+    if (h.n_inputs && !imm) fail(CLG_E_INVALID, "imm is null");
+    if (h.n_outputs && !out) fail(CLG_E_INVALID, "out is null");
+    if (h.n_state && !state) fail(CLG_E_INVALID, "state is null for a stateful program");
+    if (n_vectors == 0) return;
+    ctx->bind();
+    // chunk = a contiguous range of words of every row, ~192 MB of I/O, so copies and kernels overlap
+    const size_t rows = (size_t)h.n_inputs + h.n_outputs + 2 * (size_t)h.n_state;
+    size_t cw = ((size_t)192 << 20) / (std::max<size_t>(rows, 1) * 4);
+    if (const char *env = std::getenv("CLG_HOST_CHUNK_WORDS")) cw = std::strtoull(env, nullptr, 10);  // tuning / tests
+    cw = std::max<size_t>(4, cw) / 4 * 4;
+    const size_t padded = (words + 3) / 4 * 4;
+    cw = std::min(cw, padded);
+    if (!s_in) {
+      CU(cuStreamCreate(&s_in, CU_STREAM_NON_BLOCKING));
+      CU(cuStreamCreate(&s_run, CU_STREAM_NON_BLOCKING));
+      CU(cuStreamCreate(&s_out, CU_STREAM_NON_BLOCKING));
+      for (int b = 0; b < NBUF; b++) {
+        CU(cuEventCreate(&ev_in[b], CU_EVENT_DISABLE_TIMING));
+        CU(cuEventCreate(&ev_run[b], CU_EVENT_DISABLE_TIMING));
+        CU(cuEventCreate(&ev_out[b], CU_EVENT_DISABLE_TIMING));
+      }
+    }
+    if (cw > stage_words) {
+      CU(cuCtxSynchronize());
+      for (int b = 0; b < NBUF; b++) {
+        if (stage_in[b]) driver().cuMemFree(stage_in[b]);
+        if (stage_out[b]) driver().cuMemFree(stage_out[b]);
+        if (stage_state[b]) driver().cuMemFree(stage_state[b]);
+        CU(cuMemAlloc(&stage_in[b], std::max<size_t>(16, (size_t)h.n_inputs * cw * 4)));
+        CU(cuMemAlloc(&stage_out[b], std::max<size_t>(16, (size_t)h.n_outputs * cw * 4)));
+        CU(cuMemAlloc(&stage_state[b], std::max<size_t>(16, (size_t)h.n_state * cw * 4)));
+      }
+      stage_words = cw;
+    }
+    const size_t n_chunks = (words + cw - 1) / cw;
+    for (size_t c = 0; c < n_chunks; c++) {
+      const int b = (int)(c % NBUF);
+      const size_t w0 = c * cw, w1 = std::min(words, w0 + cw), nw = w1 - w0;
+      const size_t nv = std::min(n_vectors, w1 * 32) - w0 * 32;
+      if (c >= NBUF) {  // staging set b is free again once chunk c - NBUF has been run (inputs) and copied out (outputs)
+        CU(cuStreamWaitEvent(s_in, ev_run[b], 0));
+        CU(cuStreamWaitEvent(s_in, ev_out[b], 0));
+      }
+      copy2d(true, stage_in[b], cw * 4, imm + w0, stride * 4, nw * 4, h.n_inputs, s_in);
+      copy2d(true, stage_state[b], cw * 4, state + w0, stride * 4, nw * 4, h.n_state, s_in);
+      CU(cuEventRecord(ev_in[b], s_in));
+      CU(cuStreamWaitEvent(s_run, ev_in[b], 0));
+      if (c >= NBUF) CU(cuStreamWaitEvent(s_run, ev_out[b], 0));
+      run((const uint32_t *)stage_in[b], (uint32_t *)stage_out[b], h.n_state ? (uint32_t *)stage_state[b] : nullptr, nv, cw, s_run);
+      CU(cuEventRecord(ev_run[b], s_run));
+      CU(cuStreamWaitEvent(s_out, ev_run[b], 0));
+      copy2d(false, stage_out[b], cw * 4, out + w0, stride * 4, nw * 4, h.n_outputs, s_out);
+      copy2d(false, stage_state[b], cw * 4, state + w0, stride * 4, nw * 4, h.n_state, s_out);
+      CU(cuEventRecord(ev_out[b], s_out));
+    }
+    CU(cuStreamSynchronize(s_in));
+    CU(cuStreamSynchronize(s_run));
+    CU(cuStreamSynchronize(s_out));
   }
 
   void run(const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, CUstream stream) {
@@ -328,6 +427,9 @@ int exec_k(const Exec *e) { return e->K; }
 const std::string &exec_ptx(const Exec *e) { return e->ptx; }
 const Flat &exec_flat(const Exec *e) { return e->flat; }
 Ctx *exec_ctx(const Exec *e) { return e->ctx; }
+void exec_run_host(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride) {
+  e->run_host(imm, out, state, n_vectors, stride);
+}
 void exec_run(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, void *stream) {
   e->run(imm, out, state, n_vectors, stride, (CUstream)stream);
 }

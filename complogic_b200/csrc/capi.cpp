@@ -31,6 +31,7 @@ const std::string &exec_ptx(const Exec *);
 const Flat &exec_flat(const Exec *);
 Ctx *exec_ctx(const Exec *);
 void exec_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t, void *);
+void exec_run_host(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t);
 void launch_slice(Ctx *, bool, const void *, void *, size_t, size_t, size_t, void *);
 void launch_fill(Ctx *, uint32_t *, size_t, size_t, uint64_t, void *);
 double timed_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t);
@@ -334,25 +335,7 @@ struct DevBuf {
 int clg_exec_run_host(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride) {
   CLG_TRY
   NEED(ex);
-  Ctx *c = exec_ctx(ex->e);
-  const FlatHeader &h = exec_flat(ex->e).header();
-  const size_t row = stride * 4;
-  DevBuf di(c, h.n_inputs * row), dout(c, h.n_outputs * row), ds(c, h.n_state * row);
-  if (h.n_inputs) {
-    NEED(imm);
-    h2d(c, di.p, imm, h.n_inputs * row, nullptr);
-  }
-  if (h.n_state) {
-    NEED(state);
-    h2d(c, ds.p, state, h.n_state * row, nullptr);
-  }
-  exec_run(ex->e, (const uint32_t *)di.p, (uint32_t *)dout.p, h.n_state ? (uint32_t *)ds.p : nullptr, n_vectors, stride, nullptr);
-  if (h.n_outputs) {
-    NEED(out);
-    d2h(c, out, dout.p, h.n_outputs * row, nullptr);
-  }
-  if (h.n_state) d2h(c, state, ds.p, h.n_state * row, nullptr);
-  stream_sync(c, nullptr);
+  exec_run_host(ex->e, imm, out, state, n_vectors, stride);
   CLG_CATCH
 }
 

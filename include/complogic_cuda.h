@@ -236,7 +236,9 @@ const char *clg_exec_ptx(const clg_exec *ex);
 int clg_exec_run(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors,
                  size_t stride, void *stream);
 
-/* Host-buffer convenience wrapper: H2D, run, D2H, synchronise. Same layouts, HOST pointers. */
+/* Host-buffer entry point. Same layouts, HOST pointers (pinned memory -- clg_host_alloc_pinned -- gives full
+ * PCIe speed). The batch is cut into column chunks that are pipelined over three streams, so H2D copies,
+ * kernels and D2H copies overlap; returns when the results are in `out` (and `state`). */
 int clg_exec_run_host(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors,
                       size_t stride);
 

@@ -209,6 +209,27 @@ def test_modes_agree_at_scale_mul16():
     assert np.array_equal(unslice_int(outs[0][:, cols], n), a * b)
 
 
+def test_host_path_pipelines_many_chunks(monkeypatch):
+    """clg_exec_run_host cuts the batch into column chunks that flow through three streams; force many small,
+    ragged chunks and a stateful program, and compare with the oracle."""
+    monkeypatch.setenv("CLG_HOST_CHUNK_WORDS", "100")
+    circ = circuits.array_multiplier(8)
+    nv = 32 * 1000 + 17
+    imm = random_sliced(16, stride_for(nv), seed=5)
+    for mode in MODES:
+        assert np.array_equal(gpu_out(circ, imm, nv, mode), oracle_out(circ, imm, nv))
+    c = host.Compiler(2)
+    sim = c.compile([host.DLatch(0, 1, c.alloc())])
+    R, steps = len(sim.registers), 3
+    stride = stride_for(nv)
+    imms = np.stack([random_sliced(2, stride, 50 + s) for s in range(steps)])
+    want = oracle.run_batch_sliced(sim, R, imms, nv, list(range(R)), steps=steps, all_steps=True)
+    cs = host.CudaSimulation.from_simulation(sim, 2, None, flags=host.LV_STATEFUL)
+    state = np.zeros((cs.info["n_state"], stride), np.uint32)
+    for s_ in range(steps):
+        assert np.array_equal(mask_tail(cs.run_batch(imms[s_], nv, state=state), nv), mask_tail(want[s_], nv))
+
+
 def test_errors_are_status_codes():
     circ = circuits.ripple_adder(4)
     cs = host.CudaSimulation.from_simulation(circ.sim, 9, circ.out_regs)
