@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -129,75 +130,126 @@ struct Ctx {
 static int kidx(int K) { return K == 4 ? 2 : K == 2 ? 1 : 0; }
 
 // ---- resident program --------------------------------------------------------------------------------
-struct Exec {
-  Ctx *ctx;
-  Flat flat;  // own copy: the caller may destroy its clg_flat
-  int mode = 0, K = 4;
+// One execution mode of a program made resident on the device.
+struct Plan {
+  bool ready = false;
+  int K = 0;
   CUdeviceptr d_instr = 0, d_levels = 0;
   uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0;
   size_t smem = 0;
   CUmodule spec_mod = nullptr;
   CUfunction spec_fn = nullptr;
   std::string ptx;
+};
 
-  Exec(Ctx *c, const Flat &f, int want) : ctx(c), flat(f) {
+struct Exec {
+  Ctx *ctx;
+  Flat flat;  // own copy: the caller may destroy its clg_flat
+  int want;   // CLG_MODE_AUTO or the mode the caller pinned
+  int mode;   // mode of the most recent (or, before any run, the preferred) plan
+  Plan plan[4];
+
+  const FlatStream &level_stream() const { return flat.header().stream[STREAM_LEVEL]; }
+  const FlatStream &lane_stream() const { return flat.header().stream[STREAM_LANE]; }
+
+  // K (words per thread / per CTA) a mode would run with; 0 = the program does not fit that mode
+  int fit_k(int m) const {
+    const FlatStream &lv = level_stream(), &ln = lane_stream();
+    switch (m) {
+      case CLG_MODE_SPEC:
+        if (ln.n_instr == 0 || ln.n_instr > 400000) return 0;
+        for (int k : {4, 2, 1})
+          if ((uint64_t)ln.n_slots * k <= 200) return k;
+        return ln.n_slots <= 240 ? 1 : 0;
+      case CLG_MODE_LANE:
+        if (ln.n_instr == 0) return 0;
+        // prefer the widest vector that still leaves >= 3 CTAs (12 consumer warps) per SM
+        for (int pass = 0; pass < 2; pass++)
+          for (int k : {4, 2, 1}) {
+            size_t need = LANE_RING_BYTES + (size_t)ln.n_slots * LANE_THREADS * k * 4;
+            if (need * (pass == 0 ? 3 : 1) <= SMEM_MAX) return k;
+          }
+        return 0;
+      case CLG_MODE_COOP:
+        if (lv.n_instr == 0) return 0;
+        for (int k : {4, 2, 1})
+          if ((size_t)lv.n_slots * k * 4 <= SMEM_MAX) return k;
+        return 0;
+    }
+    return 0;
+  }
+  static uint32_t coop_threads_for(const FlatStream &lv) {
+    return std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (lv.max_level_width + 31u) / 32u * 32u));
+  }
+
+  // Rough cycle models, only used to pick between the two interpreters for a given batch: the lane mode wins on
+  // big batches of small-live-set programs, the cooperative mode on small batches of wide programs.
+  double lane_cycles(size_t words) const {
+    const int k = fit_k(CLG_MODE_LANE);
+    const FlatStream &ln = lane_stream();
+    const size_t smem = LANE_RING_BYTES + (size_t)ln.n_slots * LANE_THREADS * k * 4;
+    const double warps_per_sm = 4.0 * std::min<double>(12.0, std::floor((double)SMEM_MAX / (double)smem));
+    const double groups = std::ceil((double)words / k), per_wave = warps_per_sm * 32.0 * ctx->sm_count;
+    return std::ceil(groups / per_wave) * ln.n_instr * std::max(48.0, 17.0 * std::min(warps_per_sm, std::ceil(groups / 32.0 / ctx->sm_count)));
+  }
+  double coop_cycles(size_t words) const {
+    const int k = fit_k(CLG_MODE_COOP);
+    const FlatStream &lv = level_stream();
+    const uint32_t nt = coop_threads_for(lv), *lvl = flat.levels(STREAM_LEVEL);
+    double per_group = 0;
+    for (uint32_t l = 0; l < lv.n_levels; l++) {
+      const uint32_t n = lvl[l + 1] - lvl[l];
+      per_group += 60.0 + (n / nt) * std::max(300.0, 0.75 * nt) + ((n % nt) ? std::max(300.0, 0.75 * (n % nt)) : 0.0);
+    }
+    return std::ceil(std::ceil((double)words / k) / ctx->sm_count) * per_group;
+  }
+  int choose(size_t words) const {
+    if (want != CLG_MODE_AUTO) return want;
+    if (fit_k(CLG_MODE_SPEC)) return CLG_MODE_SPEC;
+    const bool lane_ok = fit_k(CLG_MODE_LANE) != 0, coop_ok = fit_k(CLG_MODE_COOP) != 0;
+    if (lane_ok && coop_ok) return lane_cycles(words) <= coop_cycles(words) ? CLG_MODE_LANE : CLG_MODE_COOP;
+    return lane_ok ? CLG_MODE_LANE : CLG_MODE_COOP;
+  }
+
+  Exec(Ctx *c, const Flat &f, int want_) : ctx(c), flat(f), want(want_) {
+    if (want < CLG_MODE_AUTO || want > CLG_MODE_SPEC) fail(CLG_E_INVALID, "unknown execution mode");
+    mode = choose((size_t)1 << 20);  // the plan a large batch would use; small batches may pick another (auto)
+    get(mode);
+  }
+
+  Plan &get(int m) {
+    Plan &P = plan[m];
+    if (P.ready) return P;
     ctx->bind();
-    const FlatHeader &h = flat.header();
-    const FlatStream &lv = h.stream[STREAM_LEVEL], &ln = h.stream[STREAM_LANE];
-    auto spec_k = [&]() -> int {
-      if (ln.n_instr == 0 || ln.n_instr > 400000) return 0;
-      for (int k : {4, 2, 1})
-        if ((uint64_t)ln.n_slots * k <= 200) return k;
-      return ln.n_slots <= 240 ? 1 : 0;
-    };
-    auto lane_k = [&]() -> int {
-      if (ln.n_instr == 0) return 0;
-      // prefer the widest vector that still leaves >= 3 CTAs (12 consumer warps) per SM
-      for (int pass = 0; pass < 2; pass++)
-        for (int k : {4, 2, 1}) {
-          size_t need = LANE_RING_BYTES + (size_t)ln.n_slots * LANE_THREADS * k * 4;
-          if (need * (pass == 0 ? 3 : 1) <= SMEM_MAX) return k;
-        }
-      return 0;
-    };
-    auto coop_k = [&]() -> int {
-      if (lv.n_instr == 0) return 0;
-      for (int k : {4, 2, 1})
-        if ((size_t)lv.n_slots * k * 4 <= SMEM_MAX) return k;
-      return 0;
-    };
-    mode = want;
-    if (mode == CLG_MODE_AUTO) mode = spec_k() ? CLG_MODE_SPEC : lane_k() ? CLG_MODE_LANE : CLG_MODE_COOP;
+    const FlatStream &lv = level_stream(), &ln = lane_stream();
     const FlatStream *st = nullptr;
     int sidx = STREAM_LANE;
-    switch (mode) {
+    P.K = fit_k(m);
+    switch (m) {
       case CLG_MODE_SPEC:
-        K = spec_k();
-        if (!K) fail(CLG_E_UNSUPPORTED, "program does not fit the specialised mode (no lane stream, too long, or too many live registers)");
+        if (!P.K) fail(CLG_E_UNSUPPORTED, "program does not fit the specialised mode (no lane stream, too long, or too many live registers)");
         break;
       case CLG_MODE_LANE:
-        K = lane_k();
-        if (!K) fail(CLG_E_UNSUPPORTED, "live register set does not fit a per-thread shared-memory stack; use the cooperative mode");
+        if (!P.K) fail(CLG_E_UNSUPPORTED, "live register set does not fit a per-thread shared-memory stack; use the cooperative mode");
         st = &ln;
-        smem = LANE_RING_BYTES + (size_t)ln.n_slots * LANE_THREADS * K * 4;
+        P.smem = LANE_RING_BYTES + (size_t)ln.n_slots * LANE_THREADS * P.K * 4;
         break;
       case CLG_MODE_COOP:
-        K = coop_k();
-        if (!K) fail(CLG_E_UNSUPPORTED, "live register set exceeds one SM's shared memory even at one word per register");
+        if (!P.K) fail(CLG_E_UNSUPPORTED, "live register set exceeds one SM's shared memory even at one word per register");
         st = &lv, sidx = STREAM_LEVEL;
-        smem = std::max<size_t>((size_t)lv.n_slots * K * 4, 16);
-        coop_threads = std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (lv.max_level_width + 31u) / 32u * 32u));
+        P.smem = std::max<size_t>((size_t)lv.n_slots * P.K * 4, 16);
+        P.coop_threads = coop_threads_for(lv);
         break;
       default: fail(CLG_E_INVALID, "unknown execution mode");
     }
     if (st) {
-      n_instr = st->n_instr, n_levels = st->n_levels, n_slots = st->n_slots;
+      P.n_instr = st->n_instr, P.n_levels = st->n_levels, P.n_slots = st->n_slots;
       // device encoding (kernels.cu): byte offsets pre-scaled for this mode's register-stack layout
-      const uint32_t slot_bytes = (mode == CLG_MODE_LANE ? LANE_THREADS : 1) * K * 4;
-      if ((uint64_t)n_slots * slot_bytes >= (1u << 24)) fail(CLG_E_UNSUPPORTED, "register stack exceeds the 24-bit offset field");
-      std::vector<uint32_t> enc((size_t)n_instr * 4);
+      const uint32_t slot_bytes = (m == CLG_MODE_LANE ? LANE_THREADS : 1) * P.K * 4;
+      if ((uint64_t)P.n_slots * slot_bytes >= (1u << 24)) fail(CLG_E_UNSUPPORTED, "register stack exceeds the 24-bit offset field");
+      std::vector<uint32_t> enc((size_t)P.n_instr * 4);
       const FlatInstr *src = flat.instrs(sidx);
-      for (uint32_t i = 0; i < n_instr; i++) {
+      for (uint32_t i = 0; i < P.n_instr; i++) {
         const FlatInstr &x = src[i];
         uint32_t *e = &enc[(size_t)i * 4];
         switch (x.kind) {
@@ -215,28 +267,32 @@ struct Exec {
           default: e[0] = 0, e[1] = 5u << 28 | (uint32_t)(x.flags & 1) << 24, e[2] = x.row, e[3] = 0; break;
         }
       }
-      CU(cuMemAlloc(&d_instr, std::max<size_t>(16, (size_t)n_instr * 16)));
-      CU(cuMemcpyHtoDAsync(d_instr, enc.data(), (size_t)n_instr * 16, nullptr));
-      CU(cuMemAlloc(&d_levels, ((size_t)n_levels + 1) * 4));
-      CU(cuMemcpyHtoDAsync(d_levels, flat.levels(sidx), ((size_t)n_levels + 1) * 4, nullptr));
+      CU(cuMemAlloc(&P.d_instr, std::max<size_t>(16, (size_t)P.n_instr * 16)));
+      CU(cuMemcpyHtoDAsync(P.d_instr, enc.data(), (size_t)P.n_instr * 16, nullptr));
+      CU(cuMemAlloc(&P.d_levels, ((size_t)P.n_levels + 1) * 4));
+      CU(cuMemcpyHtoDAsync(P.d_levels, flat.levels(sidx), ((size_t)P.n_levels + 1) * 4, nullptr));
       CU(cuStreamSynchronize(nullptr));
     } else {
-      ptx = emit_spec_ptx(flat, K);
+      P.ptx = emit_spec_ptx(flat, P.K);
       char log[8192] = {0}, info[4096] = {0};
       CUjit_option opt[] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES, CU_JIT_INFO_LOG_BUFFER,
                             CU_JIT_INFO_LOG_BUFFER_SIZE_BYTES};
       void *val[] = {log, (void *)(uintptr_t)sizeof log, info, (void *)(uintptr_t)sizeof info};
-      CUresult r = driver().cuModuleLoadDataEx(&spec_mod, ptx.c_str(), 4, opt, val);
+      CUresult r = driver().cuModuleLoadDataEx(&P.spec_mod, P.ptx.c_str(), 4, opt, val);
       if (r != CUDA_SUCCESS) fail(CLG_E_PTX, std::string("assembling the specialised kernel failed: ") + log);
-      CU(cuModuleGetFunction(&spec_fn, spec_mod, "clg_spec"));
+      CU(cuModuleGetFunction(&P.spec_fn, P.spec_mod, "clg_spec"));
     }
+    P.ready = true;
+    return P;
   }
   ~Exec() {
     Driver &d = driver();
     d.cuCtxSetCurrent(ctx->cu);
-    if (d_instr) d.cuMemFree(d_instr);
-    if (d_levels) d.cuMemFree(d_levels);
-    if (spec_mod) d.cuModuleUnload(spec_mod);
+    for (Plan &P : plan) {
+      if (P.d_instr) d.cuMemFree(P.d_instr);
+      if (P.d_levels) d.cuMemFree(P.d_levels);
+      if (P.spec_mod) d.cuModuleUnload(P.spec_mod);
+    }
     for (int b = 0; b < NBUF; b++) {
       if (stage_in[b]) d.cuMemFree(stage_in[b]);
       if (stage_out[b]) d.cuMemFree(stage_out[b]);
@@ -349,27 +405,31 @@ struct Exec {
     if (((uintptr_t)imm | (uintptr_t)out | (uintptr_t)state) & 15) fail(CLG_E_INVALID, "buffers must be 16-byte aligned");
     if (n_vectors == 0) return;
     ctx->bind();
+    mode = choose(words);
+    Plan &P = get(mode);
+    const int K = P.K;
     const uint32_t groups = (uint32_t)((words + K - 1) / K);
     if (mode == CLG_MODE_SPEC) {
       uint32_t stride32 = (uint32_t)stride, g = groups;
       void *args[] = {&imm, &out, &state, &stride32, &g};
       const uint32_t nt = 128;
-      CU(cuLaunchKernel(spec_fn, (groups + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, args, nullptr));
+      CU(cuLaunchKernel(P.spec_fn, (groups + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, args, nullptr));
       return;
     }
     RunParams p{};
-    p.instr = (const void *)d_instr, p.levels = (const uint32_t *)d_levels;
+    p.instr = (const void *)P.d_instr, p.levels = (const uint32_t *)P.d_levels;
     p.imm = imm, p.out = out, p.state = state;
     p.n_inputs = h.n_inputs, p.n_outputs = h.n_outputs;
-    p.n_instr = n_instr, p.n_levels = n_levels, p.n_slots = n_slots;
+    p.n_instr = P.n_instr, p.n_levels = P.n_levels, p.n_slots = P.n_slots;
     p.stride = (uint32_t)stride, p.n_groups = groups;
     void *args[] = {&p};
     if (mode == CLG_MODE_LANE) {
       const uint32_t grid = (groups + LANE_THREADS - 1) / LANE_THREADS;
-      CU(cuLaunchKernel(ctx->lane[kidx(K)], grid, 1, 1, LANE_THREADS + 32, 1, 1, (unsigned)smem, stream, args, nullptr));
+      CU(cuLaunchKernel(ctx->lane[kidx(K)], grid, 1, 1, LANE_THREADS + 32, 1, 1, (unsigned)P.smem, stream, args, nullptr));
     } else {
-      const uint32_t grid = std::min<uint32_t>(groups, (uint32_t)ctx->sm_count * (uint32_t)std::max<size_t>(1, std::min<size_t>(SMEM_MAX / (smem + 1024), 2048 / coop_threads)));
-      CU(cuLaunchKernel(ctx->coop[kidx(K)], grid, 1, 1, coop_threads, 1, 1, (unsigned)smem, stream, args, nullptr));
+      const size_t per_sm = std::max<size_t>(1, std::min<size_t>(SMEM_MAX / (P.smem + 1024), 2048 / P.coop_threads));
+      const uint32_t grid = std::min<uint32_t>(groups, (uint32_t)ctx->sm_count * (uint32_t)per_sm);
+      CU(cuLaunchKernel(ctx->coop[kidx(K)], grid, 1, 1, P.coop_threads, 1, 1, (unsigned)P.smem, stream, args, nullptr));
     }
   }
 };
@@ -423,8 +483,8 @@ void stream_sync(Ctx *c, void *stream) {
 Exec *exec_create(Ctx *c, const Flat &f, int mode) { return new Exec(c, f, mode); }
 void exec_destroy(Exec *e) { delete e; }
 int exec_mode(const Exec *e) { return e->mode; }
-int exec_k(const Exec *e) { return e->K; }
-const std::string &exec_ptx(const Exec *e) { return e->ptx; }
+int exec_k(const Exec *e) { return e->plan[e->mode].K; }
+const std::string &exec_ptx(const Exec *e) { return e->plan[CLG_MODE_SPEC].ptx; }
 const Flat &exec_flat(const Exec *e) { return e->flat; }
 Ctx *exec_ctx(const Exec *e) { return e->ctx; }
 void exec_run_host(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride) {

@@ -16,8 +16,12 @@
 //      across the threads of a CTA) and lane order (depth-first, small live set; the lane-parallel
 //      kernels run it sequentially per thread).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <queue>
 
 #include "host.hpp"
@@ -27,6 +31,17 @@ namespace clg {
 namespace {
 
 constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+// CLG_TIMING=1 prints the wall time of each phase of the pass to stderr
+struct Phase {
+  const char *name;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit Phase(const char *n) : name(n) {}
+  ~Phase() {
+    static const bool on = std::getenv("CLG_TIMING") != nullptr;
+    if (on) std::fprintf(stderr, "[clg] %-22s %8.3f s\n", name, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
 
 // ---- and-inverter graph ---------------------------------------------------------------------
 // literal = 2 * node + complement; node 0 is constant false (literal 0 = false, 1 = true).
@@ -347,11 +362,18 @@ struct Mapper {
   };
 
   void run() {
-    mark_live();
-    enumerate();
+    {
+      Phase ph("map: cut enumeration");
+      mark_live();
+      enumerate();
+    }
     if (!fuse) return;
-    for (int it = 0; it < 2; it++) reselect();
+    {
+      Phase ph("map: area flow");
+      for (int it = 0; it < 2; it++) reselect();
+    }
     // deep recursion in Exact is bounded by cone size, not graph depth, but guard huge graphs
+    Phase ph("map: exact area");
     if (g.size() < (1u << 24))
       for (int it = 0; it < 2; it++) Exact(*this).run();
   }
@@ -595,7 +617,7 @@ Sched schedule_level(const Network &net) {
   // its own LDS/STS. Three degrees of freedom are used: which 8 instructions share a quarter (greedy packing
   // from a window of candidates), which operand sits in which position (LUT inputs commute if the truth table
   // is permuted with them), and which free slot a result takes (one bank group per quarter member).
-  constexpr uint32_t BANKS = 8, WINDOW = 512;
+  constexpr uint32_t BANKS = 8, WINDOW = 2048;
   Sched s;
   s.instr.resize(V + O);
   s.levels.assign(cnt.begin(), cnt.end());
@@ -631,8 +653,12 @@ Sched schedule_level(const Network &net) {
     uint32_t x;
     uint8_t perm;  // operand k of the value goes to position PERM[perm][k]
   };
+  struct CandInfo {
+    uint8_t nops, perms, bank[3];
+  };
   std::vector<Placed> order;
   std::vector<uint8_t> taken;
+  std::vector<CandInfo> cinfo;
   for (uint32_t l = 0; l < n_levels; l++) {
     if (l > 0) {
       for (uint32_t sl : release[l - 1]) pool.put(sl);
@@ -644,9 +670,30 @@ Sched schedule_level(const Network &net) {
     // -- pack quarters
     order.clear();
     taken.assign(n, 0);
+    // per candidate: operand count, operand bank groups, and which operand orders leave its table unchanged
+    cinfo.resize(n);
+    for (uint32_t c = 0; c < n; c++) {
+      const uint32_t x = items[b + c];
+      CandInfo &ci = cinfo[c];
+      ci.perms = 1;
+      if (x >= V) {
+        ci.nops = net.outs[x - V].val == NONE ? 0 : 1;
+        if (ci.nops) ci.bank[0] = (uint8_t)(slot[net.outs[x - V].val] % BANKS);
+      } else if (net.vals[x].is_lut) {
+        const Val &v = net.vals[x];
+        ci.nops = v.nfan;
+        for (int k = 0; k < v.nfan; k++) ci.bank[k] = (uint8_t)(slot[v.fan[k]] % BANKS);
+        if (v.nfan >= 2)
+          for (int q = 1; q < 6; q++) {
+            bool fits = true;
+            for (int k = 0; k < v.nfan; k++) fits &= PERM[q][k] < v.nfan;
+            if (fits && remap(v.tt, PERM[q]) == v.tt) ci.perms |= (uint8_t)(1u << q);
+          }
+      } else {
+        ci.nops = 0;
+      }
+    }
     uint32_t head = 0, placed = 0;
-    auto n_ops = [&](uint32_t x) -> int { return x >= V ? (net.outs[x - V].val == NONE ? 0 : 1) : net.vals[x].is_lut ? net.vals[x].nfan : 0; };
-    auto op_slot = [&](uint32_t x, int k) -> uint32_t { return x >= V ? slot[net.outs[x - V].val] : slot[net.vals[x].fan[k]]; };
     while (placed < n) {
       uint32_t mask[3] = {0, 0, 0};
       uint32_t members = 0;
@@ -655,25 +702,18 @@ Sched schedule_level(const Network &net) {
       for (uint32_t c = head; c < n && members < BANKS && scanned < WINDOW; c++) {
         if (taken[c]) continue;
         scanned++;
-        const uint32_t x = items[b + c];
-        const int no = n_ops(x);
+        const CandInfo &ci = cinfo[c];
         int pick = -1;
-        const int nperm = (x < V && no >= 2) ? 6 : 1;
-        for (int q = 0; q < nperm && pick < 0; q++) {
-          // only operand orders that leave the truth table unchanged (the function's own symmetries)
-          if (q && remap(net.vals[x].tt, PERM[q]) != net.vals[x].tt) continue;
+        for (int q = 0; q < 6 && pick < 0; q++) {
+          if (!(ci.perms >> q & 1)) continue;
           bool ok = true;
-          for (int k = 0; k < no && ok; k++) {
-            const uint8_t pos = PERM[q][k];
-            if (pos >= no) ok = false;  // a 2-input LUT only has positions a, b
-            else if (mask[pos] >> (op_slot(x, k) % BANKS) & 1u) ok = false;
-          }
+          for (int k = 0; k < ci.nops && ok; k++) ok = !(mask[PERM[q][k]] >> ci.bank[k] & 1u);
           if (ok) pick = q;
         }
         if (pick < 0) continue;
-        for (int k = 0; k < no; k++) mask[PERM[pick][k]] |= 1u << (op_slot(x, k) % BANKS);
+        for (int k = 0; k < ci.nops; k++) mask[PERM[pick][k]] |= 1u << ci.bank[k];
         taken[c] = 1, members++, placed++;
-        order.push_back({x, (uint8_t)pick});
+        order.push_back({items[b + c], (uint8_t)pick});
       }
       // nothing else in the window fits without a conflict: fill the quarter in order, conflicts accepted
       for (uint32_t c = head; c < n && members < BANKS; c++) {
@@ -782,6 +822,8 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
       if (first[r] == 1) state_regs.push_back(r);
   }
 
+  Phase ph_total("levelize total");
+  std::unique_ptr<Phase> ph(new Phase("ssa + aig"));
   Aig g;
   std::vector<uint32_t> imm_lit(n_immediates);
   for (size_t i = 0; i < n_immediates; i++) imm_lit[i] = g.input((uint32_t)i);
@@ -795,8 +837,10 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
   for (uint64_t r : outs) out_lits.push_back(cur[r]);
   for (uint64_t r : state_regs) out_lits.push_back(cur[r]);
 
+  ph.reset();
   Mapper m(g, out_lits, !(flags & CLG_LV_NO_FUSE));
   m.run();
+  ph.reset(new Phase("network"));
 
   // build the value network: used input rows first, then LUT roots in topological order
   Network net;
@@ -833,13 +877,16 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
     net.outs.push_back(r);
   }
 
+  ph.reset(new Phase("schedule: level"));
   Sched level = schedule_level(net);
+  ph.reset(new Phase("schedule: lane"));
   if (!level.ok) fail(CLG_E_UNSUPPORTED, "level-ordered stream needs more than 65536 physical registers");
   Sched lane;
   lane.ok = false;
   if (!(flags & CLG_LV_NO_LANE_STREAM)) lane = schedule_lane(net);
 
   // serialise
+  ph.reset(new Phase("serialise"));
   Flat f;
   size_t off = align16(sizeof(FlatHeader));
   FlatHeader h{};
