@@ -209,6 +209,24 @@ def test_modes_agree_at_scale_mul16():
     assert np.array_equal(unslice_int(outs[0][:, cols], n), a * b)
 
 
+def test_config5_wide_single_vector():
+    """BASELINE config 5: 64x64 multiplier x 128 instances flattened (10 764 288 gates), ONE input vector.
+    AUTO must pick the cooperative intra-level mode for a single vector (the lane modes would run 1.5M
+    instructions on one thread), and the products must be right."""
+    base = circuits.array_multiplier(64)
+    circ = circuits.flatten_instances(base, 128)
+    assert circ.sim.nand_count == 10764288
+    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs)
+    for nv in (1, 32):
+        imm = random_sliced(circ.n_immediates, stride_for(nv), seed=0x5EED)
+        got = mask_tail(cs.run_batch(imm, nv), nv)
+        assert cs.mode == host.MODE_COOP
+        for m in (0, 77, 127):
+            a, b = unslice_int(imm[128 * m:128 * m + 64], nv), unslice_int(imm[128 * m + 64:128 * m + 128], nv)
+            assert list(unslice_int(got[128 * m:128 * m + 128], nv)) == [int(x) * int(y) for x, y in zip(a, b)]
+        assert np.array_equal(got, oracle_out(circ, imm, nv))
+
+
 def test_host_path_pipelines_many_chunks(monkeypatch):
     """clg_exec_run_host cuts the batch into column chunks that flow through three streams; force many small,
     ragged chunks and a stateful program, and compare with the oracle."""
@@ -228,6 +246,21 @@ def test_host_path_pipelines_many_chunks(monkeypatch):
     state = np.zeros((cs.info["n_state"], stride), np.uint32)
     for s_ in range(steps):
         assert np.array_equal(mask_tail(cs.run_batch(imms[s_], nv, state=state), nv), mask_tail(want[s_], nv))
+
+
+def test_single_process_sharded_driver():
+    """clg_run_sharded_host: one host thread + context + stream per device, contiguous 4-word-aligned shards, no
+    collective. With fewer GPUs than shards the same device is listed several times (shards still run apart)."""
+    import torch
+
+    circ = circuits.array_multiplier(16)
+    fp = host.FlatProgram.levelize(circ.sim, 32, circ.out_regs)
+    n_dev = torch.cuda.device_count()
+    for nv, devices in ((100000, [0, 0, 0]), (33, [0, 0]), (1 << 20, list(range(n_dev)) * (1 if n_dev > 1 else 2))):
+        imm = random_sliced(32, stride_for(nv), seed=123)
+        out, secs = host.run_sharded(fp, imm, nv, devices)
+        assert np.array_equal(mask_tail(out, nv), oracle_out(circ, imm, nv))
+        assert len(secs) == len(devices)
 
 
 def test_errors_are_status_codes():
