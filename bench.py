@@ -392,7 +392,16 @@ def main():
         threads = os.cpu_count() or 1
         v, nv_s, dt = cpu_reference_throughput(circ, seed, threads, args.cpu_seconds)
         v1, nv1, dt1 = cpu_reference_throughput(circ, seed, 1, min(3.0, args.cpu_seconds))
+        # extra row: the oracle's bit-sliced CPU evaluator (same op list, 64 lanes per u64 word, one thread), so the gain
+        # from bit-slicing and the gain from the GPU can be read apart
+        from tests.helpers import random_sliced, stride_for
+        nv_b = 64 * max(1, int(2e8 // max(1, circ.sim.nand_count)))
+        imm_b = random_sliced(circ.n_immediates, stride_for(nv_b), seed)
+        tb = time.perf_counter()
+        oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm_b, nv_b, circ.out_regs)
+        tb = time.perf_counter() - tb
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "bitsliced_1thread_value": circ.sim.nand_count * nv_b / tb, "bitsliced_sample": f"{nv_b} vectors in {tb:.2f} s",
                "sample": f"{nv_s} vectors of {args.workload} in {dt:.1f} s on {threads} threads (scalar VM restating "
                          f"simulation.rs:16-30; 32-byte ops, byte registers, bounds checks)",
                "single_thread_value": v1, "single_thread_sample": f"{nv1} vectors in {dt1:.1f} s"}

@@ -130,12 +130,34 @@ struct Ctx {
 static int kidx(int K) { return K == 4 ? 2 : K == 2 ? 1 : 0; }
 
 // ---- resident program --------------------------------------------------------------------------------
+// Device encoding of a flat instruction stream (kernels.cu): byte offsets pre-scaled by the register-stack stride.
+static void encode_stream(const FlatInstr *src, uint32_t n, uint32_t slot_bytes, uint32_t *enc) {
+  for (uint32_t i = 0; i < n; i++) {
+    const FlatInstr &x = src[i];
+    uint32_t *e = enc + (size_t)i * 4;
+    switch (x.kind) {
+      case K_LUT: {
+        const int nf = lut_nfan(x);
+        const uint32_t kind = nf >= 3 ? 0u : nf == 2 ? 1u : 2u;  // D_LUT3 / D_LUT2 / D_LUT1
+        e[0] = x.a * slot_bytes | (uint32_t)x.tt << 24;
+        e[1] = x.b * slot_bytes | kind << 28;
+        e[2] = x.c * slot_bytes;
+        e[3] = x.dst * slot_bytes;
+        break;
+      }
+      case K_LDIN: e[0] = 0, e[1] = 3u << 28, e[2] = x.row, e[3] = x.dst * slot_bytes; break;
+      case K_STOUT: e[0] = x.a * slot_bytes, e[1] = 4u << 28 | (uint32_t)(x.flags & 1) << 24, e[2] = x.row, e[3] = 0; break;
+      default: e[0] = 0, e[1] = 5u << 28 | (uint32_t)(x.flags & 1) << 24, e[2] = x.row, e[3] = 0; break;
+    }
+  }
+}
+
 // One execution mode of a program made resident on the device.
 struct Plan {
   bool ready = false;
   int K = 0;
-  CUdeviceptr d_instr = 0, d_levels = 0;
-  uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0;
+  CUdeviceptr d_instr = 0, d_levels = 0, d_parts = 0;
+  uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0, n_parts = 0;
   size_t smem = 0;
   CUmodule spec_mod = nullptr;
   CUfunction spec_fn = nullptr;
@@ -147,7 +169,9 @@ struct Exec {
   Flat flat;  // own copy: the caller may destroy its clg_flat
   int want;   // CLG_MODE_AUTO or the mode the caller pinned
   int mode;   // mode of the most recent (or, before any run, the preferred) plan
-  Plan plan[4];
+  int last_k = 0, last_parts = 0;
+  Plan plan[5];  // indexed by clg_mode; [PLAN_PARTS] = cooperative mode over the partitioned level stream
+  static constexpr int PLAN_PARTS = 4;
 
   const FlatStream &level_stream() const { return flat.header().stream[STREAM_LEVEL]; }
   const FlatStream &lane_stream() const { return flat.header().stream[STREAM_LANE]; }
@@ -160,7 +184,9 @@ struct Exec {
         if (ln.n_instr == 0 || ln.n_instr > 400000) return 0;
         for (int k : {4, 2, 1})
           if ((uint64_t)ln.n_slots * k <= 200) return k;
-        return ln.n_slots <= 240 ? 1 : 0;
+        // one word per thread tolerates a live set somewhat beyond the register file: ptxas spills the coldest
+        // values to L1-backed local memory (mul64: 315 live values -> 255 registers + 488 B of spills)
+        return ln.n_slots <= 512 ? 1 : 0;
       case CLG_MODE_LANE:
         if (ln.n_instr == 0) return 0;
         // prefer the widest vector that still leaves >= 3 CTAs (12 consumer warps) per SM
@@ -214,7 +240,55 @@ struct Exec {
   Exec(Ctx *c, const Flat &f, int want_) : ctx(c), flat(f), want(want_) {
     if (want < CLG_MODE_AUTO || want > CLG_MODE_SPEC) fail(CLG_E_INVALID, "unknown execution mode");
     mode = choose((size_t)1 << 20);  // the plan a large batch would use; small batches may pick another (auto)
-    get(mode);
+    last_k = get(mode).K;
+  }
+
+  // K the partitioned cooperative plan would use (stack sized for the largest part); 0 = no partitioned form
+  int parts_k() const {
+    const FlatHeader &h = flat.header();
+    if (h.n_parts < 2) return 0;
+    uint32_t slots = 0;
+    for (uint32_t q = 0; q < h.n_parts; q++) slots = std::max(slots, flat.parts()[q].n_slots);
+    for (int k : {4, 2, 1})
+      if ((size_t)slots * k * 4 <= SMEM_MAX) return k;
+    return 0;
+  }
+  Plan &get_parts() {
+    Plan &P = plan[PLAN_PARTS];
+    if (P.ready) return P;
+    ctx->bind();
+    const FlatHeader &h = flat.header();
+    P.K = parts_k();
+    if (!P.K) fail(CLG_E_UNSUPPORTED, "no partitioned level stream");
+    P.n_parts = h.n_parts;
+    uint32_t width = 0;
+    size_t total_instr = 0, total_levels = 0;
+    for (uint32_t q = 0; q < h.n_parts; q++) {
+      const FlatStream &st = flat.parts()[q];
+      P.n_slots = std::max(P.n_slots, st.n_slots), width = std::max(width, st.max_level_width);
+      total_instr += st.n_instr, total_levels += st.n_levels + 1;
+    }
+    P.smem = std::max<size_t>((size_t)P.n_slots * P.K * 4, 16);
+    P.coop_threads = std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (width + 31u) / 32u * 32u));
+    std::vector<uint32_t> enc(total_instr * 4), lv(total_levels), desc((size_t)h.n_parts * 4);
+    size_t io = 0, lo = 0;
+    for (uint32_t q = 0; q < h.n_parts; q++) {
+      const FlatStream &st = flat.parts()[q];
+      encode_stream(flat.part_instrs(q), st.n_instr, (uint32_t)P.K * 4, enc.data() + io * 4);
+      std::memcpy(lv.data() + lo, flat.part_levels(q), ((size_t)st.n_levels + 1) * 4);
+      desc[q * 4 + 0] = (uint32_t)io, desc[q * 4 + 1] = (uint32_t)lo, desc[q * 4 + 2] = st.n_levels, desc[q * 4 + 3] = 0;
+      io += st.n_instr, lo += st.n_levels + 1;
+    }
+    P.n_instr = (uint32_t)total_instr;
+    CU(cuMemAlloc(&P.d_instr, std::max<size_t>(16, enc.size() * 4)));
+    CU(cuMemcpyHtoDAsync(P.d_instr, enc.data(), enc.size() * 4, nullptr));
+    CU(cuMemAlloc(&P.d_levels, lv.size() * 4));
+    CU(cuMemcpyHtoDAsync(P.d_levels, lv.data(), lv.size() * 4, nullptr));
+    CU(cuMemAlloc(&P.d_parts, desc.size() * 4));
+    CU(cuMemcpyHtoDAsync(P.d_parts, desc.data(), desc.size() * 4, nullptr));
+    CU(cuStreamSynchronize(nullptr));
+    P.ready = true;
+    return P;
   }
 
   Plan &get(int m) {
@@ -248,25 +322,7 @@ struct Exec {
       const uint32_t slot_bytes = (m == CLG_MODE_LANE ? LANE_THREADS : 1) * P.K * 4;
       if ((uint64_t)P.n_slots * slot_bytes >= (1u << 24)) fail(CLG_E_UNSUPPORTED, "register stack exceeds the 24-bit offset field");
       std::vector<uint32_t> enc((size_t)P.n_instr * 4);
-      const FlatInstr *src = flat.instrs(sidx);
-      for (uint32_t i = 0; i < P.n_instr; i++) {
-        const FlatInstr &x = src[i];
-        uint32_t *e = &enc[(size_t)i * 4];
-        switch (x.kind) {
-          case K_LUT: {
-            const int nf = lut_nfan(x);
-            const uint32_t kind = nf >= 3 ? 0u : nf == 2 ? 1u : 2u;  // D_LUT3 / D_LUT2 / D_LUT1
-            e[0] = x.a * slot_bytes | (uint32_t)x.tt << 24;
-            e[1] = x.b * slot_bytes | kind << 28;
-            e[2] = x.c * slot_bytes;
-            e[3] = x.dst * slot_bytes;
-            break;
-          }
-          case K_LDIN: e[0] = 0, e[1] = 3u << 28, e[2] = x.row, e[3] = x.dst * slot_bytes; break;
-          case K_STOUT: e[0] = x.a * slot_bytes, e[1] = 4u << 28 | (uint32_t)(x.flags & 1) << 24, e[2] = x.row, e[3] = 0; break;
-          default: e[0] = 0, e[1] = 5u << 28 | (uint32_t)(x.flags & 1) << 24, e[2] = x.row, e[3] = 0; break;
-        }
-      }
+      encode_stream(flat.instrs(sidx), P.n_instr, slot_bytes, enc.data());
       CU(cuMemAlloc(&P.d_instr, std::max<size_t>(16, (size_t)P.n_instr * 16)));
       CU(cuMemcpyHtoDAsync(P.d_instr, enc.data(), (size_t)P.n_instr * 16, nullptr));
       CU(cuMemAlloc(&P.d_levels, ((size_t)P.n_levels + 1) * 4));
@@ -291,6 +347,7 @@ struct Exec {
     for (Plan &P : plan) {
       if (P.d_instr) d.cuMemFree(P.d_instr);
       if (P.d_levels) d.cuMemFree(P.d_levels);
+      if (P.d_parts) d.cuMemFree(P.d_parts);
       if (P.spec_mod) d.cuModuleUnload(P.spec_mod);
     }
     for (int b = 0; b < NBUF; b++) {
@@ -406,8 +463,11 @@ struct Exec {
     if (n_vectors == 0) return;
     ctx->bind();
     mode = choose(words);
-    Plan &P = get(mode);
+    // a cooperative run that cannot give every SM its own column group uses the partitioned form if there is one
+    const bool use_parts = mode == CLG_MODE_COOP && parts_k() && (words + parts_k() - 1) / parts_k() < (size_t)ctx->sm_count;
+    Plan &P = use_parts ? get_parts() : get(mode);
     const int K = P.K;
+    last_k = K, last_parts = (int)P.n_parts;
     const uint32_t groups = (uint32_t)((words + K - 1) / K);
     if (mode == CLG_MODE_SPEC) {
       uint32_t stride32 = (uint32_t)stride, g = groups;
@@ -422,13 +482,18 @@ struct Exec {
     p.n_inputs = h.n_inputs, p.n_outputs = h.n_outputs;
     p.n_instr = P.n_instr, p.n_levels = P.n_levels, p.n_slots = P.n_slots;
     p.stride = (uint32_t)stride, p.n_groups = groups;
+    p.parts = (const void *)P.d_parts, p.n_parts = P.n_parts;
     void *args[] = {&p};
     if (mode == CLG_MODE_LANE) {
       const uint32_t grid = (groups + LANE_THREADS - 1) / LANE_THREADS;
       CU(cuLaunchKernel(ctx->lane[kidx(K)], grid, 1, 1, LANE_THREADS + 32, 1, 1, (unsigned)P.smem, stream, args, nullptr));
     } else {
       const size_t per_sm = std::max<size_t>(1, std::min<size_t>(SMEM_MAX / (P.smem + 1024), 2048 / P.coop_threads));
-      const uint32_t grid = std::min<uint32_t>(groups, (uint32_t)ctx->sm_count * (uint32_t)per_sm);
+      uint32_t grid = std::min<uint32_t>(groups, (uint32_t)ctx->sm_count * (uint32_t)per_sm);
+      if (P.n_parts) {  // one CTA per (part, group slot); at least one group slot, about one wave of CTAs
+        const uint32_t slots_g = std::max<uint32_t>(1u, std::min<uint32_t>(groups, ((uint32_t)ctx->sm_count * (uint32_t)per_sm + P.n_parts - 1) / P.n_parts));
+        grid = P.n_parts * slots_g;
+      }
       CU(cuLaunchKernel(ctx->coop[kidx(K)], grid, 1, 1, P.coop_threads, 1, 1, (unsigned)P.smem, stream, args, nullptr));
     }
   }
@@ -483,7 +548,7 @@ void stream_sync(Ctx *c, void *stream) {
 Exec *exec_create(Ctx *c, const Flat &f, int mode) { return new Exec(c, f, mode); }
 void exec_destroy(Exec *e) { delete e; }
 int exec_mode(const Exec *e) { return e->mode; }
-int exec_k(const Exec *e) { return e->plan[e->mode].K; }
+int exec_k(const Exec *e) { return e->last_k; }
 const std::string &exec_ptx(const Exec *e) { return e->plan[CLG_MODE_SPEC].ptx; }
 const Flat &exec_flat(const Exec *e) { return e->flat; }
 Ctx *exec_ctx(const Exec *e) { return e->ctx; }

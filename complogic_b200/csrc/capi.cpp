@@ -202,6 +202,7 @@ int clg_flat_get_info(const clg_flat *f, clg_flat_info *info) {
   info->n_levels = h.stream[STREAM_LEVEL].n_levels, info->max_level_width = h.stream[STREAM_LEVEL].max_level_width;
   info->level_slots = h.stream[STREAM_LEVEL].n_slots, info->lane_slots = h.stream[STREAM_LANE].n_slots;
   info->level_instrs = h.stream[STREAM_LEVEL].n_instr, info->lane_instrs = h.stream[STREAM_LANE].n_instr;
+  info->n_parts = h.n_parts, info->reserved = 0;
   CLG_CATCH
 }
 int clg_flat_state_regs(const clg_flat *f, const uint64_t **regs, size_t *n) {

@@ -24,6 +24,8 @@ struct RunParams {
   uint32_t n_instr, n_levels, n_slots;
   uint32_t stride;
   uint32_t n_groups;
+  const void *parts;
+  uint32_t n_parts;
 };
 
 constexpr int LANE_THREADS = 128;

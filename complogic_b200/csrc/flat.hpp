@@ -7,7 +7,7 @@
 namespace clg {
 
 constexpr uint32_t FLAT_MAGIC = 0x46474C43u;  // "CLGF"
-constexpr uint32_t FLAT_VERSION = 3u;
+constexpr uint32_t FLAT_VERSION = 4u;
 
 enum InstrKind : uint8_t {
   K_LUT = 0,      // slot[dst] = LUT3(tt; slot[a], slot[b], slot[c])      (one LOP3 per 32 lanes)
@@ -51,7 +51,12 @@ struct FlatHeader {
   uint32_t off_state_regs; // uint64[n_state]  register behind each state row
   uint32_t off_out_regs;   // uint64[n_outputs] register behind each output row
   FlatStream stream[2];    // [STREAM_LEVEL], [STREAM_LANE] (n_instr == 0 when absent)
-  uint32_t reserved[4];
+  // Optional partitioned form of the level-ordered stream: the LUT network's connected components, bin-packed
+  // into n_parts independent programs (own levels, own slots; rows stay global). A batch too small to give every
+  // SM a column group runs one CTA per (part, group) instead. n_parts == 0 when the network is one component.
+  uint32_t n_parts;
+  uint32_t off_parts;      // FlatStream[n_parts]
+  uint32_t reserved[2];
 };
 static_assert(sizeof(FlatHeader) % 16 == 0, "header must keep 16-byte alignment");
 

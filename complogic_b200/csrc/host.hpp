@@ -54,6 +54,9 @@ struct Flat {
   const uint32_t *levels(int s) const {
     return reinterpret_cast<const uint32_t *>(bytes.data() + header().stream[s].off_levels);
   }
+  const FlatStream *parts() const { return reinterpret_cast<const FlatStream *>(bytes.data() + header().off_parts); }
+  const FlatInstr *part_instrs(uint32_t p) const { return reinterpret_cast<const FlatInstr *>(bytes.data() + parts()[p].off_instr); }
+  const uint32_t *part_levels(uint32_t p) const { return reinterpret_cast<const uint32_t *>(bytes.data() + parts()[p].off_levels); }
   const uint64_t *state_regs() const {
     return reinterpret_cast<const uint64_t *>(bytes.data() + header().off_state_regs);
   }

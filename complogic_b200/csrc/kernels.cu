@@ -47,6 +47,8 @@ struct RunParams {
   uint32_t n_instr, n_levels, n_slots;
   uint32_t stride;    // words between rows
   uint32_t n_groups;  // K-word column groups to evaluate
+  const uint4 *parts;  // coop, partitioned form: one descriptor per part {instr offset, levels offset, n_levels, -}
+  uint32_t n_parts;    // 0: the program is one part (instr / levels / n_levels above)
 };
 
 // ---- LOP3 with a compile-time immediate, dispatched on the instruction's truth table --------------
@@ -326,22 +328,33 @@ __device__ __forceinline__ void coop_body(const RunParams &p) {
   uint32_t sb = smem_u32(smem);  // register stack [slot][K] starts here (shared-space address)
   asm volatile("" : "+r"(sb));     // opaque: keep it in a register instead of re-deriving it in the loop
 
-  for (uint32_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+  // Partitioned form (small batches of separable programs): CTA b runs part b % n_parts on the column groups
+  // b / n_parts, b / n_parts + gridDim.x / n_parts, ...; otherwise every CTA runs the whole program.
+  const uint4 *instr = p.instr;
+  const uint32_t *levels = p.levels;
+  uint32_t n_levels = p.n_levels, g0 = blockIdx.x, gstep = gridDim.x;
+  if (p.n_parts) {
+    const uint4 d = __ldg(p.parts + blockIdx.x % p.n_parts);
+    instr += d.x, levels += d.y, n_levels = d.z;
+    g0 = blockIdx.x / p.n_parts, gstep = gridDim.x / p.n_parts;
+  }
+
+  for (uint32_t g = g0; g < p.n_groups; g += gstep) {
     const size_t col = (size_t)g * K;
-    uint32_t lb = __ldg(p.levels), le = __ldg(p.levels + 1);
+    uint32_t lb = __ldg(levels), le = __ldg(levels + 1);
     uint4 ins = make_uint4(0, 0, 0, 0);
-    if (lb + tid < le) ins = ld_instr(p.instr + lb + tid);
-    for (uint32_t l = 0; l < p.n_levels; l++) {
+    if (lb + tid < le) ins = ld_instr(instr + lb + tid);
+    for (uint32_t l = 0; l < n_levels; l++) {
       // this thread's first instruction of the NEXT level is requested now, so its L2 latency is hidden behind
       // this level's work and the barrier instead of being paid after it
-      const uint32_t le2 = __ldg(p.levels + min(l + 2, p.n_levels));
+      const uint32_t le2 = __ldg(levels + min(l + 2, n_levels));
       uint4 first_next = make_uint4(0, 0, 0, 0);
-      if (le + tid < le2) first_next = ld_instr(p.instr + le + tid);
+      if (le + tid < le2) first_next = ld_instr(instr + le + tid);
       uint32_t i = lb + tid;
       while (i < le) {
         const uint32_t nexti = i + nt;
         uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (nexti < le) nxt = ld_instr(p.instr + nexti);  // software prefetch of the next instruction
+        if (nexti < le) nxt = ld_instr(instr + nexti);  // software prefetch of the next instruction
         const uint32_t kind = ins.y >> 28;
         if (kind <= D_LUT1) {
           const Vec<K> a = lds<K>(sb + (ins.x & 0xFFFFFFu));

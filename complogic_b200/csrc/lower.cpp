@@ -775,6 +775,74 @@ Sched schedule_level(const Network &net) {
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// Connected components of the value network (an output belongs to the component of its value), bin-packed
+// largest-first into at most `max_parts` parts of similar LUT count. Returns part id per value / per output.
+uint32_t partition(const Network &net, uint32_t max_parts, std::vector<uint32_t> &part_of_val, std::vector<uint32_t> &part_of_out) {
+  const size_t V = net.vals.size();
+  std::vector<uint32_t> parent(V);
+  for (size_t v = 0; v < V; v++) parent[v] = (uint32_t)v;
+  auto find = [&](uint32_t x) {
+    while (parent[x] != x) x = parent[x] = parent[parent[x]];
+    return x;
+  };
+  for (size_t v = 0; v < V; v++)
+    if (net.vals[v].is_lut)
+      for (int i = 0; i < net.vals[v].nfan; i++) {
+        uint32_t a = find((uint32_t)v), b = find(net.vals[v].fan[i]);
+        if (a != b) parent[a] = b;
+      }
+  // carried state: the load and the store of one state row must stay in one part (in-place update ordering)
+  std::vector<uint32_t> state_in(net.n_state, NONE);
+  for (size_t v = 0; v < V; v++)
+    if (!net.vals[v].is_lut && net.vals[v].row >= net.n_inputs) state_in[net.vals[v].row - net.n_inputs] = (uint32_t)v;
+  for (const OutRef &o : net.outs)
+    if (o.row >= net.n_outputs && o.val != NONE && state_in[o.row - net.n_outputs] != NONE) {
+      uint32_t a = find(o.val), b = find(state_in[o.row - net.n_outputs]);
+      if (a != b) parent[a] = b;
+    }
+  std::vector<uint32_t> weight(V, 0), comp_ids;
+  for (size_t v = 0; v < V; v++) weight[find((uint32_t)v)] += 1;
+  for (size_t v = 0; v < V; v++)
+    if (find((uint32_t)v) == v) comp_ids.push_back((uint32_t)v);
+  std::sort(comp_ids.begin(), comp_ids.end(), [&](uint32_t a, uint32_t b) { return weight[a] != weight[b] ? weight[a] > weight[b] : a < b; });
+  const uint32_t P = (uint32_t)std::min<size_t>(max_parts, std::max<size_t>(1, comp_ids.size()));
+  std::priority_queue<std::pair<uint64_t, uint32_t>, std::vector<std::pair<uint64_t, uint32_t>>, std::greater<std::pair<uint64_t, uint32_t>>> bins;
+  for (uint32_t b = 0; b < P; b++) bins.push({0, b});
+  std::vector<uint32_t> part_of_comp(V, 0);
+  for (uint32_t c : comp_ids) {
+    auto [load, b] = bins.top();
+    bins.pop();
+    part_of_comp[c] = b;
+    bins.push({load + weight[c], b});
+  }
+  part_of_val.resize(V);
+  for (size_t v = 0; v < V; v++) part_of_val[v] = part_of_comp[find((uint32_t)v)];
+  part_of_out.resize(net.outs.size());
+  for (size_t o = 0; o < net.outs.size(); o++) part_of_out[o] = net.outs[o].val == NONE ? 0 : part_of_val[net.outs[o].val];
+  return P;
+}
+
+Network subnetwork(const Network &net, const std::vector<uint32_t> &part_of_val, const std::vector<uint32_t> &part_of_out, uint32_t part) {
+  Network sub;
+  sub.n_inputs = net.n_inputs, sub.n_state = net.n_state, sub.n_outputs = net.n_outputs;
+  std::vector<uint32_t> local(net.vals.size(), NONE);
+  for (size_t v = 0; v < net.vals.size(); v++)
+    if (part_of_val[v] == part) {
+      Val x = net.vals[v];
+      if (x.is_lut)
+        for (int i = 0; i < x.nfan; i++) x.fan[i] = local[x.fan[i]];
+      local[v] = (uint32_t)sub.vals.size();
+      sub.vals.push_back(x);
+    }
+  for (size_t o = 0; o < net.outs.size(); o++)
+    if (part_of_out[o] == part) {
+      OutRef r = net.outs[o];
+      if (r.val != NONE) r.val = local[r.val];
+      sub.outs.push_back(r);
+    }
+  return sub;
+}
+
 }  // namespace
 
 Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_regs, size_t n_out, uint32_t flags) {
@@ -885,6 +953,22 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
   lane.ok = false;
   if (!(flags & CLG_LV_NO_LANE_STREAM)) lane = schedule_lane(net);
 
+  // partitioned level streams for small batches of wide, separable programs (e.g. flattened instances)
+  ph.reset(new Phase("schedule: parts"));
+  std::vector<Sched> parts;
+  if (!(flags & CLG_LV_NO_PARTS) && n_luts >= 4096) {
+    std::vector<uint32_t> pv, po;
+    const uint32_t P = partition(net, 592, pv, po);
+    if (P > 1)
+      for (uint32_t q = 0; q < P; q++) {
+        parts.push_back(schedule_level(subnetwork(net, pv, po, q)));
+        if (!parts.back().ok) {
+          parts.clear();
+          break;
+        }
+      }
+  }
+
   // serialise
   ph.reset(new Phase("serialise"));
   Flat f;
@@ -904,6 +988,19 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
     st.off_levels = (uint32_t)off, off = align16(off + ss[i]->levels.size() * 4);
     st.off_instr = (uint32_t)off, off = align16(off + ss[i]->instr.size() * sizeof(FlatInstr));
   }
+  std::vector<FlatStream> part_tab(parts.size());
+  if (!parts.empty()) {
+    h.n_parts = (uint32_t)parts.size();
+    h.off_parts = (uint32_t)off, off = align16(off + parts.size() * sizeof(FlatStream));
+    for (size_t q = 0; q < parts.size(); q++) {
+      FlatStream &st = part_tab[q];
+      st = FlatStream{};
+      st.n_slots = parts[q].n_slots, st.n_instr = (uint32_t)parts[q].instr.size();
+      st.n_levels = (uint32_t)parts[q].levels.size() - 1, st.max_level_width = parts[q].max_width;
+      st.off_levels = (uint32_t)off, off = align16(off + parts[q].levels.size() * 4);
+      st.off_instr = (uint32_t)off, off = align16(off + parts[q].instr.size() * sizeof(FlatInstr));
+    }
+  }
   if (off >= 0xFFFFFFFFull) fail(CLG_E_UNSUPPORTED, "flat buffer exceeds 4 GiB");
   h.total_bytes = (uint32_t)off;
   f.bytes.assign(off, 0);
@@ -914,6 +1011,11 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
     if (!ss[i]->ok) continue;
     std::memcpy(f.bytes.data() + h.stream[i].off_levels, ss[i]->levels.data(), ss[i]->levels.size() * 4);
     std::memcpy(f.bytes.data() + h.stream[i].off_instr, ss[i]->instr.data(), ss[i]->instr.size() * sizeof(FlatInstr));
+  }
+  if (!parts.empty()) std::memcpy(f.bytes.data() + h.off_parts, part_tab.data(), part_tab.size() * sizeof(FlatStream));
+  for (size_t q = 0; q < parts.size(); q++) {
+    std::memcpy(f.bytes.data() + part_tab[q].off_levels, parts[q].levels.data(), parts[q].levels.size() * 4);
+    std::memcpy(f.bytes.data() + part_tab[q].off_instr, parts[q].instr.data(), parts[q].instr.size() * sizeof(FlatInstr));
   }
   return f;
 }
@@ -931,14 +1033,22 @@ void validate_flat(const Flat &f) {
   if (!span_ok(h.off_state_regs, (uint64_t)h.n_state * 8) || !span_ok(h.off_out_regs, (uint64_t)h.n_outputs * 8))
     bad("register tables out of range");
   const uint32_t n_in_rows = h.n_inputs + h.n_state, n_out_rows = h.n_outputs + h.n_state;
-  for (int s = 0; s < 2; s++) {
-    const FlatStream &st = h.stream[s];
+  if (h.n_parts && !span_ok(h.off_parts, (uint64_t)h.n_parts * sizeof(FlatStream))) bad("part table out of range");
+  // all output/state rows stored exactly... at most once across the parts of the partitioned form
+  std::vector<uint8_t> row_in_part(h.n_parts ? n_out_rows : 0, 0);
+  for (uint32_t sidx = 0; sidx < 2 + h.n_parts; sidx++) {
+    const int s = sidx < 2 ? (int)sidx : (int)STREAM_LEVEL;
+    const FlatStream &st = sidx < 2 ? h.stream[sidx] : f.parts()[sidx - 2];
     if (st.n_instr == 0) continue;
     if (!span_ok(st.off_levels, ((uint64_t)st.n_levels + 1) * 4) || !span_ok(st.off_instr, (uint64_t)st.n_instr * 16))
       bad("stream out of range");
     if (st.n_slots > 65536) bad("too many slots");
-    const uint32_t *lv = f.levels(s);
-    const FlatInstr *in = f.instrs(s);
+    const uint32_t *lv = reinterpret_cast<const uint32_t *>(f.bytes.data() + st.off_levels);
+    const FlatInstr *in = reinterpret_cast<const FlatInstr *>(f.bytes.data() + st.off_instr);
+    if (sidx >= 2)
+      for (uint32_t i = 0; i < st.n_instr; i++)
+        if ((in[i].kind == K_STOUT || in[i].kind == K_STCONST) && in[i].row < n_out_rows && row_in_part[in[i].row]++)
+          bad("an output row is stored by two parts");
     if (st.n_levels == 0 || lv[0] != 0 || lv[st.n_levels] != st.n_instr) bad("level table does not cover the stream");
     // a level is one hazard window; the lane stream is sequential, i.e. every instruction is its own window
     const bool seq = (s == STREAM_LANE);

@@ -157,6 +157,7 @@ const char *clg_compiler_graph_dot(const clg_compiler *c);
 #define CLG_LV_STATEFUL 1u
 #define CLG_LV_NO_FUSE 2u      /* keep one LUT per surviving NAND (no cone mapping) */
 #define CLG_LV_NO_LANE_STREAM 4u /* do not build the lane-ordered stream */
+#define CLG_LV_NO_PARTS 8u      /* do not build the partitioned (per connected component) level streams */
 
 typedef struct clg_flat clg_flat;
 int clg_levelize(const clg_simulation *sim, size_t n_immediates, const uint64_t *out_regs, size_t n_out,
@@ -180,6 +181,8 @@ typedef struct clg_flat_info {
   uint32_t lane_slots;  /* physical registers of the lane-ordered stream (0 if absent) */
   uint32_t level_instrs;
   uint32_t lane_instrs;
+  uint32_t n_parts; /* independent parts of the partitioned level stream (0: one component) */
+  uint32_t reserved;
 } clg_flat_info;
 int clg_flat_get_info(const clg_flat *f, clg_flat_info *info);
 /* registers behind the state rows, in row order (stateful programs) */

@@ -30,6 +30,13 @@ class Flat:
             instr = np.frombuffer(data, dtype=INSTR, count=n_instr, offset=off_instr) if n_instr else None
             self.streams.append(dict(n_slots=n_slots, n_instr=n_instr, n_levels=n_levels, levels=levels, instr=instr,
                                      max_level_width=max_w))
+        self.n_parts, self.off_parts = struct.unpack_from("<2I", data, 128)
+        self.parts = []
+        for q in range(self.n_parts):
+            n_slots, n_instr, n_levels, off_levels, off_instr, max_w = struct.unpack_from("<6I", data, self.off_parts + 32 * q)
+            self.parts.append(dict(n_slots=n_slots, n_instr=n_instr, n_levels=n_levels, max_level_width=max_w,
+                                   levels=np.frombuffer(data, dtype="<u4", count=n_levels + 1, offset=off_levels),
+                                   instr=np.frombuffer(data, dtype=INSTR, count=n_instr, offset=off_instr)))
         self.state_regs = np.frombuffer(data, dtype="<u8", count=self.n_state, offset=self.off_state_regs)
         self.out_regs = np.frombuffer(data, dtype="<u8", count=self.n_outputs, offset=self.off_out_regs)
 
@@ -45,13 +52,25 @@ def _lut(tt, a, b, c):
     return res
 
 
-def run(flat: Flat, stream: int, imm: np.ndarray, state: np.ndarray = None, rng=None):
+STREAM_PARTS = 2  # pseudo stream id: run every part of the partitioned level stream, one after the other
+
+
+def run(flat: Flat, stream: int, imm: np.ndarray, state: np.ndarray = None, rng=None, _part=None, _out=None):
     """imm [n_inputs][W]; state [n_state][W] is updated in place. Returns out [n_outputs][W]."""
-    st = flat.streams[stream]
-    assert st["n_instr"], "stream absent"
     W = imm.shape[1]
+    if stream == STREAM_PARTS:
+        assert flat.n_parts, "no partitioned stream"
+        out = np.zeros((flat.n_outputs, W), dtype=np.uint32)
+        order = list(range(flat.n_parts))
+        if rng is not None:
+            order = [int(x) for x in rng.permutation(flat.n_parts)]
+        for q in order:  # parts are independent: any order (the device runs them concurrently)
+            run(flat, STREAM_LEVEL, imm, state, rng, _part=flat.parts[q], _out=out)
+        return out
+    st = flat.streams[stream] if _part is None else _part
+    assert st["n_instr"], "stream absent"
     slots = np.zeros((st["n_slots"], W), dtype=np.uint32)
-    out = np.zeros((flat.n_outputs, W), dtype=np.uint32)
+    out = np.zeros((flat.n_outputs, W), dtype=np.uint32) if _out is None else _out
     ins, lv = st["instr"], st["levels"]
 
     def in_row(r):

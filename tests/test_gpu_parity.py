@@ -80,6 +80,22 @@ def test_dag_1m_gates_prefix():
     assert np.array_equal(got, oracle_out(circ, imm, nv))
 
 
+def test_partitioned_cooperative_launch():
+    """Small batches of separable programs run one CTA per (part, column group) -- every batch size from one vector up
+    to where the monolithic stream takes over -- and must agree with the oracle; NO_PARTS gives the same bits."""
+    base = circuits.array_multiplier(16)
+    circ = circuits.flatten_instances(base, 9)
+    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, mode=host.MODE_COOP)
+    assert cs.info["n_parts"] == 9
+    mono = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, mode=host.MODE_COOP,
+                                               flags=host.LV_NO_PARTS)
+    for nv in (1, 33, 128 * 3 + 5, 128 * 147, 128 * 149, 128 * 400):
+        imm = random_sliced(circ.n_immediates, stride_for(nv), seed=nv)
+        want = oracle_out(circ, imm, nv)
+        assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), want)
+        assert np.array_equal(mask_tail(mono.run_batch(imm, nv), nv), want)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_flattened_instances_single_vector(mode):
     """config 5 in miniature: independent multiplier instances flattened, ONE input vector."""

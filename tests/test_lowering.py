@@ -121,6 +121,26 @@ def test_flatten_instances():
         assert np.array_equal(got, mask_tail(want, nv))
 
 
+def test_partitioned_level_stream():
+    """Independent components (flattened instances) also come as separately scheduled parts for small batches."""
+    base = circuits.array_multiplier(16)
+    circ = circuits.flatten_instances(base, 7)
+    fp = host.FlatProgram.levelize(circ.sim, circ.n_immediates, circ.out_regs)
+    assert fp.info["n_parts"] == 7
+    flat = flat_interp.Flat(fp.to_bytes())
+    assert sum(p["n_instr"] for p in flat.parts) == flat.streams[0]["n_instr"]
+    nv = 100
+    imm = random_sliced(circ.n_immediates, stride_for(nv), seed=4)
+    want = mask_tail(oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs), nv)
+    got = mask_tail(flat_interp.run(flat, flat_interp.STREAM_PARTS, imm, rng=np.random.default_rng(1)), nv)
+    assert np.array_equal(got, want)
+    assert host.FlatProgram.levelize(circ.sim, circ.n_immediates, circ.out_regs, flags=host.LV_NO_PARTS).info["n_parts"] == 0
+    one = host.FlatProgram.levelize(base.sim, 32, base.out_regs)
+    assert one.info["n_parts"] == 0  # a single component has nothing to split
+    again = host.FlatProgram.from_bytes(fp.to_bytes())
+    assert again.info == fp.info
+
+
 def test_all_registers_observable_by_default():
     """out_regs=None: every register is read back (Simulation::registers is public, simulation.rs:11)."""
     c = host.Compiler(3)

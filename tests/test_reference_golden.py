@@ -197,3 +197,33 @@ def test_gate_nand_counts(capi):  # gates.rs:193-456: 1/1/2/3/4/6/11/16/8/19/76
     for gate, n in want:
         ops = gate.create(capi.Incrementer(100))
         assert len(ops) == n and all(o[0] == "Nand" for o in ops)
+
+
+# ---- the GUI's way of driving the Compiler (complogic-gui/src/app.rs:401-492, 529-556) -------------------------
+def test_compiler_reuse_pattern_of_the_gui(api):
+    """app.rs rebuilds the gate list when the graph changes: it bumps `immediate_count` directly (:410, :425), calls
+    reset_incrementer() (:429), allocates the And outputs, compiles, builds a Vec<bool> of length immediate_count
+    (:543-552) and runs. Recompiling with more immediates must renumber registers from scratch."""
+    c = api.Compiler(0)
+    gates = []
+    c.immediate_count += 1                      # an Immediate node appears
+    c.immediate_count += 1
+    c.reset_incrementer()
+    out1 = c.alloc()
+    gates.append(api.And(0, 1, out1))
+    sim = c.compile(gates)
+    assert len(sim.registers) == 4 and out1 == 2
+    sim.run([True, True]); assert sim.register(out1)
+    sim.run([False, True]); assert not sim.register(out1)
+    c.immediate_count += 1                      # a third immediate: everything is renumbered
+    c.reset_incrementer()
+    out1 = c.alloc()
+    out2 = c.alloc()
+    gates = [api.And(0, 1, out1), api.And(out1, 2, out2)]
+    sim = c.compile(gates)
+    assert (out1, out2) == (3, 4) and len(sim.registers) == 7
+    for a in (False, True):
+        for b in (False, True):
+            for d in (False, True):
+                sim.run([a, b, d])
+                assert sim.register(out2) is (a and b and d)
