@@ -319,6 +319,14 @@ def main():
                     "traffic": None,
                     "peak_source": f"nominal 148 SM x 64 LOP3 lanes/clk x {sm_max_mhz:.0f} MHz; measured pure-LOP3 kernel: "
                                    f"{lop3_measured / 1e12:.2f} T lane-op/s"}
+    try:  # measured DRAM traffic of this kernel from the committed ncu capture, scaled to this batch size
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f).get(args.workload)
+        if tr and tr["kernel"].startswith("clg_" + cs.mode_name):
+            roofline["traffic"] = tr["dram_bytes"] * (w["nv"] / tr["profiled_vectors"])
+            roofline["traffic_source"] = f"ncu capture at {tr['profiled_vectors']} vectors, scaled by batch size"
+    except Exception:
+        pass
     roofline.update({
         "kernel": f"clg_{cs.mode_name}" + (f"_k{cs.words_per_thread}" if cs.mode_name != "spec" else f" (K={cs.words_per_thread})"),
         "algorithmic_lane_ops_per_launch": lane_ops, "issued_lop3_lane_ops_per_launch": issued_lane_ops,

@@ -81,7 +81,7 @@ struct Ctx {
   CUcontext cu = nullptr;
   CUmodule mod = nullptr;
   int sm_count = 0;
-  CUfunction lane[3] = {}, coop[3] = {}, slice = nullptr, unslice = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, slice = nullptr, unslice = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
   std::string name;
 
   explicit Ctx(int device) {
@@ -110,6 +110,8 @@ struct Ctx {
       CU(cuModuleGetFunction(&coop[i], mod, (std::string("clg_coop_k") + ks[i]).c_str()));
       CU(cuFuncSetAttribute(lane[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
       CU(cuFuncSetAttribute(coop[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
+      CU(cuModuleGetFunction(&coop_res[i], mod, (std::string("clg_coop_res_k") + ks[i]).c_str()));
+      CU(cuFuncSetAttribute(coop_res[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
     }
     CU(cuModuleGetFunction(&slice, mod, "clg_slice"));
     CU(cuModuleGetFunction(&unslice, mod, "clg_unslice"));
@@ -157,8 +159,9 @@ struct Plan {
   bool ready = false;
   int K = 0;
   CUdeviceptr d_instr = 0, d_levels = 0, d_parts = 0;
-  uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0, n_parts = 0;
+  uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0, n_parts = 0, code_off = 0;
   size_t smem = 0;
+  bool resident = false;  // cooperative: the (largest part's) instruction stream is staged in shared memory
   CUmodule spec_mod = nullptr;
   CUfunction spec_fn = nullptr;
   std::string ptx;
@@ -253,6 +256,12 @@ struct Exec {
       if ((size_t)slots * k * 4 <= SMEM_MAX) return k;
     return 0;
   }
+  // keep the instruction stream in shared memory behind the stack when it fits: [stack | mbarrier | instructions]
+  static void make_resident(Plan &P, uint32_t n_instr, uint32_t n_levels) {
+    const size_t code_off = (P.smem + 127) / 128 * 128;
+    const size_t need = code_off + 16 + ((size_t)n_levels + 1 + 3) / 4 * 16 + (size_t)n_instr * 16;
+    if (need <= SMEM_MAX) P.resident = true, P.code_off = (uint32_t)code_off, P.smem = need;
+  }
   Plan &get_parts() {
     Plan &P = plan[PLAN_PARTS];
     if (P.ready) return P;
@@ -266,10 +275,15 @@ struct Exec {
     for (uint32_t q = 0; q < h.n_parts; q++) {
       const FlatStream &st = flat.parts()[q];
       P.n_slots = std::max(P.n_slots, st.n_slots), width = std::max(width, st.max_level_width);
-      total_instr += st.n_instr, total_levels += st.n_levels + 1;
+      total_instr += st.n_instr, total_levels += (st.n_levels + 1 + 3) / 4 * 4;
     }
     P.smem = std::max<size_t>((size_t)P.n_slots * P.K * 4, 16);
     P.coop_threads = std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (width + 31u) / 32u * 32u));
+    uint32_t biggest = 0;
+    for (uint32_t q = 0; q < h.n_parts; q++) biggest = std::max(biggest, flat.parts()[q].n_instr);
+    uint32_t deepest = 0;
+    for (uint32_t q = 0; q < h.n_parts; q++) deepest = std::max(deepest, flat.parts()[q].n_levels);
+    make_resident(P, biggest, deepest);
     std::vector<uint32_t> enc(total_instr * 4), lv(total_levels), desc((size_t)h.n_parts * 4);
     size_t io = 0, lo = 0;
     for (uint32_t q = 0; q < h.n_parts; q++) {
@@ -277,7 +291,7 @@ struct Exec {
       encode_stream(flat.part_instrs(q), st.n_instr, (uint32_t)P.K * 4, enc.data() + io * 4);
       std::memcpy(lv.data() + lo, flat.part_levels(q), ((size_t)st.n_levels + 1) * 4);
       desc[q * 4 + 0] = (uint32_t)io, desc[q * 4 + 1] = (uint32_t)lo, desc[q * 4 + 2] = st.n_levels, desc[q * 4 + 3] = 0;
-      io += st.n_instr, lo += st.n_levels + 1;
+      io += st.n_instr, lo += (st.n_levels + 1 + 3) / 4 * 4;
     }
     P.n_instr = (uint32_t)total_instr;
     CU(cuMemAlloc(&P.d_instr, std::max<size_t>(16, enc.size() * 4)));
@@ -313,6 +327,7 @@ struct Exec {
         st = &lv, sidx = STREAM_LEVEL;
         P.smem = std::max<size_t>((size_t)lv.n_slots * P.K * 4, 16);
         P.coop_threads = coop_threads_for(lv);
+        make_resident(P, lv.n_instr, lv.n_levels);
         break;
       default: fail(CLG_E_INVALID, "unknown execution mode");
     }
@@ -325,7 +340,7 @@ struct Exec {
       encode_stream(flat.instrs(sidx), P.n_instr, slot_bytes, enc.data());
       CU(cuMemAlloc(&P.d_instr, std::max<size_t>(16, (size_t)P.n_instr * 16)));
       CU(cuMemcpyHtoDAsync(P.d_instr, enc.data(), (size_t)P.n_instr * 16, nullptr));
-      CU(cuMemAlloc(&P.d_levels, ((size_t)P.n_levels + 1) * 4));
+      CU(cuMemAlloc(&P.d_levels, ((size_t)P.n_levels + 1 + 3) / 4 * 16));  // padded: the resident kernel bulk-copies it
       CU(cuMemcpyHtoDAsync(P.d_levels, flat.levels(sidx), ((size_t)P.n_levels + 1) * 4, nullptr));
       CU(cuStreamSynchronize(nullptr));
     } else {
@@ -482,7 +497,7 @@ struct Exec {
     p.n_inputs = h.n_inputs, p.n_outputs = h.n_outputs;
     p.n_instr = P.n_instr, p.n_levels = P.n_levels, p.n_slots = P.n_slots;
     p.stride = (uint32_t)stride, p.n_groups = groups;
-    p.parts = (const void *)P.d_parts, p.n_parts = P.n_parts;
+    p.parts = (const void *)P.d_parts, p.n_parts = P.n_parts, p.code_off = P.code_off;
     void *args[] = {&p};
     if (mode == CLG_MODE_LANE) {
       const uint32_t grid = (groups + LANE_THREADS - 1) / LANE_THREADS;
@@ -494,7 +509,8 @@ struct Exec {
         const uint32_t slots_g = std::max<uint32_t>(1u, std::min<uint32_t>(groups, ((uint32_t)ctx->sm_count * (uint32_t)per_sm + P.n_parts - 1) / P.n_parts));
         grid = P.n_parts * slots_g;
       }
-      CU(cuLaunchKernel(ctx->coop[kidx(K)], grid, 1, 1, P.coop_threads, 1, 1, (unsigned)P.smem, stream, args, nullptr));
+      CU(cuLaunchKernel(P.resident ? ctx->coop_res[kidx(K)] : ctx->coop[kidx(K)], grid, 1, 1, P.coop_threads, 1, 1, (unsigned)P.smem,
+                        stream, args, nullptr));
     }
   }
 };

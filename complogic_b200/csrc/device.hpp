@@ -26,6 +26,7 @@ struct RunParams {
   uint32_t n_groups;
   const void *parts;
   uint32_t n_parts;
+  uint32_t code_off;
 };
 
 constexpr int LANE_THREADS = 128;

@@ -49,6 +49,7 @@ struct RunParams {
   uint32_t n_groups;  // K-word column groups to evaluate
   const uint4 *parts;  // coop, partitioned form: one descriptor per part {instr offset, levels offset, n_levels, -}
   uint32_t n_parts;    // 0: the program is one part (instr / levels / n_levels above)
+  uint32_t code_off;   // coop, resident form: byte offset in shared memory of {mbarrier, staged instructions}
 };
 
 // ---- LOP3 with a compile-time immediate, dispatched on the instruction's truth table --------------
@@ -321,7 +322,37 @@ __device__ __forceinline__ uint4 ld_instr(const uint4 *p) {
   return v;
 }
 
+// One instruction of the cooperative kernel, executed by one lane on the CTA's shared register stack.
 template <int K>
+__device__ __forceinline__ void coop_exec(const RunParams &p, const uint4 ins, uint32_t sb, size_t col) {
+  const uint32_t kind = ins.y >> 28;
+  if (kind <= D_LUT1) {
+    const Vec<K> a = lds<K>(sb + (ins.x & 0xFFFFFFu));
+    Vec<K> b = dont_care<K>(), cc = dont_care<K>();
+    if (kind <= D_LUT2) b = lds<K>(sb + (ins.y & 0xFFFFFFu));
+    if (kind == D_LUT3) cc = lds<K>(sb + ins.z);
+    sts<K>(sb + ins.w, lut3<K, false>(ins.x >> 24, a, b, cc));
+  } else if (kind == D_LDIN) {
+    sts<K>(sb + ins.w, ld_input<K>(p, ins.z, col));
+  } else {
+    Vec<K> v;
+    const uint32_t m = (ins.y & (1u << 24)) ? 0xFFFFFFFFu : 0u;
+    if (kind == D_STOUT) {
+      v = lds<K>(sb + (ins.x & 0xFFFFFFu));
+#pragma unroll
+      for (int k = 0; k < K; k++) v.w[k] ^= m;
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; k++) v.w[k] = m;
+    }
+    st_row<K>(out_row(p, ins.z) + col, v);
+  }
+}
+
+// RESIDENT: the CTA's whole instruction stream (its part's, in the partitioned form) fits in shared memory next to
+// the register stack. It is staged there once with cp.async.bulk and every fetch is a conflict-free LDS.128
+// (~30 cycles) instead of an L2 round trip (~700): what a narrow, deep program on few vectors is bound by.
+template <int K, bool RESIDENT>
 __device__ __forceinline__ void coop_body(const RunParams &p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t tid = threadIdx.x, nt = blockDim.x;
@@ -339,6 +370,34 @@ __device__ __forceinline__ void coop_body(const RunParams &p) {
     g0 = blockIdx.x / p.n_parts, gstep = gridDim.x / p.n_parts;
   }
 
+  if constexpr (RESIDENT) {
+    // stage this CTA's level table and instructions behind the register stack: [stack | mbarrier | levels | code]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + p.code_off);
+    const uint32_t lv_bytes = (n_levels + 1 + 3) / 4 * 16;  // level table, padded to 16 bytes
+    const uint32_t *slv = reinterpret_cast<const uint32_t *>(smem + p.code_off + 16);
+    uint4 *code = reinterpret_cast<uint4 *>(smem + p.code_off + 16 + lv_bytes);
+    const uint32_t n_instr = __ldg(levels + n_levels);  // level tables start at 0 and end at the part's size
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(bar, n_instr * 16 + lv_bytes);
+      bulk_g2s(const_cast<uint32_t *>(slv), levels, lv_bytes, bar);  // (tables are padded to 16 B on the device)
+      for (uint32_t o = 0; o < n_instr; o += 2048)  // 32 KiB per bulk copy
+        bulk_g2s(code + o, instr + o, min(2048u, n_instr - o) * 16, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    for (uint32_t g = g0; g < p.n_groups; g += gstep) {
+      const size_t col = (size_t)g * K;
+      uint32_t lb = slv[0];
+      for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t le = slv[l + 1];
+        for (uint32_t i = lb + tid; i < le; i += nt) coop_exec<K>(p, code[i], sb, col);
+        lb = le;
+        __syncthreads();
+      }
+    }
+  } else {
   for (uint32_t g = g0; g < p.n_groups; g += gstep) {
     const size_t col = (size_t)g * K;
     uint32_t lb = __ldg(levels), le = __ldg(levels + 1);
@@ -355,28 +414,7 @@ __device__ __forceinline__ void coop_body(const RunParams &p) {
         const uint32_t nexti = i + nt;
         uint4 nxt = make_uint4(0, 0, 0, 0);
         if (nexti < le) nxt = ld_instr(instr + nexti);  // software prefetch of the next instruction
-        const uint32_t kind = ins.y >> 28;
-        if (kind <= D_LUT1) {
-          const Vec<K> a = lds<K>(sb + (ins.x & 0xFFFFFFu));
-          Vec<K> b = dont_care<K>(), cc = dont_care<K>();
-          if (kind <= D_LUT2) b = lds<K>(sb + (ins.y & 0xFFFFFFu));
-          if (kind == D_LUT3) cc = lds<K>(sb + ins.z);
-          sts<K>(sb + ins.w, lut3<K, false>(ins.x >> 24, a, b, cc));
-        } else if (kind == D_LDIN) {
-          sts<K>(sb + ins.w, ld_input<K>(p, ins.z, col));
-        } else {
-          Vec<K> v;
-          const uint32_t m = (ins.y & (1u << 24)) ? 0xFFFFFFFFu : 0u;
-          if (kind == D_STOUT) {
-            v = lds<K>(sb + (ins.x & 0xFFFFFFu));
-#pragma unroll
-            for (int k = 0; k < K; k++) v.w[k] ^= m;
-          } else {
-#pragma unroll
-            for (int k = 0; k < K; k++) v.w[k] = m;
-          }
-          st_row<K>(out_row(p, ins.z) + col, v);
-        }
+        coop_exec<K>(p, ins, sb, col);
         ins = nxt;
         i = nexti;
       }
@@ -384,6 +422,7 @@ __device__ __forceinline__ void coop_body(const RunParams &p) {
       ins = first_next;
       __syncthreads();  // level boundary: every slot written in this level is visible to the next
     }
+  }
   }
 }
 
@@ -464,7 +503,8 @@ extern "C" __global__ void __launch_bounds__(512) clg_lop3_peak(const uint32_t *
   extern "C" __global__ void __launch_bounds__(clg::LANE_THREADS + 32) clg_lane_k##K(const clg::RunParams p) { \
     clg::lane_body<K>(p);                                                                                      \
   }                                                                                                            \
-  extern "C" __global__ void __launch_bounds__(1024) clg_coop_k##K(const clg::RunParams p) { clg::coop_body<K>(p); }
+  extern "C" __global__ void __launch_bounds__(1024) clg_coop_k##K(const clg::RunParams p) { clg::coop_body<K, false>(p); } \
+  extern "C" __global__ void __launch_bounds__(1024) clg_coop_res_k##K(const clg::RunParams p) { clg::coop_body<K, true>(p); }
 CLG_ENTRY(1)
 CLG_ENTRY(2)
 CLG_ENTRY(4)

@@ -571,9 +571,17 @@ Sched schedule_level(const Network &net) {
       }
     }
   }
-  // loads: one level before the first reader (a load read only by a store sits at level 0)
+  // loads: a level that contains a global load cannot end before the data is back (~1 us), so loads are not
+  // sprinkled one level before their first reader: a stream with few input rows loads them all at level 0, a
+  // stream with many batches them every 16 levels (the latency is paid once per batch, the extra live registers
+  // are bounded by 16 levels' worth of inputs).
+  size_t n_loads = 0;
+  for (size_t v = 0; v < V; v++) n_loads += !net.vals[v].is_lut;
   for (size_t v = 0; v < V; v++)
-    if (!net.vals[v].is_lut) lev[v] = (ub[v] == NONE) ? 0 : ub[v];
+    if (!net.vals[v].is_lut) {
+      const uint32_t alap = (ub[v] == NONE) ? 0 : ub[v];
+      lev[v] = n_loads <= 2048 ? 0 : alap / 16 * 16;
+    }
   std::vector<uint32_t> state_in_lev(net.n_state, NONE);
   for (size_t v = 0; v < V; v++)
     if (!net.vals[v].is_lut && net.vals[v].row >= net.n_inputs) state_in_lev[net.vals[v].row - net.n_inputs] = lev[v];
