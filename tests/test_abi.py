@@ -100,3 +100,47 @@ def test_spec_ptx_assembles_for_sm100a(tmp_path):
         n_lop3 = sass.count("LOP3.LUT")
         assert n_lop3 >= fp.info["n_luts"] * k  # one LOP3 per LUT per word (+ inverted stores)
         assert (".128" in sass) if k == 4 else True
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary must be bindable from C (and so from Rust/Go/... FFI): the header compiles as strict C99."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "complogic_cuda.h"\nint main(void) { clg_op op = {CLG_OP_NAND, 0, 0, 1, 2}; '
+                   'return (int)(op.c - 2) + (int)sizeof(clg_gate) - 112 + (int)sizeof(clg_op) - 32; }\n')
+    exe = tmp_path / "t"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def _build_demo(tmp_path):
+    import subprocess
+    exe = tmp_path / "adder_demo"
+    libdir = os.path.join(ROOT, "complogic_b200")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "adder_demo.cpp"),
+                        "-L", libdir, "-lcomplogic_cuda", f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_host_links_against_the_abi(tmp_path):
+    """examples/adder_demo.cpp drives the whole path from C++ through the C ABI only; without a GPU it must stop at
+    clg_ctx_create with the no-driver error (after compiling and levelizing on the host)."""
+    import subprocess
+    exe = _build_demo(tmp_path)
+    r = subprocess.run([str(exe), "8", "100"], capture_output=True, text=True)
+    assert "adder8: 169 ops (152 NAND), 169 registers" in r.stdout
+    assert "levelized: 16 LOP3 for 152 NAND" in r.stdout
+    if not os.path.exists("/dev/nvidiactl"):
+        assert r.returncode == 1 and "no CPU execution path" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_runs_on_the_gpu(tmp_path):
+    import subprocess
+    exe = _build_demo(tmp_path)
+    r = subprocess.run([str(exe), "32", "200000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "200000 vectors on the GPU" in r.stdout and ": 0 mismatches" in r.stdout
