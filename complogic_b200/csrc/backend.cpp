@@ -208,6 +208,7 @@ struct Exec {
     return 0;
   }
   static uint32_t coop_threads_for(const FlatStream &lv) {
+    if (const char *env = std::getenv("CLG_COOP_THREADS")) return std::max(32, std::atoi(env)) / 32 * 32;  // tuning knob
     return std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (lv.max_level_width + 31u) / 32u * 32u));
   }
 
