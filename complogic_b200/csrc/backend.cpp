@@ -81,7 +81,7 @@ struct Ctx {
   CUcontext cu = nullptr;
   CUmodule mod = nullptr;
   int sm_count = 0;
-  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, slice = nullptr, unslice = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, slice = nullptr, unslice = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
   std::string name;
 
   explicit Ctx(int device) {
@@ -110,6 +110,8 @@ struct Ctx {
       CU(cuModuleGetFunction(&coop[i], mod, (std::string("clg_coop_k") + ks[i]).c_str()));
       CU(cuFuncSetAttribute(lane[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
       CU(cuFuncSetAttribute(coop[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
+      CU(cuModuleGetFunction(&coop_c[i], mod, (std::string("clg_coop_c_k") + ks[i]).c_str()));
+      CU(cuFuncSetAttribute(coop_c[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
       CU(cuModuleGetFunction(&coop_res[i], mod, (std::string("clg_coop_res_k") + ks[i]).c_str()));
       CU(cuFuncSetAttribute(coop_res[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
     }
@@ -158,7 +160,7 @@ static void encode_stream(const FlatInstr *src, uint32_t n, uint32_t slot_bytes,
 struct Plan {
   bool ready = false;
   int K = 0;
-  CUdeviceptr d_instr = 0, d_levels = 0, d_parts = 0;
+  CUdeviceptr d_instr = 0, d_levels = 0, d_parts = 0, d_cinstr = 0, d_clevels = 0;  // (compact cooperative form)
   uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0, n_parts = 0, code_off = 0;
   size_t smem = 0;
   bool resident = false;  // cooperative: the (largest part's) instruction stream is staged in shared memory
@@ -339,8 +341,37 @@ struct Exec {
       if ((uint64_t)P.n_slots * slot_bytes >= (1u << 24)) fail(CLG_E_UNSUPPORTED, "register stack exceeds the 24-bit offset field");
       std::vector<uint32_t> enc((size_t)P.n_instr * 4);
       encode_stream(flat.instrs(sidx), P.n_instr, slot_bytes, enc.data());
-      CU(cuMemAlloc(&P.d_instr, std::max<size_t>(16, (size_t)P.n_instr * 16)));
-      CU(cuMemcpyHtoDAsync(P.d_instr, enc.data(), (size_t)P.n_instr * 16, nullptr));
+      if (m == CLG_MODE_COOP && !P.resident && P.n_slots <= 16383 && !std::getenv("CLG_COOP_WIDE")) {
+        // compact form: LUTs as 8 bytes (slot indices), everything else stays 16 bytes in a per-level side list
+        const FlatInstr *src = flat.instrs(sidx);
+        const uint32_t *lvl = flat.levels(sidx);
+        std::vector<uint32_t> cenc, menc, clv(2 * ((size_t)P.n_levels + 1));
+        cenc.reserve((size_t)P.n_instr * 2);
+        for (uint32_t l = 0; l < P.n_levels; l++) {
+          clv[l] = (uint32_t)(cenc.size() / 2), clv[P.n_levels + 1 + l] = (uint32_t)(menc.size() / 4);
+          for (uint32_t i = lvl[l]; i < lvl[l + 1]; i++) {
+            const FlatInstr &x = src[i];
+            if (x.kind == K_LUT) {
+              const int nf = lut_nfan(x);
+              const uint32_t b = nf >= 2 ? x.b : 0x3FFFu, c = nf >= 3 ? x.c : 0x3FFFu;
+              cenc.push_back(x.a | b << 14 | (uint32_t)(x.tt & 15) << 28);
+              cenc.push_back(c | (uint32_t)x.dst << 14 | (uint32_t)(x.tt >> 4) << 28);
+            } else {
+              menc.insert(menc.end(), &enc[(size_t)i * 4], &enc[(size_t)i * 4 + 4]);
+            }
+          }
+        }
+        clv[P.n_levels] = (uint32_t)(cenc.size() / 2), clv[2 * (size_t)P.n_levels + 1] = (uint32_t)(menc.size() / 4);
+        CU(cuMemAlloc(&P.d_cinstr, std::max<size_t>(16, cenc.size() * 4)));
+        CU(cuMemcpyHtoDAsync(P.d_cinstr, cenc.data(), cenc.size() * 4, nullptr));
+        CU(cuMemAlloc(&P.d_clevels, clv.size() * 4));
+        CU(cuMemcpyHtoDAsync(P.d_clevels, clv.data(), clv.size() * 4, nullptr));
+        CU(cuStreamSynchronize(nullptr));
+        enc.swap(menc);  // `instr` now holds only the side list
+        enc.resize(std::max<size_t>(enc.size(), 4));
+      }
+      CU(cuMemAlloc(&P.d_instr, std::max<size_t>(16, enc.size() * 4)));
+      CU(cuMemcpyHtoDAsync(P.d_instr, enc.data(), enc.size() * 4, nullptr));
       CU(cuMemAlloc(&P.d_levels, ((size_t)P.n_levels + 1 + 3) / 4 * 16));  // padded: the resident kernel bulk-copies it
       CU(cuMemcpyHtoDAsync(P.d_levels, flat.levels(sidx), ((size_t)P.n_levels + 1) * 4, nullptr));
       CU(cuStreamSynchronize(nullptr));
@@ -364,6 +395,8 @@ struct Exec {
       if (P.d_instr) d.cuMemFree(P.d_instr);
       if (P.d_levels) d.cuMemFree(P.d_levels);
       if (P.d_parts) d.cuMemFree(P.d_parts);
+      if (P.d_cinstr) d.cuMemFree(P.d_cinstr);
+      if (P.d_clevels) d.cuMemFree(P.d_clevels);
       if (P.spec_mod) d.cuModuleUnload(P.spec_mod);
     }
     for (int b = 0; b < NBUF; b++) {
@@ -499,6 +532,7 @@ struct Exec {
     p.n_instr = P.n_instr, p.n_levels = P.n_levels, p.n_slots = P.n_slots;
     p.stride = (uint32_t)stride, p.n_groups = groups;
     p.parts = (const void *)P.d_parts, p.n_parts = P.n_parts, p.code_off = P.code_off;
+    p.cinstr = (const void *)P.d_cinstr, p.clevels = (const uint32_t *)P.d_clevels;
     void *args[] = {&p};
     if (mode == CLG_MODE_LANE) {
       const uint32_t grid = (groups + LANE_THREADS - 1) / LANE_THREADS;
@@ -510,7 +544,7 @@ struct Exec {
         const uint32_t slots_g = std::max<uint32_t>(1u, std::min<uint32_t>(groups, ((uint32_t)ctx->sm_count * (uint32_t)per_sm + P.n_parts - 1) / P.n_parts));
         grid = P.n_parts * slots_g;
       }
-      CU(cuLaunchKernel(P.resident ? ctx->coop_res[kidx(K)] : ctx->coop[kidx(K)], grid, 1, 1, P.coop_threads, 1, 1, (unsigned)P.smem,
+      CU(cuLaunchKernel(P.resident ? ctx->coop_res[kidx(K)] : P.d_cinstr ? ctx->coop_c[kidx(K)] : ctx->coop[kidx(K)], grid, 1, 1, P.coop_threads, 1, 1, (unsigned)P.smem,
                         stream, args, nullptr));
     }
   }

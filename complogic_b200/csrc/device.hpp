@@ -27,6 +27,8 @@ struct RunParams {
   const void *parts;
   uint32_t n_parts;
   uint32_t code_off;
+  const void *cinstr;
+  const uint32_t *clevels;
 };
 
 constexpr int LANE_THREADS = 128;

@@ -50,6 +50,12 @@ struct RunParams {
   const uint4 *parts;  // coop, partitioned form: one descriptor per part {instr offset, levels offset, n_levels, -}
   uint32_t n_parts;    // 0: the program is one part (instr / levels / n_levels above)
   uint32_t code_off;   // coop, resident form: byte offset in shared memory of {mbarrier, staged instructions}
+  // coop, compact form (<= 16383 slots): LUT instructions as 8 bytes each,
+  //   x = a | b << 14 | (tt & 15) << 28      y = c | dst << 14 | (tt >> 4) << 28      (slot indices; 0x3FFF = operand not read)
+  // with per-level offsets clevels[0..n_levels] into cinstr, followed by clevels[n_levels+1 ..] into `instr`, which then
+  // holds only the (rare) non-LUT instructions of each level in the 16-byte encoding.
+  const uint2 *cinstr;
+  const uint32_t *clevels;
 };
 
 // ---- LOP3 with a compile-time immediate, dispatched on the instruction's truth table --------------
@@ -426,6 +432,60 @@ __device__ __forceinline__ void coop_body(const RunParams &p) {
   }
 }
 
+// Compact streaming form of the cooperative kernel: half the instruction bytes through the LSU pipe and L2.
+__device__ __forceinline__ uint2 ld_cinstr(const uint2 *p) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
+template <int K>
+__device__ __forceinline__ void coop_exec_compact(const uint2 ins, uint32_t sb) {
+  constexpr int SH = K == 4 ? 4 : K == 2 ? 3 : 2;  // slot index -> byte offset
+  constexpr uint32_t M = 0x3FFFu << SH;
+  const uint32_t oa = (ins.x << SH) & M, ob = (ins.x >> (14 - SH)) & M, oc = (ins.y << SH) & M, od = (ins.y >> (14 - SH)) & M;
+  const uint32_t tt = (ins.x >> 28) | ((ins.y >> 28) << 4);
+  const Vec<K> a = lds<K>(sb + oa);
+  Vec<K> b = dont_care<K>(), c = dont_care<K>();
+  if (ob != M) b = lds<K>(sb + ob);
+  if (oc != M) c = lds<K>(sb + oc);
+  sts<K>(sb + od, lut3<K, false>(tt, a, b, c));
+}
+
+template <int K>
+__device__ __forceinline__ void coop_compact_body(const RunParams &p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t tid = threadIdx.x, nt = blockDim.x, nl = p.n_levels;
+  uint32_t sb = smem_u32(smem);
+  asm volatile("" : "+r"(sb));
+  const uint32_t *lv = p.clevels, *mv = p.clevels + nl + 1;
+  const uint2 zero = make_uint2(0x0FFFFFFFu, 0);  // (never executed: only assigned where i >= le)
+  for (uint32_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+    const size_t col = (size_t)g * K;
+    uint32_t lb = __ldg(lv), le = __ldg(lv + 1), mb = __ldg(mv);
+    uint2 ins = zero;
+    if (lb + tid < le) ins = ld_cinstr(p.cinstr + lb + tid);
+    for (uint32_t l = 0; l < nl; l++) {
+      const uint32_t le2 = __ldg(lv + min(l + 2, nl)), me = __ldg(mv + l + 1);
+      uint2 first_next = zero;
+      if (le + tid < le2) first_next = ld_cinstr(p.cinstr + le + tid);  // next level's first instruction, early
+      uint32_t i = lb + tid;
+      while (i < le) {
+        const uint32_t nexti = i + nt;
+        uint2 nxt = zero;
+        if (nexti < le) nxt = ld_cinstr(p.cinstr + nexti);  // software prefetch
+        coop_exec_compact<K>(ins, sb);
+        ins = nxt;
+        i = nexti;
+      }
+      for (uint32_t j = mb + tid; j < me; j += nt) coop_exec<K>(p, ld_instr(p.instr + j), sb, col);  // loads / stores
+      lb = le, le = le2, mb = me;
+      ins = first_next;
+      __syncthreads();
+    }
+  }
+}
+
 // ---- layout helpers ----------------------------------------------------------------------------------
 // bools [n_vectors][n_rows] bytes (one run()'s `&[bool]` per vector)  ->  sliced [n_rows][stride] words
 extern "C" __global__ void __launch_bounds__(256) clg_slice(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows,
@@ -504,7 +564,8 @@ extern "C" __global__ void __launch_bounds__(512) clg_lop3_peak(const uint32_t *
     clg::lane_body<K>(p);                                                                                      \
   }                                                                                                            \
   extern "C" __global__ void __launch_bounds__(1024) clg_coop_k##K(const clg::RunParams p) { clg::coop_body<K, false>(p); } \
-  extern "C" __global__ void __launch_bounds__(1024) clg_coop_res_k##K(const clg::RunParams p) { clg::coop_body<K, true>(p); }
+  extern "C" __global__ void __launch_bounds__(1024) clg_coop_res_k##K(const clg::RunParams p) { clg::coop_body<K, true>(p); } \
+  extern "C" __global__ void __launch_bounds__(1024) clg_coop_c_k##K(const clg::RunParams p) { clg::coop_compact_body<K>(p); }
 CLG_ENTRY(1)
 CLG_ENTRY(2)
 CLG_ENTRY(4)
