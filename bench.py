@@ -51,6 +51,8 @@ def build_workload(name: str, api=None):
 
     if name == "dag1m":
         return circuits.random_dag(256, 4096, 1024, 2, 1, api=api), 24, 0xDA6
+    if name == "dag1m_kinf":
+        return circuits.random_dag(256, 4096, 1024, 0, 1, api=api), 24, 0xDA7
     if name == "mul16":
         return circuits.array_multiplier(16, api=api), 26, 0xC0FFEF
     if name == "adder32":
@@ -66,6 +68,8 @@ def build_workload(name: str, api=None):
 WORKLOAD_DESC = {
     "dag1m": "synthetic random levelized NAND DAG, 1 048 576 gates (256 levels x 4096), 1024 immediates, window K=2, "
              "4096 outputs (BASELINE configs[3])",
+    "dag1m_kinf": "the same random levelized DAG with no locality window (K = infinity: inputs drawn from ALL earlier levels); "
+                  "most of its 1 048 576 gates cannot reach the 4096 outputs and are eliminated by the pass",
     "mul16": "16x16 array multiplier, 4 896 NANDs with the reference's gate expansions (BASELINE configs[2])",
     "adder32": "32-bit ripple-carry adder, 608 NANDs (BASELINE configs[1])",
     "adder8": "8-bit ripple-carry adder, 152 NANDs (BASELINE configs[0])",

@@ -554,7 +554,7 @@ Sched schedule_lane(const Network &net) {
 // level before their first reader, stores one level after their producer. A slot freed by its
 // last reader in level L is handed out again from level L + 1 on: within a level other threads may
 // still be reading it.
-Sched schedule_level(const Network &net) {
+Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
   const size_t V = net.vals.size(), O = net.outs.size();
   std::vector<uint32_t> lev(V, 0);
   for (size_t v = 0; v < V; v++)
@@ -620,22 +620,24 @@ Sched schedule_level(const Network &net) {
   for (size_t o = 0; o < O; o++) items[fill[olev[o]]++] = (uint32_t)(V + o);
 
   // ---- emission: bank-aware order, operand placement and slot choice -------------------------------------
-  // The cooperative kernel keeps the stack as [slot][4 words]: a slot is 16 bytes, 8 consecutive slots span
-  // the 32 banks, and an LDS.128/STS.128 is served one quarter-warp (8 lanes = 8 consecutive instructions of
+  // The cooperative kernel keeps the stack as [slot][K words]. At K = 4 a slot is 16 bytes, 8 consecutive slots
+  // span the 32 banks, and an LDS.128/STS.128 is served one quarter-warp (8 lanes = 8 consecutive instructions of
   // the level) at a time. A quarter is conflict-free iff its 8 addresses fall in 8 different 16-byte bank
   // groups, i.e. slot % 8 all different -- separately for operand a, b, c and the destination, since each is
-  // its own LDS/STS. Three degrees of freedom are used: which 8 instructions share a quarter (greedy packing
+  // its own LDS/STS. (K = 2: half-warps and slot % 16; K = 1: whole warps and slot % 32 -- BANKS below. The
+  // caller picks BANKS for the K the register stack will fit shared memory with.) Three degrees of freedom are used: which 8 instructions share a quarter (greedy packing
   // from a window of candidates), which operand sits in which position (LUT inputs commute if the truth table
   // is permuted with them), and which free slot a result takes (one bank group per quarter member).
-  constexpr uint32_t BANKS = 8, WINDOW = 2048;
+  constexpr uint32_t WINDOW = 2048, MAX_BANKS = 32;
   Sched s;
   s.instr.resize(V + O);
   s.levels.assign(cnt.begin(), cnt.end());
   struct BankPool {
-    std::vector<uint32_t> free_[BANKS];
-    uint32_t fresh[BANKS];
+    uint32_t BANKS;
+    std::vector<uint32_t> free_[MAX_BANKS];
+    uint32_t fresh[MAX_BANKS];
     uint32_t high = 0;
-    BankPool() {
+    explicit BankPool(uint32_t nb) : BANKS(nb) {
       for (uint32_t b = 0; b < BANKS; b++) fresh[b] = b;
     }
     bool has_free(uint32_t b) const { return !free_[b].empty(); }
@@ -647,7 +649,7 @@ Sched schedule_level(const Network &net) {
       return sl;
     }
     void put(uint32_t sl) { free_[sl % BANKS].push_back(sl); }
-  } pool;
+  } pool(BANKS);
   std::vector<uint32_t> slot(V, NONE);
   std::vector<std::vector<uint32_t>> release(n_levels + 1);
   auto klass = [&](uint32_t x) -> uint32_t {  // widest LUTs first (the kernel skips loads a LUT does not need)
@@ -956,7 +958,15 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
   }
 
   ph.reset(new Phase("schedule: level"));
-  Sched level = schedule_level(net);
+  // pack for the widest register-stack word count K that will fit one SM's shared memory (227 KB): K = 4 -> 8
+  // bank groups of 16 B, K = 2 -> 16 of 8 B, K = 1 -> 32 banks of 4 B
+  auto schedule_for_smem = [](const Network &n) {
+    Sched sc = schedule_level(n, 8);
+    if (sc.ok && (size_t)sc.n_slots * 16 > 227 * 1024) sc = schedule_level(n, 16);
+    if (sc.ok && (size_t)sc.n_slots * 16 > 227 * 1024 && (size_t)sc.n_slots * 8 > 227 * 1024) sc = schedule_level(n, 32);
+    return sc;
+  };
+  Sched level = schedule_for_smem(net);
   ph.reset(new Phase("schedule: lane"));
   if (!level.ok) fail(CLG_E_UNSUPPORTED, "level-ordered stream needs more than 65536 physical registers");
   Sched lane;
@@ -971,7 +981,7 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
     const uint32_t P = partition(net, 592, pv, po);
     if (P > 1)
       for (uint32_t q = 0; q < P; q++) {
-        parts.push_back(schedule_level(subnetwork(net, pv, po, q)));
+        parts.push_back(schedule_for_smem(subnetwork(net, pv, po, q)));
         if (!parts.back().ok) {
           parts.clear();
           break;

@@ -96,6 +96,18 @@ def test_partitioned_cooperative_launch():
         assert np.array_equal(mask_tail(mono.run_batch(imm, nv), nv), want)
 
 
+def test_dag_1m_gates_no_window():
+    """The K = infinity variant of config 4 (inputs drawn from all earlier levels): live set of ~54k values, one word
+    per register in shared memory (K = 1), whole-warp bank packing."""
+    circ = circuits.random_dag(window=0)
+    nv = 1 << 11
+    imm = random_sliced(1024, stride_for(nv), seed=0xD47)
+    cs = host.CudaSimulation.from_simulation(circ.sim, 1024, circ.out_regs)
+    got = mask_tail(cs.run_batch(imm, nv), nv)
+    assert cs.mode == host.MODE_COOP and cs.words_per_thread == 1
+    assert np.array_equal(got, oracle_out(circ, imm, nv))
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_flattened_instances_single_vector(mode):
     """config 5 in miniature: independent multiplier instances flattened, ONE input vector."""
