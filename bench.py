@@ -60,6 +60,8 @@ def build_workload(name: str, api=None):
     if name == "mul64x128":
         # config 5: ONE input vector through 128 flattened 64x64 multipliers (1.08e7 gates) -- latency, not throughput
         return circuits.flatten_instances(circuits.array_multiplier(64, api=api), 128, api=api), 0, 0x5EED
+    if name == "mul64":
+        return circuits.array_multiplier(64, api=api), 22, 0xC0FFF0
     if name == "adder8":
         return circuits.ripple_adder(8, api=api), 17, 0xC0FFED
     raise SystemExit(f"unknown workload {name}")
@@ -73,6 +75,7 @@ WORKLOAD_DESC = {
     "mul16": "16x16 array multiplier, 4 896 NANDs with the reference's gate expansions (BASELINE configs[2])",
     "adder32": "32-bit ripple-carry adder, 608 NANDs (BASELINE configs[1])",
     "adder8": "8-bit ripple-carry adder, 152 NANDs (BASELINE configs[0])",
+    "mul64": "64x64 array multiplier, 84 096 NANDs (one instance of config 5's circuit), batched",
     "mul64x128": "64x64 array multiplier (84 096 NANDs) x 128 instances flattened into one program = 10 764 288 gates, "
                  "ONE input vector: the warp-cooperative intra-level mode (BASELINE configs[4]; M = 128 instances gives the "
                  "~10M gates the config names, see SURVEY 8d)",
