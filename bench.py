@@ -329,7 +329,7 @@ def main():
     try:  # measured DRAM traffic of this kernel from the committed ncu capture, scaled to this batch size
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f).get(args.workload)
-        if tr and tr["kernel"].startswith("clg_" + cs.mode_name):
+        if tr and tr["kernel"].startswith("clg_" + cs.mode_name) and cs.words_per_thread == 4:
             roofline["traffic"] = tr["dram_bytes"] * (w["nv"] / tr["profiled_vectors"])
             roofline["traffic_source"] = f"ncu capture at {tr['profiled_vectors']} vectors, scaled by batch size"
     except Exception:
