@@ -207,3 +207,30 @@ def test_json_roundtrip():
     assert back.ops == sim.ops and back.registers == sim.registers
     with pytest.raises(host.ClgError):
         host.Simulation.from_json('{"ops":[{"Nor":[0,1,2]}],"registers":[]}')
+
+
+def test_empty_and_degenerate_programs():
+    """compile(vec![]) gives a Simulation with no ops (compile.rs:96-101); constants, pure copies and dead code."""
+    c = host.Compiler(2)
+    sim = c.compile([])
+    assert sim.ops == [] and len(sim.registers) == 2
+    fp = host.FlatProgram.levelize(sim, 2)          # every register reads back false: nothing writes them
+    flat = flat_interp.Flat(fp.to_bytes())
+    imm = exhaustive_sliced(2)
+    for s in (0, 1):
+        assert not flat_interp.run(flat, s, imm).any()
+    # outputs that are plain copies of immediates, inverted copies, and constants
+    sim = host.Simulation(ops=[host.Set_op(0, False), host.Set_op(1, True), host.Nand_op(0, 0, 2), host.Set_op(3, True),
+                               host.Nand_op(3, 3, 4), host.Nand_op(0, 1, 5)], registers=[False] * 7)
+    for n_imm in (2, 1):
+        imm = exhaustive_sliced(n_imm)
+        want = oracle.run_batch_scalar(sim, 7, imm, 1 << n_imm, list(range(7)))
+        fp = host.FlatProgram.levelize(sim, n_imm)
+        for got, _ in both_streams(fp, imm, 1 << n_imm):
+            assert np.array_equal(got, mask_tail(want, 1 << n_imm))
+    # the same register named twice as an output, and an output nobody computes
+    fp = host.FlatProgram.levelize(sim, 2, out_regs=[5, 5, 6])
+    imm = exhaustive_sliced(2)
+    want = oracle.run_batch_scalar(sim, 7, imm, 4, [5, 5, 6])
+    for got, _ in both_streams(fp, imm, 4):
+        assert np.array_equal(got, mask_tail(want, 4))
