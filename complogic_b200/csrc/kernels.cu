@@ -13,11 +13,21 @@
 //                ring with cp.async.bulk + mbarrier (full/empty pipeline); consumer warps run freely,
 //                never synchronising with each other. Instructions are warp-uniform: one broadcast
 //                128-bit LDS fetches them, the LUT immediate is dispatched through a uniform branch.
-//   clg_coop<K>  cooperative intra-level interpreter for programs whose live set cannot be held per
+//   clg_coop*    cooperative intra-level interpreter for programs whose live set cannot be held per
 //                thread (10^4..10^5 live values): one CTA shares ONE register stack for K words
 //                (32*K vectors) in shared memory as [slot][K]; the instructions of a level are
-//                independent, so the CTA's threads split them and meet at a barrier per level.
-//   clg_slice / clg_unslice / clg_fill_random  layout helpers (vector-major <-> bit-sliced).
+//                independent, so the CTA's threads split them and meet at a barrier per level. Three forms:
+//                  clg_coop_c_k<K>    compact stream: LUT instructions are 8 bytes (14-bit slot indices),
+//                                     fetched with ld.global.nc.v2 and prefetched across the level barrier
+//                                     (the 1M-gate DAG runs here);
+//                  clg_coop_k<K>      16-byte stream, for stacks of more than 16 383 slots;
+//                  clg_coop_res_k<K>  resident: the CTA's instructions and level table are staged into
+//                                     shared memory once with cp.async.bulk + mbarrier (narrow, deep
+//                                     programs on few vectors, e.g. one part of a partitioned program).
+//                The compiler pass allocates slots so that the 8 (K=4) / 16 (K=2) / 32 (K=1) lanes served
+//                together by one LDS/STS hit distinct bank groups.
+//   clg_slice / clg_unslice / clg_fill_random / clg_lop3_peak  layout helpers, input generator, and the
+//                pure-LOP3 microbenchmark that measures the roofline denominator.
 //
 // Global memory is touched only for the algorithmic traffic: each input row word is read once
 // (ld.global.nc, K*4-byte vectors, coalesced across the warp in lane mode), each output word is
