@@ -332,6 +332,9 @@ def main():
         if tr and tr["kernel"].startswith("clg_" + cs.mode_name) and cs.words_per_thread == 4:
             roofline["traffic"] = tr["dram_bytes"] * (w["nv"] / tr["profiled_vectors"])
             roofline["traffic_source"] = f"ncu capture at {tr['profiled_vectors']} vectors, scaled by batch size"
+            if "lsu_data_pipe_pct_of_peak" in tr:  # the pipe that actually bounds the shared-memory interpreter
+                roofline["ncu_lsu_data_pipe_frac"] = tr["lsu_data_pipe_pct_of_peak"] / 100.0
+                roofline["ncu_alu_pipe_frac"] = tr["alu_pipe_pct_active"] / 100.0
     except Exception:
         pass
     roofline.update({
