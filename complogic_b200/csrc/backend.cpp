@@ -81,7 +81,7 @@ struct Ctx {
   CUcontext cu = nullptr;
   CUmodule mod = nullptr;
   int sm_count = 0;
-  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, slice = nullptr, unslice = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
   std::string name;
 
   explicit Ctx(int device) {
@@ -117,6 +117,8 @@ struct Ctx {
     }
     CU(cuModuleGetFunction(&slice, mod, "clg_slice"));
     CU(cuModuleGetFunction(&unslice, mod, "clg_unslice"));
+    CU(cuModuleGetFunction(&slice_v4, mod, "clg_slice_v4"));
+    CU(cuModuleGetFunction(&unslice_v4, mod, "clg_unslice_v4"));
     CU(cuModuleGetFunction(&fill, mod, "clg_fill_random"));
     CU(cuModuleGetFunction(&lop3_peak, mod, "clg_lop3_peak"));
   }
@@ -618,10 +620,18 @@ void launch_slice(Ctx *c, bool unslice, const void *src, void *dst, size_t n_vec
   if ((n_vectors + 31) / 32 > stride) fail(CLG_E_INVALID, "n_vectors does not fit in stride words");
   c->bind();
   uint32_t nv = (uint32_t)n_vectors, nr = (uint32_t)n_rows, st = (uint32_t)stride;
+  void *args[] = {&src, &dst, &nv, &nr, &st};
+  const void *vec_side = unslice ? dst : src;
+  if (n_rows % 16 == 0 && ((uintptr_t)vec_side & 15) == 0) {
+    // tiled kernels: 128-bit accesses on the vector-major side, 32-byte segments on the sliced side
+    const uint64_t gx = ((n_vectors + 31) / 32 + 7) / 8, gy = (n_rows + 31) / 32;
+    if (gx * gy > 0x7FFFFFFFull) fail(CLG_E_INVALID, "transpose too large for one launch");
+    CU(cuLaunchKernel(unslice ? c->unslice_v4 : c->slice_v4, (unsigned)(gx * gy), 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr));
+    return;
+  }
   uint64_t warps = (uint64_t)((n_rows + 31) / 32) * ((n_vectors + 31) / 32);
   uint64_t blocks = (warps * 32 + 255) / 256;
   if (blocks > 0x7FFFFFFFull) fail(CLG_E_INVALID, "transpose too large for one launch");
-  void *args[] = {&src, &dst, &nv, &nr, &st};
   CU(cuLaunchKernel(unslice ? c->unslice : c->slice, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr));
 }
 

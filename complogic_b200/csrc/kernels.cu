@@ -529,6 +529,73 @@ extern "C" __global__ void __launch_bounds__(256) clg_unslice(const uint32_t *sl
   }
 }
 
+// ---- tiled transposes (n_rows % 16 == 0): 128-bit accesses on the vector-major side, 32-byte segments on the
+// sliced side. A CTA of 8 warps owns 256 vectors (8 words) x 32 rows; warp w owns word w. Lane k holds the 32
+// row-bytes of vector 32w+k as two uint4; bytes <-> bits with SWAR arithmetic, then 32 ballots transpose the
+// 32x32 bit matrix between "lane = vector" and "lane = row".
+__device__ __forceinline__ uint32_t pack4(uint32_t x) {  // 4 bytes (zero / non-zero) -> 4 bits
+  uint32_t y = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) >> 7 & 0x01010101u;
+  return (y | y >> 7 | y >> 14 | y >> 21) & 0xFu;
+}
+__device__ __forceinline__ uint32_t unpack4(uint32_t b) {  // 4 bits -> 4 bytes of 0/1
+  return (b | b << 7 | b << 14 | b << 21) & 0x01010101u;
+}
+
+extern "C" __global__ void __launch_bounds__(256) clg_slice_v4(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors,
+                                                              uint32_t n_rows, uint32_t stride) {
+  __shared__ uint32_t tile[32][9];  // [row][word] (+1 pad)
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // consecutive CTAs walk the row tiles of the same 256 vectors: their 32-byte pieces share DRAM pages and L2 lines
+  const uint32_t n_rt = (n_rows + 31) / 32, wg = blockIdx.x / n_rt, r0 = (blockIdx.x % n_rt) * 32;
+  const uint32_t w = wg * 8 + warp, v = w * 32 + lane;
+  uint32_t bits = 0;
+  if (v < n_vectors) {
+    const uint8_t *src = bools + (size_t)v * n_rows + r0;
+    uint4 lo = *reinterpret_cast<const uint4 *>(src), hi = make_uint4(0, 0, 0, 0);
+    if (r0 + 16 < n_rows) hi = *reinterpret_cast<const uint4 *>(src + 16);
+    bits = pack4(lo.x) | pack4(lo.y) << 4 | pack4(lo.z) << 8 | pack4(lo.w) << 12 | pack4(hi.x) << 16 | pack4(hi.y) << 20 |
+           pack4(hi.z) << 24 | pack4(hi.w) << 28;
+  }
+  uint32_t mine = 0;
+#pragma unroll
+  for (uint32_t r = 0; r < 32; r++) {
+    const uint32_t word = __ballot_sync(0xFFFFFFFFu, (bits >> r) & 1u);
+    if (lane == r) mine = word;
+  }
+  tile[lane][warp] = mine;
+  __syncthreads();
+  const uint32_t row = threadIdx.x >> 3, j = threadIdx.x & 7;  // 8 consecutive threads: 32 contiguous bytes of a row
+  if (r0 + row < n_rows && wg * 8 + j < (n_vectors + 31) / 32) sliced[(size_t)(r0 + row) * stride + wg * 8 + j] = tile[row][j];
+}
+
+extern "C" __global__ void __launch_bounds__(256) clg_unslice_v4(const uint32_t *sliced, uint8_t *bools, uint32_t n_vectors,
+                                                                uint32_t n_rows, uint32_t stride) {
+  __shared__ uint32_t tile[32][9];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_rt = (n_rows + 31) / 32, wg = blockIdx.x / n_rt, r0 = (blockIdx.x % n_rt) * 32;
+  const uint32_t words = (n_vectors + 31) / 32;
+  const uint32_t row = threadIdx.x >> 3, j = threadIdx.x & 7;
+  uint32_t x = 0;
+  if (r0 + row < n_rows && wg * 8 + j < words) x = sliced[(size_t)(r0 + row) * stride + wg * 8 + j];
+  tile[row][j] = x;
+  __syncthreads();
+  const uint32_t word = tile[lane][warp];  // lane = row, this warp's word
+  uint32_t bits = 0;                       // after the loop: lane = vector, bit r = row r0 + r
+#pragma unroll
+  for (uint32_t k = 0; k < 32; k++) {
+    const uint32_t col = __ballot_sync(0xFFFFFFFFu, (word >> k) & 1u);
+    if (lane == k) bits = col;
+  }
+  const uint32_t v = (wg * 8 + warp) * 32 + lane;
+  if (v < n_vectors) {
+    uint8_t *dst = bools + (size_t)v * n_rows + r0;
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(unpack4(bits & 15), unpack4(bits >> 4 & 15), unpack4(bits >> 8 & 15), unpack4(bits >> 12 & 15));
+    if (r0 + 16 < n_rows)
+      *reinterpret_cast<uint4 *>(dst + 16) =
+          make_uint4(unpack4(bits >> 16 & 15), unpack4(bits >> 20 & 15), unpack4(bits >> 24 & 15), unpack4(bits >> 28));
+  }
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ULL;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;

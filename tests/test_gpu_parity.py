@@ -179,6 +179,29 @@ def test_bools_api_and_transposes():
         assert np.array_equal(p, a * b)
 
 
+def test_transposes_tiled_and_fallback_paths():
+    """clg_slice_bools / clg_unslice_bools: the 128-bit tiled kernels (rows % 16 == 0) and the generic ones, ragged
+    vector counts, any non-zero byte counts as true."""
+    import torch
+
+    ctx = host.Context.default()
+    rng = np.random.default_rng(8)
+    for nv, rows in ((1, 16), (33, 16), (300, 48), (5000, 64), (257, 1024), (1000, 17), (64, 33)):
+        stride = stride_for(nv)
+        b = rng.integers(0, 2, size=(nv, rows), dtype=np.uint8) * rng.integers(1, 256, size=(nv, rows)).astype(np.uint8)
+        bools = torch.from_numpy(b).cuda()
+        sliced = torch.zeros((rows, stride), dtype=torch.int32, device="cuda")
+        back = torch.full((nv, rows), 9, dtype=torch.uint8, device="cuda")
+        ctx.slice_bools(bools.data_ptr(), sliced.data_ptr(), nv, rows, stride)
+        ctx.unslice_bools(sliced.data_ptr(), back.data_ptr(), nv, rows, stride)
+        torch.cuda.synchronize()
+        want_bits = (b != 0)
+        got = sliced.cpu().numpy().view(np.uint32)
+        bits = ((got[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(rows, -1)[:, :nv].T.astype(bool)
+        assert np.array_equal(bits, want_bits), (nv, rows)
+        assert np.array_equal(back.cpu().numpy(), want_bits.astype(np.uint8)), (nv, rows)
+
+
 def test_torch_buffers_and_stream_and_fill():
     """Device pointers from torch, torch's current stream, and the on-device input generator."""
     import torch
