@@ -198,13 +198,17 @@ struct Exec {
         return ln.n_slots <= 512 ? 1 : 0;
       case CLG_MODE_LANE:
         if (ln.n_instr == 0) return 0;
-        // prefer the widest vector that still leaves >= 3 CTAs (12 consumer warps) per SM
-        for (int pass = 0; pass < 2; pass++)
-          for (int k : {4, 2, 1}) {
-            size_t need = LANE_RING_BYTES + (size_t)ln.n_slots * LANE_THREADS * k * 4;
-            if (need * (pass == 0 ? 3 : 1) <= SMEM_MAX) return k;
-          }
-        return 0;
+        // the kernel is latency bound: what counts is resident consumer warps x K, which shared memory fixes
+        // (stack bytes per thread = slots * K * 4). Prefer the widest vector that still leaves >= 16 consumer warps.
+        for (int k : {4, 2, 1})
+          if (lane_resident(k) >= 512u) return k;
+        {  // big stacks: whatever keeps the most words in flight per SM
+          int best = 0;
+          uint32_t best_words = 0;
+          for (int k : {4, 2, 1})
+            if (lane_resident(k) * (uint32_t)k > best_words) best_words = lane_resident(k) * (uint32_t)k, best = k;
+          return best;
+        }
       case CLG_MODE_COOP:
         if (lv.n_instr == 0) return 0;
         for (int k : {4, 2, 1})
@@ -212,6 +216,22 @@ struct Exec {
         return 0;
     }
     return 0;
+  }
+  // consumer threads of one lane-kernel CTA: as many as one SM's shared memory holds stacks for (one CTA per SM
+  // when the stack is big, several when it is small)
+  uint32_t lane_consumers(int k) const {
+    const size_t per_thread = std::max<size_t>(4, (size_t)lane_stream().n_slots * k * 4);
+    const size_t fit = (SMEM_MAX - LANE_RING_BYTES) / per_thread / 32 * 32;
+    if (fit < (size_t)LANE_MIN_THREADS) return 0;
+    if (fit <= (size_t)LANE_MAX_THREADS) return (uint32_t)fit;
+    // small stacks: several CTAs per SM; 224 consumers + 1 producer warp = 8 warps per CTA
+    return 224;
+  }
+  uint32_t lane_resident(int k) const {  // consumer threads resident on one SM
+    const uint32_t nc = lane_consumers(k);
+    if (!nc) return 0;
+    const size_t smem = LANE_RING_BYTES + (size_t)lane_stream().n_slots * nc * k * 4;
+    return nc * (uint32_t)std::min<size_t>(2048 / (nc + 32), SMEM_MAX / smem);
   }
   static uint32_t coop_threads_for(const FlatStream &lv) {
     if (const char *env = std::getenv("CLG_COOP_THREADS")) return std::max(32, std::atoi(env)) / 32 * 32;  // tuning knob
@@ -223,8 +243,9 @@ struct Exec {
   double lane_cycles(size_t words) const {
     const int k = fit_k(CLG_MODE_LANE);
     const FlatStream &ln = lane_stream();
-    const size_t smem = LANE_RING_BYTES + (size_t)ln.n_slots * LANE_THREADS * k * 4;
-    const double warps_per_sm = 4.0 * std::min<double>(12.0, std::floor((double)SMEM_MAX / (double)smem));
+    const uint32_t nc = lane_consumers(k);
+    const size_t smem = LANE_RING_BYTES + (size_t)ln.n_slots * nc * k * 4;
+    const double warps_per_sm = (nc / 32.0) * std::min<double>(std::floor(2048.0 / (nc + 32)), std::floor((double)SMEM_MAX / (double)smem));
     const double groups = std::ceil((double)words / k), per_wave = warps_per_sm * 32.0 * ctx->sm_count;
     return std::ceil(groups / per_wave) * ln.n_instr * std::max(48.0, 17.0 * std::min(warps_per_sm, std::ceil(groups / 32.0 / ctx->sm_count)));
   }
@@ -327,7 +348,8 @@ struct Exec {
       case CLG_MODE_LANE:
         if (!P.K) fail(CLG_E_UNSUPPORTED, "live register set does not fit a per-thread shared-memory stack; use the cooperative mode");
         st = &ln;
-        P.smem = LANE_RING_BYTES + (size_t)ln.n_slots * LANE_THREADS * P.K * 4;
+        P.coop_threads = lane_consumers(P.K);  // (consumer threads of the lane kernel)
+        P.smem = LANE_RING_BYTES + (size_t)ln.n_slots * P.coop_threads * P.K * 4;
         break;
       case CLG_MODE_COOP:
         if (!P.K) fail(CLG_E_UNSUPPORTED, "live register set exceeds one SM's shared memory even at one word per register");
@@ -341,7 +363,7 @@ struct Exec {
     if (st) {
       P.n_instr = st->n_instr, P.n_levels = st->n_levels, P.n_slots = st->n_slots;
       // device encoding (kernels.cu): byte offsets pre-scaled for this mode's register-stack layout
-      const uint32_t slot_bytes = (m == CLG_MODE_LANE ? LANE_THREADS : 1) * P.K * 4;
+      const uint32_t slot_bytes = (m == CLG_MODE_LANE ? P.coop_threads : 1) * P.K * 4;
       if ((uint64_t)P.n_slots * slot_bytes >= (1u << 24)) fail(CLG_E_UNSUPPORTED, "register stack exceeds the 24-bit offset field");
       std::vector<uint32_t> enc((size_t)P.n_instr * 4);
       encode_stream(flat.instrs(sidx), P.n_instr, slot_bytes, enc.data());
@@ -539,8 +561,8 @@ struct Exec {
     p.cinstr = (const void *)P.d_cinstr, p.clevels = (const uint32_t *)P.d_clevels;
     void *args[] = {&p};
     if (mode == CLG_MODE_LANE) {
-      const uint32_t grid = (groups + LANE_THREADS - 1) / LANE_THREADS;
-      CU(cuLaunchKernel(ctx->lane[kidx(K)], grid, 1, 1, LANE_THREADS + 32, 1, 1, (unsigned)P.smem, stream, args, nullptr));
+      const uint32_t nc = P.coop_threads, grid = (groups + nc - 1) / nc;
+      CU(cuLaunchKernel(ctx->lane[kidx(K)], grid, 1, 1, nc + 32, 1, 1, (unsigned)P.smem, stream, args, nullptr));
     } else {
       const size_t per_sm = std::max<size_t>(1, std::min<size_t>(SMEM_MAX / (P.smem + 1024), 2048 / P.coop_threads));
       uint32_t grid = std::min<uint32_t>(groups, (uint32_t)ctx->sm_count * (uint32_t)per_sm);

@@ -31,7 +31,7 @@ struct RunParams {
   const uint32_t *clevels;
 };
 
-constexpr int LANE_THREADS = 128;
+constexpr int LANE_MIN_THREADS = 64, LANE_MAX_THREADS = 992;  // consumer threads of a lane-kernel CTA (+ 32 producer)
 constexpr int RING_STAGES = 4;
 constexpr int RING_CHUNK = 256;
 constexpr size_t LANE_RING_BYTES = RING_STAGES * RING_CHUNK * 16 + 128;

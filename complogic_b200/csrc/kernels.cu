@@ -247,7 +247,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // ---- lane-parallel interpreter -----------------------------------------------------------------------
-constexpr int LANE_THREADS = 128;  // consumer threads per CTA (+ one producer warp)
+constexpr int LANE_MAX_THREADS = 1024;  // consumers (blockDim.x - 32, chosen by the host to fill shared memory) + one producer warp
 constexpr int RING_STAGES = 4;
 constexpr int RING_CHUNK = 256;  // instructions per stage (4 KiB)
 
@@ -259,11 +259,11 @@ __device__ __forceinline__ void lane_body(const RunParams &p) {
   uint64_t *empty = full + RING_STAGES;
   Vec<K> *slots = reinterpret_cast<Vec<K> *>(smem + RING_STAGES * RING_CHUNK * 16 + 128);
 
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x, nc = blockDim.x - 32;  // nc consumer threads, then the producer warp
   if (tid == 0) {
     for (int s = 0; s < RING_STAGES; s++) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], LANE_THREADS / 32);
+      mbar_init(&empty[s], nc / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -271,9 +271,9 @@ __device__ __forceinline__ void lane_body(const RunParams &p) {
 
   const uint32_t n_chunks = (p.n_instr + RING_CHUNK - 1) / RING_CHUNK;
 
-  if (tid >= LANE_THREADS) {
+  if (tid >= nc) {
     // ---- producer warp: one elected lane feeds the ring ----
-    if (tid == LANE_THREADS) {
+    if (tid == nc) {
       for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t s = c % RING_STAGES, use = c / RING_STAGES;
         if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
@@ -286,10 +286,10 @@ __device__ __forceinline__ void lane_body(const RunParams &p) {
   }
 
   // ---- consumer warps ----
-  const uint32_t gid = blockIdx.x * LANE_THREADS + tid;
+  const uint32_t gid = blockIdx.x * nc + tid;
   const bool active = gid < p.n_groups;
   const size_t col = (size_t)(active ? gid : 0) * K;
-  uint32_t my = smem_u32(slots + tid);  // slot s lives at my + s * LANE_THREADS * K * 4 (shared-space address)
+  uint32_t my = smem_u32(slots + tid);  // slot s lives at my + s * nc * K * 4 (shared-space address)
   asm volatile("" : "+r"(my));
 
   for (uint32_t c = 0; c < n_chunks; c++) {
@@ -637,7 +637,7 @@ extern "C" __global__ void __launch_bounds__(512) clg_lop3_peak(const uint32_t *
 
 // C-named entry points the host looks up in the cubin (one per words-per-thread variant)
 #define CLG_ENTRY(K)                                                                                           \
-  extern "C" __global__ void __launch_bounds__(clg::LANE_THREADS + 32) clg_lane_k##K(const clg::RunParams p) { \
+  extern "C" __global__ void __launch_bounds__(clg::LANE_MAX_THREADS) clg_lane_k##K(const clg::RunParams p) { \
     clg::lane_body<K>(p);                                                                                      \
   }                                                                                                            \
   extern "C" __global__ void __launch_bounds__(1024) clg_coop_k##K(const clg::RunParams p) { clg::coop_body<K, false>(p); } \
