@@ -63,6 +63,7 @@ PROTOTYPES = {
     "clg_flat_get_info": (i32, [vp, P(ClgFlatInfo)]),
     "clg_flat_state_regs": (i32, [vp, P(vp), P(sz)]),
     "clg_flat_spec_ptx": (i32, [vp, i32, P(vp)]),
+    "clg_flat_spec_steps_ptx": (i32, [vp, i32, P(vp)]),
     "clg_ctx_create": (i32, [i32, P(vp)]),
     "clg_ctx_destroy": (None, [vp]),
     "clg_ctx_device_name": (i32, [vp, C.c_char_p, sz]),
@@ -82,6 +83,7 @@ PROTOTYPES = {
     "clg_exec_launches_per_run": (i32, [vp]),
     "clg_exec_ptx": (C.c_char_p, [vp]),
     "clg_exec_run": (i32, [vp, vp, vp, vp, sz, sz, vp]),
+    "clg_exec_run_steps": (i32, [vp, vp, vp, vp, sz, sz, sz, vp]),
     "clg_exec_run_host": (i32, [vp, vp, vp, vp, sz, sz]),
     "clg_exec_run_bools_host": (i32, [vp, vp, vp, sz]),
     "clg_slice_bools": (i32, [vp, vp, vp, sz, sz, sz, vp]),

@@ -403,9 +403,9 @@ class FlatProgram:
         check(lib().clg_flat_state_regs(self._h, C.byref(p), C.byref(n)))
         return np.frombuffer(C.string_at(p, n.value * 8), dtype=np.uint64).copy() if n.value else np.zeros(0, np.uint64)
 
-    def spec_ptx(self, k: int = 4) -> str:
+    def spec_ptx(self, k: int = 4, steps: bool = False) -> str:
         out = C.c_void_p()
-        check(lib().clg_flat_spec_ptx(self._h, k, C.byref(out)))
+        check((lib().clg_flat_spec_steps_ptx if steps else lib().clg_flat_spec_ptx)(self._h, k, C.byref(out)))
         s = C.string_at(out).decode()
         lib().clg_free(out)
         return s
@@ -463,6 +463,12 @@ class CudaSimulation:
     def run_device(self, imm_dptr: int, out_dptr: int, n_vectors: int, stride: int, state_dptr: int = 0, stream: int = 0) -> None:
         """clg_exec_run: device pointers, asynchronous on `stream`."""
         check(lib().clg_exec_run(self._h, imm_dptr, out_dptr, state_dptr or None, n_vectors, stride, stream or None))
+
+    def run_steps_device(self, imm_dptr: int, out_dptr: int, state_dptr: int, n_vectors: int, stride: int, n_steps: int,
+                         stream: int = 0) -> None:
+        """clg_exec_run_steps: n_steps run() calls per lane, imm [steps][n_in][stride], out [steps][n_out][stride]."""
+        check(lib().clg_exec_run_steps(self._h, imm_dptr or None, out_dptr or None, state_dptr or None, n_vectors, stride,
+                                       n_steps, stream or None))
 
     def run_batch(self, imm: np.ndarray, n_vectors: int, state: Optional[np.ndarray] = None) -> np.ndarray:
         """Host arrays in, host array out (H2D + kernel + D2H inside): imm [n_inputs][stride] uint32."""

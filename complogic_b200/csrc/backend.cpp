@@ -166,8 +166,8 @@ struct Plan {
   uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0, n_parts = 0, code_off = 0;
   size_t smem = 0;
   bool resident = false;  // cooperative: the (largest part's) instruction stream is staged in shared memory
-  CUmodule spec_mod = nullptr;
-  CUfunction spec_fn = nullptr;
+  CUmodule spec_mod = nullptr, steps_mod = nullptr;
+  CUfunction spec_fn = nullptr, steps_fn = nullptr;  // steps_fn: the fused multi-step form, assembled on first use
   std::string ptx;
 };
 
@@ -424,6 +424,7 @@ struct Exec {
       if (P.d_cinstr) d.cuMemFree(P.d_cinstr);
       if (P.d_clevels) d.cuMemFree(P.d_clevels);
       if (P.spec_mod) d.cuModuleUnload(P.spec_mod);
+      if (P.steps_mod) d.cuModuleUnload(P.steps_mod);
     }
     for (int b = 0; b < NBUF; b++) {
       if (stage_in[b]) d.cuMemFree(stage_in[b]);
@@ -523,6 +524,44 @@ struct Exec {
     CU(cuStreamSynchronize(s_in));
     CU(cuStreamSynchronize(s_run));
     CU(cuStreamSynchronize(s_out));
+  }
+
+  // n_steps consecutive run() calls per lane: imm is [n_steps][n_inputs][stride], out is [n_steps][n_outputs][stride],
+  // state is carried from step to step. The specialised mode does it in ONE launch with the carried registers held in
+  // registers across the steps; the interpreters issue one launch per step.
+  void run_steps(const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, size_t n_steps, CUstream stream) {
+    const FlatHeader &h = flat.header();
+    if (n_steps == 0 || n_vectors == 0) return;
+    const size_t words = (n_vectors + 31) / 32;
+    const size_t imm_step = (size_t)h.n_inputs * stride, out_step = (size_t)h.n_outputs * stride;
+    if (choose(words) != CLG_MODE_SPEC || n_steps == 1) {
+      for (size_t s_ = 0; s_ < n_steps; s_++) run(imm ? imm + s_ * imm_step : nullptr, out ? out + s_ * out_step : nullptr, state, n_vectors, stride, stream);
+      return;
+    }
+    if (stride % 4 != 0) fail(CLG_E_INVALID, "stride must be a multiple of 4 words (16-byte aligned rows)");
+    if (words > stride) fail(CLG_E_INVALID, "n_vectors does not fit in stride words");
+    if (h.n_inputs && !imm) fail(CLG_E_INVALID, "imm is null");
+    if (h.n_outputs && !out) fail(CLG_E_INVALID, "out is null");
+    if (h.n_state && !state) fail(CLG_E_INVALID, "state is null for a stateful program");
+    if (((uintptr_t)imm | (uintptr_t)out | (uintptr_t)state) & 15) fail(CLG_E_INVALID, "buffers must be 16-byte aligned");
+    if (n_steps > 0xFFFFFFFFull) fail(CLG_E_INVALID, "too many steps");
+    ctx->bind();
+    mode = CLG_MODE_SPEC;
+    Plan &P = get(CLG_MODE_SPEC);
+    if (!P.steps_fn) {
+      const std::string text = emit_spec_ptx(flat, P.K, true);
+      char log[8192] = {0};
+      CUjit_option opt[] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES};
+      void *val[] = {log, (void *)(uintptr_t)sizeof log};
+      if (driver().cuModuleLoadDataEx(&P.steps_mod, text.c_str(), 2, opt, val) != CUDA_SUCCESS)
+        fail(CLG_E_PTX, std::string("assembling the multi-step specialised kernel failed: ") + log);
+      CU(cuModuleGetFunction(&P.steps_fn, P.steps_mod, "clg_spec_steps"));
+    }
+    last_k = P.K, last_parts = 0;
+    uint32_t stride32 = (uint32_t)stride, g = (uint32_t)((words + P.K - 1) / P.K), steps32 = (uint32_t)n_steps;
+    uint64_t imm_b = imm_step * 4, out_b = out_step * 4;
+    void *args[] = {&imm, &out, &state, &stride32, &g, &steps32, &imm_b, &out_b};
+    CU(cuLaunchKernel(P.steps_fn, (g + 127) / 128, 1, 1, 128, 1, 1, 0, stream, args, nullptr));
   }
 
   void run(const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, CUstream stream) {
@@ -629,6 +668,10 @@ int exec_k(const Exec *e) { return e->last_k; }
 const std::string &exec_ptx(const Exec *e) { return e->plan[CLG_MODE_SPEC].ptx; }
 const Flat &exec_flat(const Exec *e) { return e->flat; }
 Ctx *exec_ctx(const Exec *e) { return e->ctx; }
+void exec_run_steps(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, size_t n_steps,
+                    void *stream) {
+  e->run_steps(imm, out, state, n_vectors, stride, n_steps, (CUstream)stream);
+}
 void exec_run_host(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride) {
   e->run_host(imm, out, state, n_vectors, stride);
 }

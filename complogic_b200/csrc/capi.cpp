@@ -32,6 +32,7 @@ const Flat &exec_flat(const Exec *);
 Ctx *exec_ctx(const Exec *);
 void exec_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t, void *);
 void exec_run_host(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t);
+void exec_run_steps(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t, size_t, void *);
 void launch_slice(Ctx *, bool, const void *, void *, size_t, size_t, size_t, void *);
 void launch_fill(Ctx *, uint32_t *, size_t, size_t, uint64_t, void *);
 double timed_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t);
@@ -211,10 +212,13 @@ int clg_flat_state_regs(const clg_flat *f, const uint64_t **regs, size_t *n) {
   *regs = f->f.state_regs(), *n = f->f.header().n_state;
   CLG_CATCH
 }
-int clg_flat_spec_ptx(const clg_flat *f, int k, char **ptx_out) {
+static int spec_ptx_text(const clg_flat *f, int k, bool steps, char **ptx_out);
+int clg_flat_spec_ptx(const clg_flat *f, int k, char **ptx_out) { return spec_ptx_text(f, k, false, ptx_out); }
+int clg_flat_spec_steps_ptx(const clg_flat *f, int k, char **ptx_out) { return spec_ptx_text(f, k, true, ptx_out); }
+static int spec_ptx_text(const clg_flat *f, int k, bool steps, char **ptx_out) {
   CLG_TRY
   NEED(f), NEED(ptx_out);
-  std::string s = emit_spec_ptx(f->f, k);
+  std::string s = emit_spec_ptx(f->f, k, steps);
   char *p = (char *)std::malloc(s.size() + 1);
   if (!p) throw std::bad_alloc();
   std::memcpy(p, s.c_str(), s.size() + 1);
@@ -316,6 +320,14 @@ int clg_exec_run(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *sta
   CLG_TRY
   NEED(ex);
   exec_run(ex->e, imm, out, state, n_vectors, stride, stream);
+  CLG_CATCH
+}
+
+int clg_exec_run_steps(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride,
+                       size_t n_steps, void *stream) {
+  CLG_TRY
+  NEED(ex);
+  exec_run_steps(ex->e, imm, out, state, n_vectors, stride, n_steps, stream);
   CLG_CATCH
 }
 

@@ -11,7 +11,7 @@
 
 namespace clg {
 
-std::string emit_spec_ptx(const Flat &f, int K);
+std::string emit_spec_ptx(const Flat &f, int K, bool multi_step = false);
 
 // mirrors kernels.cu
 struct RunParams {

@@ -190,6 +190,8 @@ int clg_flat_state_regs(const clg_flat *f, const uint64_t **regs, size_t *n);
 /* PTX text of the specialised kernel for this program at k words per thread (1, 2 or 4); needs no
  * device, so it can be assembled and inspected offline (ptxas -arch=sm_100a). Free with clg_free. */
 int clg_flat_spec_ptx(const clg_flat *f, int k, char **ptx_out);
+/* same for the fused multi-step form (clg_exec_run_steps) */
+int clg_flat_spec_steps_ptx(const clg_flat *f, int k, char **ptx_out);
 
 /* ---------------------------------------------------------------------------------------------
  * Device side. Raw CUDA driver API underneath (libcuda.so.1 is dlopen'ed when the first context
@@ -238,6 +240,14 @@ const char *clg_exec_ptx(const clg_exec *ex);
  * Asynchronous on `stream` (a CUstream / cudaStream_t; NULL = the legacy default stream). */
 int clg_exec_run(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors,
                  size_t stride, void *stream);
+
+/* n_steps consecutive run() calls per lane in one call (clocked / sequential circuits: what the reference does by
+ * calling run() repeatedly on one Simulation, e.g. gates.rs:523-534). DEVICE pointers:
+ *   imm [n_steps][n_inputs][stride]   out [n_steps][n_outputs][stride]   state [n_state][stride] (in place)
+ * In the specialised mode this is ONE launch and the carried registers never leave the register file between
+ * steps; the interpreter modes issue one launch per step. */
+int clg_exec_run_steps(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride,
+                       size_t n_steps, void *stream);
 
 /* Host-buffer entry point. Same layouts, HOST pointers (pinned memory -- clg_host_alloc_pinned -- gives full
  * PCIe speed). The batch is cut into column chunks that are pipelined over three streams, so H2D copies,

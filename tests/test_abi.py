@@ -100,6 +100,15 @@ def test_spec_ptx_assembles_for_sm100a(tmp_path):
         n_lop3 = sass.count("LOP3.LUT")
         assert n_lop3 >= fp.info["n_luts"] * k  # one LOP3 per LUT per word (+ inverted stores)
         assert (".128" in sass) if k == 4 else True
+    # the fused multi-step form of a stateful program: carried registers live in registers across the step loop
+    c = host.Compiler(2)
+    sim = c.compile([host.DLatch(0, 1, c.alloc())])
+    fp = host.FlatProgram.levelize(sim, 2, None, flags=host.LV_STATEFUL)
+    for k in (1, 4):
+        ptx = tmp_path / f"dlatch_steps{k}.ptx"
+        ptx.write_text(fp.spec_ptx(k, steps=True))
+        r = subprocess.run(["ptxas", "-arch=sm_100a", "-o", str(tmp_path / "d.cubin"), str(ptx)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
 
 
 def test_header_is_plain_c(tmp_path):

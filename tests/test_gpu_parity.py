@@ -135,6 +135,36 @@ def test_latch_sequences_per_lane(mode, gate):
         assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv)), f"step {s}"
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_fused_multi_step(mode):
+    """clg_exec_run_steps: T run() calls per lane in one call (one launch in the specialised mode, carried registers
+    kept in registers), every register after every step equal to the oracle VM's."""
+    import torch
+
+    c = host.Compiler(3)
+    q1, q2, s_, k_ = c.alloc(), c.alloc(), c.alloc(), c.alloc()
+    sim = c.compile([host.DLatch(0, 1, q1), host.RSLatch(q1, 2, q2), host.FullAdder(0, q1, q2, s_, k_)])
+    R, nv, T = len(sim.registers), 1000, 7
+    stride = stride_for(nv)
+    imm = np.stack([random_sliced(3, stride, 900 + t) for t in range(T)])
+    want = oracle.run_batch_scalar(sim, R, imm, nv, list(range(R)), steps=T, all_steps=True)
+    cs = host.CudaSimulation.from_simulation(sim, 3, None, flags=host.LV_STATEFUL, mode=mode)
+    d_imm = torch.from_numpy(imm.view(np.int32)).cuda()
+    d_out = torch.zeros((T, R, stride), dtype=torch.int32, device="cuda")
+    d_state = torch.zeros((max(1, cs.info["n_state"]), stride), dtype=torch.int32, device="cuda")
+    cs.run_steps_device(d_imm.data_ptr(), d_out.data_ptr(), d_state.data_ptr(), nv, stride, T)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.uint32)
+    for t in range(T):
+        assert np.array_equal(mask_tail(got[t], nv), mask_tail(want[t], nv)), f"step {t}"
+    # the carried registers left behind equal a step-by-step run
+    ref = host.CudaSimulation.from_simulation(sim, 3, None, flags=host.LV_STATEFUL, mode=mode)
+    state = np.zeros((cs.info["n_state"], stride), np.uint32)
+    for t in range(T):
+        ref.run_batch(imm[t], nv, state=state)
+    assert np.array_equal(mask_tail(d_state.cpu().numpy().view(np.uint32)[:cs.info["n_state"]], nv), mask_tail(state, nv))
+
+
 @st.composite
 def programs(draw):
     n_regs = draw(st.integers(1, 10))
