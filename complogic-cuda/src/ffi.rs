@@ -61,6 +61,8 @@ extern "C" {
   pub fn clg_exec_destroy(ex: *mut clg_exec);
   pub fn clg_exec_run(ex: *mut clg_exec, imm: *const u32, out: *mut u32, state: *mut u32, n_vectors: usize,
                       stride: usize, stream: *mut c_void) -> c_int;
+  pub fn clg_exec_run_steps(ex: *mut clg_exec, imm: *const u32, out: *mut u32, state: *mut u32, n_vectors: usize,
+                            stride: usize, n_steps: usize, stream: *mut c_void) -> c_int;
   pub fn clg_exec_run_host(ex: *mut clg_exec, imm: *const u32, out: *mut u32, state: *mut u32, n_vectors: usize,
                            stride: usize) -> c_int;
   pub fn clg_exec_run_bools_host(ex: *mut clg_exec, imm: *const u8, out: *mut u8, n_vectors: usize) -> c_int;
