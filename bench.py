@@ -195,7 +195,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bool (u8 per register)", "data": "synthetic",
+        "dtype": "u8", "data": "synthetic",
         "config": {"workload": args.workload, "description": WORKLOAD_DESC[args.workload], "gates": gates,
                    "vectors_per_step": nv, "note": "reference CPU VM: C restatement of simulation.rs:16-30 (the Rust "
                    "reference cannot be built in this image: no cargo/rustc), all host threads"},
@@ -428,12 +428,13 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 (bit-sliced: 32 circuit instances per lane word)", "data": "synthetic",
+            "dtype": "u32", "data": "synthetic",
             "config": {"workload": args.workload, "description": WORKLOAD_DESC[args.workload], "gates": main_gates,
                        "vectors_per_gpu": 1 << (args.log2_vectors or build_workload(args.workload)[1]), "total_vectors": total_vectors,
                        "mode": cs.mode_name, "words_per_thread_or_cta": cs.words_per_thread, "fused_lop3_instructions": cs.info["n_luts"],
                        "levels": cs.info["n_levels"], "slots": cs.info["level_slots"] if cs.mode_name == "coop" else cs.info["lane_slots"],
                        "l2": l2_note, "sharding": "independent vector shards per rank, no collective",
+                       "bit_slicing": "one u32 lane word carries 32 circuit instances; NAND over 32 instances is one LOP3",
                        "compile_seconds": main_compile_s},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * cs.launches_per_run,
             "roofline": roofline, "cpu_baseline": cpu,
