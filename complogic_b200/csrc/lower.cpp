@@ -668,6 +668,13 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
   struct CandInfo {
     uint8_t nops, perms, bank[3];
   };
+  std::vector<uint32_t> fanout(V, 0);  // operand reads of each value (LUT operands + stores)
+  for (size_t v = 0; v < V; v++)
+    if (net.vals[v].is_lut)
+      for (int k = 0; k < net.vals[v].nfan; k++) fanout[net.vals[v].fan[k]]++;
+  for (const OutRef &o : net.outs)
+    if (o.val != NONE) fanout[o.val]++;
+  uint64_t bank_weight[MAX_BANKS] = {};
   std::vector<Placed> order;
   std::vector<uint8_t> taken;
   std::vector<CandInfo> cinfo;
@@ -727,17 +734,63 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
         taken[c] = 1, members++, placed++;
         order.push_back({items[b + c], (uint8_t)pick});
       }
-      // nothing else in the window fits without a conflict: fill the quarter in order, conflicts accepted
-      for (uint32_t c = head; c < n && members < BANKS; c++) {
-        if (taken[c]) continue;
-        taken[c] = 1, members++, placed++;
-        order.push_back({items[b + c], 0});
+      // nothing else in the window fits without a conflict (the tail of a class): fill the group with the
+      // candidates that collide least, so that the replays spread over banks instead of piling onto one
+      if (members < BANKS && placed < n) {
+        uint8_t cnt[3][MAX_BANKS] = {};
+        for (uint32_t k = order.size() - members; k < order.size(); k++) {
+          const uint32_t x = order[k].x;
+          const uint8_t *pm = PERM[order[k].perm];
+          const int no = x >= V ? (net.outs[x - V].val == NONE ? 0 : 1) : net.vals[x].is_lut ? net.vals[x].nfan : 0;
+          for (int j = 0; j < no; j++) cnt[pm[j]][(x >= V ? slot[net.outs[x - V].val] : slot[net.vals[x].fan[j]]) % BANKS]++;
+        }
+        while (members < BANKS && placed < n) {
+          uint32_t best_c = NONE, best_cost = NONE, seen = 0;
+          int best_q = 0;
+          for (uint32_t c = head; c < n && seen < 64; c++) {
+            if (taken[c]) continue;
+            seen++;
+            const CandInfo &ci = cinfo[c];
+            for (int q = 0; q < 6; q++) {
+              if (!(ci.perms >> q & 1)) continue;
+              uint32_t cost = 0;
+              for (int k = 0; k < ci.nops; k++) cost += cnt[PERM[q][k]][ci.bank[k]];
+              if (cost < best_cost) best_cost = cost, best_c = c, best_q = q;
+            }
+            if (best_cost == 0) break;
+          }
+          const CandInfo &ci = cinfo[best_c];
+          for (int k = 0; k < ci.nops; k++) cnt[PERM[best_q][k]][ci.bank[k]]++;
+          taken[best_c] = 1, members++, placed++;
+          order.push_back({items[b + best_c], (uint8_t)best_q});
+        }
       }
     }
     // -- emit, choosing destination bank groups quarter by quarter
-    uint32_t dmask = 0;
+    // The members of a group take distinct bank groups (conflict-free STS). WHICH member takes which is chosen so
+    // that the read traffic per bank group stays level: values are handed out most-read first to the bank group
+    // that has accumulated the least fan-out so far. (With a round-robin choice the readers of a level see up to
+    // +/-25 % imbalance between bank groups, which no packing of the readers can undo.)
+    uint32_t bank_of[MAX_BANKS] = {};
     for (uint32_t i = 0; i < n; i++) {
-      if (i % BANKS == 0) dmask = 0;
+      if (i % BANKS == 0) {
+        uint32_t idx[MAX_BANKS], m = 0, dmask = 0;
+        for (uint32_t k = i; k < std::min(n, i + BANKS); k++)
+          if (order[k].x < V) idx[m++] = k;
+        std::stable_sort(idx, idx + m, [&](uint32_t p, uint32_t q) { return fanout[order[p].x] > fanout[order[q].x]; });
+        for (uint32_t j = 0; j < m; j++) {
+          uint32_t bank = NONE;
+          for (uint32_t cand = 0; cand < BANKS; cand++) {
+            if (dmask >> cand & 1u) continue;
+            if (bank == NONE || bank_weight[cand] < bank_weight[bank] ||
+                (bank_weight[cand] == bank_weight[bank] && pool.has_free(cand) && !pool.has_free(bank)))
+              bank = cand;
+          }
+          dmask |= 1u << bank;
+          bank_weight[bank] += fanout[order[idx[j]].x];
+          bank_of[idx[j] % BANKS] = bank;
+        }
+      }
       const uint32_t x = order[i].x;
       FlatInstr in{};
       if (x >= V) {
@@ -760,16 +813,7 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
         } else {
           in.kind = K_LDIN, in.row = v.row;
         }
-        uint32_t bank = NONE;
-        for (uint32_t t = 0; t < BANKS && bank == NONE; t++) {
-          const uint32_t cand = (i + t) % BANKS;
-          if (!(dmask >> cand & 1u) && pool.has_free(cand)) bank = cand;
-        }
-        for (uint32_t t = 0; t < BANKS && bank == NONE; t++) {
-          const uint32_t cand = (i + t) % BANKS;
-          if (!(dmask >> cand & 1u)) bank = cand;
-        }
-        dmask |= 1u << bank;
+        const uint32_t bank = bank_of[i % BANKS];
         slot[x] = pool.get(bank);
         if (slot[x] > 0xFFFF) {
           s.ok = false;
