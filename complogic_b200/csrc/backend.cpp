@@ -738,20 +738,4 @@ double measure_lop3_peak(Ctx *c, int reps) {
   return best;
 }
 
-// event-timed run used by the sharded driver
-double timed_run(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride) {
-  e->ctx->bind();
-  CUevent a, b;
-  CU(cuEventCreate(&a, CU_EVENT_DEFAULT));
-  CU(cuEventCreate(&b, CU_EVENT_DEFAULT));
-  CU(cuEventRecord(a, nullptr));
-  e->run(imm, out, state, n_vectors, stride, nullptr);
-  CU(cuEventRecord(b, nullptr));
-  CU(cuEventSynchronize(b));
-  float ms = 0;
-  CU(cuEventElapsedTime(&ms, a, b));
-  driver().cuEventDestroy(a), driver().cuEventDestroy(b);
-  return ms * 1e-3;
-}
-
 }  // namespace clg

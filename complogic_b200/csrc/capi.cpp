@@ -1,5 +1,6 @@
 // extern "C" surface (include/complogic_cuda.h). Exceptions never cross it: every entry point
 // catches clg::Error and turns it into a status code + thread-local message.
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -35,7 +36,6 @@ void exec_run_host(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, siz
 void exec_run_steps(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t, size_t, void *);
 void launch_slice(Ctx *, bool, const void *, void *, size_t, size_t, size_t, void *);
 void launch_fill(Ctx *, uint32_t *, size_t, size_t, uint64_t, void *);
-double timed_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t);
 double measure_lop3_peak(Ctx *, int);
 
 static thread_local std::string g_err;
@@ -495,17 +495,14 @@ int clg_run_sharded_host(const clg_flat *flat, int mode, const int *devices, int
         shard_range(n_vectors, n_devices, d, w0, w1);
         if (seconds_out) seconds_out[d] = 0;
         if (w1 <= w0) return;
-        const size_t sw = (w1 - w0 + 3) / 4 * 4, nv = std::min(n_vectors, w1 * 32) - w0 * 32;
+        const size_t nv = std::min(n_vectors, w1 * 32) - w0 * 32;
         std::unique_ptr<Ctx, void (*)(Ctx *)> c(ctx_create(devices[d]), ctx_destroy);
         std::unique_ptr<Exec, void (*)(Exec *)> e(exec_create(c.get(), flat->f, mode), exec_destroy);
-        DevBuf di(c.get(), h.n_inputs * sw * 4), dout(c.get(), h.n_outputs * sw * 4);
-        for (size_t r = 0; r < h.n_inputs; r++)
-          h2d(c.get(), (char *)di.p + r * sw * 4, imm + r * stride + w0, (w1 - w0) * 4, nullptr);
-        double t = timed_run(e.get(), (const uint32_t *)di.p, (uint32_t *)dout.p, nullptr, nv, sw);
-        if (seconds_out) seconds_out[d] = t;
-        for (size_t r = 0; r < h.n_outputs; r++)
-          d2h(c.get(), out + r * stride + w0, (char *)dout.p + r * sw * 4, (w1 - w0) * 4, nullptr);
-        stream_sync(c.get(), nullptr);
+        // this device's shard is words [w0, w1) of every row: same row stride, pointers moved by w0; the host-buffer
+        // path pipelines H2D | kernel | D2H chunks on this device's own streams
+        const auto t0 = std::chrono::steady_clock::now();
+        exec_run_host(e.get(), imm ? imm + w0 : nullptr, out ? out + w0 : nullptr, nullptr, nv, stride);
+        if (seconds_out) seconds_out[d] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       } catch (const Error &e) {
         errs[d] = e;
       } catch (const std::exception &e) {

@@ -291,7 +291,8 @@ int clg_shard_range(size_t n_vectors, int n_shards, int shard, size_t *w0, size_
 /* Single-process multi-GPU driver (north-star: the vector batch shards independently across the
  * GPUs of one box, per-GPU device-side result buffers copied back by the host; no collective).
  * HOST pointers; words are split into contiguous multiples-of-4 ranges, one host thread, context
- * and stream per device. seconds_out (optional, n_devices entries) = per-device kernel time. */
+ * and streams per device; every shard runs through the pipelined host-buffer path. seconds_out (optional, n_devices
+ * entries) = wall time of each device's shard, copies included. */
 int clg_run_sharded_host(const clg_flat *flat, int mode, const int *devices, int n_devices,
                          const uint32_t *imm, uint32_t *out, size_t n_vectors, size_t stride,
                          double *seconds_out);

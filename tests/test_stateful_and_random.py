@@ -97,7 +97,7 @@ def programs(draw):
     return ops, n_regs, n_imm, steps
 
 
-@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=int(__import__('os').environ.get('CLG_HYPOTHESIS_EXAMPLES', '150')), deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(programs(), st.integers(0, 2 ** 31))
 def test_random_programs_match_the_vm(prog, seed):
     """Hand-built style programs: registers written more than once, read before written, Sets anywhere with
