@@ -191,6 +191,7 @@ struct Exec {
         // assembling straight-line code is super-linear in its length (12k instructions: 2 s, 50k: 9 s, 200k: 75 s),
         // so AUTO only specialises up to 64k instructions; a caller who pins CLG_MODE_SPEC may go to 400k
         if (ln.n_instr == 0 || ln.n_instr > (want == CLG_MODE_SPEC ? 400000u : 65536u)) return 0;
+        if (const char *env = std::getenv("CLG_SPEC_K")) return std::atoi(env);  // tuning knob
         for (int k : {4, 2, 1})
           if ((uint64_t)ln.n_slots * k <= 200) return k;
         // one word per thread tolerates a live set somewhat beyond the register file: ptxas spills the coldest

@@ -227,3 +227,22 @@ def test_compiler_reuse_pattern_of_the_gui(api):
             for d in (False, True):
                 sim.run([a, b, d])
                 assert sim.register(out2) is (a and b and d)
+
+
+# ---- the same known-answer tests as language-neutral data (tests/golden/reference_kats.json) ----------------------
+def _kats():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kats.json")) as f:
+        return json.load(f)["kats"]
+
+
+@pytest.mark.parametrize("kat", _kats(), ids=lambda k: k["name"])
+def test_golden_fixture_replay(api, kat):
+    """Every step of every fixture: run(immediates) on one Simulation, registers carried between steps."""
+    ops = [api.Nand_op(*op[1:]) if op[0] == "Nand" else api.Set_op(op[1], op[2]) for op in kat["ops"]]
+    sim = api.Simulation(ops=ops, registers=[False] * kat["n_registers"])
+    for step in kat["steps"]:
+        sim.run(step["immediates"])
+        for reg, want in step["expect"].items():
+            assert sim.registers[int(reg)] is want, (kat["name"], kat["cite"], step)
