@@ -212,6 +212,7 @@ struct Exec {
         }
       case CLG_MODE_COOP:
         if (lv.n_instr == 0) return 0;
+        if (const char *env = std::getenv("CLG_COOP_K")) return std::atoi(env);  // tuning knob
         for (int k : {4, 2, 1})
           if ((size_t)lv.n_slots * k * 4 <= SMEM_MAX) return k;
         return 0;

@@ -1005,6 +1005,7 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
   // pack for the widest register-stack word count K that will fit one SM's shared memory (227 KB): K = 4 -> 8
   // bank groups of 16 B, K = 2 -> 16 of 8 B, K = 1 -> 32 banks of 4 B
   auto schedule_for_smem = [](const Network &n) {
+    if (const char *env = std::getenv("CLG_LEVEL_BANKS")) return schedule_level(n, (uint32_t)std::atoi(env));  // tuning knob
     Sched sc = schedule_level(n, 8);
     if (sc.ok && (size_t)sc.n_slots * 16 > 227 * 1024) sc = schedule_level(n, 16);
     if (sc.ok && (size_t)sc.n_slots * 16 > 227 * 1024 && (size_t)sc.n_slots * 8 > 227 * 1024) sc = schedule_level(n, 32);
