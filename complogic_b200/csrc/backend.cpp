@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -166,6 +167,11 @@ struct Plan {
   uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0, n_parts = 0, code_off = 0;
   size_t smem = 0;
   bool resident = false;  // cooperative: the (largest part's) instruction stream is staged in shared memory
+  // long programs: the lane stream cut into SPEC_CHUNK-instruction kernels; live registers cross the cuts through `scratch`
+  std::vector<CUmodule> chunk_mods;
+  std::vector<CUfunction> chunk_fns;
+  CUdeviceptr scratch = 0;
+  size_t scratch_stride = 0;
   CUmodule spec_mod = nullptr, steps_mod = nullptr;
   CUfunction spec_fn = nullptr, steps_fn = nullptr;  // steps_fn: the fused multi-step form, assembled on first use
   std::string ptx;
@@ -189,8 +195,10 @@ struct Exec {
     switch (m) {
       case CLG_MODE_SPEC:
         // assembling straight-line code is super-linear in its length (12k instructions: 2 s, 50k: 9 s, 200k: 75 s),
-        // so AUTO only specialises up to 64k instructions; a caller who pins CLG_MODE_SPEC may go to 400k
-        if (ln.n_instr == 0 || ln.n_instr > (want == CLG_MODE_SPEC ? 400000u : 65536u)) return 0;
+        // so programs beyond SPEC_CHUNK instructions are cut into chunk kernels that are assembled in parallel
+        // (~3 s per 16k instructions per host thread). AUTO specialises up to 400k instructions, a caller who pins
+        // CLG_MODE_SPEC up to 4M.
+        if (ln.n_instr == 0 || ln.n_instr > (want == CLG_MODE_SPEC ? 4000000u : 400000u)) return 0;
         if (const char *env = std::getenv("CLG_SPEC_K")) return std::atoi(env);  // tuning knob
         for (int k : {4, 2, 1})
           if ((uint64_t)ln.n_slots * k <= 200) return k;
@@ -403,6 +411,33 @@ struct Exec {
       CU(cuMemAlloc(&P.d_levels, ((size_t)P.n_levels + 1 + 3) / 4 * 16));  // padded: the resident kernel bulk-copies it
       CU(cuMemcpyHtoDAsync(P.d_levels, flat.levels(sidx), ((size_t)P.n_levels + 1) * 4, nullptr));
       CU(cuStreamSynchronize(nullptr));
+    } else if (ln.n_instr > SPEC_CHUNK) {
+      // chunked specialisation: cut points every SPEC_CHUNK instructions, live registers listed per cut
+      const uint32_t n_chunks = spec_n_chunks(ln.n_instr);
+      std::vector<std::vector<uint32_t>> live(n_chunks + 1);
+      for (uint32_t c = 1; c < n_chunks; c++) live[c] = spec_live_slots(flat, spec_chunk_begin(ln.n_instr, c));
+      P.chunk_mods.assign(n_chunks, nullptr), P.chunk_fns.assign(n_chunks, nullptr);
+      std::vector<std::string> errors(n_chunks);
+      std::atomic<uint32_t> next{0};
+      auto worker = [&]() {
+        driver().cuCtxSetCurrent(ctx->cu);
+        for (uint32_t c; (c = next.fetch_add(1)) < n_chunks;) {
+          const std::string text = emit_spec_chunk_ptx(flat, P.K, spec_chunk_begin(ln.n_instr, c), spec_chunk_begin(ln.n_instr, c + 1), live[c], live[c + 1]);
+          if (c == 0) P.ptx = text;
+          char log[4096] = {0};
+          CUjit_option opt[] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES};
+          void *val[] = {log, (void *)(uintptr_t)sizeof log};
+          if (driver().cuModuleLoadDataEx(&P.chunk_mods[c], text.c_str(), 2, opt, val) != CUDA_SUCCESS ||
+              driver().cuModuleGetFunction(&P.chunk_fns[c], P.chunk_mods[c], "clg_spec_chunk") != CUDA_SUCCESS)
+            errors[c] = std::string("chunk ") + std::to_string(c) + ": " + log;
+        }
+      };
+      std::vector<std::thread> pool;
+      const unsigned nthreads = std::min<unsigned>(n_chunks, std::max(1u, std::min(8u, std::thread::hardware_concurrency())));
+      for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(worker);
+      for (auto &t : pool) t.join();
+      for (const std::string &e : errors)
+        if (!e.empty()) fail(CLG_E_PTX, "assembling the specialised kernel failed: " + e);
     } else {
       P.ptx = emit_spec_ptx(flat, P.K);
       char log[8192] = {0}, info[4096] = {0};
@@ -427,6 +462,9 @@ struct Exec {
       if (P.d_clevels) d.cuMemFree(P.d_clevels);
       if (P.spec_mod) d.cuModuleUnload(P.spec_mod);
       if (P.steps_mod) d.cuModuleUnload(P.steps_mod);
+      for (CUmodule m : P.chunk_mods)
+        if (m) d.cuModuleUnload(m);
+      if (P.scratch) d.cuMemFree(P.scratch);
     }
     for (int b = 0; b < NBUF; b++) {
       if (stage_in[b]) d.cuMemFree(stage_in[b]);
@@ -536,7 +574,7 @@ struct Exec {
     if (n_steps == 0 || n_vectors == 0) return;
     const size_t words = (n_vectors + 31) / 32;
     const size_t imm_step = (size_t)h.n_inputs * stride, out_step = (size_t)h.n_outputs * stride;
-    if (choose(words) != CLG_MODE_SPEC || n_steps == 1) {
+    if (choose(words) != CLG_MODE_SPEC || n_steps == 1 || lane_stream().n_instr > SPEC_CHUNK) {
       for (size_t s_ = 0; s_ < n_steps; s_++) run(imm ? imm + s_ * imm_step : nullptr, out ? out + s_ * out_step : nullptr, state, n_vectors, stride, stream);
       return;
     }
@@ -587,8 +625,20 @@ struct Exec {
     const uint32_t groups = (uint32_t)((words + K - 1) / K);
     if (mode == CLG_MODE_SPEC) {
       uint32_t stride32 = (uint32_t)stride, g = groups;
-      void *args[] = {&imm, &out, &state, &stride32, &g};
       const uint32_t nt = 128;
+      if (!P.chunk_fns.empty()) {
+        if (stride > P.scratch_stride) {  // registers that are live across chunk cuts: [slot][stride] words
+          CU(cuCtxSynchronize());
+          if (P.scratch) driver().cuMemFree(P.scratch);
+          P.scratch = 0, P.scratch_stride = 0;
+          CU(cuMemAlloc(&P.scratch, (size_t)lane_stream().n_slots * stride * 4));
+          P.scratch_stride = stride;
+        }
+        void *cargs[] = {&imm, &out, &state, &stride32, &g, &P.scratch};
+        for (CUfunction fn : P.chunk_fns) CU(cuLaunchKernel(fn, (groups + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, cargs, nullptr));
+        return;
+      }
+      void *args[] = {&imm, &out, &state, &stride32, &g};
       CU(cuLaunchKernel(P.spec_fn, (groups + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, args, nullptr));
       return;
     }
@@ -667,6 +717,9 @@ Exec *exec_create(Ctx *c, const Flat &f, int mode) { return new Exec(c, f, mode)
 void exec_destroy(Exec *e) { delete e; }
 int exec_mode(const Exec *e) { return e->mode; }
 int exec_k(const Exec *e) { return e->last_k; }
+int exec_launches(const Exec *e) {
+  return e->mode == CLG_MODE_SPEC && !e->plan[CLG_MODE_SPEC].chunk_fns.empty() ? (int)e->plan[CLG_MODE_SPEC].chunk_fns.size() : 1;
+}
 const std::string &exec_ptx(const Exec *e) { return e->plan[CLG_MODE_SPEC].ptx; }
 const Flat &exec_flat(const Exec *e) { return e->flat; }
 Ctx *exec_ctx(const Exec *e) { return e->ctx; }

@@ -28,6 +28,7 @@ Exec *exec_create(Ctx *, const Flat &, int);
 void exec_destroy(Exec *);
 int exec_mode(const Exec *);
 int exec_k(const Exec *);
+int exec_launches(const Exec *);
 const std::string &exec_ptx(const Exec *);
 const Flat &exec_flat(const Exec *);
 Ctx *exec_ctx(const Exec *);
@@ -225,6 +226,21 @@ static int spec_ptx_text(const clg_flat *f, int k, bool steps, char **ptx_out) {
   *ptx_out = p;
   CLG_CATCH
 }
+int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, char **ptx_out) {
+  CLG_TRY
+  NEED(f), NEED(ptx_out);
+  const uint32_t n = f->f.header().stream[STREAM_LANE].n_instr, total = spec_n_chunks(n);
+  if (n_chunks) *n_chunks = total;
+  if (chunk >= total) fail(CLG_E_INVALID, "chunk index out of range");
+  const uint32_t begin = spec_chunk_begin(n, chunk), end = spec_chunk_begin(n, chunk + 1);
+  std::string s = emit_spec_chunk_ptx(f->f, k, begin, end, chunk ? spec_live_slots(f->f, begin) : std::vector<uint32_t>(),
+                                      end < n ? spec_live_slots(f->f, end) : std::vector<uint32_t>());
+  char *p = (char *)std::malloc(s.size() + 1);
+  if (!p) throw std::bad_alloc();
+  std::memcpy(p, s.c_str(), s.size() + 1);
+  *ptx_out = p;
+  CLG_CATCH
+}
 
 // ---- device -------------------------------------------------------------------------------------------------
 int clg_ctx_create(int device, clg_ctx **out) {
@@ -313,7 +329,7 @@ void clg_exec_destroy(clg_exec *ex) {
 }
 int clg_exec_mode(const clg_exec *ex) { return ex ? exec_mode(ex->e) : 0; }
 int clg_exec_words_per_thread(const clg_exec *ex) { return ex ? exec_k(ex->e) : 0; }
-int clg_exec_launches_per_run(const clg_exec *) { return 1; }
+int clg_exec_launches_per_run(const clg_exec *ex) { return ex ? exec_launches(ex->e) : 0; }
 const char *clg_exec_ptx(const clg_exec *ex) { return ex ? exec_ptx(ex->e).c_str() : ""; }
 
 int clg_exec_run(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, void *stream) {

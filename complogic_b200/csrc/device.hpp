@@ -12,6 +12,9 @@
 namespace clg {
 
 std::string emit_spec_ptx(const Flat &f, int K, bool multi_step = false);
+std::vector<uint32_t> spec_live_slots(const Flat &f, uint32_t at);
+std::string emit_spec_chunk_ptx(const Flat &f, int K, uint32_t begin, uint32_t end, const std::vector<uint32_t> &live_in,
+                                const std::vector<uint32_t> &live_out);
 
 // mirrors kernels.cu
 struct RunParams {
@@ -36,6 +39,13 @@ constexpr int RING_STAGES = 4;
 constexpr int RING_CHUNK = 256;
 constexpr size_t LANE_RING_BYTES = RING_STAGES * RING_CHUNK * 16 + 128;
 constexpr size_t SMEM_MAX = 227 * 1024;
+constexpr uint32_t SPEC_CHUNK = 16384;  // most instructions per kernel of a chunked specialised program
+inline uint32_t spec_n_chunks(uint32_t n_instr) { return n_instr ? (n_instr + SPEC_CHUNK - 1) / SPEC_CHUNK : 1; }
+// first instruction of chunk c (c == n_chunks: the end); chunks are equal-sized
+inline uint32_t spec_chunk_begin(uint32_t n_instr, uint32_t c) {
+  const uint32_t n = spec_n_chunks(n_instr);
+  return (uint32_t)(((uint64_t)n_instr * c + n - 1) / n);
+}
 
 }  // namespace clg
 

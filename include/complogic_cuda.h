@@ -192,6 +192,10 @@ int clg_flat_state_regs(const clg_flat *f, const uint64_t **regs, size_t *n);
 int clg_flat_spec_ptx(const clg_flat *f, int k, char **ptx_out);
 /* same for the fused multi-step form (clg_exec_run_steps) */
 int clg_flat_spec_steps_ptx(const clg_flat *f, int k, char **ptx_out);
+/* Programs longer than 16384 lane-order instructions are specialised as a chain of chunk kernels (entry
+ * clg_spec_chunk) that hand their live registers over through a device scratch buffer. Text of chunk `chunk`;
+ * *n_chunks (optional) receives the chain length (1 for a short program, whose only chunk has no hand-over). */
+int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, char **ptx_out);
 
 /* ---------------------------------------------------------------------------------------------
  * Device side. Raw CUDA driver API underneath (libcuda.so.1 is dlopen'ed when the first context
@@ -227,7 +231,7 @@ int clg_exec_create(clg_ctx *ctx, const clg_flat *flat, int mode, clg_exec **out
 void clg_exec_destroy(clg_exec *ex);
 int clg_exec_mode(const clg_exec *ex); /* the mode actually chosen */
 int clg_exec_words_per_thread(const clg_exec *ex); /* K: 32-bit words of each row one thread (lane/spec) or CTA (coop) owns */
-/* kernel launches one clg_exec_run issues (for bench accounting) */
+/* kernel launches one clg_exec_run issues in the mode last used (1, or the chain length of a chunked specialised program) */
 int clg_exec_launches_per_run(const clg_exec *ex);
 /* specialised mode only: generated PTX text (NUL-terminated) for inspection */
 const char *clg_exec_ptx(const clg_exec *ex);

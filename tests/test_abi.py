@@ -100,6 +100,15 @@ def test_spec_ptx_assembles_for_sm100a(tmp_path):
         n_lop3 = sass.count("LOP3.LUT")
         assert n_lop3 >= fp.info["n_luts"] * k  # one LOP3 per LUT per word (+ inverted stores)
         assert (".128" in sass) if k == 4 else True
+    # one kernel out of the middle of a chunked chain (live registers reloaded from / stored to the scratch buffer)
+    dag = circuits.random_dag(levels=1500, width=48, n_immediates=64, window=2, seed=31)
+    fp = host.FlatProgram.levelize(dag.sim, 64, dag.out_regs)
+    text, n = fp.spec_chunk_ptx(4, 1)
+    assert n == 3 and ".entry clg_spec_chunk" in text
+    (tmp_path / "chunk.ptx").write_text(text)
+    r = subprocess.run(["ptxas", "-arch=sm_100a", "-v", "-o", str(tmp_path / "c.cubin"), str(tmp_path / "chunk.ptx")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
     # the fused multi-step form of a stateful program: carried registers live in registers across the step loop
     c = host.Compiler(2)
     sim = c.compile([host.DLatch(0, 1, c.alloc())])

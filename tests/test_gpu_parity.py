@@ -10,6 +10,7 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 import complogic_b200 as host
 from complogic_b200 import circuits
 from oracle import oracle
+from tests.test_spec_ptx import feedback_dag
 from tests.helpers import exhaustive_sliced, mask_tail, random_sliced, stride_for, unslice_int
 
 pytestmark = pytest.mark.gpu
@@ -133,6 +134,38 @@ def test_latch_sequences_per_lane(mode, gate):
     for s in range(steps):
         got = cs.run_batch(imm[s], nv, state=state)
         assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv)), f"step {s}"
+
+
+def test_chunked_specialised_long_programs():
+    """Lane-order programs beyond 16384 instructions run as a chain of specialised kernels that hand their live
+    registers over through a device scratch buffer: cuts between instances (multipliers) and in the middle of a
+    DAG with a few hundred live values must both give the oracle's bits, at several strides with one executor."""
+    mul = circuits.flatten_instances(circuits.array_multiplier(64), 5)
+    dag = circuits.random_dag(levels=1500, width=48, n_immediates=64, window=2, seed=31)
+    for circ in (mul, dag):
+        cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, mode=host.MODE_SPEC)
+        assert cs.info["lane_instrs"] > 16384 and cs.mode == host.MODE_SPEC
+        assert cs.launches_per_run > 1
+        for nv in (300, 70000, 33):  # the scratch buffer grows with the stride and is kept when it shrinks
+            imm = random_sliced(circ.n_immediates, stride_for(nv), seed=nv + 5)
+            assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), oracle_out(circ, imm, nv)), (circ.name, nv)
+
+
+def test_chunked_specialised_stateful():
+    """Carried registers across a chunked program: the state row is loaded by the first kernel of the chain and stored
+    by the last; several steps, against the oracle VM stepping the same ops."""
+    sim, outs = feedback_dag()
+    R, nv, T = len(sim.registers), 200, 4
+    stride = stride_for(nv)
+    cs = host.CudaSimulation.from_simulation(sim, 64, outs, flags=host.LV_STATEFUL, mode=host.MODE_SPEC)
+    assert cs.info["lane_instrs"] > 16384 and cs.info["n_state"] == len(outs) and cs.launches_per_run > 1
+    imm = np.stack([random_sliced(64, stride, 40 + t) for t in range(T)])
+    want = oracle.run_batch_scalar(sim, R, imm, nv, outs, steps=T, all_steps=True)
+    state = np.zeros((cs.info["n_state"], stride), np.uint32)
+    for t in range(T):
+        got = cs.run_batch(imm[t], nv, state=state)
+        assert np.array_equal(mask_tail(got, nv), mask_tail(want[t], nv)), f"step {t}"
+    assert np.array_equal(mask_tail(state, nv), mask_tail(want[T - 1], nv))  # state rows ARE the output registers here
 
 
 @pytest.mark.parametrize("mode", MODES)

@@ -1,0 +1,64 @@
+"""CPU-only checks of the specialised mode's generated PTX (complogic_b200/csrc/spec.cpp), evaluated by the numpy
+PTX interpreter in tests/ptx_interp.py against the oracle VM: the straight-line kernels at every K, and the chunked
+chain long programs are cut into (live registers handed over through the scratch buffer)."""
+import numpy as np
+import pytest
+
+import complogic_b200 as host
+from complogic_b200 import circuits
+from oracle import oracle
+from tests import ptx_interp
+from tests.helpers import mask_tail, random_sliced
+
+
+def feedback_dag(levels=1500, width=48, n_imm=64, seed=33):
+    """A long thin DAG whose first level also reads the LAST level's registers: in program order those are read
+    before they are written, so they carry the previous run's values (state rows, rewritten in place)."""
+    dag = circuits.random_dag(levels=levels, width=width, n_immediates=n_imm, window=2, seed=seed)
+    ops = dag.sim.ops_array.copy()
+    last = n_imm + (levels - 1) * width
+    ops["b"][n_imm:n_imm + width] = np.arange(last, last + width)
+    return host.Simulation(registers=[False] * len(dag.sim.registers), _ops_array=ops), list(range(last, last + width))
+
+
+@pytest.mark.parametrize("k", [1, 2, 4])
+def test_straight_line_kernel_matches_oracle(k):
+    for circ in (circuits.ripple_adder(32), circuits.array_multiplier(16)):
+        fp = host.FlatProgram.levelize(circ.sim, circ.n_immediates, circ.out_regs)
+        nv, stride = 32 * 8, 8
+        imm = random_sliced(circ.n_immediates, stride, seed=7 + k)
+        want = oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs)
+        mem = {"imm": imm, "out": np.zeros((len(circ.out_regs), stride), np.uint32), "state": np.zeros((1, stride), np.uint32)}
+        ptx_interp.run_kernel(fp.spec_ptx(k), k, stride // k, mem)
+        assert np.array_equal(mem["out"], want)
+        got = ptx_interp.run_program(fp, k, imm, None, len(circ.out_regs), fp.info["lane_slots"])
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("k", [1, 4])
+def test_chunked_chain_hands_registers_over(k):
+    """Cuts in the middle of a DAG: each kernel's prologue must reload exactly what later code reads."""
+    circ = circuits.random_dag(levels=1500, width=48, n_immediates=64, window=2, seed=31)
+    fp = host.FlatProgram.levelize(circ.sim, 64, circ.out_regs)
+    _, n = fp.spec_chunk_ptx(k, 0)
+    assert fp.info["lane_instrs"] > 16384 and n == -(-fp.info["lane_instrs"] // 16384)
+    nv, stride = 32 * 4, 4
+    imm = random_sliced(64, stride, seed=99)
+    want = oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs)
+    got = ptx_interp.run_program(fp, k, imm, None, len(circ.out_regs), fp.info["lane_slots"])
+    assert np.array_equal(got, want)
+    with pytest.raises(host.ClgError):
+        fp.spec_chunk_ptx(k, n)
+
+
+def test_chunked_chain_stateful_steps():
+    sim, outs = feedback_dag()
+    fp = host.FlatProgram.levelize(sim, 64, outs, flags=host.LV_STATEFUL)
+    assert fp.info["n_state"] == len(outs) and fp.spec_chunk_ptx(1, 0)[1] > 1
+    nv, stride, T = 64, 4, 3
+    imm = np.stack([random_sliced(64, stride, 40 + t) for t in range(T)])
+    want = oracle.run_batch_scalar(sim, len(sim.registers), imm, nv, outs, steps=T, all_steps=True)
+    state = np.zeros((fp.info["n_state"], stride), np.uint32)
+    for t in range(T):
+        got = ptx_interp.run_program(fp, 4, imm[t], state, len(outs), fp.info["lane_slots"])
+        assert np.array_equal(mask_tail(got, nv), mask_tail(want[t], nv)), f"step {t}"
