@@ -410,13 +410,14 @@ class FlatProgram:
         lib().clg_free(out)
         return s
 
-    def spec_chunk_ptx(self, k: int, chunk: int) -> tuple[str, int]:
-        """PTX of one kernel of the chunked specialised form, and the length of the chain."""
-        out, n = C.c_void_p(), C.c_uint32()
-        check(lib().clg_flat_spec_chunk_ptx(self._h, k, chunk, C.byref(n), C.byref(out)))
+    def spec_chunk_ptx(self, k: int, chunk: int, with_bases: bool = False):
+        """PTX of one kernel of the chunked specialised form and the length of the chain (and, with_bases, the rows
+        (imm, out, state) the kernel's pointers are advanced by)."""
+        out, n, bases = C.c_void_p(), C.c_uint32(), (C.c_uint32 * 3)()
+        check(lib().clg_flat_spec_chunk_ptx(self._h, k, chunk, C.byref(n), bases, C.byref(out)))
         s = C.string_at(out).decode()
         lib().clg_free(out)
-        return s, n.value
+        return (s, n.value, tuple(bases)) if with_bases else (s, n.value)
 
     def __del__(self):
         try:

@@ -3,7 +3,6 @@
 #include <dlfcn.h>
 
 #include <algorithm>
-#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -168,8 +167,13 @@ struct Plan {
   size_t smem = 0;
   bool resident = false;  // cooperative: the (largest part's) instruction stream is staged in shared memory
   // long programs: the lane stream cut into SPEC_CHUNK-instruction kernels; live registers cross the cuts through `scratch`
-  std::vector<CUmodule> chunk_mods;
-  std::vector<CUfunction> chunk_fns;
+  struct ChunkLaunch {
+    CUfunction fn;
+    uint32_t imm_base, out_base, state_base;  // rows
+  };
+  std::vector<CUmodule> chunk_mods;  // one per DISTINCT chunk
+  std::vector<ChunkLaunch> chunks;   // the chain, in order
+  uint32_t chunk_kernels = 0;
   CUdeviceptr scratch = 0;
   size_t scratch_stride = 0;
   CUmodule spec_mod = nullptr, steps_mod = nullptr;
@@ -177,12 +181,26 @@ struct Plan {
   std::string ptx;
 };
 
+// Assemble generated PTX with the driver's JIT (it serialises concurrent calls internally: 13 kernels took 12.7 s on
+// one host thread and 14.2 s on sixteen, so there is no thread pool here). CLG_SPEC_MAXREG caps registers per thread.
+static void assemble(const std::string &text, const char *entry, const std::string &what, CUmodule *mod, CUfunction *fn) {
+  char log[8192] = {0};
+  CUjit_option opt[3] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES, CU_JIT_MAX_REGISTERS};
+  void *val[3] = {log, (void *)(uintptr_t)sizeof log, nullptr};
+  unsigned n_opt = 2;
+  if (const char *env = std::getenv("CLG_SPEC_MAXREG")) val[2] = (void *)(uintptr_t)std::max(16, std::atoi(env)), n_opt = 3;
+  if (driver().cuModuleLoadDataEx(mod, text.c_str(), n_opt, opt, val) != CUDA_SUCCESS)
+    fail(CLG_E_PTX, "assembling " + what + " failed: " + log);
+  CU(cuModuleGetFunction(fn, *mod, entry));
+}
+
 struct Exec {
   Ctx *ctx;
   Flat flat;  // own copy: the caller may destroy its clg_flat
   int want;   // CLG_MODE_AUTO or the mode the caller pinned
   int mode;   // mode of the most recent (or, before any run, the preferred) plan
   int last_k = 0, last_parts = 0;
+  mutable int spec_distinct = -1;  // distinct kernels of the chunked specialised form (computed on demand)
   Plan plan[5];  // indexed by clg_mode; [PLAN_PARTS] = cooperative mode over the partitioned level stream
   static constexpr int PLAN_PARTS = 4;
 
@@ -194,17 +212,31 @@ struct Exec {
     const FlatStream &lv = level_stream(), &ln = lane_stream();
     switch (m) {
       case CLG_MODE_SPEC:
-        // assembling straight-line code is super-linear in its length (12k instructions: 2 s, 50k: 9 s, 200k: 75 s),
-        // so programs beyond SPEC_CHUNK instructions are cut into chunk kernels that are assembled in parallel
-        // (~3 s per 16k instructions per host thread). AUTO specialises up to 400k instructions, a caller who pins
-        // CLG_MODE_SPEC up to 4M.
-        if (ln.n_instr == 0 || ln.n_instr > (want == CLG_MODE_SPEC ? 4000000u : 400000u)) return 0;
-        if (const char *env = std::getenv("CLG_SPEC_K")) return std::atoi(env);  // tuning knob
-        for (int k : {4, 2, 1})
-          if ((uint64_t)ln.n_slots * k <= 200) return k;
-        // one word per thread tolerates a live set somewhat beyond the register file: ptxas spills the coldest
-        // values to L1-backed local memory (mul64: 315 live values -> 255 registers + 488 B of spills)
-        return ln.n_slots <= 512 ? 1 : 0;
+        // Assembling straight-line code is super-linear in its length (12k instructions: 2 s, 50k: 9 s, 200k: 75 s),
+        // so long programs are cut into chunk kernels of about a second each. A caller who pins CLG_MODE_SPEC
+        // gets any program up to 4M instructions; AUTO only specialises when at most 4 DISTINCT kernels have to be
+        // assembled (a short program, or a flattened one whose instances share their kernels).
+        if (ln.n_instr == 0 || ln.n_instr > 4000000u) return 0;
+        {
+          int k = 0;
+          if (const char *env = std::getenv("CLG_SPEC_K")) k = std::atoi(env);  // tuning knob
+          for (int c : {4, 2, 1})
+            if (!k && (uint64_t)ln.n_slots * c <= 200) k = c;
+          // one word per thread tolerates a live set somewhat beyond the register file: ptxas spills the coldest
+          // values to L1-backed local memory (mul64: 315 live values -> 255 registers + 488 B of spills)
+          if (!k && ln.n_slots <= 512) k = 1;
+          if (k && want != CLG_MODE_SPEC && ln.n_instr > 4 * spec_chunk_limit(k)) {
+            if (spec_distinct < 0) {
+              const std::vector<SpecChunk> chunks = spec_chunks(flat, k);
+              std::vector<const SpecChunk *> unique;
+              for (const SpecChunk &c : chunks)
+                if (std::none_of(unique.begin(), unique.end(), [&](const SpecChunk *u) { return u->same_kernel(c); })) unique.push_back(&c);
+              spec_distinct = (int)unique.size();
+            }
+            if (spec_distinct > 4) return 0;
+          }
+          return k;
+        }
       case CLG_MODE_LANE:
         if (ln.n_instr == 0) return 0;
         // the kernel is latency bound: what counts is resident consumer warps x K, which shared memory fixes
@@ -270,10 +302,29 @@ struct Exec {
     }
     return std::ceil(std::ceil((double)words / k) / ctx->sm_count) * per_group;
   }
+  // the chunked specialised form: a chain of launches of dependent straight-line code. One warp alone is bound by
+  // the LOP3 latency (~4 cycles an instruction), a full SM by issue (2 cycles per warp instruction per scheduler;
+  // measured on mul64 x 8: 7 cycles per instruction at 8 resident warps).
+  double spec_cycles(size_t words) const {
+    const int k = fit_k(CLG_MODE_SPEC);
+    const FlatStream &ln = lane_stream();
+    const double regs = std::min(255.0, (double)ln.n_slots * k + 24.0);
+    const double resident = std::min(2048.0, std::floor(65536.0 / regs / 128.0) * 128.0);
+    const double groups = std::ceil((double)words / k), warps = std::min(resident, std::ceil(groups / ctx->sm_count / 32.0) * 32.0) / 32.0;
+    const double launches = std::ceil((double)ln.n_instr / spec_chunk_limit(k));
+    return std::ceil(groups / (resident * ctx->sm_count)) * ln.n_instr * k * std::max(4.0, 0.85 * warps) + launches * 5000.0;
+  }
   int choose(size_t words) const {
     if (want != CLG_MODE_AUTO) return want;
-    if (fit_k(CLG_MODE_SPEC)) return CLG_MODE_SPEC;
+    const int spec_k = fit_k(CLG_MODE_SPEC);
     const bool lane_ok = fit_k(CLG_MODE_LANE) != 0, coop_ok = fit_k(CLG_MODE_COOP) != 0;
+    if (spec_k) {
+      // a program that is ONE kernel always runs specialised; a chain has to beat the interpreters at this batch size
+      // (one vector through 128 flattened multipliers is 128 dependent launches: the cooperative mode's case)
+      if (lane_stream().n_instr <= spec_chunk_limit(spec_k)) return CLG_MODE_SPEC;
+      const double sc = spec_cycles(words);
+      if ((!lane_ok || sc <= lane_cycles(words)) && (!coop_ok || sc <= coop_cycles(words))) return CLG_MODE_SPEC;
+    }
     if (lane_ok && coop_ok) return lane_cycles(words) <= coop_cycles(words) ? CLG_MODE_LANE : CLG_MODE_COOP;
     return lane_ok ? CLG_MODE_LANE : CLG_MODE_COOP;
   }
@@ -411,42 +462,31 @@ struct Exec {
       CU(cuMemAlloc(&P.d_levels, ((size_t)P.n_levels + 1 + 3) / 4 * 16));  // padded: the resident kernel bulk-copies it
       CU(cuMemcpyHtoDAsync(P.d_levels, flat.levels(sidx), ((size_t)P.n_levels + 1) * 4, nullptr));
       CU(cuStreamSynchronize(nullptr));
-    } else if (ln.n_instr > SPEC_CHUNK) {
-      // chunked specialisation: cut points every SPEC_CHUNK instructions, live registers listed per cut
-      const uint32_t n_chunks = spec_n_chunks(ln.n_instr);
-      std::vector<std::vector<uint32_t>> live(n_chunks + 1);
-      for (uint32_t c = 1; c < n_chunks; c++) live[c] = spec_live_slots(flat, spec_chunk_begin(ln.n_instr, c));
-      P.chunk_mods.assign(n_chunks, nullptr), P.chunk_fns.assign(n_chunks, nullptr);
-      std::vector<std::string> errors(n_chunks);
-      std::atomic<uint32_t> next{0};
-      auto worker = [&]() {
-        driver().cuCtxSetCurrent(ctx->cu);
-        for (uint32_t c; (c = next.fetch_add(1)) < n_chunks;) {
-          const std::string text = emit_spec_chunk_ptx(flat, P.K, spec_chunk_begin(ln.n_instr, c), spec_chunk_begin(ln.n_instr, c + 1), live[c], live[c + 1]);
-          if (c == 0) P.ptx = text;
-          char log[4096] = {0};
-          CUjit_option opt[] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES};
-          void *val[] = {log, (void *)(uintptr_t)sizeof log};
-          if (driver().cuModuleLoadDataEx(&P.chunk_mods[c], text.c_str(), 2, opt, val) != CUDA_SUCCESS ||
-              driver().cuModuleGetFunction(&P.chunk_fns[c], P.chunk_mods[c], "clg_spec_chunk") != CUDA_SUCCESS)
-            errors[c] = std::string("chunk ") + std::to_string(c) + ": " + log;
-        }
-      };
-      std::vector<std::thread> pool;
-      const unsigned nthreads = std::min<unsigned>(n_chunks, std::max(1u, std::min(8u, std::thread::hardware_concurrency())));
-      for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(worker);
-      for (auto &t : pool) t.join();
-      for (const std::string &e : errors)
-        if (!e.empty()) fail(CLG_E_PTX, "assembling the specialised kernel failed: " + e);
+    } else if (ln.n_instr > spec_chunk_limit(P.K)) {
+      // chunked specialisation: cut where few registers are live; equal chunks (the instances of a flattened program)
+      // share one assembled kernel and differ only in the rows their pointers are advanced by
+      const std::vector<SpecChunk> chunks = spec_chunks(flat, P.K);
+      std::vector<uint32_t> unique;  // indices of the chunks that get assembled
+      std::vector<uint32_t> kernel_of(chunks.size());
+      for (uint32_t c = 0; c < chunks.size(); c++) {
+        uint32_t u = 0;
+        while (u < unique.size() && !chunks[c].same_kernel(chunks[unique[u]])) u++;
+        if (u == unique.size()) unique.push_back(c);
+        kernel_of[c] = u;
+      }
+      P.chunk_mods.assign(unique.size(), nullptr);
+      std::vector<CUfunction> fns(unique.size(), nullptr);
+      for (uint32_t u = 0; u < unique.size(); u++) {
+        const std::string text = emit_spec_chunk_ptx(flat, P.K, chunks[unique[u]]);
+        if (u == 0) P.ptx = text;
+        assemble(text, "clg_spec_chunk", "chunk " + std::to_string(unique[u]) + " of the specialised program", &P.chunk_mods[u], &fns[u]);
+      }
+      for (uint32_t c = 0; c < chunks.size(); c++)
+        P.chunks.push_back({fns[kernel_of[c]], chunks[c].imm_base, chunks[c].out_base, chunks[c].state_base});
+      P.chunk_kernels = (uint32_t)unique.size();
     } else {
       P.ptx = emit_spec_ptx(flat, P.K);
-      char log[8192] = {0}, info[4096] = {0};
-      CUjit_option opt[] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES, CU_JIT_INFO_LOG_BUFFER,
-                            CU_JIT_INFO_LOG_BUFFER_SIZE_BYTES};
-      void *val[] = {log, (void *)(uintptr_t)sizeof log, info, (void *)(uintptr_t)sizeof info};
-      CUresult r = driver().cuModuleLoadDataEx(&P.spec_mod, P.ptx.c_str(), 4, opt, val);
-      if (r != CUDA_SUCCESS) fail(CLG_E_PTX, std::string("assembling the specialised kernel failed: ") + log);
-      CU(cuModuleGetFunction(&P.spec_fn, P.spec_mod, "clg_spec"));
+      assemble(P.ptx, "clg_spec", "the specialised kernel", &P.spec_mod, &P.spec_fn);
     }
     P.ready = true;
     return P;
@@ -574,7 +614,7 @@ struct Exec {
     if (n_steps == 0 || n_vectors == 0) return;
     const size_t words = (n_vectors + 31) / 32;
     const size_t imm_step = (size_t)h.n_inputs * stride, out_step = (size_t)h.n_outputs * stride;
-    if (choose(words) != CLG_MODE_SPEC || n_steps == 1 || lane_stream().n_instr > SPEC_CHUNK) {
+    if (choose(words) != CLG_MODE_SPEC || n_steps == 1 || lane_stream().n_instr > 65536u) {  // the fused form is one kernel: not for programs that long
       for (size_t s_ = 0; s_ < n_steps; s_++) run(imm ? imm + s_ * imm_step : nullptr, out ? out + s_ * out_step : nullptr, state, n_vectors, stride, stream);
       return;
     }
@@ -590,12 +630,7 @@ struct Exec {
     Plan &P = get(CLG_MODE_SPEC);
     if (!P.steps_fn) {
       const std::string text = emit_spec_ptx(flat, P.K, true);
-      char log[8192] = {0};
-      CUjit_option opt[] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES};
-      void *val[] = {log, (void *)(uintptr_t)sizeof log};
-      if (driver().cuModuleLoadDataEx(&P.steps_mod, text.c_str(), 2, opt, val) != CUDA_SUCCESS)
-        fail(CLG_E_PTX, std::string("assembling the multi-step specialised kernel failed: ") + log);
-      CU(cuModuleGetFunction(&P.steps_fn, P.steps_mod, "clg_spec_steps"));
+      assemble(text, "clg_spec_steps", "the multi-step specialised kernel", &P.steps_mod, &P.steps_fn);
     }
     last_k = P.K, last_parts = 0;
     uint32_t stride32 = (uint32_t)stride, g = (uint32_t)((words + P.K - 1) / P.K), steps32 = (uint32_t)n_steps;
@@ -626,7 +661,7 @@ struct Exec {
     if (mode == CLG_MODE_SPEC) {
       uint32_t stride32 = (uint32_t)stride, g = groups;
       const uint32_t nt = 128;
-      if (!P.chunk_fns.empty()) {
+      if (!P.chunks.empty()) {
         if (stride > P.scratch_stride) {  // registers that are live across chunk cuts: [slot][stride] words
           CU(cuCtxSynchronize());
           if (P.scratch) driver().cuMemFree(P.scratch);
@@ -634,8 +669,12 @@ struct Exec {
           CU(cuMemAlloc(&P.scratch, (size_t)lane_stream().n_slots * stride * 4));
           P.scratch_stride = stride;
         }
-        void *cargs[] = {&imm, &out, &state, &stride32, &g, &P.scratch};
-        for (CUfunction fn : P.chunk_fns) CU(cuLaunchKernel(fn, (groups + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, cargs, nullptr));
+        for (const Plan::ChunkLaunch &c : P.chunks) {
+          const uint32_t *c_imm = imm + (size_t)c.imm_base * stride;
+          uint32_t *c_out = out + (size_t)c.out_base * stride, *c_state = state + (size_t)c.state_base * stride;
+          void *cargs[] = {&c_imm, &c_out, &c_state, &stride32, &g, &P.scratch};
+          CU(cuLaunchKernel(c.fn, (groups + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, cargs, nullptr));
+        }
         return;
       }
       void *args[] = {&imm, &out, &state, &stride32, &g};
@@ -718,7 +757,7 @@ void exec_destroy(Exec *e) { delete e; }
 int exec_mode(const Exec *e) { return e->mode; }
 int exec_k(const Exec *e) { return e->last_k; }
 int exec_launches(const Exec *e) {
-  return e->mode == CLG_MODE_SPEC && !e->plan[CLG_MODE_SPEC].chunk_fns.empty() ? (int)e->plan[CLG_MODE_SPEC].chunk_fns.size() : 1;
+  return e->mode == CLG_MODE_SPEC && !e->plan[CLG_MODE_SPEC].chunks.empty() ? (int)e->plan[CLG_MODE_SPEC].chunks.size() : 1;
 }
 const std::string &exec_ptx(const Exec *e) { return e->plan[CLG_MODE_SPEC].ptx; }
 const Flat &exec_flat(const Exec *e) { return e->flat; }

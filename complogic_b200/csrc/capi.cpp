@@ -226,15 +226,15 @@ static int spec_ptx_text(const clg_flat *f, int k, bool steps, char **ptx_out) {
   *ptx_out = p;
   CLG_CATCH
 }
-int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, char **ptx_out) {
+int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, uint32_t *row_bases, char **ptx_out) {
   CLG_TRY
   NEED(f), NEED(ptx_out);
-  const uint32_t n = f->f.header().stream[STREAM_LANE].n_instr, total = spec_n_chunks(n);
-  if (n_chunks) *n_chunks = total;
-  if (chunk >= total) fail(CLG_E_INVALID, "chunk index out of range");
-  const uint32_t begin = spec_chunk_begin(n, chunk), end = spec_chunk_begin(n, chunk + 1);
-  std::string s = emit_spec_chunk_ptx(f->f, k, begin, end, chunk ? spec_live_slots(f->f, begin) : std::vector<uint32_t>(),
-                                      end < n ? spec_live_slots(f->f, end) : std::vector<uint32_t>());
+  const std::vector<SpecChunk> chunks = spec_chunks(f->f, k);
+  if (n_chunks) *n_chunks = (uint32_t)chunks.size();
+  if (chunk >= chunks.size()) fail(CLG_E_INVALID, "chunk index out of range");
+  const SpecChunk &c = chunks[chunk];
+  if (row_bases) row_bases[0] = c.imm_base, row_bases[1] = c.out_base, row_bases[2] = c.state_base;
+  std::string s = emit_spec_chunk_ptx(f->f, k, c);
   char *p = (char *)std::malloc(s.size() + 1);
   if (!p) throw std::bad_alloc();
   std::memcpy(p, s.c_str(), s.size() + 1);

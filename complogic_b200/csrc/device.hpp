@@ -3,6 +3,7 @@
 // loads -- and the host-side passes work -- on machines without a driver), contexts, resident
 // programs and launches.
 #pragma once
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <vector>
@@ -13,8 +14,19 @@ namespace clg {
 
 std::string emit_spec_ptx(const Flat &f, int K, bool multi_step = false);
 std::vector<uint32_t> spec_live_slots(const Flat &f, uint32_t at);
-std::string emit_spec_chunk_ptx(const Flat &f, int K, uint32_t begin, uint32_t end, const std::vector<uint32_t> &live_in,
-                                const std::vector<uint32_t> &live_out);
+uint32_t spec_chunk_limit(int K);                        // longest chunk, in lane-order instructions
+std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K);  // n_chunks + 1 instruction indices
+// One kernel of the chunked specialised form, in chunk-local terms (spec.cpp)
+constexpr uint16_t FLAG_STATE_ROW = 0x10;  // chunk-local code only: `row` indexes the state buffer
+struct SpecChunk {
+  std::vector<FlatInstr> code;              // rows relative to the bases below
+  std::vector<uint32_t> live_in, live_out;  // registers handed over through the scratch buffer
+  uint32_t n_slots = 0;
+  uint32_t imm_base = 0, out_base = 0, state_base = 0;  // rows the kernel's pointers are advanced by at launch
+  bool same_kernel(const SpecChunk &o) const;           // equal code: the two chunks can share one assembled kernel
+};
+std::vector<SpecChunk> spec_chunks(const Flat &f, int K);
+std::string emit_spec_chunk_ptx(const Flat &f, int K, const SpecChunk &c);
 
 // mirrors kernels.cu
 struct RunParams {
@@ -39,12 +51,14 @@ constexpr int RING_STAGES = 4;
 constexpr int RING_CHUNK = 256;
 constexpr size_t LANE_RING_BYTES = RING_STAGES * RING_CHUNK * 16 + 128;
 constexpr size_t SMEM_MAX = 227 * 1024;
-constexpr uint32_t SPEC_CHUNK = 16384;  // most instructions per kernel of a chunked specialised program
-inline uint32_t spec_n_chunks(uint32_t n_instr) { return n_instr ? (n_instr + SPEC_CHUNK - 1) / SPEC_CHUNK : 1; }
-// first instruction of chunk c (c == n_chunks: the end); chunks are equal-sized
-inline uint32_t spec_chunk_begin(uint32_t n_instr, uint32_t c) {
-  const uint32_t n = spec_n_chunks(n_instr);
-  return (uint32_t)(((uint64_t)n_instr * c + n - 1) / n);
+constexpr uint32_t SPEC_CHUNK = 16384;  // most instructions per kernel of a chunked specialised program ...
+inline uint32_t spec_chunk_limit() {    // ... unless CLG_SPEC_CHUNK says otherwise (tuning; read once)
+  static const uint32_t v = [] {
+    const char *e = std::getenv("CLG_SPEC_CHUNK");
+    const long n = e ? std::atol(e) : 0;
+    return n >= 256 ? (uint32_t)n : SPEC_CHUNK;
+  }();
+  return v;
 }
 
 }  // namespace clg

@@ -6,7 +6,11 @@
 //
 // The text is assembled by the CUDA driver (cuModuleLoadDataEx) for the device it runs on; tests
 // assemble it with ptxas on the build host.
+#include <algorithm>
+#include <climits>
+#include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -42,28 +46,125 @@ std::vector<uint32_t> spec_live_slots(const Flat &f, uint32_t at) {
   return out;
 }
 
-static std::string emit_spec(const Flat &f, int K, bool multi_step, uint32_t begin, uint32_t end, const std::vector<uint32_t> *live_in,
-                             const std::vector<uint32_t> *live_out);
+// Cut points of the chunked form: n_chunks + 1 instruction indices, first 0, last n_instr. Every cut costs a store
+// and a reload of each register live across it (and the reloads crowd the next kernel's register file), so each
+// chunk ends, somewhere in the second half of the longest length allowed, where the fewest registers are live --
+// between two instances of a flattened program that is zero. The assembler's time grows with the number of PTX
+// instructions (K per LUT), so the allowed length shrinks with K.
+uint32_t spec_chunk_limit(int K) { return K == 1 ? spec_chunk_limit() : K == 2 ? spec_chunk_limit() / 2 : spec_chunk_limit() * 3 / 8; }
+
+std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K) {
+  const FlatStream &st = f.header().stream[STREAM_LANE];
+  const FlatInstr *in = f.instrs(STREAM_LANE);
+  const uint32_t n = st.n_instr, limit = spec_chunk_limit(K);
+  std::vector<uint32_t> cuts{0};
+  if (n > limit) {
+    std::vector<uint32_t> live_at(n + 1, 0);  // registers live at the boundary before instruction i
+    std::vector<uint8_t> live(st.n_slots, 0);
+    uint32_t count = 0;
+    for (uint32_t i = n; i-- > 0;) {
+      const FlatInstr &x = in[i];
+      if ((x.kind == K_LUT || x.kind == K_LDIN) && live[x.dst]) live[x.dst] = 0, count--;
+      auto rd = [&](uint16_t sl) {
+        if (!live[sl]) live[sl] = 1, count++;
+      };
+      if (x.kind == K_LUT) {
+        rd(x.a);
+        if (lut_nfan(x) >= 2) rd(x.b);
+        if (lut_nfan(x) >= 3) rd(x.c);
+      } else if (x.kind == K_STOUT)
+        rd(x.a);
+      live_at[i] = count;
+    }
+    while (n - cuts.back() > limit) {
+      const uint32_t lo = cuts.back() + limit / 2 + 1, hi = cuts.back() + limit;
+      uint32_t best = hi;
+      for (uint32_t i = hi; i >= lo; i--)
+        if (live_at[i] < live_at[best]) best = i;
+      cuts.push_back(best);
+    }
+  }
+  cuts.push_back(n);
+  return cuts;
+}
+
+// Instructions [begin, end) of the lane stream in chunk-local terms. An isolated chunk (nothing live across either
+// of its cuts) has its registers renumbered by first appearance and its rows made relative to the lowest row it
+// touches in each buffer, so that two instances of the same sub-circuit produce EQUAL chunks and share one kernel.
+static SpecChunk local_code(const Flat &f, uint32_t begin, uint32_t end, std::vector<uint32_t> live_in, std::vector<uint32_t> live_out,
+                            bool may_rebase) {
+  const FlatHeader &h = f.header();
+  const FlatInstr *in = f.instrs(STREAM_LANE);
+  SpecChunk c;
+  c.live_in = std::move(live_in), c.live_out = std::move(live_out);
+  c.n_slots = h.stream[STREAM_LANE].n_slots;
+  c.code.assign(in + begin, in + end);
+  for (FlatInstr &x : c.code) {
+    if (x.kind == K_LDIN && x.row >= h.n_inputs) x.row -= h.n_inputs, x.flags |= FLAG_STATE_ROW;
+    if ((x.kind == K_STOUT || x.kind == K_STCONST) && x.row >= h.n_outputs) x.row -= h.n_outputs, x.flags |= FLAG_STATE_ROW;
+  }
+  if (!may_rebase || !c.live_in.empty() || !c.live_out.empty()) return c;
+  uint32_t lo[3] = {UINT32_MAX, UINT32_MAX, UINT32_MAX};  // imm, out, state
+  std::vector<uint16_t> name(c.n_slots, UINT16_MAX);
+  uint16_t next = 0;
+  auto rn = [&](uint16_t &sl) {
+    if (name[sl] == UINT16_MAX) name[sl] = next++;
+    sl = name[sl];
+  };
+  for (FlatInstr &x : c.code) {
+    if (x.kind == K_LUT) rn(x.a), rn(x.b), rn(x.c), rn(x.dst);
+    if (x.kind == K_LDIN) rn(x.dst);
+    if (x.kind == K_STOUT) rn(x.a);
+    if (x.kind != K_LUT) {
+      uint32_t &l = lo[(x.flags & FLAG_STATE_ROW) ? 2 : x.kind == K_LDIN ? 0 : 1];
+      l = std::min(l, x.row);
+    }
+  }
+  c.imm_base = lo[0] == UINT32_MAX ? 0 : lo[0], c.out_base = lo[1] == UINT32_MAX ? 0 : lo[1], c.state_base = lo[2] == UINT32_MAX ? 0 : lo[2];
+  for (FlatInstr &x : c.code)
+    if (x.kind != K_LUT) x.row -= (x.flags & FLAG_STATE_ROW) ? c.state_base : x.kind == K_LDIN ? c.imm_base : c.out_base;
+  c.n_slots = next;
+  return c;
+}
+
+bool SpecChunk::same_kernel(const SpecChunk &o) const {
+  return n_slots == o.n_slots && code.size() == o.code.size() && live_in == o.live_in && live_out == o.live_out &&
+         std::memcmp(code.data(), o.code.data(), code.size() * sizeof(FlatInstr)) == 0;
+}
+
+// The chain a long program runs as: cuts where few registers are live, the live sets at the cuts, chunk-local code.
+std::vector<SpecChunk> spec_chunks(const Flat &f, int K) {
+  const std::vector<uint32_t> cuts = spec_chunk_cuts(f, K);
+  const size_t n = cuts.size() - 1;
+  std::vector<std::vector<uint32_t>> live(n + 1);
+  for (size_t c = 1; c < n; c++) live[c] = spec_live_slots(f, cuts[c]);
+  std::vector<SpecChunk> out;
+  for (size_t c = 0; c < n; c++) out.push_back(local_code(f, cuts[c], cuts[c + 1], live[c], live[c + 1], true));
+  return out;
+}
+
+static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecChunk &cc, bool chunk);
 
 std::string emit_spec_ptx(const Flat &f, int K, bool multi_step) {
-  return emit_spec(f, K, multi_step, 0, f.header().stream[STREAM_LANE].n_instr, nullptr, nullptr);
+  const uint32_t n = f.header().stream[STREAM_LANE].n_instr;
+  if (n == 0) fail(CLG_E_UNSUPPORTED, "no lane-ordered stream in this flat buffer");
+  return emit_spec(f, K, multi_step, local_code(f, 0, n, {}, {}, false), false);
 }
 
-// One chunk [begin, end) of a long program as its own kernel `clg_spec_chunk`: the registers that are live across
-// the chunk boundaries travel through a scratch buffer in global memory ([slot][stride] words, coalesced like rows).
-std::string emit_spec_chunk_ptx(const Flat &f, int K, uint32_t begin, uint32_t end, const std::vector<uint32_t> &live_in,
-                                const std::vector<uint32_t> &live_out) {
-  return emit_spec(f, K, false, begin, end, &live_in, &live_out);
-}
+// One chunk of a long program as its own kernel `clg_spec_chunk`: the registers that are live across the chunk's
+// cuts travel through a scratch buffer in global memory ([slot][stride] words, coalesced like rows). The caller
+// advances the imm / out / state pointers by the chunk's row bases.
+std::string emit_spec_chunk_ptx(const Flat &f, int K, const SpecChunk &c) { return emit_spec(f, K, false, c, true); }
 
-static std::string emit_spec(const Flat &f, int K, bool multi_step, uint32_t begin, uint32_t end, const std::vector<uint32_t> *live_in,
-                             const std::vector<uint32_t> *live_out) {
-  const bool chunk = live_in != nullptr;
+static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecChunk &cc, bool chunk) {
   const FlatHeader &h = f.header();
   const FlatStream &st = h.stream[STREAM_LANE];
-  if (st.n_instr == 0) fail(CLG_E_UNSUPPORTED, "no lane-ordered stream in this flat buffer");
   if (K != 1 && K != 2 && K != 4) fail(CLG_E_INVALID, "K must be 1, 2 or 4");
-  const FlatInstr *in = f.instrs(STREAM_LANE);
+  const FlatInstr *in = cc.code.data();
+  const uint32_t begin = 0, end = (uint32_t)cc.code.size(), n_slots = cc.n_slots;
+  const std::vector<uint32_t> *live_in = &cc.live_in, *live_out = &cc.live_out;
+  std::vector<uint8_t> need_load;
+  std::vector<uint32_t> store_at;
   std::string s;
   s.reserve((size_t)(end - begin) * (size_t)(40 * K + 60) + 4096);
   char buf[512];
@@ -75,7 +176,7 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, uint32_t beg
   };
   const char *vt = K == 4 ? ".v4" : K == 2 ? ".v2" : "";
   s += "//\n// generated by complogic_b200: specialised NAND-VM evaluator, " + std::to_string(st.n_instr) +
-       " instructions, " + std::to_string(st.n_slots) + " registers x " + std::to_string(K) + " words\n//\n";
+       " instructions, " + std::to_string(n_slots) + " registers x " + std::to_string(K) + " words\n//\n";
   s += ".version 8.7\n.target sm_100a\n.address_size 64\n\n";
   // multi_step: the same straight-line body inside a loop over n_steps run() calls. Carried registers stay in
   // REGISTERS between steps (loaded from `state` once before the loop, stored once after it); every step reads its
@@ -88,7 +189,7 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, uint32_t beg
   std::snprintf(buf, sizeof buf,
                 "  .reg .b32 %%s<%u>;\n  .reg .b32 %%t<%d>;\n  .reg .b32 %%rtid, %%rcta, %%rntid, %%gid, %%stride, %%groups;\n"
                 "  .reg .b64 %%imm, %%out, %%state, %%off, %%sb, %%addr;\n  .reg .pred %%p;\n\n",
-                st.n_slots * K + 1, K + 1);
+                n_slots * K + 1, K + 1);
   s += buf;
   auto C = [&](uint32_t k_state, int k) { return "%c" + std::to_string(k_state * K + k); };
   if (multi_step) {
@@ -108,11 +209,29 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, uint32_t beg
   s += buf;
   if (chunk) {
     s += "  .reg .b64 %scr;\n  ld.param.u64 %scr, [p_scratch];\n  cvta.to.global.u64 %scr, %scr;\n  add.u64 %scr, %scr, %off;\n";
-    for (uint32_t sl : *live_in) {
-      std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  ld.global%s.u32 %s, [%%addr];\n", sl, vt, vec(sl).c_str());
-      s += buf;
-    }
+    // Hand-over: a live-in register is reloaded from the scratch buffer right before its first use here (not at
+    // the top, where hundreds of reloads would all be live at once), a live-out one is stored right after its last
+    // definition here. A register that is live across the whole chunk untouched is already in the scratch buffer.
+    need_load.assign(n_slots, 0), store_at.assign(n_slots, UINT32_MAX);
+    for (uint32_t sl : *live_in) need_load[sl] = 1;
+    std::vector<uint8_t> out_live(n_slots, 0);
+    for (uint32_t sl : *live_out) out_live[sl] = 1;
+    for (uint32_t i = begin; i < end; i++)
+      if ((in[i].kind == K_LUT || in[i].kind == K_LDIN) && out_live[in[i].dst]) store_at[in[i].dst] = i;
   }
+  auto reload = [&](uint32_t sl) {
+    if (!chunk || !need_load[sl]) return;
+    need_load[sl] = 0;
+    std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  ld.global%s.u32 %s, [%%addr];\n", sl, vt, vec(sl).c_str());
+    s += buf;
+  };
+  auto hand_over = [&](uint32_t i, uint32_t sl) {
+    if (!chunk) return;
+    need_load[sl] = 0;
+    if (store_at[sl] != i) return;
+    std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  st.global%s.u32 [%%addr], %s;\n", sl, vt, vec(sl).c_str());
+    s += buf;
+  };
   const char *cvt = K == 4 ? ".v4" : K == 2 ? ".v2" : "";
   auto cvec = [&](uint32_t ks) {
     std::string v = K == 1 ? "" : "{";
@@ -131,17 +250,19 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, uint32_t beg
     const FlatInstr &x = in[i];
     switch (x.kind) {
       case K_LUT:
+        reload(x.a), reload(x.b), reload(x.c);  // operands a LUT does not read alias one it does
         for (int k = 0; k < K; k++) {
           std::snprintf(buf, sizeof buf, "  lop3.b32 %s, %s, %s, %s, 0x%02x;\n", R(x.dst, k).c_str(), R(x.a, k).c_str(),
                         R(x.b, k).c_str(), R(x.c, k).c_str(), x.tt);
           s += buf;
         }
+        hand_over(i, x.dst);
         break;
       case K_LDIN: {
-        const bool st_row = x.row >= h.n_inputs;
+        const bool st_row = x.flags & FLAG_STATE_ROW;
         if (multi_step && st_row) {
           for (int k = 0; k < K; k++) {
-            std::snprintf(buf, sizeof buf, "  mov.b32 %s, %s;\n", R(x.dst, k).c_str(), C(x.row - h.n_inputs, k).c_str());
+            std::snprintf(buf, sizeof buf, "  mov.b32 %s, %s;\n", R(x.dst, k).c_str(), C(x.row, k).c_str());
             s += buf;
           }
           break;
@@ -149,22 +270,24 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, uint32_t beg
         // immediates are read-only for the whole launch (.nc); carried state rows are rewritten in place later
         // by this same thread, so their loads must stay ordered before those stores: plain coherent loads
         std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %s;\n  ld.global%s%s.u32 %s, [%%addr];\n",
-                      st_row ? x.row - h.n_inputs : x.row, st_row ? "%state" : "%imm", st_row ? "" : ".nc.L1::no_allocate", vt,
+                      x.row, st_row ? "%state" : "%imm", st_row ? "" : ".nc.L1::no_allocate", vt,
                       vec(x.dst).c_str());
         s += buf;
+        hand_over(i, x.dst);
         break;
       }
       case K_STOUT:
       case K_STCONST: {
-        const bool st_row = x.row >= h.n_outputs;
+        const bool st_row = x.flags & FLAG_STATE_ROW;
+        if (x.kind == K_STOUT) reload(x.a);
         if (multi_step && st_row) {
           for (int k = 0; k < K; k++) {
             if (x.kind == K_STCONST)
-              std::snprintf(buf, sizeof buf, "  mov.b32 %s, 0x%08x;\n", C(x.row - h.n_outputs, k).c_str(), (x.flags & 1) ? 0xFFFFFFFFu : 0u);
+              std::snprintf(buf, sizeof buf, "  mov.b32 %s, 0x%08x;\n", C(x.row, k).c_str(), (x.flags & 1) ? 0xFFFFFFFFu : 0u);
             else if (x.flags & 1)
-              std::snprintf(buf, sizeof buf, "  not.b32 %s, %s;\n", C(x.row - h.n_outputs, k).c_str(), R(x.a, k).c_str());
+              std::snprintf(buf, sizeof buf, "  not.b32 %s, %s;\n", C(x.row, k).c_str(), R(x.a, k).c_str());
             else
-              std::snprintf(buf, sizeof buf, "  mov.b32 %s, %s;\n", C(x.row - h.n_outputs, k).c_str(), R(x.a, k).c_str());
+              std::snprintf(buf, sizeof buf, "  mov.b32 %s, %s;\n", C(x.row, k).c_str(), R(x.a, k).c_str());
             s += buf;
           }
           break;
@@ -182,7 +305,7 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, uint32_t beg
         }
         v += (K == 1 ? "" : "}");
         std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %s;\n  st.global.L1::no_allocate%s.u32 [%%addr], %s;\n",
-                      st_row ? x.row - h.n_outputs : x.row, st_row ? "%state" : "%out", vt, v.c_str());
+                      x.row, st_row ? "%state" : "%out", vt, v.c_str());
         s += buf;
         break;
       }
@@ -197,11 +320,6 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, uint32_t beg
       s += buf;
     }
   }
-  if (chunk)
-    for (uint32_t sl : *live_out) {
-      std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  st.global%s.u32 [%%addr], %s;\n", sl, vt, vec(sl).c_str());
-      s += buf;
-    }
   s += "DONE:\n  ret;\n}\n";
   return s;
 }

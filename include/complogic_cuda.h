@@ -192,10 +192,13 @@ int clg_flat_state_regs(const clg_flat *f, const uint64_t **regs, size_t *n);
 int clg_flat_spec_ptx(const clg_flat *f, int k, char **ptx_out);
 /* same for the fused multi-step form (clg_exec_run_steps) */
 int clg_flat_spec_steps_ptx(const clg_flat *f, int k, char **ptx_out);
-/* Programs longer than 16384 lane-order instructions are specialised as a chain of chunk kernels (entry
- * clg_spec_chunk) that hand their live registers over through a device scratch buffer. Text of chunk `chunk`;
- * *n_chunks (optional) receives the chain length (1 for a short program, whose only chunk has no hand-over). */
-int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, char **ptx_out);
+/* Programs longer than 16384 lane-order instructions (fewer at k > 1) are specialised as a chain of chunk kernels
+ * (entry clg_spec_chunk), cut where few registers are live; registers live across a cut are handed over through a
+ * device scratch buffer. A chunk with nothing live at either end addresses its rows relative to the lowest row it
+ * touches, so that the instances of a flattened program share one kernel: row_bases (optional, [3]) receives the
+ * rows by which the imm / out / state pointers are advanced for this chunk. Text of chunk `chunk`; *n_chunks
+ * (optional) receives the chain length (1 for a short program). Free with clg_free. */
+int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, uint32_t *row_bases, char **ptx_out);
 
 /* ---------------------------------------------------------------------------------------------
  * Device side. Raw CUDA driver API underneath (libcuda.so.1 is dlopen'ed when the first context

@@ -87,6 +87,7 @@ def run_program(flat_program, k: int, imm: np.ndarray, state: np.ndarray, n_outp
     mem = {"imm": imm, "out": out, "state": state if state is not None else np.zeros((1, stride), np.uint32), "scr": scr}
     _, n = flat_program.spec_chunk_ptx(k, 0)
     for c in range(n):
-        text, _ = flat_program.spec_chunk_ptx(k, c)
-        run_kernel(text, k, stride // k, mem)
+        text, _, (bi, bo, bs) = flat_program.spec_chunk_ptx(k, c, with_bases=True)
+        view = {"imm": mem["imm"][bi:], "out": mem["out"][bo:], "state": mem["state"][bs:], "scr": scr}
+        run_kernel(text, k, stride // k, view)
     return out[:n_outputs]

@@ -104,7 +104,7 @@ def test_spec_ptx_assembles_for_sm100a(tmp_path):
     dag = circuits.random_dag(levels=1500, width=48, n_immediates=64, window=2, seed=31)
     fp = host.FlatProgram.levelize(dag.sim, 64, dag.out_regs)
     text, n = fp.spec_chunk_ptx(4, 1)
-    assert n == 3 and ".entry clg_spec_chunk" in text
+    assert n >= 3 and ".entry clg_spec_chunk" in text
     (tmp_path / "chunk.ptx").write_text(text)
     r = subprocess.run(["ptxas", "-arch=sm_100a", "-v", "-o", str(tmp_path / "c.cubin"), str(tmp_path / "chunk.ptx")],
                        capture_output=True, text=True)

@@ -41,7 +41,7 @@ def test_chunked_chain_hands_registers_over(k):
     circ = circuits.random_dag(levels=1500, width=48, n_immediates=64, window=2, seed=31)
     fp = host.FlatProgram.levelize(circ.sim, 64, circ.out_regs)
     _, n = fp.spec_chunk_ptx(k, 0)
-    assert fp.info["lane_instrs"] > 16384 and n == -(-fp.info["lane_instrs"] // 16384)
+    assert fp.info["lane_instrs"] > 16384 and n >= -(-fp.info["lane_instrs"] // 16384)  # cuts move to where few registers are live
     nv, stride = 32 * 4, 4
     imm = random_sliced(64, stride, seed=99)
     want = oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs)
@@ -62,3 +62,27 @@ def test_chunked_chain_stateful_steps():
     for t in range(T):
         got = ptx_interp.run_program(fp, 4, imm[t], state, len(outs), fp.info["lane_slots"])
         assert np.array_equal(mask_tail(got, nv), mask_tail(want[t], nv)), f"step {t}"
+
+
+def test_cuts_fall_between_flattened_instances_and_kernels_are_shared():
+    """Multipliers flattened: every cut lands on an instance boundary, where nothing is live, so no kernel of the
+    chain touches the scratch buffer; registers are renumbered and rows made relative per chunk, so all instances
+    produce the SAME kernel text (assembled once) and differ only in their row bases."""
+    m = 3
+    base = circuits.array_multiplier(64)
+    circ = circuits.flatten_instances(base, m)
+    fp = host.FlatProgram.levelize(circ.sim, circ.n_immediates, circ.out_regs)
+    texts = []
+    for c in range(m):
+        text, n, bases = fp.spec_chunk_ptx(1, c, with_bases=True)
+        assert n == m
+        assert "%scr;\n  ld.global" not in text and "%scr;\n  st.global" not in text
+        assert text.count("lop3.b32") == fp.info["n_luts"] // m
+        assert bases == (c * base.n_immediates, c * len(base.out_regs), 0)
+        texts.append(text)
+    assert texts[0] == texts[1] == texts[2]
+    nv, stride = 64, 4
+    imm = random_sliced(circ.n_immediates, stride, seed=5)
+    want = oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs)
+    got = ptx_interp.run_program(fp, 1, imm, None, len(circ.out_regs), fp.info["lane_slots"])
+    assert np.array_equal(mask_tail(got, nv), mask_tail(want, nv))
