@@ -62,8 +62,9 @@ def build_workload(name: str, api=None):
         return circuits.flatten_instances(circuits.array_multiplier(64, api=api), 128, api=api), 0, 0x5EED
     if name == "mul64":
         return circuits.array_multiplier(64, api=api), 22, 0xC0FFF0
-    if name == "mul64x8" or name == "mul64x4":
-        return circuits.flatten_instances(circuits.array_multiplier(64, api=api), int(name[6:]), api=api), 21, 0xC0FFF1
+    if name in ("mul64x4", "mul64x8", "mul64x12"):
+        m = int(name[6:])
+        return circuits.flatten_instances(circuits.array_multiplier(64, api=api), m, api=api), 24 if m == 12 else 21, 0xC0FFF1
     if name == "adder8":
         return circuits.ripple_adder(8, api=api), 17, 0xC0FFED
     raise SystemExit(f"unknown workload {name}")
@@ -79,6 +80,8 @@ WORKLOAD_DESC = {
     "adder8": "8-bit ripple-carry adder, 152 NANDs (BASELINE configs[0])",
     "mul64": "64x64 array multiplier, 84 096 NANDs (one instance of config 5's circuit), batched",
     "mul64x4": "64x64 array multiplier x 4 instances flattened, batched (49 408 instructions)",
+    "mul64x12": "a STRUCTURED 1M-gate circuit: 64x64 array multiplier x 12 instances flattened = 1 009 152 NANDs, 2^24 vectors; "
+                "runs as a chain of 12 launches of one specialised kernel",
     "mul64x8": "64x64 array multiplier x 8 instances flattened = 672 768 NANDs, batched: a program too long for one "
                "specialised kernel (98 816 instructions), run as a chain of chunk kernels",
     "mul64x128": "64x64 array multiplier (84 096 NANDs) x 128 instances flattened into one program = 10 764 288 gates, "
@@ -392,7 +395,7 @@ def main():
     extras = None
     if args.extras and rank == 0 and world == 1:
         extras = {}
-        for name in ("adder32", "mul16", "dag1m"):
+        for name in ("adder32", "mul16", "mul64x12", "dag1m"):
             if name == args.workload:
                 continue
             del w
