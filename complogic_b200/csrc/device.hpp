@@ -52,13 +52,10 @@ constexpr int RING_CHUNK = 256;
 constexpr size_t LANE_RING_BYTES = RING_STAGES * RING_CHUNK * 16 + 128;
 constexpr size_t SMEM_MAX = 227 * 1024;
 constexpr uint32_t SPEC_CHUNK = 16384;  // most instructions per kernel of a chunked specialised program ...
-inline uint32_t spec_chunk_limit() {    // ... unless CLG_SPEC_CHUNK says otherwise (tuning; read once)
-  static const uint32_t v = [] {
-    const char *e = std::getenv("CLG_SPEC_CHUNK");
-    const long n = e ? std::atol(e) : 0;
-    return n >= 256 ? (uint32_t)n : SPEC_CHUNK;
-  }();
-  return v;
+inline uint32_t spec_chunk_limit() {    // ... unless CLG_SPEC_CHUNK says otherwise (tuning and tests; read at every plan build)
+  const char *e = std::getenv("CLG_SPEC_CHUNK");
+  const long n = e ? std::atol(e) : 0;
+  return n >= 2 ? (uint32_t)n : SPEC_CHUNK;
 }
 
 }  // namespace clg

@@ -51,7 +51,10 @@ std::vector<uint32_t> spec_live_slots(const Flat &f, uint32_t at) {
 // chunk ends, somewhere in the second half of the longest length allowed, where the fewest registers are live --
 // between two instances of a flattened program that is zero. The assembler's time grows with the number of PTX
 // instructions (K per LUT), so the allowed length shrinks with K.
-uint32_t spec_chunk_limit(int K) { return K == 1 ? spec_chunk_limit() : K == 2 ? spec_chunk_limit() / 2 : spec_chunk_limit() * 3 / 8; }
+uint32_t spec_chunk_limit(int K) {
+  const uint32_t n = spec_chunk_limit();
+  return std::max(2u, K == 1 ? n : K == 2 ? n / 2 : (uint32_t)((uint64_t)n * 3 / 8));
+}
 
 std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K) {
   const FlatStream &st = f.header().stream[STREAM_LANE];

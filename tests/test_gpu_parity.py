@@ -228,6 +228,34 @@ def test_random_programs(prog, seed):
         assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv))
 
 
+@settings(max_examples=int(__import__("os").environ.get("CLG_HYPOTHESIS_EXAMPLES", "40")), deadline=None,
+          suppress_health_check=[HealthCheck.too_slow])
+@given(programs(), st.integers(0, 2 ** 31), st.integers(2, 9))
+def test_random_programs_in_tiny_spec_chunks(prog, seed, chunk):
+    """The chunked specialised chain on arbitrary stateful programs, cut every few instructions (CLG_SPEC_CHUNK)."""
+    import os
+    ops, n_regs, n_imm, _ = prog
+    sim = host.Simulation(ops=ops, registers=[False] * n_regs)
+    nv, steps = 200, 2
+    stride = stride_for(nv)
+    imm = np.stack([random_sliced(n_imm, stride, seed + s) for s in range(steps)]) if n_imm else \
+        np.zeros((steps, 0, stride), np.uint32)
+    want = oracle.run_batch_scalar(ops, n_regs, imm, nv, list(range(n_regs)), steps=steps, all_steps=True)
+    old = os.environ.get("CLG_SPEC_CHUNK")
+    os.environ["CLG_SPEC_CHUNK"] = str(chunk)
+    try:
+        cs = host.CudaSimulation.from_simulation(sim, n_imm, None, flags=host.LV_STATEFUL, mode=host.MODE_SPEC)
+        state = np.zeros((cs.info["n_state"], stride), np.uint32)
+        for s in range(steps):
+            got = cs.run_batch(imm[s], nv, state=state)
+            assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv))
+    finally:
+        if old is None:
+            del os.environ["CLG_SPEC_CHUNK"]
+        else:
+            os.environ["CLG_SPEC_CHUNK"] = old
+
+
 def test_bools_api_and_transposes():
     """`&[bool]`-shaped entry point (one run()'s immediates per row) through the device transposes."""
     circ = circuits.array_multiplier(8)

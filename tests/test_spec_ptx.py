@@ -1,8 +1,11 @@
 """CPU-only checks of the specialised mode's generated PTX (complogic_b200/csrc/spec.cpp), evaluated by the numpy
 PTX interpreter in tests/ptx_interp.py against the oracle VM: the straight-line kernels at every K, and the chunked
 chain long programs are cut into (live registers handed over through the scratch buffer)."""
+import os
+
 import numpy as np
 import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
 
 import complogic_b200 as host
 from complogic_b200 import circuits
@@ -86,3 +89,40 @@ def test_cuts_fall_between_flattened_instances_and_kernels_are_shared():
     want = oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs)
     got = ptx_interp.run_program(fp, 1, imm, None, len(circ.out_regs), fp.info["lane_slots"])
     assert np.array_equal(mask_tail(got, nv), mask_tail(want, nv))
+
+
+@st.composite
+def programs(draw):
+    n_regs = draw(st.integers(1, 12))
+    ops = []
+    for _ in range(draw(st.integers(0, 60))):
+        if draw(st.integers(0, 5)) == 0:
+            ops.append(host.Set_op(draw(st.integers(0, n_regs - 1)), draw(st.booleans())))
+        else:
+            ops.append(host.Nand_op(*[draw(st.integers(0, n_regs - 1)) for _ in range(3)]))
+    return ops, n_regs, draw(st.integers(0, n_regs + 1)), draw(st.sampled_from([1, 2, 4])), draw(st.integers(2, 9))
+
+
+@settings(max_examples=int(os.environ.get("CLG_HYPOTHESIS_EXAMPLES", "150")), deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(programs(), st.integers(0, 2 ** 31))
+def test_random_stateful_programs_in_tiny_chunks(prog, seed):
+    """Arbitrary programs (multi-writer, read-before-write, carried registers) cut every few instructions
+    (CLG_SPEC_CHUNK), two steps: the chain must reproduce the oracle VM register for register."""
+    ops, n_regs, n_imm, k, chunk = prog
+    sim = host.Simulation(ops=ops, registers=[False] * n_regs)
+    nv, stride, steps = 100, 4, 2
+    imm = np.stack([random_sliced(n_imm, stride, seed + s) for s in range(steps)]) if n_imm else np.zeros((steps, 0, stride), np.uint32)
+    want = oracle.run_batch_scalar(ops, n_regs, imm, nv, list(range(n_regs)), steps=steps, all_steps=True)
+    fp = host.FlatProgram.levelize(sim, n_imm, None, flags=host.LV_STATEFUL)
+    state = np.zeros((max(1, fp.info["n_state"]), stride), np.uint32)
+    old = os.environ.get("CLG_SPEC_CHUNK")
+    os.environ["CLG_SPEC_CHUNK"] = str(chunk)
+    try:
+        for s in range(steps):
+            got = ptx_interp.run_program(fp, k, imm[s], state, n_regs, max(1, fp.info["lane_slots"]))
+            assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv)), f"step {s}"
+    finally:
+        if old is None:
+            del os.environ["CLG_SPEC_CHUNK"]
+        else:
+            os.environ["CLG_SPEC_CHUNK"] = old
