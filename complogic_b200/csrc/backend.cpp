@@ -417,7 +417,7 @@ struct Exec {
         st = &lv, sidx = STREAM_LEVEL;
         P.smem = std::max<size_t>((size_t)lv.n_slots * P.K * 4, 16);
         P.coop_threads = coop_threads_for(lv);
-        make_resident(P, lv.n_instr, lv.n_levels);
+        if (!std::getenv("CLG_COOP_NO_RESIDENT")) make_resident(P, lv.n_instr, lv.n_levels);  // (knob: tests drive the streaming kernels with small programs)
         break;
       default: fail(CLG_E_INVALID, "unknown execution mode");
     }
@@ -666,7 +666,7 @@ struct Exec {
           CU(cuCtxSynchronize());
           if (P.scratch) driver().cuMemFree(P.scratch);
           P.scratch = 0, P.scratch_stride = 0;
-          CU(cuMemAlloc(&P.scratch, (size_t)lane_stream().n_slots * stride * 4));
+          CU(cuMemAlloc(&P.scratch, std::max<size_t>(16, (size_t)lane_stream().n_slots * stride * 4)));
           P.scratch_stride = stride;
         }
         for (const Plan::ChunkLaunch &c : P.chunks) {

@@ -256,6 +256,45 @@ def test_random_programs_in_tiny_spec_chunks(prog, seed, chunk):
             os.environ["CLG_SPEC_CHUNK"] = old
 
 
+@settings(max_examples=int(__import__("os").environ.get("CLG_HYPOTHESIS_EXAMPLES", "40")), deadline=None,
+          suppress_health_check=[HealthCheck.too_slow])
+@given(programs(), st.integers(0, 2 ** 31))
+def test_random_programs_streaming_cooperative_kernel(prog, seed):
+    """Small programs normally run the shared-memory-resident cooperative kernel; CLG_COOP_NO_RESIDENT sends them
+    through the streaming one (compact 8-byte instructions fetched from global memory) that big programs use."""
+    import os
+    ops, n_regs, n_imm, _ = prog
+    sim = host.Simulation(ops=ops, registers=[False] * n_regs)
+    nv, steps = 300, 2
+    stride = stride_for(nv)
+    imm = np.stack([random_sliced(n_imm, stride, seed + s) for s in range(steps)]) if n_imm else \
+        np.zeros((steps, 0, stride), np.uint32)
+    want = oracle.run_batch_scalar(ops, n_regs, imm, nv, list(range(n_regs)), steps=steps, all_steps=True)
+    os.environ["CLG_COOP_NO_RESIDENT"] = "1"
+    try:
+        cs = host.CudaSimulation.from_simulation(sim, n_imm, None, flags=host.LV_STATEFUL, mode=host.MODE_COOP)
+        state = np.zeros((cs.info["n_state"], stride), np.uint32)
+        for s in range(steps):
+            got = cs.run_batch(imm[s], nv, state=state)
+            assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv))
+    finally:
+        del os.environ["CLG_COOP_NO_RESIDENT"]
+
+
+def test_streaming_cooperative_kernel_deep_dag():
+    """A deep, narrow DAG through the streaming cooperative kernel, from one vector to several column groups per CTA."""
+    import os
+    circ = circuits.random_dag(levels=300, width=96, n_immediates=64, window=6, seed=17)
+    os.environ["CLG_COOP_NO_RESIDENT"] = "1"
+    try:
+        cs = host.CudaSimulation.from_simulation(circ.sim, 64, circ.out_regs, mode=host.MODE_COOP)
+    finally:
+        del os.environ["CLG_COOP_NO_RESIDENT"]
+    for nv in (1, 129, 40000, 128 * 148 * 3 + 77):
+        imm = random_sliced(64, stride_for(nv), seed=nv)
+        assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), oracle_out(circ, imm, nv))
+
+
 def test_bools_api_and_transposes():
     """`&[bool]`-shaped entry point (one run()'s immediates per row) through the device transposes."""
     circ = circuits.array_multiplier(8)
