@@ -425,6 +425,13 @@ Sched schedule_lane(const Network &net) {
     if (!net.vals[v].is_lut && net.vals[v].row >= net.n_inputs) state_in_val[net.vals[v].row - net.n_inputs] = (uint32_t)v;
   for (size_t o = 0; o < net.outs.size(); o++)
     if (net.outs[o].val != NONE) outs_of[net.outs[o].val].push_back((uint32_t)o);
+  std::vector<std::vector<uint32_t>> users(V);  // LUTs reading each carried-state load
+  for (size_t v = 0; v < V; v++)
+    if (net.vals[v].is_lut)
+      for (int i = 0; i < net.vals[v].nfan; i++) {
+        const uint32_t f = net.vals[v].fan[i];
+        if (!net.vals[f].is_lut && net.vals[f].row >= net.n_inputs && (users[f].empty() || users[f].back() != (uint32_t)v)) users[f].push_back((uint32_t)v);
+      }
 
   // order: positive = value id (LDIN or LUT), stores as (V + out index). Depth-first from the outputs, taller
   // operand first. (A greedy "least live-set growth" list scheduler was tried and was 3-13x worse on the
@@ -434,21 +441,45 @@ Sched schedule_lane(const Network &net) {
   order.clear();
   order.reserve(V + net.outs.size());
   std::vector<uint8_t> done(V, 0), stored(net.outs.size(), 0);
-  std::function<void(uint32_t)> emit_value;
-  auto emit_store = [&](uint32_t o) {
-    if (stored[o]) return;
-    uint32_t row = net.outs[o].row;
-    if (row >= net.n_outputs) {  // in-place state row: its old value must have been read first
-      uint32_t sv = state_in_val[row - net.n_outputs];
-      if (sv != NONE && !done[sv]) emit_value(sv);
-    }
-    stored[o] = 1;
-    order.push_back((uint32_t)V + o);
-  };
-  emit_value = [&](uint32_t v) {
+  // emission is driven by a work list (no recursion: a chain of 10^6 latches is 10^6 nested forced loads)
+  std::vector<uint32_t> work;  // value id, or V + out index for a store
+  auto emit_value = [&](uint32_t v) {
     done[v] = 1;
     order.push_back(v);
-    for (uint32_t o : outs_of[v]) emit_store(o);
+    for (size_t k = outs_of[v].size(); k-- > 0;) work.push_back((uint32_t)V + outs_of[v][k]);
+  };
+  auto drain = [&]() {
+    while (!work.empty()) {
+      const uint32_t x = work.back();
+      work.pop_back();
+      if (x < V) {  // a reader of a forced load that was ready when it was queued
+        if (!done[x]) emit_value(x);
+        continue;
+      }
+      const uint32_t o = x - (uint32_t)V;
+      if (stored[o]) continue;
+      const uint32_t row = net.outs[o].row;
+      uint32_t forced = NONE;
+      if (row >= net.n_outputs) {  // in-place state row: its old value must have been read first
+        const uint32_t sv = state_in_val[row - net.n_outputs];
+        if (sv != NONE && !done[sv]) done[sv] = 1, order.push_back(sv), forced = sv;
+      }
+      stored[o] = 1;
+      order.push_back((uint32_t)V + o);
+      if (forced != NONE) {
+        // The old value was loaded only to get it out of the way of this store; whoever reads it may be far down
+        // the depth-first order, and it would sit in a register until then (a chain of n latches kept 2n values
+        // live). Run the readers that are ready right now -- their own stores may free further rows the same way.
+        for (size_t k = users[forced].size(); k-- > 0;) {
+          const uint32_t c = users[forced][k];
+          if (done[c]) continue;
+          bool ready = true;
+          for (int i = 0; i < net.vals[c].nfan; i++) ready &= done[net.vals[c].fan[i]] != 0;
+          if (ready) work.push_back(c);
+        }
+        for (size_t k = outs_of[forced].size(); k-- > 0;) work.push_back((uint32_t)V + outs_of[forced][k]);
+      }
+    }
   };
   struct Frame {
     uint32_t v;
@@ -484,16 +515,19 @@ Sched schedule_lane(const Network &net) {
       uint32_t v = f.v;
       stack.pop_back();
       emit_value(v);
+      drain();
     }
   };
   for (size_t o = 0; o < net.outs.size(); o++) {
     if (net.outs[o].val != NONE) visit(net.outs[o].val);
-    emit_store((uint32_t)o);  // (a constant stored to an in-place state row also waits for that row's load)
+    work.push_back((uint32_t)V + (uint32_t)o);  // (a constant stored to an in-place state row also waits for that row's load)
+    drain();
   }
   };
 
   build_dfs(order);
 
+  auto allocate = [&](const std::vector<uint32_t> &order) {
   // last use positions
   std::vector<uint32_t> last(V, 0);
   for (size_t i = 0; i < order.size(); i++) {
@@ -548,6 +582,39 @@ Sched schedule_lane(const Network &net) {
   s.levels = {0, (uint32_t)s.instr.size()};
   s.max_width = (uint32_t)s.instr.size();
   return s;
+  };
+
+  Sched s = allocate(order);
+  if (!s.ok || net.n_state == 0) return s;
+  // Carried-state rows are rewritten in place, so their loads are ordinary (coherent) loads that neither the
+  // assembler nor the hardware may move above an earlier store: "load at first use" leaves one load in flight per
+  // thread, and a latch chain ran at one memory latency per latch. Hoist each state load up to LOOKAHEAD positions,
+  // at most `budget` of them in flight -- as many as the registers left over at this program's K allow.
+  const uint32_t k0 = s.n_slots * 4 <= 200 ? 4 : s.n_slots * 2 <= 200 ? 2 : 1;
+  const uint32_t budget = 200 / k0 > s.n_slots ? std::min<uint32_t>(24, 200 / k0 - s.n_slots) : 0;
+  if (budget < 4) return s;
+  constexpr size_t LOOKAHEAD = 512;
+  auto is_state_load = [&](uint32_t x) { return x < V && !net.vals[x].is_lut && net.vals[x].row >= net.n_inputs; };
+  std::vector<uint32_t> hoisted;
+  hoisted.reserve(order.size());
+  std::vector<uint8_t> pulled(V, 0);
+  size_t scan = 0;
+  uint32_t in_flight = 0;
+  for (size_t i = 0; i < order.size(); i++) {
+    scan = std::max(scan, i + 1);
+    while (in_flight < budget && scan < order.size() && scan <= i + LOOKAHEAD) {
+      const uint32_t y = order[scan++];
+      if (is_state_load(y)) hoisted.push_back(y), pulled[y] = 1, in_flight++;
+    }
+    const uint32_t x = order[i];
+    if (x < V && pulled[x]) {  // its original position: from here on it counts as an ordinary live value
+      in_flight--;
+      continue;
+    }
+    hoisted.push_back(x);
+  }
+  Sched h = allocate(hoisted);
+  return h.ok ? h : s;
 }
 
 // Level order. LUT levels are as late as the consumers allow (short live ranges), loads sit one
@@ -1013,15 +1080,17 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
   };
   Sched level = schedule_for_smem(net);
   ph.reset(new Phase("schedule: lane"));
-  if (!level.ok) fail(CLG_E_UNSUPPORTED, "level-ordered stream needs more than 65536 physical registers");
   Sched lane;
   lane.ok = false;
   if (!(flags & CLG_LV_NO_LANE_STREAM)) lane = schedule_lane(net);
+  // a very wide, shallow program (10^5 latches side by side) can exceed the 65536 slots of the level order and
+  // still need only a handful in lane order: the buffer then carries the lane stream alone
+  if (!level.ok && !lane.ok) fail(CLG_E_UNSUPPORTED, "program needs more than 65536 physical registers in level order and in lane order");
 
   // partitioned level streams for small batches of wide, separable programs (e.g. flattened instances)
   ph.reset(new Phase("schedule: parts"));
   std::vector<Sched> parts;
-  if (!(flags & CLG_LV_NO_PARTS) && n_luts >= 4096) {
+  if (!(flags & CLG_LV_NO_PARTS) && n_luts >= 4096 && level.ok) {
     std::vector<uint32_t> pv, po;
     const uint32_t P = partition(net, 592, pv, po);
     if (P > 1)

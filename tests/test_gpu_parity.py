@@ -168,6 +168,54 @@ def test_chunked_specialised_stateful():
     assert np.array_equal(mask_tail(state, nv), mask_tail(want[T - 1], nv))  # state rows ARE the output registers here
 
 
+def latch_chain(n):
+    """n D latches in a row behind one enable: latch i's data input is latch i-1's output."""
+    c = host.Compiler(2)
+    qs = [c.alloc() for _ in range(n)]
+    return c.compile([host.DLatch(0 if i == 0 else qs[i - 1], 1, qs[i]) for i in range(n)]), qs
+
+
+def test_latch_chain_needs_few_registers_in_lane_order():
+    """Wide and shallow sequential logic: thousands of carried registers, every state row rewritten in place. The lane
+    order keeps a handful of values live (forced state loads drag their ready readers along), so the chain runs
+    specialised -- as a chain of chunk kernels -- and in the lane interpreter; all modes agree with the oracle VM."""
+    sim, qs = latch_chain(1500)
+    R, nv, T = len(sim.registers), 300, 5
+    stride = stride_for(nv)
+    imm = np.stack([random_sliced(2, stride, 70 + t) for t in range(T)])
+    imm[:, 1] |= np.uint32(0x0F0F0F0F)  # enable high in many lanes so that data actually moves down the chain
+    want = oracle.run_batch_scalar(sim, R, imm, nv, qs, steps=T, all_steps=True)
+    for mode in MODES:
+        cs = host.CudaSimulation.from_simulation(sim, 2, qs, flags=host.LV_STATEFUL, mode=mode)
+        assert cs.info["lane_slots"] <= 32
+        if mode == host.MODE_SPEC:
+            assert cs.launches_per_run > 1
+        state = np.zeros((cs.info["n_state"], stride), np.uint32)
+        for t in range(T):
+            got = cs.run_batch(imm[t], nv, state=state)
+            assert np.array_equal(mask_tail(got, nv), mask_tail(want[t], nv)), (host.MODE_NAMES[mode], t)
+
+
+def test_lane_only_program_when_level_order_needs_too_many_registers():
+    """20 000 latches side by side need > 65 536 registers in level order: the flat buffer then carries the lane stream
+    alone and AUTO runs the lane interpreter."""
+    sim, qs = latch_chain(20000)
+    outs = qs[::997]
+    R, nv, T = len(sim.registers), 64, 2
+    stride = stride_for(nv)
+    imm = np.stack([random_sliced(2, stride, 80 + t) for t in range(T)])
+    imm[:, 1] = np.uint32(0xFFFFFFFF)
+    want = oracle.run_batch_scalar(sim, R, imm, nv, outs, steps=T, all_steps=True)
+    cs = host.CudaSimulation.from_simulation(sim, 2, outs, flags=host.LV_STATEFUL)
+    assert cs.info["level_instrs"] == 0 and cs.info["lane_slots"] <= 128 and cs.mode == host.MODE_LANE
+    state = np.zeros((cs.info["n_state"], stride), np.uint32)
+    for t in range(T):
+        got = cs.run_batch(imm[t], nv, state=state)
+        assert np.array_equal(mask_tail(got, nv), mask_tail(want[t], nv)), t
+    with pytest.raises(host.ClgError):
+        host.CudaSimulation.from_simulation(sim, 2, outs, flags=host.LV_STATEFUL, mode=host.MODE_COOP)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_fused_multi_step(mode):
     """clg_exec_run_steps: T run() calls per lane in one call (one launch in the specialised mode, carried registers

@@ -234,3 +234,32 @@ def test_empty_and_degenerate_programs():
     want = oracle.run_batch_scalar(sim, 7, imm, 4, [5, 5, 6])
     for got, _ in both_streams(fp, imm, 4):
         assert np.array_equal(got, mask_tail(want, 4))
+
+
+def test_latch_chain_lane_order_keeps_few_values_live():
+    """Sequential logic rewrites its state rows in place, which forces every row's old value to be loaded before the
+    store. The lane order runs the ready readers of such a forced load at once, so a chain of n latches needs a
+    handful of registers plus the state loads hoisted for memory-level parallelism (it needed 2n + 2 when the loaded values waited for the depth-first order to reach them);
+    when the level order needs more than 65 536 registers the buffer carries the lane stream alone."""
+    def chain(n):
+        c = host.Compiler(2)
+        qs = [c.alloc() for _ in range(n)]
+        return c.compile([host.DLatch(0 if i == 0 else qs[i - 1], 1, qs[i]) for i in range(n)]), qs
+
+    sim, qs = chain(400)
+    fp = host.FlatProgram.levelize(sim, 2, qs, flags=host.LV_STATEFUL)
+    assert fp.info["lane_slots"] <= 32 < fp.info["level_slots"]
+    nv, T = 96, 4
+    stride = stride_for(nv)
+    imm = np.stack([random_sliced(2, stride, 11 + t) for t in range(T)])
+    imm[:, 1] |= np.uint32(0x33333333)
+    want = oracle.run_batch_scalar(sim, len(sim.registers), imm, nv, qs, steps=T, all_steps=True)
+    flat = flat_interp.Flat(fp.to_bytes())
+    for stream in (flat_interp.STREAM_LEVEL, flat_interp.STREAM_LANE):
+        state = np.zeros((flat.n_state, stride), np.uint32)
+        for t in range(T):
+            got = flat_interp.run(flat, stream, imm[t], state)
+            assert np.array_equal(mask_tail(got, nv), mask_tail(want[t], nv)), (stream, t)
+    sim, qs = chain(12000)
+    fp = host.FlatProgram.levelize(sim, 2, qs[-3:], flags=host.LV_STATEFUL)
+    assert fp.info["level_instrs"] == 0 and fp.info["lane_instrs"] > 0 and fp.info["lane_slots"] <= 32
