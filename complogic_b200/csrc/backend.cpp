@@ -314,6 +314,12 @@ struct Exec {
     const double launches = std::ceil((double)ln.n_instr / spec_chunk_limit(k));
     return std::ceil(groups / (resident * ctx->sm_count)) * ln.n_instr * k * std::max(4.0, 0.85 * warps) + launches * 5000.0;
   }
+  // CTA size of the specialised kernels: 128 threads, narrower when the batch would otherwise leave SMs without a CTA
+  // (2^20 lanes at K = 4 are 8192 threads: 64 CTAs of 128 for 148 SMs)
+  uint32_t spec_threads(uint32_t groups) const {
+    const uint32_t sms = (uint32_t)ctx->sm_count;
+    return groups >= 2 * sms * 128 ? 128 : groups >= 2 * sms * 64 ? 64 : 32;
+  }
   int choose(size_t words) const {
     if (want != CLG_MODE_AUTO) return want;
     const int spec_k = fit_k(CLG_MODE_SPEC);
@@ -636,7 +642,8 @@ struct Exec {
     uint32_t stride32 = (uint32_t)stride, g = (uint32_t)((words + P.K - 1) / P.K), steps32 = (uint32_t)n_steps;
     uint64_t imm_b = imm_step * 4, out_b = out_step * 4;
     void *args[] = {&imm, &out, &state, &stride32, &g, &steps32, &imm_b, &out_b};
-    CU(cuLaunchKernel(P.steps_fn, (g + 127) / 128, 1, 1, 128, 1, 1, 0, stream, args, nullptr));
+    const uint32_t nt = spec_threads(g);
+    CU(cuLaunchKernel(P.steps_fn, (g + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, args, nullptr));
   }
 
   void run(const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, CUstream stream) {
@@ -660,7 +667,7 @@ struct Exec {
     const uint32_t groups = (uint32_t)((words + K - 1) / K);
     if (mode == CLG_MODE_SPEC) {
       uint32_t stride32 = (uint32_t)stride, g = groups;
-      const uint32_t nt = 128;
+      const uint32_t nt = spec_threads(groups);
       if (!P.chunks.empty()) {
         if (stride > P.scratch_stride) {  // registers that are live across chunk cuts: [slot][stride] words
           CU(cuCtxSynchronize());
