@@ -67,6 +67,8 @@ def build_workload(name: str, api=None):
         return circuits.flatten_instances(circuits.array_multiplier(64, api=api), m, api=api), 24 if m == 12 else 21, 0xC0FFF1
     if name == "adder8":
         return circuits.ripple_adder(8, api=api), 17, 0xC0FFED
+    if name == "latch1500":
+        return circuits.latch_chain(1500, api=api), 24, 0x1A7C4
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -80,6 +82,8 @@ WORKLOAD_DESC = {
     "adder8": "8-bit ripple-carry adder, 152 NANDs (BASELINE configs[0])",
     "mul64": "64x64 array multiplier, 84 096 NANDs (one instance of config 5's circuit), batched",
     "mul64x4": "64x64 array multiplier x 4 instances flattened, batched (49 408 instructions)",
+    "latch1500": "a SEQUENTIAL circuit: 1 500 D latches in a row (24 000 NANDs), 6 000 carried registers per lane rewritten "
+                 "in place every step; one step per launch on 2^24 lanes: bound by HBM (13 502 rows of 2 MB per step)",
     "mul64x12": "a STRUCTURED 1M-gate circuit: 64x64 array multiplier x 12 instances flattened = 1 009 152 NANDs, 2^24 vectors; "
                 "runs as a chain of 12 launches of one specialised kernel",
     "mul64x8": "64x64 array multiplier x 8 instances flattened = 672 768 NANDs, batched: a program too long for one "
@@ -268,12 +272,14 @@ def main():
         circ, lg_default, seed = build_workload(workload)
         lg2 = lg_default if lg2 is None else lg2
         t0 = time.perf_counter()
-        cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=mode)
+        cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=mode,
+                                                 flags=host.LV_STATEFUL if circ.stateful else 0)
         compile_s = time.perf_counter() - t0
         nv = 1 << lg2
         stride = host.round_stride(nv)
-        n_in, n_out = cs.info["n_inputs"], cs.info["n_outputs"]
-        io_bytes = (n_in + n_out) * stride * 4
+        n_in, n_out, n_state = cs.info["n_inputs"], cs.info["n_outputs"], cs.info["n_state"]
+        io_bytes = (n_in + n_out + 2 * n_state) * stride * 4  # carried registers are read and written every step
+        state = torch.zeros((max(1, n_state), stride), dtype=torch.int32, device=dev) if n_state else None
         # inputs larger than L2, or rotate enough buffer sets that a step never finds its rows in L2
         sets = 1 if n_in * stride * 4 > 2 * L2_BYTES else max(2, int(np.ceil(3 * L2_BYTES / max(1, io_bytes))))
         bufs = []
@@ -283,15 +289,16 @@ def main():
             ctx.fill_random(imm.data_ptr(), n_in, stride, seed + 1000 * rank + b, torch.cuda.current_stream().cuda_stream)
             bufs.append((imm, out))
         torch.cuda.synchronize()
-        return dict(circ=circ, cs=cs, nv=nv, stride=stride, bufs=bufs, seed=seed, compile_s=compile_s, io_bytes=io_bytes,
+        return dict(circ=circ, cs=cs, nv=nv, stride=stride, bufs=bufs, seed=seed, compile_s=compile_s, io_bytes=io_bytes, state=state,
                     gates=cs.info["ref_nand_count"], name=workload)
 
     def timed_steps(w, steps, warmup, sample_clocks=False):
         cs, bufs, nv, stride = w["cs"], w["bufs"], w["nv"], w["stride"]
+        state_ptr = w["state"].data_ptr() if w["state"] is not None else 0
         stream = torch.cuda.current_stream().cuda_stream
         for s in range(warmup):
             imm, out = bufs[s % len(bufs)]
-            cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride, stream=stream)
+            cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride, state_dptr=state_ptr, stream=stream)
         barrier()
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
@@ -301,7 +308,7 @@ def main():
         e0.record()
         for s in range(steps):
             imm, out = bufs[s % len(bufs)]
-            cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride, stream=stream)
+            cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride, state_dptr=state_ptr, stream=stream)
         e1.record()
         torch.cuda.synchronize()
         t1 = time.time()
@@ -313,6 +320,8 @@ def main():
     w = prepare(args.workload, args.log2_vectors)
     cs = w["cs"]
     ms, clocks = timed_steps(w, args.steps, args.warmup, sample_clocks=True)
+    # what the timed launches ran as (the host-buffer e2e leg below works on column chunks and may pick another mode)
+    run_mode, run_k, run_launches = cs.mode_name, cs.words_per_thread, cs.launches_per_run
     total_vectors = w["nv"] * world
     value = w["gates"] * total_vectors / (ms * 1e-3)
 
@@ -337,7 +346,7 @@ def main():
     try:  # measured DRAM traffic of this kernel from the committed ncu capture, scaled to this batch size
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f).get(args.workload)
-        if tr and tr["kernel"].startswith("clg_" + cs.mode_name) and cs.words_per_thread == 4:
+        if tr and tr["kernel"].startswith("clg_" + run_mode) and run_k == 4:
             roofline["traffic"] = tr["dram_bytes"] * (w["nv"] / tr["profiled_vectors"])
             roofline["traffic_source"] = f"ncu capture at {tr['profiled_vectors']} vectors, scaled by batch size"
             if "lsu_data_pipe_pct_of_peak" in tr:  # the pipe that actually bounds the shared-memory interpreter
@@ -346,13 +355,13 @@ def main():
     except Exception:
         pass
     roofline.update({
-        "kernel": f"clg_{cs.mode_name}" + (f"_k{cs.words_per_thread}" if cs.mode_name != "spec" else f" (K={cs.words_per_thread})"),
+        "kernel": f"clg_{run_mode}" + (f"_k{run_k}" if run_mode != "spec" else f" (K={run_k})"),
         "algorithmic_lane_ops_per_launch": lane_ops, "issued_lop3_lane_ops_per_launch": issued_lane_ops,
         "frac_of_measured_lop3": (lane_ops / per_gpu_s / lop3_measured) if lop3_measured else None,
         "frac_issued_of_nominal_lop3": issued_lane_ops / per_gpu_s / lop3_nominal,
         "hbm_GBps": hbm_achieved, "hbm_frac": hbm_achieved / hbm_peak, "algorithmic_bytes_per_launch": w["io_bytes"],
         "gates_per_io_byte": gates_per_byte,
-        "smem_interpreter_bound_frac": None if cs.mode_name == "spec" else 1.0 / 6.0,
+        "smem_interpreter_bound_frac": None if run_mode == "spec" else 1.0 / 6.0,
     })
 
     # ---- e2e: the C-ABI call with HOST buffers, H2D + kernel + D2H inside the timed region ----------------------
@@ -362,6 +371,8 @@ def main():
         h_imm = torch.empty((n_in, stride), dtype=torch.int32, pin_memory=True)
         h_out = torch.empty((n_out, stride), dtype=torch.int32, pin_memory=True)
         h_imm.copy_(w["bufs"][0][0])
+        n_state = cs.info["n_state"]  # a sequential circuit's carried registers travel with every call as well
+        h_state = torch.zeros((n_state, stride), dtype=torch.int32, pin_memory=True) if n_state else None
         torch.cuda.synchronize()
         d_imm, d_out = w["bufs"][0]
         stream = torch.cuda.current_stream().cuda_stream
@@ -369,7 +380,7 @@ def main():
 
         def e2e_step():
             # the public host-buffer call: column chunks pipelined over H2D / kernel / D2H streams inside
-            host._lib.check(lib.clg_exec_run_host(cs._h, h_imm.data_ptr(), h_out.data_ptr(), None, nv, stride))
+            host._lib.check(lib.clg_exec_run_host(cs._h, h_imm.data_ptr(), h_out.data_ptr(), h_state.data_ptr() if n_state else None, nv, stride))
 
         for _ in range(2):
             e2e_step()
@@ -383,8 +394,8 @@ def main():
         barrier()
         e_ms = max_over_ranks(e_ms)
         checksum = int(h_out.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFFFFFF  # the result is really on the host
-        e2e = {"value": w["gates"] * total_vectors / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_in * stride * 4,
-               "d2h_bytes_per_step": n_out * stride * 4, "ms_per_step": e_ms, "steps": e2e_steps,
+        e2e = {"value": w["gates"] * total_vectors / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (n_in + n_state) * stride * 4,
+               "d2h_bytes_per_step": (n_out + n_state) * stride * 4, "ms_per_step": e_ms, "steps": e2e_steps,
                "api": "clg_exec_run_host (pinned host buffers; chunked H2D | kernel | D2H pipeline on three streams)",
                "out_checksum": f"{checksum:016x}"}
         del h_imm, h_out
@@ -395,7 +406,7 @@ def main():
     extras = None
     if args.extras and rank == 0 and world == 1:
         extras = {}
-        for name in ("adder32", "mul16", "mul64x12", "dag1m"):
+        for name in ("adder32", "mul16", "mul64x12", "latch1500", "dag1m"):
             if name == args.workload:
                 continue
             del w
@@ -439,12 +450,12 @@ def main():
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": args.workload, "description": WORKLOAD_DESC[args.workload], "gates": main_gates,
                        "vectors_per_gpu": 1 << (args.log2_vectors or build_workload(args.workload)[1]), "total_vectors": total_vectors,
-                       "mode": cs.mode_name, "words_per_thread_or_cta": cs.words_per_thread, "fused_lop3_instructions": cs.info["n_luts"],
-                       "levels": cs.info["n_levels"], "slots": cs.info["level_slots"] if cs.mode_name == "coop" else cs.info["lane_slots"],
+                       "mode": run_mode, "words_per_thread_or_cta": run_k, "fused_lop3_instructions": cs.info["n_luts"],
+                       "levels": cs.info["n_levels"], "slots": cs.info["level_slots"] if run_mode == "coop" else cs.info["lane_slots"],
                        "l2": l2_note, "sharding": "independent vector shards per rank, no collective",
                        "bit_slicing": "one u32 lane word carries 32 circuit instances; NAND over 32 instances is one LOP3",
                        "compile_seconds": main_compile_s},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * cs.launches_per_run,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * run_launches,
             "roofline": roofline, "cpu_baseline": cpu,
         }
         if extras:

@@ -20,6 +20,7 @@ class Circuit:
     n_immediates: int
     out_regs: List[int]
     note: str = ""
+    stateful: bool = False  # registers carry over from one run() to the next (levelize with LV_STATEFUL)
 
 
 def _api(api):
@@ -160,3 +161,13 @@ def flatten_instances(base: Circuit, copies: int, api=None) -> Circuit:
     for m in range(M):
         outs += [int(x) for x in remap(np.array(base.out_regs), m)]
     return Circuit(f"{base.name}x{M}", sim, M * I, outs)
+
+
+def latch_chain(n: int, api=None) -> Circuit:
+    """A sequential circuit: n D latches in a row behind one enable (immediates: data, enable); latch i's data input
+    is latch i-1's output. 16 NANDs and 4 carried registers per latch with the reference's DLatch expansion."""
+    api = _api(api)
+    c = api.Compiler(2)
+    qs = [c.alloc() for _ in range(n)]
+    sim = c.compile([api.DLatch(0 if i == 0 else qs[i - 1], 1, qs[i]) for i in range(n)])
+    return Circuit(f"latch{n}", sim, 2, qs, note="D-latch chain", stateful=True)
