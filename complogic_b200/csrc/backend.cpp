@@ -7,7 +7,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
-#include <thread>
 
 #include "device.hpp"
 
@@ -173,7 +172,6 @@ struct Plan {
   };
   std::vector<CUmodule> chunk_mods;  // one per DISTINCT chunk
   std::vector<ChunkLaunch> chunks;   // the chain, in order
-  uint32_t chunk_kernels = 0;
   CUdeviceptr scratch = 0;
   size_t scratch_stride = 0;
   CUmodule spec_mod = nullptr, steps_mod = nullptr;
@@ -482,14 +480,20 @@ struct Exec {
       }
       P.chunk_mods.assign(unique.size(), nullptr);
       std::vector<CUfunction> fns(unique.size(), nullptr);
-      for (uint32_t u = 0; u < unique.size(); u++) {
-        const std::string text = emit_spec_chunk_ptx(flat, P.K, chunks[unique[u]]);
-        if (u == 0) P.ptx = text;
-        assemble(text, "clg_spec_chunk", "chunk " + std::to_string(unique[u]) + " of the specialised program", &P.chunk_mods[u], &fns[u]);
+      try {
+        for (uint32_t u = 0; u < unique.size(); u++) {
+          const std::string text = emit_spec_chunk_ptx(flat, P.K, chunks[unique[u]]);
+          if (u == 0) P.ptx = text;
+          assemble(text, "clg_spec_chunk", "chunk " + std::to_string(unique[u]) + " of the specialised program", &P.chunk_mods[u], &fns[u]);
+        }
+      } catch (...) {  // leave no half-built chain behind: a later run() would build it again from scratch
+        for (CUmodule m : P.chunk_mods)
+          if (m) driver().cuModuleUnload(m);
+        P.chunk_mods.clear();
+        throw;
       }
       for (uint32_t c = 0; c < chunks.size(); c++)
         P.chunks.push_back({fns[kernel_of[c]], chunks[c].imm_base, chunks[c].out_base, chunks[c].state_base});
-      P.chunk_kernels = (uint32_t)unique.size();
     } else {
       P.ptx = emit_spec_ptx(flat, P.K);
       assemble(P.ptx, "clg_spec", "the specialised kernel", &P.spec_mod, &P.spec_fn);

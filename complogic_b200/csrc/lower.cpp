@@ -437,7 +437,7 @@ Sched schedule_lane(const Network &net) {
   // operand first. (A greedy "least live-set growth" list scheduler was tried and was 3-13x worse on the
   // multipliers: it opens every partial product before closing any adder row.)
   std::vector<uint32_t> order;
-  auto build_dfs = [&](std::vector<uint32_t> &order) {
+  auto build_dfs = [&]() {
   order.clear();
   order.reserve(V + net.outs.size());
   std::vector<uint8_t> done(V, 0), stored(net.outs.size(), 0);
@@ -525,13 +525,13 @@ Sched schedule_lane(const Network &net) {
   }
   };
 
-  build_dfs(order);
+  build_dfs();
 
-  auto allocate = [&](const std::vector<uint32_t> &order) {
+  auto allocate = [&](const std::vector<uint32_t> &seq) {
   // last use positions
   std::vector<uint32_t> last(V, 0);
-  for (size_t i = 0; i < order.size(); i++) {
-    uint32_t x = order[i];
+  for (size_t i = 0; i < seq.size(); i++) {
+    uint32_t x = seq[i];
     if (x >= V) {
       const OutRef &o = net.outs[x - V];
       if (o.val != NONE) last[o.val] = (uint32_t)i;
@@ -541,8 +541,8 @@ Sched schedule_lane(const Network &net) {
   Sched s;
   SlotPool pool;
   std::vector<uint32_t> slot(V, NONE);
-  for (size_t i = 0; i < order.size(); i++) {
-    uint32_t x = order[i];
+  for (size_t i = 0; i < seq.size(); i++) {
+    uint32_t x = seq[i];
     FlatInstr in{};
     if (x >= V) {
       const OutRef &o = net.outs[x - V];
@@ -804,12 +804,12 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
       // nothing else in the window fits without a conflict (the tail of a class): fill the group with the
       // candidates that collide least, so that the replays spread over banks instead of piling onto one
       if (members < BANKS && placed < n) {
-        uint8_t cnt[3][MAX_BANKS] = {};
+        uint8_t hits[3][MAX_BANKS] = {};
         for (uint32_t k = order.size() - members; k < order.size(); k++) {
           const uint32_t x = order[k].x;
           const uint8_t *pm = PERM[order[k].perm];
           const int no = x >= V ? (net.outs[x - V].val == NONE ? 0 : 1) : net.vals[x].is_lut ? net.vals[x].nfan : 0;
-          for (int j = 0; j < no; j++) cnt[pm[j]][(x >= V ? slot[net.outs[x - V].val] : slot[net.vals[x].fan[j]]) % BANKS]++;
+          for (int j = 0; j < no; j++) hits[pm[j]][(x >= V ? slot[net.outs[x - V].val] : slot[net.vals[x].fan[j]]) % BANKS]++;
         }
         while (members < BANKS && placed < n) {
           uint32_t best_c = NONE, best_cost = NONE, seen = 0;
@@ -821,13 +821,13 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
             for (int q = 0; q < 6; q++) {
               if (!(ci.perms >> q & 1)) continue;
               uint32_t cost = 0;
-              for (int k = 0; k < ci.nops; k++) cost += cnt[PERM[q][k]][ci.bank[k]];
+              for (int k = 0; k < ci.nops; k++) cost += hits[PERM[q][k]][ci.bank[k]];
               if (cost < best_cost) best_cost = cost, best_c = c, best_q = q;
             }
             if (best_cost == 0) break;
           }
           const CandInfo &ci = cinfo[best_c];
-          for (int k = 0; k < ci.nops; k++) cnt[PERM[best_q][k]][ci.bank[k]]++;
+          for (int k = 0; k < ci.nops; k++) hits[PERM[best_q][k]][ci.bank[k]]++;
           taken[best_c] = 1, members++, placed++;
           order.push_back({items[b + best_c], (uint8_t)best_q});
         }
