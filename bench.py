@@ -89,8 +89,9 @@ WORKLOAD_DESC = {
     "mul64x8": "64x64 array multiplier x 8 instances flattened = 672 768 NANDs, batched: a program too long for one "
                "specialised kernel (98 816 instructions), run as a chain of chunk kernels",
     "mul64x128": "64x64 array multiplier (84 096 NANDs) x 128 instances flattened into one program = 10 764 288 gates, "
-                 "ONE input vector: the warp-cooperative intra-level mode (BASELINE configs[4]; M = 128 instances gives the "
-                 "~10M gates the config names, see SURVEY 8d)",
+                 "ONE input vector (BASELINE configs[4]; M = 128 instances gives the ~10M gates the config names, see SURVEY "
+                 "8d). --mode coop: the warp-cooperative intra-level mode, one CTA per part; auto: the instances are equal "
+                 "independent chunks, so ONE launch of one specialised kernel with an instance per blockIdx.y",
 }
 
 

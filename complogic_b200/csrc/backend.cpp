@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <iterator>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -168,10 +169,11 @@ struct Plan {
   // long programs: the lane stream cut into SPEC_CHUNK-instruction kernels; live registers cross the cuts through `scratch`
   struct ChunkLaunch {
     CUfunction fn;
-    uint32_t imm_base, out_base, state_base;  // rows
+    uint32_t first, count;  // entries of the row-base table: `count` equal, independent chunks run side by side (grid.y)
   };
   std::vector<CUmodule> chunk_mods;  // one per DISTINCT chunk
   std::vector<ChunkLaunch> chunks;   // the chain, in order
+  CUdeviceptr d_bases = 0;           // uint32[chunks of the program][4]: imm / out / state row base of each chunk
   CUdeviceptr scratch = 0;
   size_t scratch_stride = 0;
   CUmodule spec_mod = nullptr, steps_mod = nullptr;
@@ -198,7 +200,21 @@ struct Exec {
   int want;   // CLG_MODE_AUTO or the mode the caller pinned
   int mode;   // mode of the most recent (or, before any run, the preferred) plan
   int last_k = 0, last_parts = 0;
-  mutable int spec_distinct = -1;  // distinct kernels of the chunked specialised form (computed on demand)
+  // shape of the chunked specialised chain (computed on demand, for the mode choice): distinct kernels to assemble, and
+  // per launch {instructions, instances side by side}
+  struct ChainShape {
+    int k = 0, distinct = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> launches;
+  };
+  mutable ChainShape shape_;
+  const ChainShape &chain_shape(int k) const {
+    if (shape_.k != k) {
+      const SpecChain ch = spec_chain(flat, k);
+      shape_ = ChainShape{k, (int)ch.unique.size(), {}};
+      for (const SpecChain::Launch &l : ch.launches) shape_.launches.push_back({(uint32_t)ch.chunks[l.first].code.size(), l.count});
+    }
+    return shape_;
+  }
   Plan plan[5];  // indexed by clg_mode; [PLAN_PARTS] = cooperative mode over the partitioned level stream
   static constexpr int PLAN_PARTS = 4;
 
@@ -224,14 +240,7 @@ struct Exec {
           // values to L1-backed local memory (mul64: 315 live values -> 255 registers + 488 B of spills)
           if (!k && ln.n_slots <= 512) k = 1;
           if (k && want != CLG_MODE_SPEC && ln.n_instr > 4 * spec_chunk_limit(k)) {
-            if (spec_distinct < 0) {
-              const std::vector<SpecChunk> chunks = spec_chunks(flat, k);
-              std::vector<const SpecChunk *> unique;
-              for (const SpecChunk &c : chunks)
-                if (std::none_of(unique.begin(), unique.end(), [&](const SpecChunk *u) { return u->same_kernel(c); })) unique.push_back(&c);
-              spec_distinct = (int)unique.size();
-            }
-            if (spec_distinct > 4) return 0;
+            if (chain_shape(k).distinct > 4) return 0;
           }
           return k;
         }
@@ -308,9 +317,15 @@ struct Exec {
     const FlatStream &ln = lane_stream();
     const double regs = std::min(255.0, (double)ln.n_slots * k + 24.0);
     const double resident = std::min(2048.0, std::floor(65536.0 / regs / 128.0) * 128.0);
-    const double groups = std::ceil((double)words / k), warps = std::min(resident, std::ceil(groups / ctx->sm_count / 32.0) * 32.0) / 32.0;
-    const double launches = std::ceil((double)ln.n_instr / spec_chunk_limit(k));
-    return std::ceil(groups / (resident * ctx->sm_count)) * ln.n_instr * k * std::max(4.0, 0.85 * warps) + launches * 5000.0;
+    const double groups = std::ceil((double)words / k);
+    auto launch = [&](double n_instr, double instances) {
+      const double threads = groups * instances, warps = std::min(resident, std::ceil(threads / ctx->sm_count / 32.0) * 32.0) / 32.0;
+      return std::ceil(threads / (resident * ctx->sm_count)) * n_instr * k * std::max(4.0, 0.85 * warps) + 5000.0;
+    };
+    if (ln.n_instr <= spec_chunk_limit(k)) return launch(ln.n_instr, 1);
+    double cycles = 0;
+    for (const auto &l : chain_shape(k).launches) cycles += launch(l.first, l.second);
+    return cycles;
   }
   // CTA size of the specialised kernels: 128 threads, narrower when the batch would otherwise leave SMs without a CTA
   // (2^20 lanes at K = 4 are 8192 threads: 64 CTAs of 128 for 148 SMs)
@@ -469,15 +484,9 @@ struct Exec {
     } else if (ln.n_instr > spec_chunk_limit(P.K)) {
       // chunked specialisation: cut where few registers are live; equal chunks (the instances of a flattened program)
       // share one assembled kernel and differ only in the rows their pointers are advanced by
-      const std::vector<SpecChunk> chunks = spec_chunks(flat, P.K);
-      std::vector<uint32_t> unique;  // indices of the chunks that get assembled
-      std::vector<uint32_t> kernel_of(chunks.size());
-      for (uint32_t c = 0; c < chunks.size(); c++) {
-        uint32_t u = 0;
-        while (u < unique.size() && !chunks[c].same_kernel(chunks[unique[u]])) u++;
-        if (u == unique.size()) unique.push_back(c);
-        kernel_of[c] = u;
-      }
+      const SpecChain chain = spec_chain(flat, P.K);
+      const std::vector<SpecChunk> &chunks = chain.chunks;
+      const std::vector<uint32_t> &unique = chain.unique;
       P.chunk_mods.assign(unique.size(), nullptr);
       std::vector<CUfunction> fns(unique.size(), nullptr);
       try {
@@ -492,8 +501,13 @@ struct Exec {
         P.chunk_mods.clear();
         throw;
       }
+      std::vector<uint32_t> bases(chunks.size() * 4, 0);
       for (uint32_t c = 0; c < chunks.size(); c++)
-        P.chunks.push_back({fns[kernel_of[c]], chunks[c].imm_base, chunks[c].out_base, chunks[c].state_base});
+        bases[4 * c] = chunks[c].imm_base, bases[4 * c + 1] = chunks[c].out_base, bases[4 * c + 2] = chunks[c].state_base;
+      for (const SpecChain::Launch &l : chain.launches) P.chunks.push_back({fns[chain.kernel_of[l.first]], l.first, l.count});
+      CU(cuMemAlloc(&P.d_bases, bases.size() * 4));
+      CU(cuMemcpyHtoDAsync(P.d_bases, bases.data(), bases.size() * 4, nullptr));
+      CU(cuStreamSynchronize(nullptr));
     } else {
       P.ptx = emit_spec_ptx(flat, P.K);
       assemble(P.ptx, "clg_spec", "the specialised kernel", &P.spec_mod, &P.spec_fn);
@@ -515,6 +529,7 @@ struct Exec {
       for (CUmodule m : P.chunk_mods)
         if (m) d.cuModuleUnload(m);
       if (P.scratch) d.cuMemFree(P.scratch);
+      if (P.d_bases) d.cuMemFree(P.d_bases);
     }
     for (int b = 0; b < NBUF; b++) {
       if (stage_in[b]) d.cuMemFree(stage_in[b]);
@@ -681,10 +696,10 @@ struct Exec {
           P.scratch_stride = stride;
         }
         for (const Plan::ChunkLaunch &c : P.chunks) {
-          const uint32_t *c_imm = imm + (size_t)c.imm_base * stride;
-          uint32_t *c_out = out + (size_t)c.out_base * stride, *c_state = state + (size_t)c.state_base * stride;
-          void *cargs[] = {&c_imm, &c_out, &c_state, &stride32, &g, &P.scratch};
-          CU(cuLaunchKernel(c.fn, (groups + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, cargs, nullptr));
+          const uint32_t ntc = spec_threads(groups * c.count);
+          CUdeviceptr table = P.d_bases + (size_t)c.first * 16;
+          void *cargs[] = {&imm, &out, &state, &stride32, &g, &P.scratch, &table};
+          CU(cuLaunchKernel(c.fn, (groups + ntc - 1) / ntc, c.count, 1, ntc, 1, 1, 0, stream, cargs, nullptr));
         }
         return;
       }

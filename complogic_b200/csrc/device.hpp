@@ -26,6 +26,16 @@ struct SpecChunk {
   bool same_kernel(const SpecChunk &o) const;           // equal code: the two chunks can share one assembled kernel
 };
 std::vector<SpecChunk> spec_chunks(const Flat &f, int K);
+struct SpecChain {
+  std::vector<SpecChunk> chunks;
+  std::vector<uint32_t> unique;     // chunks that get assembled (one per distinct kernel)
+  std::vector<uint32_t> kernel_of;  // chunk -> index into `unique`
+  struct Launch {
+    uint32_t first, count;  // chunks [first, first + count) run side by side in one launch (grid.y = count)
+  };
+  std::vector<Launch> launches;
+};
+SpecChain spec_chain(const Flat &f, int K);
 std::string emit_spec_chunk_ptx(const Flat &f, int K, const SpecChunk &c);
 
 // mirrors kernels.cu

@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <iterator>
 #include <string>
 #include <vector>
 
@@ -146,6 +147,50 @@ std::vector<SpecChunk> spec_chunks(const Flat &f, int K) {
   return out;
 }
 
+// The launches of the chain: which chunks get assembled (one per distinct kernel) and which consecutive chunks run
+// side by side in one launch. Consecutive chunks that share a kernel, hand nothing over and touch disjoint
+// carried-state rows are independent of each other; blockIdx.y then selects the instance's row bases.
+SpecChain spec_chain(const Flat &f, int K) {
+  SpecChain ch;
+  ch.chunks = spec_chunks(f, K);
+  const std::vector<SpecChunk> &chunks = ch.chunks;
+  ch.kernel_of.resize(chunks.size());
+  for (uint32_t c = 0; c < chunks.size(); c++) {
+    uint32_t u = 0;
+    while (u < ch.unique.size() && !chunks[c].same_kernel(chunks[ch.unique[u]])) u++;
+    if (u == ch.unique.size()) ch.unique.push_back(c);
+    ch.kernel_of[c] = u;
+  }
+  auto state_rows = [&](const SpecChunk &c) {
+    std::vector<uint32_t> r;
+    for (const FlatInstr &x : c.code)
+      if (x.kind != K_LUT && (x.flags & FLAG_STATE_ROW)) r.push_back(c.state_base + x.row);
+    std::sort(r.begin(), r.end());
+    r.erase(std::unique(r.begin(), r.end()), r.end());
+    return r;
+  };
+  std::vector<uint32_t> rows_of_run;  // absolute state rows touched by the chunks of the current launch
+  for (uint32_t c = 0; c < chunks.size(); c++) {
+    auto isolated = [&](uint32_t i) { return chunks[i].live_in.empty() && chunks[i].live_out.empty(); };
+    std::vector<uint32_t> rows = state_rows(chunks[c]), both;
+    bool merge = c > 0 && isolated(c) && isolated(c - 1) && ch.kernel_of[c] == ch.kernel_of[c - 1] && ch.launches.back().count < 65535;
+    if (merge) {
+      std::set_intersection(rows.begin(), rows.end(), rows_of_run.begin(), rows_of_run.end(), std::back_inserter(both));
+      merge = both.empty();
+    }
+    if (merge) {
+      ch.launches.back().count++;
+      std::vector<uint32_t> all;
+      std::merge(rows.begin(), rows.end(), rows_of_run.begin(), rows_of_run.end(), std::back_inserter(all));
+      rows_of_run.swap(all);
+    } else {
+      ch.launches.push_back({c, 1});
+      rows_of_run.swap(rows);
+    }
+  }
+  return ch;
+}
+
 static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecChunk &cc, bool chunk);
 
 std::string emit_spec_ptx(const Flat &f, int K, bool multi_step) {
@@ -188,7 +233,7 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
        "(\n  .param .u64 p_imm,\n  .param .u64 p_out,\n  .param .u64 p_state,\n"
        "  .param .u32 p_stride,\n  .param .u32 p_groups" +
        (multi_step ? ",\n  .param .u32 p_steps,\n  .param .u64 p_imm_step,\n  .param .u64 p_out_step" : "") +
-       (chunk ? ",\n  .param .u64 p_scratch" : "") + "\n)\n{\n";
+       (chunk ? ",\n  .param .u64 p_scratch,\n  .param .u64 p_bases" : "") + "\n)\n{\n";
   std::snprintf(buf, sizeof buf,
                 "  .reg .b32 %%s<%u>;\n  .reg .b32 %%t<%d>;\n  .reg .b32 %%rtid, %%rcta, %%rntid, %%gid, %%stride, %%groups;\n"
                 "  .reg .b64 %%imm, %%out, %%state, %%off, %%sb, %%addr;\n  .reg .pred %%p;\n\n",
@@ -212,6 +257,12 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
   s += buf;
   if (chunk) {
     s += "  .reg .b64 %scr;\n  ld.param.u64 %scr, [p_scratch];\n  cvta.to.global.u64 %scr, %scr;\n  add.u64 %scr, %scr, %off;\n";
+    // Row bases: blockIdx.y picks one entry {imm, out, state, -} of the launch's table, so that equal chunks (the
+    // instances of a flattened program) run side by side in ONE launch, each on its own rows.
+    s += "  .reg .b64 %bases, %row;\n  .reg .b32 %inst, %b<4>;\n  ld.param.u64 %bases, [p_bases];\n  cvta.to.global.u64 %bases, %bases;\n"
+         "  mov.u32 %inst, %ctaid.y;\n  mad.wide.u32 %bases, %inst, 16, %bases;\n  ld.global.nc.v4.u32 {%b0,%b1,%b2,%b3}, [%bases];\n"
+         "  cvt.u64.u32 %row, %b0;\n  mad.lo.u64 %imm, %sb, %row, %imm;\n  cvt.u64.u32 %row, %b1;\n  mad.lo.u64 %out, %sb, %row, %out;\n"
+         "  cvt.u64.u32 %row, %b2;\n  mad.lo.u64 %state, %sb, %row, %state;\n";
     // Hand-over: a live-in register is reloaded from the scratch buffer right before its first use here (not at
     // the top, where hundreds of reloads would all be live at once), a live-out one is stored right after its last
     // definition here. A register that is live across the whole chunk untouched is already in the scratch buffer.
@@ -241,6 +292,7 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
     for (int k = 0; k < K; k++) v += (k ? "," : "") + C(ks, k);
     return v + (K == 1 ? "" : "}");
   };
+  s += "  // body\n";
   if (multi_step) {
     s += "  ld.param.u32 %steps, [p_steps];\n  ld.param.u64 %immstep, [p_imm_step];\n  ld.param.u64 %outstep, [p_out_step];\n";
     for (uint32_t ks = 0; ks < h.n_state; ks++) {

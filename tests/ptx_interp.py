@@ -19,7 +19,7 @@ def run_kernel(ptx: str, k: int, groups: int, mem: dict):
     """Execute one generated kernel. mem: {"imm","out","state","scr"} -> uint32 [rows][stride] (modified in place);
     thread g owns words [g*k, (g+1)*k) of every row. Loops (the multi-step form) are not supported."""
     lines = [l.strip() for l in ptx.splitlines()]
-    start = lines.index("mul.wide.u32 %sb, %stride, 4;") + 1
+    start = lines.index("// body") + 1  # (the prologue computes the thread's column offset and row bases)
     reg = {}
     addr = None
     cols = np.arange(groups)[:, None] * k + np.arange(k)[None, :]  # [groups][k]
@@ -39,8 +39,6 @@ def run_kernel(ptx: str, k: int, groups: int, mem: dict):
             d, sb, n, base = _regs(rest)
             assert d == "%addr" and sb == "%sb" and base[1:] in _BASES, l
             addr = (base[1:], int(n))
-        elif op in ("ld.param.u64", "cvta.to.global.u64", "add.u64"):
-            assert "%scr" in rest, l  # scratch base set-up of a chunk kernel
         elif op.startswith("ld.global"):
             m = re.fullmatch(r"(\{[^}]*\}|%\w+), \[%addr\]", rest)
             assert m, l

@@ -145,7 +145,8 @@ def test_chunked_specialised_long_programs():
     for circ in (mul, dag):
         cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, mode=host.MODE_SPEC)
         assert cs.info["lane_instrs"] > 16384 and cs.mode == host.MODE_SPEC
-        assert cs.launches_per_run > 1
+        # the five multipliers are five equal, independent chunks: ONE launch, blockIdx.y picks the instance's rows
+        assert cs.launches_per_run == 1 if circ is mul else cs.launches_per_run > 1
         for nv in (300, 70000, 33):  # the scratch buffer grows with the stride and is kept when it shrinks
             imm = random_sliced(circ.n_immediates, stride_for(nv), seed=nv + 5)
             assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), oracle_out(circ, imm, nv)), (circ.name, nv)
@@ -439,21 +440,26 @@ def test_modes_agree_at_scale_mul16():
 
 
 def test_config5_wide_single_vector():
-    """BASELINE config 5: 64x64 multiplier x 128 instances flattened (10 764 288 gates), ONE input vector.
-    AUTO must pick the cooperative intra-level mode for a single vector (the lane modes would run 1.5M
-    instructions on one thread), and the products must be right."""
+    """BASELINE config 5: 64x64 multiplier x 128 instances flattened (10 764 288 gates), ONE input vector, through
+    (i) the cooperative intra-level mode (one CTA per part: the general answer for a wide single-vector circuit) and
+    (ii) what AUTO picks here, because the 128 instances are equal, independent chunks: ONE launch of one specialised
+    kernel with an instance per blockIdx.y. Neither runs 1.5M instructions on one thread; both must be right."""
     base = circuits.array_multiplier(64)
     circ = circuits.flatten_instances(base, 128)
     assert circ.sim.nand_count == 10764288
-    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs)
+    coop = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, mode=host.MODE_COOP)
+    auto = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs)
     for nv in (1, 32):
         imm = random_sliced(circ.n_immediates, stride_for(nv), seed=0x5EED)
-        got = mask_tail(cs.run_batch(imm, nv), nv)
-        assert cs.mode == host.MODE_COOP
+        want = oracle_out(circ, imm, nv)
+        got = mask_tail(coop.run_batch(imm, nv), nv)
+        assert coop.mode == host.MODE_COOP
         for m in (0, 77, 127):
             a, b = unslice_int(imm[128 * m:128 * m + 64], nv), unslice_int(imm[128 * m + 64:128 * m + 128], nv)
             assert list(unslice_int(got[128 * m:128 * m + 128], nv)) == [int(x) * int(y) for x, y in zip(a, b)]
-        assert np.array_equal(got, oracle_out(circ, imm, nv))
+        assert np.array_equal(got, want)
+        assert np.array_equal(mask_tail(auto.run_batch(imm, nv), nv), want)
+        assert auto.mode == host.MODE_SPEC and auto.launches_per_run == 1
 
 
 def test_host_path_pipelines_many_chunks(monkeypatch):
