@@ -425,6 +425,29 @@ def test_full_size_adder32_2p24():
     assert np.array_equal(unslice_int(out_h[:, sample], n), a + b + cin)
 
 
+def test_full_size_dag_1m_2p24_periodic_inputs():
+    """BASELINE config 4 at full size: the 1 048 576-gate DAG on 2^24 lanes. The inputs repeat with a period of 2^12
+    lanes, so every one of the 4096 blocks of output words must equal the first, and the first must equal the
+    oracle: all column groups of all CTAs are checked, not a prefix."""
+    import torch
+
+    circ = circuits.random_dag()
+    nv, period = 1 << 24, 1 << 12
+    stride, pw = stride_for(nv), period // 32
+    block = random_sliced(1024, pw, seed=0xD4A)
+    cs = host.CudaSimulation.from_simulation(circ.sim, 1024, circ.out_regs)
+    imm = torch.from_numpy(block.view(np.int32)).cuda().repeat(1, stride // pw).contiguous()
+    out = torch.zeros((4096, stride), dtype=torch.int32, device="cuda:0")
+    cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    assert cs.mode == host.MODE_COOP
+    blocks = out.view(4096, stride // pw, pw)
+    assert bool((blocks == blocks[:, :1, :]).all())
+    first = blocks[:, 0, :].contiguous().cpu().numpy().view(np.uint32)
+    del imm, out, blocks
+    assert np.array_equal(first, oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), block, period, circ.out_regs))
+
+
 def test_modes_agree_at_scale_mul16():
     """Size-independent property at 2^22 vectors: the three execution modes produce identical buffers, and they
     equal a*b on a strided sample."""
