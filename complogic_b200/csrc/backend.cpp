@@ -227,9 +227,9 @@ struct Exec {
     switch (m) {
       case CLG_MODE_SPEC:
         // Assembling straight-line code is super-linear in its length (12k instructions: 2 s, 50k: 9 s, 200k: 75 s),
-        // so long programs are cut into chunk kernels of about a second each. A caller who pins CLG_MODE_SPEC
-        // gets any program up to 4M instructions; AUTO only specialises when at most 4 DISTINCT kernels have to be
-        // assembled (a short program, or a flattened one whose instances share their kernels).
+        // so long programs are cut into chunk kernels of about a second each, up to 4M instructions. (When AUTO
+        // takes such a chain is decided in choose(): at once if few distinct kernels have to be assembled, else after
+        // the interpreters have cost as much GPU time as the assembly will.)
         if (ln.n_instr == 0 || ln.n_instr > 4000000u) return 0;
         {
           int k = 0;
@@ -239,9 +239,6 @@ struct Exec {
           // one word per thread tolerates a live set somewhat beyond the register file: ptxas spills the coldest
           // values to L1-backed local memory (mul64: 315 live values -> 255 registers + 488 B of spills)
           if (!k && ln.n_slots <= 512) k = 1;
-          if (k && want != CLG_MODE_SPEC && ln.n_instr > 4 * spec_chunk_limit(k)) {
-            if (chain_shape(k).distinct > 4) return 0;
-          }
           return k;
         }
       case CLG_MODE_LANE:
@@ -333,7 +330,14 @@ struct Exec {
     const uint32_t sms = (uint32_t)ctx->sm_count;
     return groups >= 2 * sms * 128 ? 128 : groups >= 2 * sms * 64 ? 64 : 32;
   }
+  mutable double interp_seconds = 0;  // estimated GPU time spent interpreting a program that could be specialised
+  mutable bool tier_pending = false;
+  static double tier_seconds_per_kernel() {
+    if (const char *env = std::getenv("CLG_TIER_SECONDS_PER_KERNEL")) return std::atof(env);  // knob (tests: tier up at once)
+    return 1.0;
+  }
   int choose(size_t words) const {
+    tier_pending = false;
     if (want != CLG_MODE_AUTO) return want;
     const int spec_k = fit_k(CLG_MODE_SPEC);
     const bool lane_ok = fit_k(CLG_MODE_LANE) != 0, coop_ok = fit_k(CLG_MODE_COOP) != 0;
@@ -342,7 +346,15 @@ struct Exec {
       // (one vector through 128 flattened multipliers is 128 dependent launches: the cooperative mode's case)
       if (lane_stream().n_instr <= spec_chunk_limit(spec_k)) return CLG_MODE_SPEC;
       const double sc = spec_cycles(words);
-      if ((!lane_ok || sc <= lane_cycles(words)) && (!coop_ok || sc <= coop_cycles(words))) return CLG_MODE_SPEC;
+      if ((!lane_ok || sc <= lane_cycles(words)) && (!coop_ok || sc <= coop_cycles(words))) {
+        // Tiered specialisation: every distinct kernel of the chain costs about a second of assembly. Up to 4 of them
+        // are paid at once; beyond that the program runs in an interpreter until that has cost as much GPU time as
+        // the assembly will (run() keeps the tally), and is specialised then.
+        const int distinct = chain_shape(spec_k).distinct;
+        if (distinct <= 4 || plan[CLG_MODE_SPEC].ready || interp_seconds >= distinct * tier_seconds_per_kernel()) return CLG_MODE_SPEC;
+        tier_pending = lane_ok || coop_ok;
+        if (!tier_pending) return CLG_MODE_SPEC;  // nothing else can run it
+      }
     }
     if (lane_ok && coop_ok) return lane_cycles(words) <= coop_cycles(words) ? CLG_MODE_LANE : CLG_MODE_COOP;
     return lane_ok ? CLG_MODE_LANE : CLG_MODE_COOP;
@@ -678,6 +690,7 @@ struct Exec {
     if (n_vectors == 0) return;
     ctx->bind();
     mode = choose(words);
+    if (tier_pending) interp_seconds += (mode == CLG_MODE_LANE ? lane_cycles(words) : coop_cycles(words)) / 1.9e9;
     // a cooperative run that cannot give every SM its own column group uses the partitioned form if there is one
     const bool use_parts = mode == CLG_MODE_COOP && parts_k() && (words + parts_k() - 1) / parts_k() < (size_t)ctx->sm_count;
     Plan &P = use_parts ? get_parts() : get(mode);

@@ -169,6 +169,29 @@ def test_chunked_specialised_stateful():
     assert np.array_equal(mask_tail(state, nv), mask_tail(want[T - 1], nv))  # state rows ARE the output registers here
 
 
+def test_auto_tiers_up_to_the_specialised_chain():
+    """A long program whose chain needs more than 4 distinct kernels: AUTO starts in an interpreter and specialises
+    once the interpreter has cost as much GPU time as the assembly will (here at once: the knob sets the price of a
+    kernel to ~0). Same bits before and after."""
+    import os
+    circ = circuits.random_dag(levels=3400, width=48, n_immediates=64, window=2, seed=37)
+    nv = 4096
+    imm = random_sliced(64, stride_for(nv), seed=3)
+    want = oracle_out(circ, imm, nv)
+    cs = host.CudaSimulation.from_simulation(circ.sim, 64, circ.out_regs)
+    assert cs.info["lane_instrs"] > 5 * 16384  # at least 6 kernels, all different
+    assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), want)
+    assert cs.mode in (host.MODE_LANE, host.MODE_COOP)  # one short run has not paid for ~5 s of assembly
+    os.environ["CLG_TIER_SECONDS_PER_KERNEL"] = "1e-9"
+    try:
+        assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), want)
+    finally:
+        del os.environ["CLG_TIER_SECONDS_PER_KERNEL"]
+    assert cs.mode == host.MODE_SPEC and cs.launches_per_run >= 5
+    assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), want)
+    assert cs.mode == host.MODE_SPEC  # the chain is built: it stays
+
+
 def latch_chain(n):
     """n D latches in a row behind one enable: latch i's data input is latch i-1's output."""
     c = host.Compiler(2)
