@@ -51,6 +51,8 @@ def build_workload(name: str, api=None):
 
     if name == "dag1m":
         return circuits.random_dag(256, 4096, 1024, 2, 1, api=api), 24, 0xDA6
+    if name == "dag64k":
+        return circuits.random_dag(64, 1024, 256, 2, 3, api=api), 23, 0xDA8
     if name == "dag1m_kinf":
         return circuits.random_dag(256, 4096, 1024, 0, 1, api=api), 24, 0xDA7
     if name == "mul16":
@@ -75,6 +77,8 @@ def build_workload(name: str, api=None):
 WORKLOAD_DESC = {
     "dag1m": "synthetic random levelized NAND DAG, 1 048 576 gates (256 levels x 4096), 1024 immediates, window K=2, "
              "4096 outputs (BASELINE configs[3])",
+    "dag64k": "a smaller random levelized DAG: 65 536 gates (64 levels x 1024), 256 immediates, window K=2 -- narrow levels, "
+              "several cooperative CTAs per SM",
     "dag1m_kinf": "the same random levelized DAG with no locality window (K = infinity: inputs drawn from ALL earlier levels); "
                   "most of its 1 048 576 gates cannot reach the 4096 outputs and are eliminated by the pass",
     "mul16": "16x16 array multiplier, 4 896 NANDs with the reference's gate expansions (BASELINE configs[2])",

@@ -165,6 +165,7 @@ struct Plan {
   CUdeviceptr d_instr = 0, d_levels = 0, d_parts = 0, d_cinstr = 0, d_clevels = 0;  // (compact cooperative form)
   uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0, n_parts = 0, code_off = 0;
   size_t smem = 0;
+  uint32_t tuned_threads = 0;  // cooperative, big batches: CTA size found by timing candidates on this device (0: not tuned yet)
   bool resident = false;  // cooperative: the (largest part's) instruction stream is staged in shared memory
   // long programs: the lane stream cut into SPEC_CHUNK-instruction kernels; live registers cross the cuts through `scratch`
   struct ChunkLaunch {
@@ -720,6 +721,27 @@ struct Exec {
       CU(cuLaunchKernel(P.spec_fn, (groups + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, args, nullptr));
       return;
     }
+    if (mode == CLG_MODE_LANE) {
+      RunParams p = params(P, imm, out, state, stride, groups);
+      void *args[] = {&p};
+      const uint32_t nc = P.coop_threads, grid = (groups + nc - 1) / nc;
+      CU(cuLaunchKernel(ctx->lane[kidx(K)], grid, 1, 1, nc + 32, 1, 1, (unsigned)P.smem, stream, args, nullptr));
+      return;
+    }
+    // Cooperative CTA size. One wave of column groups or less is a latency problem: as many threads as the widest
+    // level has instructions. More than that is a throughput problem whose optimum depends on how many CTAs fit an
+    // SM and how wide the levels are (a 65k-gate DAG with ~570 instructions a level: 15.0 ms with 1024 threads,
+    // 7.1 ms with 256), so it is measured once per plan on this device.
+    uint32_t nt = P.coop_threads;
+    if (!P.n_parts && groups > (uint32_t)ctx->sm_count * coop_ctas_per_sm(P, nt)) {
+      if (!P.tuned_threads) P.tuned_threads = tune_coop_threads(P);
+      nt = P.tuned_threads;
+    }
+    launch_coop(P, params(P, imm, out, state, stride, groups), nt, stream);
+  }
+
+  RunParams params(const Plan &P, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t stride, uint32_t groups) const {
+    const FlatHeader &h = flat.header();
     RunParams p{};
     p.instr = (const void *)P.d_instr, p.levels = (const uint32_t *)P.d_levels;
     p.imm = imm, p.out = out, p.state = state;
@@ -728,20 +750,66 @@ struct Exec {
     p.stride = (uint32_t)stride, p.n_groups = groups;
     p.parts = (const void *)P.d_parts, p.n_parts = P.n_parts, p.code_off = P.code_off;
     p.cinstr = (const void *)P.d_cinstr, p.clevels = (const uint32_t *)P.d_clevels;
-    void *args[] = {&p};
-    if (mode == CLG_MODE_LANE) {
-      const uint32_t nc = P.coop_threads, grid = (groups + nc - 1) / nc;
-      CU(cuLaunchKernel(ctx->lane[kidx(K)], grid, 1, 1, nc + 32, 1, 1, (unsigned)P.smem, stream, args, nullptr));
-    } else {
-      const size_t per_sm = std::max<size_t>(1, std::min<size_t>(SMEM_MAX / (P.smem + 1024), 2048 / P.coop_threads));
-      uint32_t grid = std::min<uint32_t>(groups, (uint32_t)ctx->sm_count * (uint32_t)per_sm);
-      if (P.n_parts) {  // one CTA per (part, group slot); at least one group slot, about one wave of CTAs
-        const uint32_t slots_g = std::max<uint32_t>(1u, std::min<uint32_t>(groups, ((uint32_t)ctx->sm_count * (uint32_t)per_sm + P.n_parts - 1) / P.n_parts));
-        grid = P.n_parts * slots_g;
-      }
-      CU(cuLaunchKernel(P.resident ? ctx->coop_res[kidx(K)] : P.d_cinstr ? ctx->coop_c[kidx(K)] : ctx->coop[kidx(K)], grid, 1, 1, P.coop_threads, 1, 1, (unsigned)P.smem,
-                        stream, args, nullptr));
+    return p;
+  }
+  uint32_t coop_ctas_per_sm(const Plan &P, uint32_t nt) const {
+    return (uint32_t)std::max<size_t>(1, std::min<size_t>(SMEM_MAX / (P.smem + 1024), 2048 / nt));
+  }
+  void launch_coop(const Plan &P, RunParams p, uint32_t nt, CUstream stream) {
+    const uint32_t per_sm = coop_ctas_per_sm(P, nt), groups = p.n_groups;
+    uint32_t grid = std::min<uint32_t>(groups, (uint32_t)ctx->sm_count * per_sm);
+    if (P.n_parts) {  // one CTA per (part, group slot); at least one group slot, about one wave of CTAs
+      const uint32_t slots_g = std::max<uint32_t>(1u, std::min<uint32_t>(groups, ((uint32_t)ctx->sm_count * per_sm + P.n_parts - 1) / P.n_parts));
+      grid = P.n_parts * slots_g;
     }
+    void *args[] = {&p};
+    const int k = kidx(P.K);
+    CU(cuLaunchKernel(P.resident ? ctx->coop_res[k] : P.d_cinstr ? ctx->coop_c[k] : ctx->coop[k], grid, 1, 1, nt, 1, 1, (unsigned)P.smem, stream, args, nullptr));
+  }
+  // Time the cooperative kernel of this plan on scratch buffers (zero inputs: the work does not depend on the data)
+  // for a few CTA sizes, each on enough column groups for 8 passes per CTA, and keep the fastest per group.
+  uint32_t tune_coop_threads(const Plan &P) {
+    const uint32_t wide = P.coop_threads;
+    if (std::getenv("CLG_COOP_THREADS") || std::getenv("CLG_COOP_NO_TUNE") || wide <= 64) return wide;
+    const FlatHeader &h = flat.header();
+    const uint32_t groups = (uint32_t)ctx->sm_count * 16;
+    const size_t stride = ((size_t)groups * P.K + 3) / 4 * 4;
+    const size_t rows[3] = {h.n_inputs, h.n_outputs, h.n_state};
+    CUdeviceptr buf[3] = {0, 0, 0};
+    CUevent e0 = nullptr, e1 = nullptr;
+    uint32_t best = wide;
+    bool ok = true;
+    for (int i = 0; i < 3 && ok; i++) {
+      const size_t bytes = std::max<size_t>(16, rows[i] * stride * 4);
+      ok = driver().cuMemAlloc(&buf[i], bytes) == CUDA_SUCCESS && driver().cuMemsetD8Async(buf[i], 0, bytes, nullptr) == CUDA_SUCCESS;
+    }
+    ok = ok && driver().cuEventCreate(&e0, CU_EVENT_DEFAULT) == CUDA_SUCCESS && driver().cuEventCreate(&e1, CU_EVENT_DEFAULT) == CUDA_SUCCESS;
+    if (ok) {
+      const RunParams p = params(P, (const uint32_t *)buf[0], (uint32_t *)buf[1], (uint32_t *)buf[2], stride, groups);
+      double best_ms = 1e30;
+      for (uint32_t nt : {1024u, 768u, 512u, 384u, 256u, 128u}) {
+        if (nt > wide && nt != 1024u) continue;
+        nt = std::min(nt, wide);
+        float ms = 1e30f;
+        launch_coop(P, p, nt, nullptr);  // warm-up
+        for (int rep = 0; rep < 2; rep++) {
+          float t = 0;
+          CU(cuEventRecord(e0, nullptr));
+          launch_coop(P, p, nt, nullptr);
+          CU(cuEventRecord(e1, nullptr));
+          CU(cuEventSynchronize(e1));
+          CU(cuEventElapsedTime(&t, e0, e1));
+          ms = std::min(ms, t);
+        }
+        if (ms < best_ms * 0.97) best_ms = ms, best = nt;  // (a smaller CTA has to win by 3 %)
+      }
+    }
+    driver().cuStreamSynchronize(nullptr);
+    if (e0) driver().cuEventDestroy(e0);
+    if (e1) driver().cuEventDestroy(e1);
+    for (CUdeviceptr b : buf)
+      if (b) driver().cuMemFree(b);
+    return best;
   }
 };
 
