@@ -710,7 +710,7 @@ struct Exec {
           P.scratch_stride = stride;
         }
         for (const Plan::ChunkLaunch &c : P.chunks) {
-          const uint32_t ntc = spec_threads(groups * c.count);
+          const uint32_t ntc = spec_threads((uint32_t)std::min<uint64_t>((uint64_t)groups * c.count, 0xFFFFFFFFull));
           CUdeviceptr table = P.d_bases + (size_t)c.first * 16;
           void *cargs[] = {&imm, &out, &state, &stride32, &g, &P.scratch, &table};
           CU(cuLaunchKernel(c.fn, (groups + ntc - 1) / ntc, c.count, 1, ntc, 1, 1, 0, stream, cargs, nullptr));
