@@ -239,7 +239,9 @@ struct Exec {
             if (!k && (uint64_t)ln.n_slots * c <= 200) k = c;
           // one word per thread tolerates a live set somewhat beyond the register file: ptxas spills the coldest
           // values to L1-backed local memory (mul64: 315 live values -> 255 registers + 488 B of spills)
-          if (!k && ln.n_slots <= 512) k = 1;
+          // (the assembler's time explodes with the spill count: 315 live values 2 s, 681 live values 54 s per
+          // kernel -- so AUTO stops at 400, a caller who pins the mode may go to 512)
+          if (!k && ln.n_slots <= (want == CLG_MODE_SPEC ? 512u : 400u)) k = 1;
           return k;
         }
       case CLG_MODE_LANE:
