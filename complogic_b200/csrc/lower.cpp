@@ -621,7 +621,7 @@ Sched schedule_lane(const Network &net) {
 // level before their first reader, stores one level after their producer. A slot freed by its
 // last reader in level L is handed out again from level L + 1 on: within a level other threads may
 // still be reading it.
-Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
+Sched schedule_level(const Network &net, uint32_t BANKS = 8, bool estimate_only = false) {
   const size_t V = net.vals.size(), O = net.outs.size();
   std::vector<uint32_t> lev(V, 0);
   for (size_t v = 0; v < V; v++)
@@ -677,6 +677,15 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
   for (size_t o = 0; o < O; o++)
     if (net.outs[o].val != NONE) last[net.outs[o].val] = std::max(last[net.outs[o].val], olev[o]);
 
+  if (estimate_only) {  // peak number of values alive in one level: what the register stack will need, within a few %
+    std::vector<int64_t> diff(n_levels + 2, 0);
+    for (size_t v = 0; v < V; v++) diff[lev[v]]++, diff[last[v] + 1]--;
+    int64_t live = 0, peak = 0;
+    for (uint32_t l = 0; l < n_levels; l++) live += diff[l], peak = std::max(peak, live);
+    Sched est;
+    est.n_slots = (uint32_t)peak;
+    return est;
+  }
   // bucket by level
   std::vector<uint32_t> cnt(n_levels + 1, 0);
   for (size_t v = 0; v < V; v++) cnt[lev[v] + 1]++;
@@ -695,7 +704,7 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
   // caller picks BANKS for the K the register stack will fit shared memory with.) Three degrees of freedom are used: which 8 instructions share a quarter (greedy packing
   // from a window of candidates), which operand sits in which position (LUT inputs commute if the truth table
   // is permuted with them), and which free slot a result takes (one bank group per quarter member).
-  constexpr uint32_t WINDOW = 2048, MAX_BANKS = 32;
+  constexpr uint32_t MAX_BANKS = 32;
   Sched s;
   s.instr.resize(V + O);
   s.levels.assign(cnt.begin(), cnt.end());
@@ -743,7 +752,7 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
     if (o.val != NONE) fanout[o.val]++;
   uint64_t bank_weight[MAX_BANKS] = {};
   std::vector<Placed> order;
-  std::vector<uint8_t> taken;
+  std::vector<uint32_t> nxt;
   std::vector<CandInfo> cinfo;
   for (uint32_t l = 0; l < n_levels; l++) {
     if (l > 0) {
@@ -755,7 +764,6 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
     std::stable_sort(items.begin() + b, items.begin() + e, [&](uint32_t x, uint32_t y) { return key(x) < key(y); });
     // -- pack quarters
     order.clear();
-    taken.assign(n, 0);
     // per candidate: operand count, operand bank groups, and which operand orders leave its table unchanged
     cinfo.resize(n);
     for (uint32_t c = 0; c < n; c++) {
@@ -779,14 +787,24 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
         ci.nops = 0;
       }
     }
+    // how far a group looks for members that fit without a conflict; very wide levels (flattened instances: tens of
+    // thousands of similar instructions) have plenty of choice close by, and a long look-ahead there made the pass
+    // quadratic
+    const uint32_t WINDOW = n > 16384 ? 256 : n > 8192 ? 512 : 2048;
+    // (the candidates not placed yet form a linked list in their sorted order: a window scan steps over the ones
+    // already taken in O(1) instead of re-reading them for every group)
+    nxt.resize(n + 1);
+    for (uint32_t c = 0; c <= n; c++) nxt[c] = c + 1;
     uint32_t head = 0, placed = 0;
+    auto unlink = [&](uint32_t prev, uint32_t c) {
+      if (prev == NONE) head = nxt[c];
+      else nxt[prev] = nxt[c];
+    };
     while (placed < n) {
       uint32_t mask[3] = {0, 0, 0};
       uint32_t members = 0;
-      while (head < n && taken[head]) head++;
       uint32_t scanned = 0;
-      for (uint32_t c = head; c < n && members < BANKS && scanned < WINDOW; c++) {
-        if (taken[c]) continue;
+      for (uint32_t c = head, prev = NONE; c < n && members < BANKS && scanned < WINDOW;) {
         scanned++;
         const CandInfo &ci = cinfo[c];
         int pick = -1;
@@ -796,10 +814,15 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
           for (int k = 0; k < ci.nops && ok; k++) ok = !(mask[PERM[q][k]] >> ci.bank[k] & 1u);
           if (ok) pick = q;
         }
-        if (pick < 0) continue;
+        if (pick < 0) {
+          prev = c, c = nxt[c];
+          continue;
+        }
         for (int k = 0; k < ci.nops; k++) mask[PERM[pick][k]] |= 1u << ci.bank[k];
-        taken[c] = 1, members++, placed++;
+        members++, placed++;
         order.push_back({items[b + c], (uint8_t)pick});
+        unlink(prev, c);
+        c = nxt[c];
       }
       // nothing else in the window fits without a conflict (the tail of a class): fill the group with the
       // candidates that collide least, so that the replays spread over banks instead of piling onto one
@@ -812,24 +835,24 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8) {
           for (int j = 0; j < no; j++) hits[pm[j]][(x >= V ? slot[net.outs[x - V].val] : slot[net.vals[x].fan[j]]) % BANKS]++;
         }
         while (members < BANKS && placed < n) {
-          uint32_t best_c = NONE, best_cost = NONE, seen = 0;
+          uint32_t best_c = NONE, best_prev = NONE, best_cost = NONE, seen = 0;
           int best_q = 0;
-          for (uint32_t c = head; c < n && seen < 64; c++) {
-            if (taken[c]) continue;
+          for (uint32_t c = head, prev = NONE; c < n && seen < 64; prev = c, c = nxt[c]) {
             seen++;
             const CandInfo &ci = cinfo[c];
             for (int q = 0; q < 6; q++) {
               if (!(ci.perms >> q & 1)) continue;
               uint32_t cost = 0;
               for (int k = 0; k < ci.nops; k++) cost += hits[PERM[q][k]][ci.bank[k]];
-              if (cost < best_cost) best_cost = cost, best_c = c, best_q = q;
+              if (cost < best_cost) best_cost = cost, best_c = c, best_prev = prev, best_q = q;
             }
             if (best_cost == 0) break;
           }
           const CandInfo &ci = cinfo[best_c];
           for (int k = 0; k < ci.nops; k++) hits[PERM[best_q][k]][ci.bank[k]]++;
-          taken[best_c] = 1, members++, placed++;
+          members++, placed++;
           order.push_back({items[b + best_c], (uint8_t)best_q});
+          unlink(best_prev, best_c);
         }
       }
     }
@@ -1073,9 +1096,13 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
   // bank groups of 16 B, K = 2 -> 16 of 8 B, K = 1 -> 32 banks of 4 B
   auto schedule_for_smem = [](const Network &n) {
     if (const char *env = std::getenv("CLG_LEVEL_BANKS")) return schedule_level(n, (uint32_t)std::atoi(env));  // tuning knob
-    Sched sc = schedule_level(n, 8);
-    if (sc.ok && (size_t)sc.n_slots * 16 > 227 * 1024) sc = schedule_level(n, 16);
-    if (sc.ok && (size_t)sc.n_slots * 16 > 227 * 1024 && (size_t)sc.n_slots * 8 > 227 * 1024) sc = schedule_level(n, 32);
+    // the bank count follows from the K the stack will fit with, i.e. from the slot count, which is only known after
+    // scheduling: start from the peak live count (slots end up 2-4 % above it) instead of trying 8, 16 and 32 in turn
+    const size_t cap = 227 * 1024;
+    auto banks_for = [&](double slots) { return slots * 16 <= cap ? 8u : slots * 8 <= cap ? 16u : 32u; };
+    const uint32_t guess = banks_for(schedule_level(n, 8, true).n_slots * 1.06);
+    Sched sc = schedule_level(n, guess);
+    if (sc.ok && banks_for(sc.n_slots) != guess) sc = schedule_level(n, banks_for(sc.n_slots));  // off near a boundary
     return sc;
   };
   Sched level = schedule_for_smem(net);
