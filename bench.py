@@ -51,6 +51,8 @@ def build_workload(name: str, api=None):
 
     if name == "dag1m":
         return circuits.random_dag(256, 4096, 1024, 2, 1, api=api), 24, 0xDA6
+    if name == "dag_thin":
+        return circuits.random_dag(1500, 48, 64, 2, 31, api=api), 23, 0xDA9
     if name == "dag64k":
         return circuits.random_dag(64, 1024, 256, 2, 3, api=api), 23, 0xDA8
     if name == "dag1m_kinf":
@@ -77,6 +79,7 @@ def build_workload(name: str, api=None):
 WORKLOAD_DESC = {
     "dag1m": "synthetic random levelized NAND DAG, 1 048 576 gates (256 levels x 4096), 1024 immediates, window K=2, "
              "4096 outputs (BASELINE configs[3])",
+    "dag_thin": "a long thin random DAG: 72 000 gates (1500 levels x 48), 64 immediates -- ~90 live values, 39 k instructions",
     "dag64k": "a smaller random levelized DAG: 65 536 gates (64 levels x 1024), 256 immediates, window K=2 -- narrow levels, "
               "several cooperative CTAs per SM",
     "dag1m_kinf": "the same random levelized DAG with no locality window (K = infinity: inputs drawn from ALL earlier levels); "

@@ -235,8 +235,15 @@ struct Exec {
         {
           int k = 0;
           if (const char *env = std::getenv("CLG_SPEC_K")) k = std::atoi(env);  // tuning knob
+          // Wide words (K = 4, 2) make every load and store a 128/64-bit access, which is what an I/O-bound program
+          // wants; a long compute-bound one runs at the instruction-fetch rate and wants resident warps instead, i.e.
+          // few registers per thread (a 39k-instruction DAG with 91 live values: K = 1 0.81 ms, K = 2 1.21 ms,
+          // K = 4 2.27 ms; the 784-instruction mul16: K = 2 0.114 ms, K = 1 0.138 ms).
+          const FlatHeader &h = flat.header();
+          const uint64_t io_rows = (uint64_t)h.n_inputs + h.n_outputs + 2ull * h.n_state;
+          const bool long_compute_bound = ln.n_instr > 4096 && io_rows * 4 < ln.n_instr;
           for (int c : {4, 2, 1})
-            if (!k && (uint64_t)ln.n_slots * c <= 200) k = c;
+            if (!k && (uint64_t)ln.n_slots * c <= 200 && (c == 1 || !long_compute_bound)) k = c;
           // one word per thread tolerates a live set somewhat beyond the register file: ptxas spills the coldest
           // values to L1-backed local memory (mul64: 315 live values -> 255 registers + 488 B of spills)
           // (the assembler's time explodes with the spill count: 315 live values 2 s, 681 live values 54 s per

@@ -585,6 +585,39 @@ Sched schedule_lane(const Network &net) {
   };
 
   Sched s = allocate(order);
+  // Second candidate: the order the program was written in. Values are numbered in source order (the SSA pass walks
+  // the ops front to back), inputs are loaded at first use, outputs stored as soon as they exist. A demand-driven
+  // depth-first walk computes exactly the cone of each output, which for a row-by-row design (an array multiplier)
+  // is a diagonal through every row -- two live values per row, 315 for the 64x64 multiplier -- while its author's
+  // order finishes one row before the next. Keep whichever needs fewer registers.
+  {
+    std::vector<uint32_t> src;
+    src.reserve(order.size());
+    std::vector<uint8_t> done(V, 0), stored(net.outs.size(), 0);
+    auto load = [&](uint32_t v) {
+      if (!done[v]) done[v] = 1, src.push_back(v);
+    };
+    auto store = [&](uint32_t o) {
+      if (stored[o]) return;
+      const uint32_t row = net.outs[o].row;
+      if (row >= net.n_outputs && state_in_val[row - net.n_outputs] != NONE) load(state_in_val[row - net.n_outputs]);
+      stored[o] = 1, src.push_back((uint32_t)V + o);
+    };
+    for (uint32_t v = 0; v < V; v++) {
+      if (!net.vals[v].is_lut) continue;
+      for (int i = 0; i < net.vals[v].nfan; i++)
+        if (!net.vals[net.vals[v].fan[i]].is_lut) load(net.vals[v].fan[i]);
+      done[v] = 1, src.push_back(v);
+      for (uint32_t o : outs_of[v]) store(o);
+    }
+    for (uint32_t o = 0; o < net.outs.size(); o++) {  // constants, and inputs stored straight to outputs
+      if (net.outs[o].val != NONE) load(net.outs[o].val);
+      store(o);
+    }
+    for (uint32_t v = 0; v < V; v++) load(v);  // (inputs nothing reads still get their slot, as in the other order)
+    Sched alt = allocate(src);
+    if (alt.ok && (!s.ok || alt.n_slots < s.n_slots)) s = std::move(alt), order.swap(src);
+  }
   if (!s.ok || net.n_state == 0) return s;
   // Carried-state rows are rewritten in place, so their loads are ordinary (coherent) loads that neither the
   // assembler nor the hardware may move above an earlier store: "load at first use" leaves one load in flight per
