@@ -618,6 +618,123 @@ Sched schedule_lane(const Network &net) {
     Sched alt = allocate(src);
     if (alt.ok && (!s.ok || alt.n_slots < s.n_slots)) s = std::move(alt), order.swap(src);
   }
+  // Third candidate: a forward list schedule that always runs the ready instruction with the best register balance
+  // (values it kills minus the one it creates), and among equals the one whose reader is closest to being ready, then
+  // source order. On a row-by-row design this walks along the rows instead of across them.
+  if (!std::getenv("CLG_LANE_NO_LIST")) {
+    std::vector<uint32_t> coff(V + 1, 0), cons;  // readers (LUTs) of each value
+    auto each_operand = [&](uint32_t v, auto &&fn) {
+      const Val &x = net.vals[v];
+      for (int i = 0; i < x.nfan; i++) {
+        bool seen = false;
+        for (int j = 0; j < i; j++) seen |= x.fan[j] == x.fan[i];
+        if (!seen) fn(x.fan[i]);
+      }
+    };
+    for (uint32_t v = 0; v < V; v++)
+      if (net.vals[v].is_lut) each_operand(v, [&](uint32_t f) { coff[f + 1]++; });
+    for (uint32_t v = 0; v < V; v++) coff[v + 1] += coff[v];
+    cons.resize(coff[V]);
+    {
+      std::vector<uint32_t> fill(coff.begin(), coff.end() - 1);
+      for (uint32_t v = 0; v < V; v++)
+        if (net.vals[v].is_lut) each_operand(v, [&](uint32_t f) { cons[fill[f]++] = v; });
+    }
+    std::vector<uint32_t> uses_left(V), need(V, 0), have(V, 0);  // readers not run yet (+ stores); operands: wanted / done
+    for (uint32_t v = 0; v < V; v++) {
+      uses_left[v] = coff[v + 1] - coff[v];
+      if (net.vals[v].is_lut) each_operand(v, [&](uint32_t) { need[v]++; });
+    }
+    std::vector<uint8_t> done(V, 0), stored(net.outs.size(), 0), queued(V, 0);
+    std::vector<uint64_t> key_of(V, ~0ull);
+    std::priority_queue<std::pair<uint64_t, uint32_t>, std::vector<std::pair<uint64_t, uint32_t>>, std::greater<>> heap;
+    auto key = [&](uint32_t v) {
+      int delta = 1;  // the value it creates
+      uint32_t close = 0;
+      if (net.vals[v].is_lut) each_operand(v, [&](uint32_t f) { delta -= uses_left[f] == 1 && outs_of[f].empty(); });
+      for (uint32_t k = coff[v]; k < coff[v + 1]; k++) {
+        const uint32_t c = cons[k];
+        close = std::max(close, need[c] ? (have[c] + 1) * 4 / need[c] : 0u);
+      }
+      return (uint64_t)(delta + 4) << 40 | (uint64_t)(7 - std::min(close, 7u)) << 36 | v;
+    };
+    auto offer = [&](uint32_t v) {
+      if (done[v]) return;
+      const uint64_t k = key(v);
+      if (queued[v] && k >= key_of[v]) return;
+      queued[v] = 1, key_of[v] = k, heap.push({k, v});
+    };
+    std::vector<uint32_t> lst;
+    lst.reserve(order.size());
+    std::function<void(uint32_t)> run_value;
+    auto store = [&](uint32_t o) {
+      if (stored[o]) return;
+      const uint32_t row = net.outs[o].row;
+      if (row >= net.n_outputs) {
+        const uint32_t sv = state_in_val[row - net.n_outputs];
+        if (sv != NONE && !done[sv]) run_value(sv);
+      }
+      stored[o] = 1, lst.push_back((uint32_t)V + o);
+    };
+    run_value = [&](uint32_t v) {
+      done[v] = 1, lst.push_back(v);
+      if (net.vals[v].is_lut)
+        each_operand(v, [&](uint32_t f) {
+          if (--uses_left[f] == 1)  // its last reader now kills it: that reader's balance improved
+            for (uint32_t k = coff[f]; k < coff[f + 1]; k++)
+              if (!done[cons[k]] && have[cons[k]] == need[cons[k]]) offer(cons[k]);
+        });
+      for (uint32_t o : outs_of[v]) store(o);
+      for (uint32_t k = coff[v]; k < coff[v + 1]; k++) {
+        const uint32_t c = cons[k];
+        if (++have[c] == need[c]) offer(c);
+        else  // the other operands of this reader are now closer to enabling it
+          each_operand(c, [&](uint32_t f) {
+            if (!done[f] && (!net.vals[f].is_lut || have[f] == need[f])) offer(f);
+          });
+      }
+    };
+    // one connected component after the other (flattened instances: finish one before opening the next)
+    std::vector<uint32_t> comp(V);
+    for (uint32_t v = 0; v < V; v++) comp[v] = v;
+    auto find = [&](uint32_t x) {
+      while (comp[x] != x) x = comp[x] = comp[comp[x]];
+      return x;
+    };
+    for (uint32_t v = 0; v < V; v++)
+      if (net.vals[v].is_lut) each_operand(v, [&](uint32_t f) { comp[find(v)] = find(f); });
+    std::vector<uint32_t> seeds;
+    for (uint32_t v = 0; v < V; v++)
+      if ((!net.vals[v].is_lut || need[v] == 0) && uses_left[v] + outs_of[v].size() > 0) seeds.push_back(v);
+    std::vector<uint32_t> first_of(V, NONE);  // component root -> its lowest value id
+    for (uint32_t v = 0; v < V; v++)
+      if (first_of[find(v)] == NONE) first_of[find(v)] = v;
+    std::stable_sort(seeds.begin(), seeds.end(), [&](uint32_t a, uint32_t b) { return first_of[find(a)] < first_of[find(b)]; });
+    for (size_t i = 0; i < seeds.size();) {
+      const uint32_t c = find(seeds[i]);
+      for (; i < seeds.size() && find(seeds[i]) == c; i++) offer(seeds[i]);
+      while (!heap.empty()) {
+        const auto [k, v] = heap.top();
+        heap.pop();
+        if (done[v] || k != key_of[v]) continue;
+        run_value(v);
+      }
+    }
+    for (uint32_t o = 0; o < net.outs.size(); o++) {
+      if (net.outs[o].val != NONE && !done[net.outs[o].val]) run_value(net.outs[o].val);
+      store(o);
+    }
+    bool complete = true;
+    for (uint32_t v = 0; v < V; v++) {
+      if (!done[v] && net.vals[v].is_lut) complete = false;
+      if (!done[v] && !net.vals[v].is_lut) done[v] = 1, lst.push_back(v);
+    }
+    if (complete) {
+      Sched alt = allocate(lst);
+      if (std::getenv("CLG_TIMING")) std::fprintf(stderr, "[clg]   lane: list schedule %u slots, best other %u\n", alt.n_slots, s.n_slots);
+      if (alt.ok && (!s.ok || alt.n_slots < s.n_slots)) s = std::move(alt), order.swap(lst);
+    }
+  }
   if (!s.ok || net.n_state == 0) return s;
   // Carried-state rows are rewritten in place, so their loads are ordinary (coherent) loads that neither the
   // assembler nor the hardware may move above an earlier store: "load at first use" leaves one load in flight per
