@@ -621,7 +621,14 @@ Sched schedule_lane(const Network &net) {
   // Third candidate: a forward list schedule that always runs the ready instruction with the best register balance
   // (values it kills minus the one it creates), and among equals the one whose reader is closest to being ready, then
   // source order. On a row-by-row design this walks along the rows instead of across them.
-  if (!std::getenv("CLG_LANE_NO_LIST")) {
+  // (inputs are offered to the scheduler like any other instruction, or loaded on demand right before their first
+  // reader -- the multipliers: 132 live values instead of 222, a thin DAG: 86 instead of 77)
+  for (const bool on_demand : {false, true}) {
+    if (std::getenv("CLG_LANE_NO_LIST")) break;
+    // The on-demand order is the tightest (it finishes a multiplier row before it starts the next) and for that very
+    // reason the slowest to run when both fit the register file: one dependent carry chain per warp, no second row to
+    // overlap with (mul64 x 12: 7.9 ms against 7.2 ms). It is only tried when everything else would spill.
+    if (on_demand && s.ok && s.n_slots <= 230) break;
     std::vector<uint32_t> coff(V + 1, 0), cons;  // readers (LUTs) of each value
     auto each_operand = [&](uint32_t v, auto &&fn) {
       const Val &x = net.vals[v];
@@ -643,7 +650,7 @@ Sched schedule_lane(const Network &net) {
     std::vector<uint32_t> uses_left(V), need(V, 0), have(V, 0);  // readers not run yet (+ stores); operands: wanted / done
     for (uint32_t v = 0; v < V; v++) {
       uses_left[v] = coff[v + 1] - coff[v];
-      if (net.vals[v].is_lut) each_operand(v, [&](uint32_t) { need[v]++; });
+      if (net.vals[v].is_lut) each_operand(v, [&](uint32_t f) { need[v] += !on_demand || net.vals[f].is_lut; });
     }
     std::vector<uint8_t> done(V, 0), stored(net.outs.size(), 0), queued(V, 0);
     std::vector<uint64_t> key_of(V, ~0ull);
@@ -651,7 +658,11 @@ Sched schedule_lane(const Network &net) {
     auto key = [&](uint32_t v) {
       int delta = 1;  // the value it creates
       uint32_t close = 0;
-      if (net.vals[v].is_lut) each_operand(v, [&](uint32_t f) { delta -= uses_left[f] == 1 && outs_of[f].empty(); });
+      if (net.vals[v].is_lut)
+        each_operand(v, [&](uint32_t f) {
+          delta -= uses_left[f] == 1 && outs_of[f].empty();
+          delta += on_demand && !net.vals[f].is_lut && !done[f];  // an input it would have to load first
+        });
       for (uint32_t k = coff[v]; k < coff[v + 1]; k++) {
         const uint32_t c = cons[k];
         close = std::max(close, need[c] ? (have[c] + 1) * 4 / need[c] : 0u);
@@ -677,7 +688,18 @@ Sched schedule_lane(const Network &net) {
       stored[o] = 1, lst.push_back((uint32_t)V + o);
     };
     run_value = [&](uint32_t v) {
+      if (net.vals[v].is_lut)
+        each_operand(v, [&](uint32_t f) {
+          if (on_demand && !net.vals[f].is_lut && !done[f]) run_value(f);  // load at first use
+        });
       done[v] = 1, lst.push_back(v);
+      if (on_demand && !net.vals[v].is_lut) {
+        for (uint32_t o : outs_of[v]) store(o);
+        // readers that were waiting only for balance reasons see one load less to pay for
+        for (uint32_t k = coff[v]; k < coff[v + 1]; k++)
+          if (!done[cons[k]] && have[cons[k]] == need[cons[k]]) offer(cons[k]);
+        return;
+      }
       if (net.vals[v].is_lut)
         each_operand(v, [&](uint32_t f) {
           if (--uses_left[f] == 1)  // its last reader now kills it: that reader's balance improved
@@ -690,7 +712,7 @@ Sched schedule_lane(const Network &net) {
         if (++have[c] == need[c]) offer(c);
         else  // the other operands of this reader are now closer to enabling it
           each_operand(c, [&](uint32_t f) {
-            if (!done[f] && (!net.vals[f].is_lut || have[f] == need[f])) offer(f);
+            if (!done[f] && (net.vals[f].is_lut ? have[f] == need[f] : !on_demand)) offer(f);
           });
       }
     };
@@ -705,7 +727,7 @@ Sched schedule_lane(const Network &net) {
       if (net.vals[v].is_lut) each_operand(v, [&](uint32_t f) { comp[find(v)] = find(f); });
     std::vector<uint32_t> seeds;
     for (uint32_t v = 0; v < V; v++)
-      if ((!net.vals[v].is_lut || need[v] == 0) && uses_left[v] + outs_of[v].size() > 0) seeds.push_back(v);
+      if (on_demand ? net.vals[v].is_lut && need[v] == 0 : (!net.vals[v].is_lut || need[v] == 0) && uses_left[v] + outs_of[v].size() > 0) seeds.push_back(v);
     std::vector<uint32_t> first_of(V, NONE);  // component root -> its lowest value id
     for (uint32_t v = 0; v < V; v++)
       if (first_of[find(v)] == NONE) first_of[find(v)] = v;
