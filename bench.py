@@ -102,6 +102,26 @@ WORKLOAD_DESC = {
 }
 
 
+def bind_to_gpu_numa_node(device: int):
+    """One process per GPU: run this process on the CPUs next to its GPU, so that the pinned host buffers of the e2e
+    leg (first touched, and therefore placed, by this process) sit on the GPU's own NUMA node. Without it eight ranks
+    share whatever node the launcher started them on and the copies queue behind one memory controller."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if m >> b & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": len(cpus), "first_cpu": min(cpus)}
+    except Exception as e:  # no NVML, no permission: run unbound
+        return {"error": str(e)[:80]}
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -256,6 +276,7 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -405,7 +426,7 @@ def main():
         e2e = {"value": w["gates"] * total_vectors / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (n_in + n_state) * stride * 4,
                "d2h_bytes_per_step": (n_out + n_state) * stride * 4, "ms_per_step": e_ms, "steps": e2e_steps,
                "api": "clg_exec_run_host (pinned host buffers; chunked H2D | kernel | D2H pipeline on three streams)",
-               "out_checksum": f"{checksum:016x}"}
+               "out_checksum": f"{checksum:016x}", "numa_binding": numa}
         del h_imm, h_out
 
     main_gates, main_compile_s = w["gates"], w["compile_s"]
