@@ -625,6 +625,9 @@ Sched schedule_lane(const Network &net) {
   // reader -- the multipliers: 132 live values instead of 222, a thin DAG: 86 instead of 77)
   for (const bool on_demand : {false, true}) {
     if (std::getenv("CLG_LANE_NO_LIST")) break;
+    // (no order will bring a live set of thousands down to the few hundred the lane modes can use: do not spend the
+    // second on it -- the 1M-gate DAG: 6 622 live values in the orders above, 5 252 in this one)
+    if (s.ok && s.n_slots > 3000) break;
     // The on-demand order is the tightest (it finishes a multiplier row before it starts the next) and for that very
     // reason the slowest to run when both fit the register file: one dependent carry chain per warp, no second row to
     // overlap with (mul64 x 12: 7.9 ms against 7.2 ms). It is only tried when everything else would spill.
