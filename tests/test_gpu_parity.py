@@ -471,6 +471,38 @@ def test_full_size_dag_1m_2p24_periodic_inputs():
     assert np.array_equal(first, oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), block, period, circ.out_regs))
 
 
+def test_full_size_structured_1m_gate_circuit_2p24():
+    """Twelve flattened 64x64 multipliers (1 009 152 gates) on 2^24 lanes through the instance-parallel specialised
+    launch: every instance gets the same inputs, so all twelve output blocks must be equal, block 0 must be a * b on a
+    sample of lanes, and a prefix must equal the oracle."""
+    import torch
+
+    base = circuits.array_multiplier(64)
+    circ = circuits.flatten_instances(base, 12)
+    nv = 1 << 24
+    stride = stride_for(nv)
+    ctx = host.Context.default()
+    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx)
+    one = torch.empty((128, stride), dtype=torch.int32, device="cuda:0")
+    ctx.fill_random(one.data_ptr(), 128, stride, 0x12A, 0)
+    imm = one.repeat(12, 1).contiguous()
+    out = torch.zeros((12 * 128, stride), dtype=torch.int32, device="cuda:0")
+    cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    assert cs.mode == host.MODE_SPEC and cs.launches_per_run == 1
+    blocks = out.view(12, 128, stride)
+    assert bool((blocks == blocks[:1]).all())
+    n = 1 << 12
+    imm_h = one[:, :n // 32].contiguous().cpu().numpy().view(np.uint32)
+    got = blocks[0, :, :n // 32].contiguous().cpu().numpy().view(np.uint32)
+    a = [int(x) for x in unslice_int(imm_h[:64], n)]
+    b = [int(x) for x in unslice_int(imm_h[64:], n)]
+    lo, hi = unslice_int(got[:64], n), unslice_int(got[64:], n)
+    assert [int(l) | int(h) << 64 for l, h in zip(lo, hi)] == [x * y for x, y in zip(a, b)]
+    want = oracle.run_batch_sliced(base.sim, len(base.sim.registers), imm_h, n, base.out_regs)
+    assert np.array_equal(got, want)
+
+
 def test_modes_agree_at_scale_mul16():
     """Size-independent property at 2^22 vectors: the three execution modes produce identical buffers, and they
     equal a*b on a strided sample."""
