@@ -503,6 +503,28 @@ def test_full_size_structured_1m_gate_circuit_2p24():
     assert np.array_equal(got, want)
 
 
+def test_full_size_mul16_2p26_periodic_inputs():
+    """BASELINE config 3 at full size (2^26 lanes): inputs repeat every 2^16 lanes, so each of the 1024 output blocks
+    must equal the first, which must be a * b lane for lane."""
+    import torch
+
+    circ = circuits.array_multiplier(16)
+    nv, period = 1 << 26, 1 << 16
+    stride, pw = stride_for(nv), period // 32
+    block = random_sliced(32, pw, seed=0x316)
+    cs = host.CudaSimulation.from_simulation(circ.sim, 32, circ.out_regs)
+    imm = torch.from_numpy(block.view(np.int32)).cuda().repeat(1, stride // pw).contiguous()
+    out = torch.zeros((32, stride), dtype=torch.int32, device="cuda:0")
+    cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    assert cs.mode == host.MODE_SPEC
+    blocks = out.view(32, stride // pw, pw)
+    assert bool((blocks == blocks[:, :1, :]).all())
+    first = blocks[:, 0, :].contiguous().cpu().numpy().view(np.uint32)
+    a, b = unslice_int(block[:16], period), unslice_int(block[16:], period)
+    assert np.array_equal(unslice_int(first, period), a * b)
+
+
 def test_modes_agree_at_scale_mul16():
     """Size-independent property at 2^22 vectors: the three execution modes produce identical buffers, and they
     equal a*b on a strided sample."""
