@@ -199,6 +199,9 @@ int clg_flat_spec_steps_ptx(const clg_flat *f, int k, char **ptx_out);
  * rows by which the imm / out / state pointers are advanced for this chunk. Text of chunk `chunk`; *n_chunks
  * (optional) receives the chain length (1 for a short program). Free with clg_free. */
 int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, uint32_t *row_bases, char **ptx_out);
+/* Shape of that chain without generating any code: chunks, distinct kernels that would have to be assembled (about a
+ * second each on the first run), and launches per run (equal independent chunks share one launch). Any may be NULL. */
+int clg_flat_spec_chain_info(const clg_flat *f, int k, uint32_t *n_chunks, uint32_t *n_kernels, uint32_t *n_launches);
 
 /* ---------------------------------------------------------------------------------------------
  * Device side. Raw CUDA driver API underneath (libcuda.so.1 is dlopen'ed when the first context

@@ -126,3 +126,23 @@ def test_random_stateful_programs_in_tiny_chunks(prog, seed):
             del os.environ["CLG_SPEC_CHUNK"]
         else:
             os.environ["CLG_SPEC_CHUNK"] = old
+
+
+def test_chain_shape_kernels_and_launches():
+    """What a host can ask before the first run: how many kernels will be assembled, how many launches a run takes."""
+    mul = circuits.flatten_instances(circuits.array_multiplier(64), 5)
+    fp = host.FlatProgram.levelize(mul.sim, mul.n_immediates, mul.out_regs)
+    assert fp.spec_chain_info(1) == {"chunks": 5, "kernels": 1, "launches": 1}  # equal, independent: one kernel, one launch
+    dag = circuits.random_dag(levels=1500, width=48, n_immediates=64, window=2, seed=31)
+    fp = host.FlatProgram.levelize(dag.sim, 64, dag.out_regs)
+    info = fp.spec_chain_info(1)
+    assert info["chunks"] == info["kernels"] == info["launches"] >= 3  # cut mid-circuit: all different, run in sequence
+    small = circuits.ripple_adder(32)
+    fp = host.FlatProgram.levelize(small.sim, 65, small.out_regs)
+    assert fp.spec_chain_info(4) == {"chunks": 1, "kernels": 1, "launches": 1}
+    # two independent latch banks that rewrite the SAME carried registers cannot share a launch -- but these do not:
+    sim, outs = feedback_dag(levels=40, width=16)
+    fp = host.FlatProgram.levelize(sim, 64, outs, flags=host.LV_STATEFUL)
+    assert fp.spec_chain_info(1)["chunks"] == 1
+    with pytest.raises(host.ClgError):
+        fp.spec_chain_info(3)
