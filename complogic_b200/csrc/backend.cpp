@@ -784,6 +784,7 @@ struct Exec {
     const uint32_t groups = (uint32_t)ctx->sm_count * 16;
     const size_t stride = ((size_t)groups * P.K + 3) / 4 * 4;
     const size_t rows[3] = {h.n_inputs, h.n_outputs, h.n_state};
+    if ((rows[0] + rows[1] + rows[2]) * stride * 4 > ((size_t)1 << 30)) return wide;  // (not worth a gigabyte of scratch)
     CUdeviceptr buf[3] = {0, 0, 0};
     CUevent e0 = nullptr, e1 = nullptr;
     uint32_t best = wide;
