@@ -297,8 +297,10 @@ __device__ __forceinline__ void lane_body(const RunParams &p) {
     mbar_wait(&full[s], use & 1);
     const uint32_t n = min((uint32_t)RING_CHUNK, p.n_instr - c * RING_CHUNK);
     const uint4 *code = ring + s * RING_CHUNK;
+    uint4 nxt = code[0];  // warp-uniform address: one broadcast LDS.128, fetched one instruction ahead
     for (uint32_t i = 0; i < n; i++) {
-      const uint4 ins = code[i];  // warp-uniform address: one broadcast LDS.128
+      const uint4 ins = nxt;
+      if (i + 1 < n) nxt = code[i + 1];
       const uint32_t kind = ins.y >> 28;
       if (kind <= D_LUT1) {
         const Vec<K> a = lds<K>(my + (ins.x & 0xFFFFFFu));
