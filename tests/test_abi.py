@@ -162,3 +162,30 @@ def test_cpp_host_runs_on_the_gpu(tmp_path):
     r = subprocess.run([str(exe), "32", "200000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "200000 vectors on the GPU" in r.stdout and ": 0 mismatches" in r.stdout
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product tree may import, link or execute it (comments may
+    mention it), the shared library must not depend on it, and bench.py may only use it for the CPU baseline legs."""
+    import re
+    import subprocess
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|liborc|clg_oracle\.c|\borc_[a-z_]+\(", re.M)
+    for top in ("complogic_b200", "include", "complogic-cuda", "examples", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            if "_build" in dirpath or "__pycache__" in dirpath:
+                continue
+            for name in files:
+                if not name.endswith((".py", ".cpp", ".hpp", ".h", ".cu", ".rs", ".sh", ".toml")):
+                    continue
+                text = open(os.path.join(dirpath, name), errors="replace").read()
+                code = "\n".join(l for l in text.splitlines() if not l.lstrip().startswith(("#", "//", "*", "/*")))
+                assert not pat.search(code), f"{top}/{name} references the oracle"
+    so = os.path.join(ROOT, "complogic_b200", "libcomplogic_cuda.so")
+    needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+    assert "liborc" not in needed and "libcuda" not in needed  # (libcuda is dlopen'ed at run time)
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"from oracle import|import oracle", bench)]
+    assert uses, "bench.py times the CPU baseline with the oracle"
+    for pos in uses:  # each use sits inside a CPU-baseline / reference-arm block
+        context = bench[max(0, pos - 1500):pos]
+        assert "cpu" in context.lower() or "reference" in context.lower()
