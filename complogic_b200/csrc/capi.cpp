@@ -229,6 +229,8 @@ static int spec_ptx_text(const clg_flat *f, int k, bool steps, char **ptx_out) {
 int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, uint32_t *row_bases, char **ptx_out) {
   CLG_TRY
   NEED(f), NEED(ptx_out);
+  if (k != 1 && k != 2 && k != 4) fail(CLG_E_INVALID, "K must be 1, 2 or 4");
+  if (f->f.header().stream[STREAM_LANE].n_instr == 0) fail(CLG_E_UNSUPPORTED, "no lane-ordered stream in this flat buffer");
   const std::vector<SpecChunk> chunks = spec_chunks(f->f, k);
   if (n_chunks) *n_chunks = (uint32_t)chunks.size();
   if (chunk >= chunks.size()) fail(CLG_E_INVALID, "chunk index out of range");

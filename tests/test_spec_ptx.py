@@ -146,3 +146,12 @@ def test_chain_shape_kernels_and_launches():
     assert fp.spec_chain_info(1)["chunks"] == 1
     with pytest.raises(host.ClgError):
         fp.spec_chain_info(3)
+
+
+def test_specialised_text_needs_a_lane_stream():
+    c = circuits.ripple_adder(8)
+    fp = host.FlatProgram.levelize(c.sim, c.n_immediates, c.out_regs, flags=host.LV_NO_LANE_STREAM)
+    assert fp.info["lane_instrs"] == 0
+    for call in (lambda: fp.spec_ptx(4), lambda: fp.spec_chunk_ptx(1, 0), lambda: fp.spec_chain_info(1)):
+        with pytest.raises(host.ClgError):
+            call()
