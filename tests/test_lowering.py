@@ -263,3 +263,32 @@ def test_latch_chain_lane_order_keeps_few_values_live():
     sim, qs = chain(12000)
     fp = host.FlatProgram.levelize(sim, 2, qs[-3:], flags=host.LV_STATEFUL)
     assert fp.info["level_instrs"] == 0 and fp.info["lane_instrs"] > 0 and fp.info["lane_slots"] <= 32
+
+
+def test_mutated_flat_buffers_are_rejected_or_safe():
+    """clg_flat_from_bytes is the trust boundary of the device code (kernels carry no bounds checks): random byte
+    flips in a valid buffer must either be rejected with a status code or yield a buffer that still passes every
+    index and hazard check -- and that the text generators can walk -- never a crash."""
+    rng = np.random.default_rng(7)
+    progs = [circuits.array_multiplier(8), circuits.latch_chain(20), circuits.flatten_instances(circuits.array_multiplier(16), 9)]
+    accepted = rejected = 0
+    for c in progs:
+        fp = host.FlatProgram.levelize(c.sim, c.n_immediates, c.out_regs, flags=host.LV_STATEFUL if c.stateful else 0)
+        data = fp.to_bytes()
+        for _ in range(250):
+            d = bytearray(data)
+            for _ in range(int(rng.integers(1, 4))):
+                d[int(rng.integers(0, len(d)))] = int(rng.integers(0, 256))
+            try:
+                g = host.FlatProgram.from_bytes(bytes(d))
+            except host.ClgError:
+                rejected += 1
+                continue
+            accepted += 1
+            assert g.info["n_inputs"] >= 0
+            try:
+                g.spec_chain_info(1)
+                g.spec_chunk_ptx(1, 0)
+            except host.ClgError:
+                pass
+    assert rejected > 100 and accepted + rejected == 750
