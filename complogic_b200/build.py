@@ -52,6 +52,31 @@ def _gen_dispatch() -> None:
             if not os.path.exists(path) or open(path).read() != text:
                 with open(path, "w") as f:
                     f.write(text)
+    # row kernel (clg_coop_rows, K = 4): ONE warp-uniform table per pass, applied in place to the lanes whose
+    # table index (%13) equals the pass (%14); operand a / the result live in %0..%3
+    path = os.path.join(BUILD, "lut_dispatch_k4p.inc")
+    lines = ['"{\\n"', '".reg .pred q;\\n"', '"setp.eq.u32 q, %13, %14;\\n"',
+             '"TBL_%=: .branchtargets ' + ", ".join(f"L{n}_%=" for n in range(256)) + ';\\n"', '"brx.idx.uni %12, TBL_%=;\\n"']
+    for n in range(256):
+        body = " ".join(f"@q lop3.b32 %{k}, %{k}, %{4 + k}, %{8 + k}, {n};" for k in range(4))
+        lines.append(f'"L{n}_%=: {body} bra.uni DONE_%=;\\n"')
+    lines += ['"DONE_%=:\\n"', '"}\\n"']
+    text = "\n".join(lines) + "\n"
+    if not os.path.exists(path) or open(path).read() != text:
+        with open(path, "w") as f:
+            f.write(text)
+    # ... and the form for rows with a single table: no predicate (ptxas turns a predicated in-place LOP3 into
+    # LOP3 + SEL, twice the ALU work; lanes without an instruction compute a value nobody reads)
+    path = os.path.join(BUILD, "lut_dispatch_k4r.inc")
+    lines = ['"{\\n"', '"TBL_%=: .branchtargets ' + ", ".join(f"L{n}_%=" for n in range(256)) + ';\\n"', '"brx.idx.uni %12, TBL_%=;\\n"']
+    for n in range(256):
+        body = " ".join(f"lop3.b32 %{k}, %{k}, %{4 + k}, %{8 + k}, {n};" for k in range(4))
+        lines.append(f'"L{n}_%=: {body} bra.uni DONE_%=;\\n"')
+    lines += ['"DONE_%=:\\n"', '"}\\n"']
+    text = "\n".join(lines) + "\n"
+    if not os.path.exists(path) or open(path).read() != text:
+        with open(path, "w") as f:
+            f.write(text)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -81,7 +81,7 @@ struct Ctx {
   CUcontext cu = nullptr;
   CUmodule mod = nullptr;
   int sm_count = 0;
-  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
   std::string name;
 
   explicit Ctx(int device) {
@@ -115,6 +115,8 @@ struct Ctx {
       CU(cuModuleGetFunction(&coop_res[i], mod, (std::string("clg_coop_res_k") + ks[i]).c_str()));
       CU(cuFuncSetAttribute(coop_res[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
     }
+    CU(cuModuleGetFunction(&coop_rows, mod, "clg_coop_rows"));
+    CU(cuFuncSetAttribute(coop_rows, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
     CU(cuModuleGetFunction(&slice, mod, "clg_slice"));
     CU(cuModuleGetFunction(&unslice, mod, "clg_unslice"));
     CU(cuModuleGetFunction(&slice_v4, mod, "clg_slice_v4"));
@@ -167,6 +169,9 @@ struct Plan {
   size_t smem = 0;
   uint32_t tuned_threads = 0;  // cooperative, big batches: CTA size found by timing candidates on this device (0: not tuned yet)
   bool resident = false;  // cooperative: the (largest part's) instruction stream is staged in shared memory
+  // cooperative, row form (clg_coop_rows): the level stream re-encoded as rows of 32 LUTs for a CTA of rows_nt threads
+  CUdeviceptr d_rinstr = 0, d_rhdr = 0, d_rside = 0;
+  uint32_t rows_nt = 0, n_segs = 0;
   // long programs: the lane stream cut into SPEC_CHUNK-instruction kernels; live registers cross the cuts through `scratch`
   struct ChunkLaunch {
     CUfunction fn;
@@ -546,6 +551,9 @@ struct Exec {
       if (P.d_parts) d.cuMemFree(P.d_parts);
       if (P.d_cinstr) d.cuMemFree(P.d_cinstr);
       if (P.d_clevels) d.cuMemFree(P.d_clevels);
+      if (P.d_rinstr) d.cuMemFree(P.d_rinstr);
+      if (P.d_rhdr) d.cuMemFree(P.d_rhdr);
+      if (P.d_rside) d.cuMemFree(P.d_rside);
       if (P.spec_mod) d.cuModuleUnload(P.spec_mod);
       if (P.steps_mod) d.cuModuleUnload(P.steps_mod);
       for (CUmodule m : P.chunk_mods)
@@ -661,7 +669,9 @@ struct Exec {
     if (n_steps == 0 || n_vectors == 0) return;
     const size_t words = (n_vectors + 31) / 32;
     const size_t imm_step = (size_t)h.n_inputs * stride, out_step = (size_t)h.n_outputs * stride;
-    if (choose(words) != CLG_MODE_SPEC || n_steps == 1 || lane_stream().n_instr > 65536u) {  // the fused form is one kernel: not for programs that long
+    // the fused form is ONE kernel of n_instr * K instructions: a program that needs a chunk chain runs step by step
+    // (building the fused kernel would first assemble the whole unused chain and then minutes of straight-line code)
+    if (choose(words) != CLG_MODE_SPEC || n_steps == 1 || lane_stream().n_instr > spec_chunk_limit(fit_k(CLG_MODE_SPEC))) {
       for (size_t s_ = 0; s_ < n_steps; s_++) run(imm ? imm + s_ * imm_step : nullptr, out ? out + s_ * out_step : nullptr, state, n_vectors, stride, stream);
       return;
     }
@@ -741,12 +751,131 @@ struct Exec {
     // level has instructions. More than that is a throughput problem whose optimum depends on how many CTAs fit an
     // SM and how wide the levels are (a 65k-gate DAG with ~570 instructions a level: 15.0 ms with 1024 threads,
     // 7.1 ms with 256), so it is measured once per plan on this device.
+    if (rows_ok(P)) {
+      launch_rows(P, params(P, imm, out, state, stride, groups), stream);
+      return;
+    }
     uint32_t nt = P.coop_threads;
     if (!P.n_parts && groups > (uint32_t)ctx->sm_count * coop_ctas_per_sm(P, nt)) {
       if (!P.tuned_threads) P.tuned_threads = tune_coop_threads(P);
       nt = P.tuned_threads;
     }
     launch_coop(P, params(P, imm, out, state, stride, groups), nt, stream);
+  }
+
+  // ---- row form of the cooperative mode (clg_coop_rows; layout in kernels.cu, RunParams) ---------------------
+  // The LUTs of a level, in the order the pass packed them (8 consecutive ones are conflict-free), become rows of 32;
+  // a row keeps its three most frequent truth tables, LUTs with another one join the loads and stores of the level in
+  // the 16-byte side list. A level wider than n_warps * ROW_SLOTS rows is cut into several segments.
+  bool rows_ok(const Plan &P) const {
+    return P.K == 4 && !P.resident && !P.n_parts && P.n_slots <= 16383 && std::getenv("CLG_COOP_ROWS");  // (off until it beats clg_coop_c)
+  }
+  void build_rows(Plan &P, uint32_t nt) {
+    if (P.rows_nt == nt) return;
+    ctx->bind();
+    if (P.rows_nt) {
+      CU(cuCtxSynchronize());
+      driver().cuMemFree(P.d_rinstr), driver().cuMemFree(P.d_rhdr), driver().cuMemFree(P.d_rside);
+      P.d_rinstr = P.d_rhdr = P.d_rside = 0, P.rows_nt = 0;
+    }
+    const uint32_t nw = nt / 32, seg_rows = nw * ROW_SLOTS;
+    const FlatInstr *src = flat.instrs(STREAM_LEVEL);
+    const uint32_t *lvl = flat.levels(STREAM_LEVEL);
+    const FlatStream &st = level_stream();
+    std::vector<uint32_t> rinstr, rhdr, side;  // 2 / 4 / 4 words per entry
+    std::vector<uint32_t> luts;
+    auto side_push = [&](const FlatInstr &x) {
+      uint32_t e[4];
+      encode_stream(&x, 1, 16, e);
+      side.insert(side.end(), e, e + 4);
+    };
+    uint32_t n_segs = 0;
+    for (uint32_t l = 0; l < st.n_levels; l++) {
+      luts.clear();
+      for (uint32_t i = lvl[l]; i < lvl[l + 1]; i++)
+        if (src[i].kind == K_LUT) luts.push_back(i);
+      const uint32_t n_rows = ((uint32_t)luts.size() + 31) / 32;
+      const uint32_t segs_here = std::max<uint32_t>(1, (n_rows + seg_rows - 1) / seg_rows);
+      for (uint32_t sg = 0; sg < segs_here; sg++, n_segs++) {
+        const size_t ibase = rinstr.size(), hbase = rhdr.size();
+        rinstr.resize(ibase + (size_t)seg_rows * 32 * 2, 0x80000000u);  // (no load of a, no store: a lane without a LUT)
+        rhdr.resize(hbase + (size_t)nw * 4, 0);
+        for (uint32_t w = 0; w < nw; w++) rhdr[hbase + w * 4 + 3] = (uint32_t)(side.size() / 4);
+        if (sg == 0)
+          for (uint32_t i = lvl[l]; i < lvl[l + 1]; i++)
+            if (src[i].kind != K_LUT) side_push(src[i]);
+        for (uint32_t r = 0; r < seg_rows && (size_t)(sg * seg_rows + r) * 32 < luts.size(); r++) {
+          const size_t first = (size_t)(sg * seg_rows + r) * 32, last = std::min(luts.size(), first + 32);
+          // the row's tables, most frequent first
+          uint32_t count[256] = {};
+          for (size_t q = first; q < last; q++) count[src[luts[q]].tt]++;
+          uint8_t tts[3] = {0, 0, 0};
+          uint32_t n_tt = 0;
+          for (; n_tt < 3; n_tt++) {
+            uint32_t best = 256;
+            for (uint32_t t = 0; t < 256; t++)
+              if (count[t] && (best == 256 || count[t] > count[best])) best = t;
+            if (best == 256) break;
+            tts[n_tt] = (uint8_t)best, count[best] = 0;
+          }
+          const uint32_t w = r % nw, j = r / nw;
+          bool reads_c = false;
+          uint32_t in_row = 0;
+          for (size_t q = first; q < last; q++) {
+            const FlatInstr &x = src[luts[q]];
+            uint32_t k = 0;
+            while (k < n_tt && tts[k] != x.tt) k++;
+            if (k == n_tt) {  // a fourth table: leave the lane empty, run the LUT from the side list
+              side_push(x);
+              continue;
+            }
+            const int nf = lut_nfan(x);
+            const uint32_t a = x.a, b = nf >= 2 ? x.b : x.a, c = nf >= 3 ? x.c : b;  // operands it does not read alias one it does
+            reads_c |= nf >= 3;
+            uint32_t *e = &rinstr[ibase + ((size_t)(j * nw + w) * 32 + (q - first)) * 2];
+            e[0] = a | b << 14 | k << 28;
+            e[1] = c | (uint32_t)x.dst << 14;
+            in_row++;
+          }
+          if (in_row) rhdr[hbase + w * 4 + j] = tts[0] | (uint32_t)tts[1] << 8 | (uint32_t)tts[2] << 16 | n_tt << 24 | (reads_c ? 1u << 26 : 0u);
+        }
+      }
+    }
+    // closing header entry: no rows, end of the side list
+    if (side.size() / 4 >= (1u << 29)) fail(CLG_E_UNSUPPORTED, "side list of the row form too long");
+    for (uint32_t w = 0; w < nw; w++) {
+      const uint32_t e[4] = {0, 0, 0, (uint32_t)(side.size() / 4)};
+      rhdr.insert(rhdr.end(), e, e + 4);
+    }
+    // each header also says which rows its warp has in the NEXT segment (the kernel requests them one segment ahead)
+    for (uint32_t sg = 0; sg < n_segs; sg++)
+      for (uint32_t w = 0; w < nw; w++)
+        for (uint32_t j = 0; j < (uint32_t)ROW_SLOTS; j++)
+          if (rhdr[((size_t)(sg + 1) * nw + w) * 4 + j] >> 24 & 3u) rhdr[((size_t)sg * nw + w) * 4 + 3] |= 1u << (29 + j);
+    side.resize(std::max<size_t>(side.size(), 4));
+    CU(cuMemAlloc(&P.d_rinstr, std::max<size_t>(16, rinstr.size() * 4)));
+    CU(cuMemcpyHtoDAsync(P.d_rinstr, rinstr.data(), rinstr.size() * 4, nullptr));
+    CU(cuMemAlloc(&P.d_rhdr, rhdr.size() * 4));
+    CU(cuMemcpyHtoDAsync(P.d_rhdr, rhdr.data(), rhdr.size() * 4, nullptr));
+    CU(cuMemAlloc(&P.d_rside, side.size() * 4));
+    CU(cuMemcpyHtoDAsync(P.d_rside, side.data(), side.size() * 4, nullptr));
+    CU(cuStreamSynchronize(nullptr));
+    P.rows_nt = nt, P.n_segs = n_segs;
+  }
+  uint32_t rows_threads() const {
+    if (const char *env = std::getenv("CLG_ROWS_THREADS")) return std::min(1024, std::max(32, std::atoi(env))) / 32 * 32;  // tuning knob
+    // as many warps as the widest level has rows per row slot
+    const uint32_t rows = (level_stream().max_level_width + 31) / 32;
+    return std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (rows + ROW_SLOTS - 1) / ROW_SLOTS * 32u));
+  }
+  void launch_rows(Plan &P, RunParams p, CUstream stream) {
+    const uint32_t nt = rows_threads();
+    build_rows(P, nt);
+    p.instr = (const void *)P.d_rside, p.rinstr = (const void *)P.d_rinstr, p.rhdr = (const void *)P.d_rhdr, p.n_segs = P.n_segs;
+    const uint32_t per_sm = coop_ctas_per_sm(P, nt);
+    const uint32_t grid = std::min<uint32_t>(p.n_groups, (uint32_t)ctx->sm_count * per_sm);
+    void *args[] = {&p};
+    CU(cuLaunchKernel(ctx->coop_rows, grid, 1, 1, nt, 1, 1, (unsigned)P.smem, stream, args, nullptr));
   }
 
   RunParams params(const Plan &P, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t stride, uint32_t groups) const {

@@ -163,6 +163,7 @@ int clg_levelize(const clg_simulation *sim, size_t n_immediates, const uint64_t 
                  clg_flat **out) {
   CLG_TRY
   NEED(sim), NEED(out);
+  if (n_out) NEED(out_regs);  // (NULL with n_out == 0 means "every register")
   auto *f = new clg_flat();
   try {
     f->f = levelize(sim->sim, n_immediates, out_regs, n_out, flags);

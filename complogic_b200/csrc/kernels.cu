@@ -24,6 +24,9 @@
 //                  clg_coop_res_k<K>  resident: the CTA's instructions and level table are staged into
 //                                     shared memory once with cp.async.bulk + mbarrier (narrow, deep
 //                                     programs on few vectors, e.g. one part of a partitioned program).
+//                  clg_coop_rows      row form (K = 4, <= 16383 slots): warp-uniform LOP3 dispatch per row, the next level's
+//                                     instruction words prefetched into registers, producer-to-consumer forwarding through
+//                                     registers (see the kernel);
 //                The compiler pass allocates slots so that the 8 (K=4) / 16 (K=2) / 32 (K=1) lanes served
 //                together by one LDS/STS hit distinct bank groups.
 //   clg_slice / clg_unslice / clg_fill_random / clg_lop3_peak  layout helpers, input generator, and the
@@ -66,6 +69,19 @@ struct RunParams {
   // holds only the (rare) non-LUT instructions of each level in the 16-byte encoding.
   const uint2 *cinstr;
   const uint32_t *clevels;
+  // coop, row form (clg_coop_rows, K = 4, <= 16383 slots): the LUTs of a segment (a level, or a piece of a very wide
+  // one) are laid out as rows of 32, row r of segment s belongs to warp r % n_warps as its row slot r / n_warps (< ROW_SLOTS):
+  //   rinstr[((s * ROW_SLOTS + j) * n_warps + w) * 32 + lane] = {x, y}
+  //       x = a | b << 14 | k << 28 | from_register << 31     y = c | dst << 14 | no_store << 31      (slot indices)
+  //     k: which of the row's (at most three) truth tables this lane uses; from_register: operand a is the result this
+  //     thread computed in the same row slot of the previous segment (it is not loaded); no_store: the result is only
+  //     read that way (it gets no slot).
+  //   rhdr[s * n_warps + w] = {h0, h1, h2, first entry of segment s in `instr` | rows of segment s + 1 << 29}  (n_segs + 1
+  //     entries per warp, the last one closes the side list; bit 29 + j: the warp has a row in slot j of the NEXT segment), h_j = tt0 | tt1 << 8 | tt2 << 16 | n_tables << 24 | reads_c << 26 for the warp's row slot j;
+  //     n_tables == 0: no row. `instr` holds what is not a row LUT (loads, stores, LUTs with a fourth table in their row).
+  const uint2 *rinstr;
+  const uint4 *rhdr;
+  uint32_t n_segs;
 };
 
 // ---- LOP3 with a compile-time immediate, dispatched on the instruction's truth table --------------
@@ -498,6 +514,101 @@ __device__ __forceinline__ void coop_compact_body(const RunParams &p) {
   }
 }
 
+// ---- row form of the cooperative kernel ----------------------------------------------------------------
+// The same evaluation as clg_coop_c (one CTA, one K = 4 register stack in shared memory, a barrier per level) with the
+// per-LUT overhead taken out of the loop:
+//   * a warp's 32 LUTs (a row) share at most three truth tables, named by a per-row header word, so the LOP3 dispatch
+//     is a warp-UNIFORM brx.idx per table instead of a divergent one per lane;
+//   * every thread executes at most ROW_SLOTS rows per segment, statically unrolled, and fetches the instruction words
+//     and headers of the NEXT segment at the top of this one (registers, one segment ahead: their L2 latency is never
+//     exposed and nothing is software-pipelined inside the level);
+//   * the result of row slot j stays in the thread's registers P[j]; a LUT marked from_register takes it as operand a
+//     without touching shared memory, and a result that is only read that way is not stored (the compiler pass
+//     places producer and consumer on the same thread and row slot of consecutive segments).
+constexpr int ROW_SLOTS = 3;
+
+__device__ __forceinline__ void lut3_rows(uint32_t t, uint32_t k, uint32_t pass, Vec<4> &P, const Vec<4> &B, const Vec<4> &C) {
+  asm volatile(
+#include "lut_dispatch_k4p.inc"
+      : "+r"(P.w[0]), "+r"(P.w[1]), "+r"(P.w[2]), "+r"(P.w[3])
+      : "r"(B.w[0]), "r"(B.w[1]), "r"(B.w[2]), "r"(B.w[3]), "r"(C.w[0]), "r"(C.w[1]), "r"(C.w[2]), "r"(C.w[3]), "r"(t), "r"(k), "r"(pass));
+}
+__device__ __forceinline__ void lut3_row1(uint32_t t, Vec<4> &P, const Vec<4> &B, const Vec<4> &C) {  // every lane of the row uses table t
+  asm volatile(
+#include "lut_dispatch_k4r.inc"
+      : "+r"(P.w[0]), "+r"(P.w[1]), "+r"(P.w[2]), "+r"(P.w[3])
+      : "r"(B.w[0]), "r"(B.w[1]), "r"(B.w[2]), "r"(B.w[3]), "r"(C.w[0]), "r"(C.w[1]), "r"(C.w[2]), "r"(C.w[3]), "r"(t));
+}
+
+__device__ __forceinline__ uint4 ld_hdr(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void row_exec(const uint2 ins, uint32_t h, Vec<4> &P, uint32_t sb) {
+  constexpr uint32_t M = 0x3FFF0u;
+  const uint32_t oa = (ins.x << 4) & M, ob = (ins.x >> 10) & M, oc = (ins.y << 4) & M, od = (ins.y >> 10) & M;
+  if ((int32_t)ins.x >= 0) P = lds<4>(sb + oa);  // else: operand a is this thread's previous result in this row slot
+  const Vec<4> B = lds<4>(sb + ob);
+  Vec<4> C = dont_care<4>();
+  if (h & (1u << 26)) C = lds<4>(sb + oc);  // (warp-uniform: no lane of the row has a third operand otherwise)
+  const uint32_t n = (h >> 24) & 3u;
+  if (n == 1) {
+    lut3_row1(h & 0xFFu, P, B, C);
+  } else {
+    const uint32_t k = (ins.x >> 28) & 3u;
+#pragma unroll 1
+    for (uint32_t pass = 0; pass < n; pass++) {
+      lut3_rows(h & 0xFFu, k, pass, P, B, C);
+      h >>= 8;
+    }
+  }
+  if ((int32_t)ins.y >= 0) sts<4>(sb + od, P);
+}
+
+template <int R>
+__device__ __forceinline__ void coop_rows_body(const RunParams &p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t tid = threadIdx.x, nt = blockDim.x, nw = nt >> 5;
+  uint32_t sb = smem_u32(smem);
+  asm volatile("" : "+r"(sb));
+  const size_t seg_stride = (size_t)R * nt;  // instruction words of one segment
+  constexpr uint32_t SIDE = 0x1FFFFFFFu;     // hdr.w: first side-list entry | (rows this warp has in the NEXT segment) << 29
+  for (uint32_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+    const size_t col = (size_t)g * 4;
+    const uint4 *hp = p.rhdr + (tid >> 5);  // this warp's header of the segment being fetched
+    const uint2 *ip = p.rinstr + tid;       // row (s * R + j) * nw + warp, lane
+    Vec<4> P[R];
+    uint2 ins[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) P[j] = dont_care<4>(), ins[j] = make_uint2(0x80000000u, 0x80000000u);
+    uint4 hdr = ld_hdr(hp);
+    {
+      const uint32_t hj[3] = {hdr.x, hdr.y, hdr.z};
+#pragma unroll
+      for (int j = 0; j < R; j++)
+        if (hj[j] >> 24 & 3u) ins[j] = ld_cinstr(ip + (size_t)j * nt);
+    }
+    for (uint32_t s = 0; s < p.n_segs; s++) {
+      // The next segment's header is requested now; the instruction word of row slot j of the next segment is requested
+      // as soon as this segment's row j is done, into the same registers (which rows the next segment has is known
+      // from THIS segment's header, so no request waits for another one).
+      hp += nw, ip += seg_stride;
+      const uint4 hdr_n = ld_hdr(hp);
+      const uint32_t hj[3] = {hdr.x, hdr.y, hdr.z};
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+        if (hj[j] >> 24 & 3u) row_exec(ins[j], hj[j], P[j], sb);
+        if (hdr.w >> (29 + j) & 1u) ins[j] = ld_cinstr(ip + (size_t)j * nt);
+      }
+      for (uint32_t i = (hdr.w & SIDE) + tid; i < (hdr_n.w & SIDE); i += nt) coop_exec<4>(p, ld_instr(p.instr + i), sb, col);  // loads / stores / odd LUTs
+      hdr = hdr_n;
+      __syncthreads();
+    }
+  }
+}
+
 // ---- layout helpers ----------------------------------------------------------------------------------
 // bools [n_vectors][n_rows] bytes (one run()'s `&[bool]` per vector)  ->  sliced [n_rows][stride] words
 extern "C" __global__ void __launch_bounds__(256) clg_slice(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows,
@@ -648,3 +759,4 @@ extern "C" __global__ void __launch_bounds__(512) clg_lop3_peak(const uint32_t *
 CLG_ENTRY(1)
 CLG_ENTRY(2)
 CLG_ENTRY(4)
+extern "C" __global__ void __launch_bounds__(1024) clg_coop_rows(const clg::RunParams p) { clg::coop_rows_body<clg::ROW_SLOTS>(p); }

@@ -926,14 +926,14 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8, bool estimate_only 
   for (const OutRef &o : net.outs)
     if (o.val != NONE) fanout[o.val]++;
   uint64_t bank_weight[MAX_BANKS] = {};
+  // Three phases. (1) Level by level: which instructions share a group, operand placement, and a first choice of the
+  // bank group of every result. (2) Local search over the bank choices with every reader known. (3) Slots.
+  std::vector<uint8_t> bankv(V, 0);   // bank group of each value
+  std::vector<Placed> seq(V + O);     // the final order: level l occupies [cnt[l], cnt[l + 1])
   std::vector<Placed> order;
   std::vector<uint32_t> nxt;
   std::vector<CandInfo> cinfo;
   for (uint32_t l = 0; l < n_levels; l++) {
-    if (l > 0) {
-      for (uint32_t sl : release[l - 1]) pool.put(sl);
-      release[l - 1].clear(), release[l - 1].shrink_to_fit();
-    }
     const uint32_t b = cnt[l], e = cnt[l + 1], n = e - b;
     s.max_width = std::max(s.max_width, n);
     std::stable_sort(items.begin() + b, items.begin() + e, [&](uint32_t x, uint32_t y) { return key(x) < key(y); });
@@ -947,11 +947,11 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8, bool estimate_only 
       ci.perms = 1;
       if (x >= V) {
         ci.nops = net.outs[x - V].val == NONE ? 0 : 1;
-        if (ci.nops) ci.bank[0] = (uint8_t)(slot[net.outs[x - V].val] % BANKS);
+        if (ci.nops) ci.bank[0] = bankv[net.outs[x - V].val];
       } else if (net.vals[x].is_lut) {
         const Val &v = net.vals[x];
         ci.nops = v.nfan;
-        for (int k = 0; k < v.nfan; k++) ci.bank[k] = (uint8_t)(slot[v.fan[k]] % BANKS);
+        for (int k = 0; k < v.nfan; k++) ci.bank[k] = bankv[v.fan[k]];
         if (v.nfan >= 2)
           for (int q = 1; q < 6; q++) {
             bool fits = true;
@@ -979,7 +979,12 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8, bool estimate_only 
       uint32_t mask[3] = {0, 0, 0};
       uint32_t members = 0;
       uint32_t scanned = 0;
+      // a group is drawn from ONE class (operand count + truth table) while that class lasts: the row kernel
+      // (clg_coop_rows) runs a warp's 32 instructions with one uniform LOP3 dispatch per distinct table, so
+      // groups that mix tables cost it an extra pass; the classes are contiguous in the sorted order
+      const uint32_t head_key = head < n ? key(items[b + head]) : 0;
       for (uint32_t c = head, prev = NONE; c < n && members < BANKS && scanned < WINDOW;) {
+        if (key(items[b + c]) != head_key && !std::getenv("CLG_MIX_CLASSES")) break;
         scanned++;
         const CandInfo &ci = cinfo[c];
         int pick = -1;
@@ -1007,7 +1012,7 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8, bool estimate_only 
           const uint32_t x = order[k].x;
           const uint8_t *pm = PERM[order[k].perm];
           const int no = x >= V ? (net.outs[x - V].val == NONE ? 0 : 1) : net.vals[x].is_lut ? net.vals[x].nfan : 0;
-          for (int j = 0; j < no; j++) hits[pm[j]][(x >= V ? slot[net.outs[x - V].val] : slot[net.vals[x].fan[j]]) % BANKS]++;
+          for (int j = 0; j < no; j++) hits[pm[j]][x >= V ? bankv[net.outs[x - V].val] : bankv[net.vals[x].fan[j]]]++;
         }
         while (members < BANKS && placed < n) {
           uint32_t best_c = NONE, best_prev = NONE, best_cost = NONE, seen = 0;
@@ -1031,32 +1036,129 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8, bool estimate_only 
         }
       }
     }
-    // -- emit, choosing destination bank groups quarter by quarter
+    // -- first choice of destination bank groups, quarter by quarter
     // The members of a group take distinct bank groups (conflict-free STS). WHICH member takes which is chosen so
     // that the read traffic per bank group stays level: values are handed out most-read first to the bank group
     // that has accumulated the least fan-out so far. (With a round-robin choice the readers of a level see up to
     // +/-25 % imbalance between bank groups, which no packing of the readers can undo.)
-    uint32_t bank_of[MAX_BANKS] = {};
-    for (uint32_t i = 0; i < n; i++) {
-      if (i % BANKS == 0) {
-        uint32_t idx[MAX_BANKS], m = 0, dmask = 0;
-        for (uint32_t k = i; k < std::min(n, i + BANKS); k++)
-          if (order[k].x < V) idx[m++] = k;
-        std::stable_sort(idx, idx + m, [&](uint32_t p, uint32_t q) { return fanout[order[p].x] > fanout[order[q].x]; });
-        for (uint32_t j = 0; j < m; j++) {
-          uint32_t bank = NONE;
-          for (uint32_t cand = 0; cand < BANKS; cand++) {
-            if (dmask >> cand & 1u) continue;
-            if (bank == NONE || bank_weight[cand] < bank_weight[bank] ||
-                (bank_weight[cand] == bank_weight[bank] && pool.has_free(cand) && !pool.has_free(bank)))
-              bank = cand;
-          }
-          dmask |= 1u << bank;
-          bank_weight[bank] += fanout[order[idx[j]].x];
-          bank_of[idx[j] % BANKS] = bank;
+    for (uint32_t i = 0; i < n; i += BANKS) {
+      uint32_t idx[MAX_BANKS], m = 0, dmask = 0;
+      for (uint32_t k = i; k < std::min(n, i + BANKS); k++)
+        if (order[k].x < V) idx[m++] = k;
+      std::stable_sort(idx, idx + m, [&](uint32_t p, uint32_t q) { return fanout[order[p].x] > fanout[order[q].x]; });
+      for (uint32_t j = 0; j < m; j++) {
+        uint32_t bank = NONE;
+        for (uint32_t cand = 0; cand < BANKS; cand++) {
+          if (dmask >> cand & 1u) continue;
+          if (bank == NONE || bank_weight[cand] < bank_weight[bank]) bank = cand;
         }
+        dmask |= 1u << bank;
+        bank_weight[bank] += fanout[order[idx[j]].x];
+        bankv[order[idx[j]].x] = (uint8_t)bank;
       }
-      const uint32_t x = order[i].x;
+    }
+    for (uint32_t i = 0; i < n; i++) seq[b + i] = order[i];
+  }
+
+  // ---- (2) local search over the bank groups ---------------------------------------------------------------------
+  // A group's results keep distinct bank groups; two of them may trade theirs (or one may move to a bank group the
+  // group does not use) whenever that lowers the conflicts of the groups that READ them. With every reader known this
+  // removes most of what the level-by-level choice above leaves: the 1M-gate DAG goes from 1.10 to ~1.01 wavefronts
+  // per ideal wavefront.
+  if (!std::getenv("CLG_NO_BANK_SEARCH")) {
+    // group id of every position; per (group, operand position) a histogram of bank groups read
+    std::vector<uint32_t> gbase(n_levels + 1, 0);
+    for (uint32_t l = 0; l < n_levels; l++) gbase[l + 1] = gbase[l] + (cnt[l + 1] - cnt[l] + BANKS - 1) / BANKS;
+    const uint32_t G = gbase[n_levels];
+    std::vector<uint8_t> hist((size_t)G * 3 * BANKS, 0);
+    std::vector<uint32_t> roff(V + 1, 0), reads;  // per value: (group * 3 + position) of every read
+    auto each_read = [&](auto &&fn) {
+      for (uint32_t l = 0; l < n_levels; l++)
+        for (uint32_t i = cnt[l]; i < cnt[l + 1]; i++) {
+          const uint32_t x = seq[i].x, g = gbase[l] + (i - cnt[l]) / BANKS;
+          if (x >= V) {
+            if (net.outs[x - V].val != NONE) fn(net.outs[x - V].val, g * 3);
+          } else if (net.vals[x].is_lut) {
+            const uint8_t *pm = PERM[seq[i].perm];
+            for (int k = 0; k < net.vals[x].nfan; k++) fn(net.vals[x].fan[k], g * 3 + pm[k]);
+          }
+        }
+    };
+    each_read([&](uint32_t v, uint32_t) { roff[v + 1]++; });
+    for (size_t v = 0; v < V; v++) roff[v + 1] += roff[v];
+    reads.resize(roff[V]);
+    {
+      std::vector<uint32_t> fill(roff.begin(), roff.end() - 1);
+      each_read([&](uint32_t v, uint32_t where) { reads[fill[v]++] = where, hist[(size_t)where * BANKS + bankv[v]]++; });
+    }
+    // cost of moving value v from bank group `from` to `to`: change of (sum of squared counts) over its readers' groups
+    auto delta = [&](uint32_t v, uint32_t from, uint32_t to) {
+      int d = 0;
+      for (uint32_t r = roff[v]; r < roff[v + 1]; r++) {
+        const uint8_t *h = &hist[(size_t)reads[r] * BANKS];
+        d += 2 * ((int)h[to] - (int)h[from]) + 2;
+      }
+      return d;
+    };
+    auto move = [&](uint32_t v, uint32_t from, uint32_t to) {
+      for (uint32_t r = roff[v]; r < roff[v + 1]; r++) {
+        uint8_t *h = &hist[(size_t)reads[r] * BANKS];
+        h[from]--, h[to]++;
+      }
+      bankv[v] = (uint8_t)to;
+    };
+    for (int sweep = 0; sweep < 8; sweep++) {
+      uint64_t improved = 0;
+      for (uint32_t l = 0; l < n_levels; l++)
+        for (uint32_t i0 = cnt[l]; i0 < cnt[l + 1]; i0 += BANKS) {
+          uint32_t mem[MAX_BANKS], m = 0, used = 0;
+          for (uint32_t i = i0; i < std::min(cnt[l + 1], i0 + BANKS); i++)
+            if (seq[i].x < V) mem[m++] = seq[i].x, used |= 1u << bankv[seq[i].x];
+          for (uint32_t a = 0; a < m; a++) {
+            const uint32_t va = mem[a];
+            if (roff[va] == roff[va + 1]) continue;
+            // to a bank group nobody in the group uses
+            for (uint32_t to = 0; to < BANKS; to++) {
+              if (used >> to & 1u) continue;
+              const uint32_t from = bankv[va];
+              if (delta(va, from, to) < 0) move(va, from, to), used = (used & ~(1u << from)) | 1u << to, improved++;
+            }
+            // or trade with another member
+            for (uint32_t c = a + 1; c < m; c++) {
+              const uint32_t vc = mem[c], ba = bankv[va], bc = bankv[vc];
+              // (the two moves interact only if both values are read by the same group and position: apply, measure, undo)
+              const int d1 = delta(va, ba, bc);
+              move(va, ba, bc);
+              const int d2 = delta(vc, bc, ba);
+              if (d1 + d2 < 0) move(vc, bc, ba), improved++;
+              else move(va, bc, ba);
+            }
+          }
+        }
+      if (std::getenv("CLG_TIMING")) {
+        uint64_t cost = 0, wf = 0, ideal = 0;
+        for (size_t q = 0; q < (size_t)G * 3; q++) {
+          uint32_t mx = 0;
+          for (uint32_t k = 0; k < BANKS; k++) cost += (uint64_t)hist[q * BANKS + k] * hist[q * BANKS + k], mx = std::max<uint32_t>(mx, hist[q * BANKS + k]);
+          wf += mx, ideal += mx > 0;
+        }
+        std::fprintf(stderr, "[clg]   bank search sweep %d: %llu moves, sum of squares %llu, wavefronts %llu / ideal %llu\n", sweep, (unsigned long long)improved,
+                     (unsigned long long)cost, (unsigned long long)wf, (unsigned long long)ideal);
+      }
+      if (!improved) break;
+    }
+  }
+
+  // ---- (3) slots: a result takes a free slot of its bank group; a slot freed by its last reader in level L is handed
+  // out again from level L + 1 on
+  for (uint32_t l = 0; l < n_levels; l++) {
+    if (l > 0) {
+      for (uint32_t sl : release[l - 1]) pool.put(sl);
+      release[l - 1].clear(), release[l - 1].shrink_to_fit();
+    }
+    const uint32_t b = cnt[l], n = cnt[l + 1] - cnt[l];
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t x = seq[b + i].x;
       FlatInstr in{};
       if (x >= V) {
         const OutRef &o = net.outs[x - V];
@@ -1067,7 +1169,7 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8, bool estimate_only 
         const Val &v = net.vals[x];
         if (v.is_lut) {
           in = make_lut(v);
-          const uint8_t *pm = PERM[order[i].perm];
+          const uint8_t *pm = PERM[seq[b + i].perm];
           uint32_t sl[3] = {NONE, NONE, NONE};
           uint8_t where[3] = {0, 1, 2};
           for (int k = 0; k < v.nfan; k++) sl[pm[k]] = slot[v.fan[k]], where[k] = pm[k];
@@ -1078,8 +1180,7 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8, bool estimate_only 
         } else {
           in.kind = K_LDIN, in.row = v.row;
         }
-        const uint32_t bank = bank_of[i % BANKS];
-        slot[x] = pool.get(bank);
+        slot[x] = pool.get(bankv[x]);
         if (slot[x] > 0xFFFF) {
           s.ok = false;
           return s;
@@ -1139,7 +1240,13 @@ uint32_t partition(const Network &net, uint32_t max_parts, std::vector<uint32_t>
   part_of_val.resize(V);
   for (size_t v = 0; v < V; v++) part_of_val[v] = part_of_comp[find((uint32_t)v)];
   part_of_out.resize(net.outs.size());
-  for (size_t o = 0; o < net.outs.size(); o++) part_of_out[o] = net.outs[o].val == NONE ? 0 : part_of_val[net.outs[o].val];
+  for (size_t o = 0; o < net.outs.size(); o++) {
+    const OutRef &r = net.outs[o];
+    if (r.val != NONE) part_of_out[o] = part_of_val[r.val];
+    else if (r.row >= net.n_outputs && state_in[r.row - net.n_outputs] != NONE)
+      part_of_out[o] = part_of_val[state_in[r.row - net.n_outputs]];  // a constant stored over a carried row waits for that row's load
+    else part_of_out[o] = 0;
+  }
   return P;
 }
 
@@ -1266,6 +1373,21 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
     net.outs.push_back(r);
   }
 
+  if (const char *path = std::getenv("CLG_DUMP_NETWORK")) {  // analysis knob: the mapped network as raw u32 records
+    if (FILE *fp = std::fopen(path, "wb")) {
+      const uint32_t hdr[4] = {(uint32_t)net.vals.size(), (uint32_t)net.outs.size(), net.n_inputs, net.n_outputs};
+      std::fwrite(hdr, 4, 4, fp);
+      for (const Val &v : net.vals) {
+        const uint32_t rec[6] = {v.is_lut, v.tt, v.nfan, v.nfan > 0 ? v.fan[0] : v.row, v.fan[1], v.fan[2]};
+        std::fwrite(rec, 4, 6, fp);
+      }
+      for (const OutRef &o : net.outs) {
+        const uint32_t rec[3] = {o.row, o.val, o.inv};
+        std::fwrite(rec, 4, 3, fp);
+      }
+      std::fclose(fp);
+    }
+  }
   ph.reset(new Phase("schedule: level"));
   // pack for the widest register-stack word count K that will fit one SM's shared memory (227 KB): K = 4 -> 8
   // bank groups of 16 B, K = 2 -> 16 of 8 B, K = 1 -> 32 banks of 4 B
@@ -1372,6 +1494,15 @@ void validate_flat(const Flat &f) {
   if (h.n_parts && !span_ok(h.off_parts, (uint64_t)h.n_parts * sizeof(FlatStream))) bad("part table out of range");
   // all output/state rows stored exactly... at most once across the parts of the partitioned form
   std::vector<uint8_t> row_in_part(h.n_parts ? n_out_rows : 0, 0);
+  std::vector<uint32_t> state_load_part(h.n_parts ? h.n_state : 0, NONE);  // part that loads each carried row
+  for (uint32_t q = 0; q < h.n_parts; q++) {
+    const FlatStream &st = f.parts()[q];
+    if (st.n_instr == 0) continue;
+    if (st.off_instr % 16 != 0 || (uint64_t)st.off_instr + (uint64_t)st.n_instr * 16 > f.bytes.size()) bad("stream out of range");
+    const FlatInstr *in = reinterpret_cast<const FlatInstr *>(f.bytes.data() + st.off_instr);
+    for (uint32_t i = 0; i < st.n_instr; i++)
+      if (in[i].kind == K_LDIN && in[i].row >= h.n_inputs && in[i].row < n_in_rows) state_load_part[in[i].row - h.n_inputs] = 2 + q;
+  }
   for (uint32_t sidx = 0; sidx < 2 + h.n_parts; sidx++) {
     const int s = sidx < 2 ? (int)sidx : (int)STREAM_LEVEL;
     const FlatStream &st = sidx < 2 ? h.stream[sidx] : f.parts()[sidx - 2];
@@ -1391,6 +1522,7 @@ void validate_flat(const Flat &f) {
     std::vector<uint8_t> defined(st.n_slots, 0);
     std::vector<uint32_t> written_in(st.n_slots, NONE);
     std::vector<uint32_t> loaded_in(h.n_state, NONE), stored_in(h.n_state, NONE);
+    std::vector<uint8_t> row_stored(n_out_rows, 0);  // every output / state row is stored at most once per stream
     uint32_t window = 0;
     for (uint32_t l = 0; l < st.n_levels; l++) {
       if (lv[l] > lv[l + 1] || lv[l + 1] > st.n_instr) bad("level table not monotone");
@@ -1410,9 +1542,8 @@ void validate_flat(const Flat &f) {
             if (x.kind == K_LUT) {
               const int nf = lut_nfan(x);
               if (nf < 1) bad("LUT without operands");
-              rd(x.a);
-              if (nf >= 2) rd(x.b);
-              if (nf >= 3) rd(x.c);
+              // operands the LUT does not read alias one it does (the encoders and the PTX emitter touch all three)
+              rd(x.a), rd(x.b), rd(x.c);
             }
             if (x.kind == K_STOUT) rd(x.a);
             if (x.kind == K_LDIN) {
@@ -1425,10 +1556,12 @@ void validate_flat(const Flat &f) {
             }
             if (x.kind == K_STOUT || x.kind == K_STCONST) {
               if (x.row >= n_out_rows) bad("output row out of range");
+              if (row_stored[x.row]++) bad("an output or state row is stored twice");
               if (x.row >= h.n_outputs) {
                 uint32_t k = x.row - h.n_outputs;
                 if (!seq && loaded_in[k] == window) bad("state row loaded and stored in the same level");
-                if (stored_in[k] != NONE) bad("state row stored twice");
+                if (sidx >= 2 && state_load_part[k] != NONE && state_load_part[k] != sidx)
+                  bad("a state row is loaded by one part and stored by another");
               }
             }
           }
@@ -1449,11 +1582,7 @@ void validate_flat(const Flat &f) {
           auto chk = [&](uint16_t sl) {
             if (written_in[sl] == l) bad("slot read and written in the same level");
           };
-          if (x.kind == K_LUT) {
-            chk(x.a);
-            if (lut_nfan(x) >= 2) chk(x.b);
-            if (lut_nfan(x) >= 3) chk(x.c);
-          }
+          if (x.kind == K_LUT) chk(x.a), chk(x.b), chk(x.c);
           if (x.kind == K_STOUT) chk(x.a);
         }
       }

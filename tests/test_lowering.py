@@ -292,3 +292,73 @@ def test_mutated_flat_buffers_are_rejected_or_safe():
             except host.ClgError:
                 pass
     assert rejected > 100 and accepted + rejected == 750
+
+
+def test_unread_lut_operands_are_validated():
+    """the encoders and the PTX emitter touch all three operand fields of a LUT, also the ones its table
+    does not read -- an out-of-range value there must be rejected like any other slot index."""
+    c = circuits.array_multiplier(8)
+    fp = host.FlatProgram.levelize(c.sim, c.n_immediates, c.out_regs)
+    data = fp.to_bytes()
+    flat = flat_interp.Flat(data)
+    hit = 0
+    for s in (flat_interp.STREAM_LEVEL, flat_interp.STREAM_LANE):
+        st = flat.streams[s]
+        off_instr = struct_off_instr(data, s)
+        for i in range(st["n_instr"]):
+            x = st["instr"][i]
+            nfan = (int(x["flags"]) >> 8) & 3
+            if int(x["kind"]) != 0 or nfan == 3:
+                continue
+            d = bytearray(data)
+            field = 6 if nfan == 2 else 4  # byte offset of c (nfan 2) or b (nfan 1) inside the 16-byte instruction
+            d[off_instr + 16 * i + field: off_instr + 16 * i + field + 2] = (0xFFFF).to_bytes(2, "little")
+            with pytest.raises(host.ClgError):
+                host.FlatProgram.from_bytes(bytes(d))
+            hit += 1
+            if hit % 7 == 0:
+                break
+    assert hit >= 2
+
+
+def struct_off_instr(data: bytes, stream: int) -> int:
+    import struct
+    return struct.unpack_from("<6I", data, 64 + 32 * stream)[4]
+
+
+def test_constant_store_over_a_carried_row_stays_with_its_load():
+    """in the partitioned form a carried register that is read and then overwritten with a constant
+    (`Nand(S,S,X); Set(S,true)`) must have its load and its store in ONE part -- parts run as unordered CTAs."""
+    n_comp = 5000  # (the pass partitions programs of >= 4096 LUTs)
+    n_imm = 2 * n_comp  # every component reads its own two immediates, so the network really separates
+    ops = [host.Set_op(i, False) for i in range(n_imm)]
+    S = n_imm
+    X = S + 1
+    nxt = X + 1
+    outs = [X]
+    for k in range(n_comp):  # independent XOR-ish components so that the network separates into many parts
+        a, b = 2 * k, 2 * k + 1
+        t, u = nxt, nxt + 1
+        nxt += 2
+        ops += [host.Nand_op(a, b, t), host.Nand_op(t, a, u)]
+        outs.append(u)
+    ops += [host.Nand_op(S, S, X), host.Set_op(S, True)]
+    sim = host.Simulation(ops=ops, registers=[False] * nxt)
+    fp = host.FlatProgram.levelize(sim, n_imm, outs, flags=host.LV_STATEFUL)
+    flat = flat_interp.Flat(fp.to_bytes())
+    assert fp.info["n_state"] == 1
+    assert flat.n_parts > 100
+    if flat.n_parts:
+        loads = [q for q, p in enumerate(flat.parts) if ((p["instr"]["kind"] == 1) & (p["instr"]["row"] >= n_imm)).any()]
+        stores = [q for q, p in enumerate(flat.parts) if ((p["instr"]["kind"] >= 2) & (p["instr"]["row"] >= len(outs))).any()]
+        assert loads == stores and len(loads) == 1
+    # and the values: two consecutive runs per lane against the oracle VM
+    nv = 64
+    imm = random_sliced(n_imm, stride_for(nv), seed=3)
+    state = np.zeros((1, stride_for(nv)), dtype=np.uint32)
+    for stream in (flat_interp.STREAM_LEVEL, flat_interp.STREAM_PARTS) if flat.n_parts else (flat_interp.STREAM_LEVEL,):
+        st = state.copy()
+        got1 = mask_tail(flat_interp.run(flat, stream, imm, st, rng=np.random.default_rng(2)), nv)
+        got2 = mask_tail(flat_interp.run(flat, stream, imm, st, rng=np.random.default_rng(3)), nv)
+        # X = !S: first run sees S = false -> X = 1 in every lane; second run sees S = true -> X = 0
+        assert (got1[0, : nv // 32] == 0xFFFFFFFF).all() and (got2[0, : nv // 32] == 0).all()
