@@ -11,7 +11,7 @@ SO_PATH = os.path.join(HERE, "libcomplogic_cuda.so")
  CLG_E_FORMAT) = range(9)
 MODE_AUTO, MODE_LANE, MODE_COOP, MODE_SPEC = range(4)
 MODE_NAMES = {MODE_AUTO: "auto", MODE_LANE: "lane", MODE_COOP: "coop", MODE_SPEC: "spec"}
-LV_STATEFUL, LV_NO_FUSE, LV_NO_LANE_STREAM, LV_NO_PARTS = 1, 2, 4, 8
+LV_STATEFUL, LV_NO_FUSE, LV_NO_LANE_STREAM, LV_NO_PARTS, LV_NO_ROWS = 1, 2, 4, 8, 16
 
 
 class ClgOp(C.Structure):
@@ -26,7 +26,9 @@ class ClgFlatInfo(C.Structure):
     _fields_ = [("ref_nand_count", C.c_uint64), ("ref_set_count", C.c_uint64), ("n_inputs", C.c_uint32),
                 ("n_outputs", C.c_uint32), ("n_state", C.c_uint32), ("n_luts", C.c_uint32), ("n_levels", C.c_uint32),
                 ("max_level_width", C.c_uint32), ("level_slots", C.c_uint32), ("lane_slots", C.c_uint32),
-                ("level_instrs", C.c_uint32), ("lane_instrs", C.c_uint32), ("n_parts", C.c_uint32), ("reserved", C.c_uint32)]
+                ("level_instrs", C.c_uint32), ("lane_instrs", C.c_uint32), ("n_parts", C.c_uint32), ("reserved", C.c_uint32),
+                ("rows_segments", C.c_uint32), ("rows_slots", C.c_uint32), ("rows_instrs", C.c_uint32),
+                ("rows_from_reg", C.c_uint32), ("rows_no_store", C.c_uint32), ("rows_warps", C.c_uint32)]
 
 
 vp, sz, u64, u32, i32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int

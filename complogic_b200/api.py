@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (ClgError, ClgFlatInfo, ClgGate, ClgOp, ReferencePanic, check, lib, MODE_AUTO, MODE_COOP, MODE_LANE,
-                   MODE_SPEC, MODE_NAMES, LV_STATEFUL, LV_NO_FUSE, LV_NO_LANE_STREAM, LV_NO_PARTS)
+                   MODE_SPEC, MODE_NAMES, LV_STATEFUL, LV_NO_FUSE, LV_NO_LANE_STREAM, LV_NO_PARTS, LV_NO_ROWS)
 
 OP_DTYPE = np.dtype([("tag", "<u4"), ("reserved", "<u4"), ("a", "<u8"), ("b", "<u8"), ("c", "<u8")])
 assert OP_DTYPE.itemsize == C.sizeof(ClgOp) == 32

@@ -169,9 +169,9 @@ struct Plan {
   size_t smem = 0;
   uint32_t tuned_threads = 0;  // cooperative, big batches: CTA size found by timing candidates on this device (0: not tuned yet)
   bool resident = false;  // cooperative: the (largest part's) instruction stream is staged in shared memory
-  // cooperative, row form (clg_coop_rows): the level stream re-encoded as rows of 32 LUTs for a CTA of rows_nt threads
-  CUdeviceptr d_rinstr = 0, d_rhdr = 0, d_rside = 0;
-  uint32_t rows_nt = 0, n_segs = 0;
+  // cooperative, row form (clg_coop_rows): the row stream of the flat buffer, encoded for the device
+  CUdeviceptr d_rinstr = 0, d_rwarp = 0, d_rside = 0, d_rside_off = 0;
+  uint32_t rows_nt = 0;
   // long programs: the lane stream cut into SPEC_CHUNK-instruction kernels; live registers cross the cuts through `scratch`
   struct ChunkLaunch {
     CUfunction fn;
@@ -206,6 +206,7 @@ struct Exec {
   int want;   // CLG_MODE_AUTO or the mode the caller pinned
   int mode;   // mode of the most recent (or, before any run, the preferred) plan
   int last_k = 0, last_parts = 0;
+  bool last_rows = false;  // the most recent cooperative run used the row kernel
   // shape of the chunked specialised chain (computed on demand, for the mode choice): distinct kernels to assemble, and
   // per launch {instructions, instances side by side}
   struct ChainShape {
@@ -221,8 +222,8 @@ struct Exec {
     }
     return shape_;
   }
-  Plan plan[5];  // indexed by clg_mode; [PLAN_PARTS] = cooperative mode over the partitioned level stream
-  static constexpr int PLAN_PARTS = 4;
+  Plan plan[6];  // indexed by clg_mode; [PLAN_PARTS] = cooperative mode over the partitioned level stream, [PLAN_ROWS] = over the row stream
+  static constexpr int PLAN_PARTS = 4, PLAN_ROWS = 5;
 
   const FlatStream &level_stream() const { return flat.header().stream[STREAM_LEVEL]; }
   const FlatStream &lane_stream() const { return flat.header().stream[STREAM_LANE]; }
@@ -552,7 +553,8 @@ struct Exec {
       if (P.d_cinstr) d.cuMemFree(P.d_cinstr);
       if (P.d_clevels) d.cuMemFree(P.d_clevels);
       if (P.d_rinstr) d.cuMemFree(P.d_rinstr);
-      if (P.d_rhdr) d.cuMemFree(P.d_rhdr);
+      if (P.d_rwarp) d.cuMemFree(P.d_rwarp);
+      if (P.d_rside_off) d.cuMemFree(P.d_rside_off);
       if (P.d_rside) d.cuMemFree(P.d_rside);
       if (P.spec_mod) d.cuModuleUnload(P.spec_mod);
       if (P.steps_mod) d.cuModuleUnload(P.steps_mod);
@@ -713,6 +715,14 @@ struct Exec {
     if (tier_pending) interp_seconds += (mode == CLG_MODE_LANE ? lane_cycles(words) : coop_cycles(words)) / 1.9e9;
     // a cooperative run that cannot give every SM its own column group uses the partitioned form if there is one
     const bool use_parts = mode == CLG_MODE_COOP && parts_k() && (words + parts_k() - 1) / parts_k() < (size_t)ctx->sm_count;
+    // a batch that gives every SM a column group runs the row stream when the pass built one
+    if (mode == CLG_MODE_COOP && !use_parts && has_rows() && (words + 3) / 4 >= (size_t)ctx->sm_count) {
+      Plan &R = get_rows();
+      last_k = 4, last_parts = 0, last_rows = true;
+      launch_rows(R, params(R, imm, out, state, stride, (uint32_t)((words + 3) / 4)), stream);
+      return;
+    }
+    last_rows = false;
     Plan &P = use_parts ? get_parts() : get(mode);
     const int K = P.K;
     last_k = K, last_parts = (int)P.n_parts;
@@ -751,10 +761,6 @@ struct Exec {
     // level has instructions. More than that is a throughput problem whose optimum depends on how many CTAs fit an
     // SM and how wide the levels are (a 65k-gate DAG with ~570 instructions a level: 15.0 ms with 1024 threads,
     // 7.1 ms with 256), so it is measured once per plan on this device.
-    if (rows_ok(P)) {
-      launch_rows(P, params(P, imm, out, state, stride, groups), stream);
-      return;
-    }
     uint32_t nt = P.coop_threads;
     if (!P.n_parts && groups > (uint32_t)ctx->sm_count * coop_ctas_per_sm(P, nt)) {
       if (!P.tuned_threads) P.tuned_threads = tune_coop_threads(P);
@@ -763,119 +769,88 @@ struct Exec {
     launch_coop(P, params(P, imm, out, state, stride, groups), nt, stream);
   }
 
-  // ---- row form of the cooperative mode (clg_coop_rows; layout in kernels.cu, RunParams) ---------------------
-  // The LUTs of a level, in the order the pass packed them (8 consecutive ones are conflict-free), become rows of 32;
-  // a row keeps its three most frequent truth tables, LUTs with another one join the loads and stores of the level in
-  // the 16-byte side list. A level wider than n_warps * ROW_SLOTS rows is cut into several segments.
-  bool rows_ok(const Plan &P) const {
-    return P.K == 4 && !P.resident && !P.n_parts && P.n_slots <= 16383 && std::getenv("CLG_COOP_ROWS");  // (off until it beats clg_coop_c)
-  }
-  void build_rows(Plan &P, uint32_t nt) {
-    if (P.rows_nt == nt) return;
+  // ---- row form of the cooperative mode (clg_coop_rows; device layout in kernels.cu, RunParams) -----------------
+  bool has_rows() const { return flat.rows().n_instr != 0 && !std::getenv("CLG_COOP_NO_ROWS"); }
+  Plan &get_rows() {
+    Plan &P = plan[PLAN_ROWS];
+    if (P.ready) return P;
     ctx->bind();
-    if (P.rows_nt) {
-      CU(cuCtxSynchronize());
-      driver().cuMemFree(P.d_rinstr), driver().cuMemFree(P.d_rhdr), driver().cuMemFree(P.d_rside);
-      P.d_rinstr = P.d_rhdr = P.d_rside = 0, P.rows_nt = 0;
-    }
-    const uint32_t nw = nt / 32, seg_rows = nw * ROW_SLOTS;
-    const FlatInstr *src = flat.instrs(STREAM_LEVEL);
-    const uint32_t *lvl = flat.levels(STREAM_LEVEL);
-    const FlatStream &st = level_stream();
-    std::vector<uint32_t> rinstr, rhdr, side;  // 2 / 4 / 4 words per entry
-    std::vector<uint32_t> luts;
-    auto side_push = [&](const FlatInstr &x) {
-      uint32_t e[4];
-      encode_stream(&x, 1, 16, e);
-      side.insert(side.end(), e, e + 4);
-    };
-    uint32_t n_segs = 0;
-    for (uint32_t l = 0; l < st.n_levels; l++) {
-      luts.clear();
-      for (uint32_t i = lvl[l]; i < lvl[l + 1]; i++)
-        if (src[i].kind == K_LUT) luts.push_back(i);
-      const uint32_t n_rows = ((uint32_t)luts.size() + 31) / 32;
-      const uint32_t segs_here = std::max<uint32_t>(1, (n_rows + seg_rows - 1) / seg_rows);
-      for (uint32_t sg = 0; sg < segs_here; sg++, n_segs++) {
-        const size_t ibase = rinstr.size(), hbase = rhdr.size();
-        rinstr.resize(ibase + (size_t)seg_rows * 32 * 2, 0x80000000u);  // (no load of a, no store: a lane without a LUT)
-        rhdr.resize(hbase + (size_t)nw * 4, 0);
-        for (uint32_t w = 0; w < nw; w++) rhdr[hbase + w * 4 + 3] = (uint32_t)(side.size() / 4);
-        if (sg == 0)
-          for (uint32_t i = lvl[l]; i < lvl[l + 1]; i++)
-            if (src[i].kind != K_LUT) side_push(src[i]);
-        for (uint32_t r = 0; r < seg_rows && (size_t)(sg * seg_rows + r) * 32 < luts.size(); r++) {
-          const size_t first = (size_t)(sg * seg_rows + r) * 32, last = std::min(luts.size(), first + 32);
-          // the row's tables, most frequent first
-          uint32_t count[256] = {};
-          for (size_t q = first; q < last; q++) count[src[luts[q]].tt]++;
-          uint8_t tts[3] = {0, 0, 0};
-          uint32_t n_tt = 0;
-          for (; n_tt < 3; n_tt++) {
-            uint32_t best = 256;
-            for (uint32_t t = 0; t < 256; t++)
-              if (count[t] && (best == 256 || count[t] > count[best])) best = t;
-            if (best == 256) break;
-            tts[n_tt] = (uint8_t)best, count[best] = 0;
-          }
-          const uint32_t w = r % nw, j = r / nw;
-          bool reads_c = false;
-          uint32_t in_row = 0;
-          for (size_t q = first; q < last; q++) {
-            const FlatInstr &x = src[luts[q]];
-            uint32_t k = 0;
-            while (k < n_tt && tts[k] != x.tt) k++;
-            if (k == n_tt) {  // a fourth table: leave the lane empty, run the LUT from the side list
-              side_push(x);
-              continue;
+    const FlatRows &r = flat.rows();
+    const uint32_t nw = r.n_warps, S = r.n_segs;
+    const FlatInstr *src = flat.row_instrs();
+    const uint32_t *rt = flat.row_tab(), *stab = flat.row_sidetab();
+    P.K = 4, P.n_slots = r.n_slots, P.rows_nt = nw * 32;
+    P.code_off = (uint32_t)(((size_t)r.n_slots * 16 + 15) / 16 * 16);
+    P.smem = P.code_off + 16;  // register stack + two mbarriers
+    if (P.smem > SMEM_MAX) fail(CLG_E_UNSUPPORTED, "row stream: register stack exceeds one SM's shared memory");
+    std::vector<uint32_t> words, wbase(nw);  // 2 words per lane instruction
+    words.reserve(((size_t)r.n_instr + (size_t)(S + 3) * nw * 32) * 2);
+    constexpr uint32_t EMPTY_X = 0x80000000u, EMPTY_Y = 0x80000000u;  // no load of a, no store
+    for (uint32_t w = 0; w < nw; w++) {
+      wbase[w] = (uint32_t)(words.size() / 2);
+      for (uint32_t sgm = 0; sgm < S; sgm++) {
+        const uint32_t b = rt[(size_t)sgm * nw + w], e = rt[(size_t)sgm * nw + w + 1];
+        const uint32_t n_rows = std::max<uint32_t>(1, (e - b) / 32);  // at least one (empty) row: it carries the end-of-segment mark
+        for (uint32_t q = 0; q < n_rows; q++) {
+          uint32_t hdr = 0;
+          uint32_t x[32], y[32];
+          for (uint32_t i = 0; i < 32; i++) x[i] = EMPTY_X, y[i] = EMPTY_Y;
+          if (b + q * 32 < e) {
+            const FlatInstr *row = src + b + q * 32;
+            uint8_t tts[3] = {0, 0, 0};
+            uint32_t n_tt = 0;
+            bool reads_c = false;
+            for (uint32_t i = 0; i < 32; i++) {
+              const FlatInstr &in = row[i];
+              if (in.kind != K_LUT) continue;
+              uint32_t k = 0;
+              while (k < n_tt && tts[k] != in.tt) k++;
+              if (k == n_tt) {
+                if (n_tt == 3) fail(CLG_E_FORMAT, "row stream: more than three truth tables in one row");
+                tts[n_tt++] = in.tt;
+              }
+              const int nf = lut_nfan(in);
+              const bool from_reg = in.flags & FLAG_FROM_REG, no_store = in.flags & FLAG_NO_STORE;
+              const uint32_t a = from_reg ? 0u : in.a, bb = nf >= 2 ? in.b : a, c = nf >= 3 ? in.c : bb;  // operands it does not read alias one it does
+              reads_c |= nf >= 3;
+              x[i] = a | bb << 14 | k << 28 | (from_reg ? 1u << 31 : 0u);
+              y[i] = c | (no_store ? 0u : (uint32_t)in.dst << 14) | (no_store ? 1u << 31 : 0u);
             }
-            const int nf = lut_nfan(x);
-            const uint32_t a = x.a, b = nf >= 2 ? x.b : x.a, c = nf >= 3 ? x.c : b;  // operands it does not read alias one it does
-            reads_c |= nf >= 3;
-            uint32_t *e = &rinstr[ibase + ((size_t)(j * nw + w) * 32 + (q - first)) * 2];
-            e[0] = a | b << 14 | k << 28;
-            e[1] = c | (uint32_t)x.dst << 14;
-            in_row++;
+            if (n_tt) hdr = tts[0] | (uint32_t)tts[1] << 8 | (uint32_t)tts[2] << 16 | n_tt << 24 | (reads_c ? 1u << 26 : 0u);
           }
-          if (in_row) rhdr[hbase + w * 4 + j] = tts[0] | (uint32_t)tts[1] << 8 | (uint32_t)tts[2] << 16 | n_tt << 24 | (reads_c ? 1u << 26 : 0u);
+          if (q == 0 && sgm >= 2) hdr |= 1u << 30;
+          if (q + 1 == n_rows) {
+            hdr |= 1u << 27;
+            if (stab[sgm + 1] > stab[sgm]) hdr |= 1u << 28;
+            if (sgm + 1 == S) hdr |= 1u << 29;
+          }
+          for (uint32_t i = 0; i < 32; i++) words.push_back(x[i] | ((hdr >> i & 1u) << 30)), words.push_back(y[i]);
         }
       }
+      for (uint32_t i = 0; i < 64; i++) words.push_back(EMPTY_X), words.push_back(EMPTY_Y);  // the fetch runs two rows ahead
     }
-    // closing header entry: no rows, end of the side list
-    if (side.size() / 4 >= (1u << 29)) fail(CLG_E_UNSUPPORTED, "side list of the row form too long");
-    for (uint32_t w = 0; w < nw; w++) {
-      const uint32_t e[4] = {0, 0, 0, (uint32_t)(side.size() / 4)};
-      rhdr.insert(rhdr.end(), e, e + 4);
-    }
-    // each header also says which rows its warp has in the NEXT segment (the kernel requests them one segment ahead)
-    for (uint32_t sg = 0; sg < n_segs; sg++)
-      for (uint32_t w = 0; w < nw; w++)
-        for (uint32_t j = 0; j < (uint32_t)ROW_SLOTS; j++)
-          if (rhdr[((size_t)(sg + 1) * nw + w) * 4 + j] >> 24 & 3u) rhdr[((size_t)sg * nw + w) * 4 + 3] |= 1u << (29 + j);
-    side.resize(std::max<size_t>(side.size(), 4));
-    CU(cuMemAlloc(&P.d_rinstr, std::max<size_t>(16, rinstr.size() * 4)));
-    CU(cuMemcpyHtoDAsync(P.d_rinstr, rinstr.data(), rinstr.size() * 4, nullptr));
-    CU(cuMemAlloc(&P.d_rhdr, rhdr.size() * 4));
-    CU(cuMemcpyHtoDAsync(P.d_rhdr, rhdr.data(), rhdr.size() * 4, nullptr));
+    if (words.size() / 2 >= (1ull << 32)) fail(CLG_E_UNSUPPORTED, "row stream too long");
+    std::vector<uint32_t> side((size_t)std::max<uint32_t>(r.n_side, 1) * 4, 0);
+    encode_stream(flat.row_side(), r.n_side, 16, side.data());
+    CU(cuMemAlloc(&P.d_rinstr, words.size() * 4));
+    CU(cuMemcpyHtoDAsync(P.d_rinstr, words.data(), words.size() * 4, nullptr));
+    CU(cuMemAlloc(&P.d_rwarp, wbase.size() * 4));
+    CU(cuMemcpyHtoDAsync(P.d_rwarp, wbase.data(), wbase.size() * 4, nullptr));
     CU(cuMemAlloc(&P.d_rside, side.size() * 4));
     CU(cuMemcpyHtoDAsync(P.d_rside, side.data(), side.size() * 4, nullptr));
+    CU(cuMemAlloc(&P.d_rside_off, ((size_t)S + 1) * 4));
+    CU(cuMemcpyHtoDAsync(P.d_rside_off, stab, ((size_t)S + 1) * 4, nullptr));
     CU(cuStreamSynchronize(nullptr));
-    P.rows_nt = nt, P.n_segs = n_segs;
-  }
-  uint32_t rows_threads() const {
-    if (const char *env = std::getenv("CLG_ROWS_THREADS")) return std::min(1024, std::max(32, std::atoi(env))) / 32 * 32;  // tuning knob
-    // as many warps as the widest level has rows per row slot
-    const uint32_t rows = (level_stream().max_level_width + 31) / 32;
-    return std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (rows + ROW_SLOTS - 1) / ROW_SLOTS * 32u));
+    P.ready = true;
+    return P;
   }
   void launch_rows(Plan &P, RunParams p, CUstream stream) {
-    const uint32_t nt = rows_threads();
-    build_rows(P, nt);
-    p.instr = (const void *)P.d_rside, p.rinstr = (const void *)P.d_rinstr, p.rhdr = (const void *)P.d_rhdr, p.n_segs = P.n_segs;
-    const uint32_t per_sm = coop_ctas_per_sm(P, nt);
+    p.instr = (const void *)P.d_rside, p.rinstr = (const void *)P.d_rinstr, p.rwarp = (const uint32_t *)P.d_rwarp;
+    p.rside_off = (const uint32_t *)P.d_rside_off, p.code_off = P.code_off;
+    const uint32_t per_sm = coop_ctas_per_sm(P, P.rows_nt);
     const uint32_t grid = std::min<uint32_t>(p.n_groups, (uint32_t)ctx->sm_count * per_sm);
     void *args[] = {&p};
-    CU(cuLaunchKernel(ctx->coop_rows, grid, 1, 1, nt, 1, 1, (unsigned)P.smem, stream, args, nullptr));
+    CU(cuLaunchKernel(ctx->coop_rows, grid, 1, 1, P.rows_nt, 1, 1, (unsigned)P.smem, stream, args, nullptr));
   }
 
   RunParams params(const Plan &P, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t stride, uint32_t groups) const {

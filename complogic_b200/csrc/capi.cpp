@@ -206,6 +206,8 @@ int clg_flat_get_info(const clg_flat *f, clg_flat_info *info) {
   info->level_slots = h.stream[STREAM_LEVEL].n_slots, info->lane_slots = h.stream[STREAM_LANE].n_slots;
   info->level_instrs = h.stream[STREAM_LEVEL].n_instr, info->lane_instrs = h.stream[STREAM_LANE].n_instr;
   info->n_parts = h.n_parts, info->reserved = 0;
+  info->rows_segments = h.rows.n_segs, info->rows_slots = h.rows.n_instr ? h.rows.n_slots : 0, info->rows_instrs = h.rows.n_instr;
+  info->rows_from_reg = h.rows.n_from_reg, info->rows_no_store = h.rows.n_no_store, info->rows_warps = h.rows.n_instr ? h.rows.n_warps : 0;
   CLG_CATCH
 }
 int clg_flat_state_regs(const clg_flat *f, const uint64_t **regs, size_t *n) {

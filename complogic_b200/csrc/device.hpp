@@ -55,10 +55,9 @@ struct RunParams {
   const void *cinstr;
   const uint32_t *clevels;
   const void *rinstr;  // row form (clg_coop_rows)
-  const void *rhdr;
-  uint32_t n_segs;
+  const uint32_t *rwarp;
+  const uint32_t *rside_off;
 };
-constexpr int ROW_SLOTS = 3;  // rows a warp of clg_coop_rows executes per segment (kernels.cu)
 
 constexpr int LANE_MIN_THREADS = 64, LANE_MAX_THREADS = 992;  // consumer threads of a lane-kernel CTA (+ 32 producer)
 constexpr int RING_STAGES = 4;

@@ -7,13 +7,14 @@
 namespace clg {
 
 constexpr uint32_t FLAT_MAGIC = 0x46474C43u;  // "CLGF"
-constexpr uint32_t FLAT_VERSION = 4u;
+constexpr uint32_t FLAT_VERSION = 5u;
 
 enum InstrKind : uint8_t {
   K_LUT = 0,      // slot[dst] = LUT3(tt; slot[a], slot[b], slot[c])      (one LOP3 per 32 lanes)
   K_LDIN = 1,     // slot[dst] = input row `row`   (immediates first, then carried state rows)
   K_STOUT = 2,    // output row `row` = slot[a] (inverted if flags & 1)   (named outputs, then state)
   K_STCONST = 3,  // output row `row` = all-zeros / all-ones (flags & 1)
+  K_NOP = 4,      // row stream only: a lane of a row without an instruction
 };
 
 // 16 bytes, one 128-bit load. Slots are physical registers of the bit-sliced register stack.
@@ -25,6 +26,8 @@ struct FlatInstr {
   uint32_t row;
 };
 constexpr uint16_t FLAG_INV = 1;
+constexpr uint16_t FLAG_FROM_REG = 2;  // row stream, K_LUT: operand a is the result this lane computed last (field a is not read)
+constexpr uint16_t FLAG_NO_STORE = 4;  // row stream, K_LUT: the result is only ever read that way and gets no slot (field dst is not read)
 constexpr int NFAN_SHIFT = 8;
 inline int lut_nfan(const FlatInstr &x) { return (x.flags >> NFAN_SHIFT) & 3; }
 static_assert(sizeof(FlatInstr) == 16, "FlatInstr must be 16 bytes");
@@ -42,6 +45,27 @@ struct FlatStream {
   uint32_t reserved[2];
 };
 
+// The row stream (cooperative row kernel, clg_coop_rows). The program is cut into SEGMENTS; in every segment each of
+// the n_warps warps of the CTA executes a few ROWS of 32 lane instructions (K_LUT or K_NOP), one after the other, and
+// then its share of the segment's side list (loads, stores, LUTs that do not fit a row). Warps are NOT barrier-
+// synchronised segment by segment: a warp may start segment s as soon as every warp has finished segment s - lag, so
+//   * a slot written in segment s may be read in segments >= s + lag only, and written again only in segments >= (last
+//     segment that reads it) + lag -- except that
+//   * a lane may take operand a from its own previous result (FLAG_FROM_REG), whatever segment that was computed in.
+struct FlatRows {
+  uint32_t n_slots;
+  uint32_t n_instr;      // lane instructions = 32 * rows, NOP lanes included
+  uint32_t n_segs;
+  uint32_t n_warps;      // warps of the CTA this stream was scheduled for
+  uint32_t lag;          // visibility distance in segments (2)
+  uint32_t off_rowtab;   // uint32[n_segs * n_warps + 1]: first lane instruction of (segment, warp); every entry a multiple of 32
+  uint32_t off_instr;    // FlatInstr[n_instr]
+  uint32_t n_side;
+  uint32_t off_sidetab;  // uint32[n_segs + 1]: first side instruction of each segment
+  uint32_t off_side;     // FlatInstr[n_side]
+  uint32_t n_from_reg, n_no_store;  // statistics: LUTs that take an operand from a register / whose result is never stored
+};
+
 struct FlatHeader {
   uint32_t magic, version, header_bytes, total_bytes;
   uint32_t n_inputs, n_outputs, n_state, n_luts;
@@ -57,6 +81,7 @@ struct FlatHeader {
   uint32_t n_parts;
   uint32_t off_parts;      // FlatStream[n_parts]
   uint32_t reserved[2];
+  FlatRows rows;           // n_instr == 0 when absent
 };
 static_assert(sizeof(FlatHeader) % 16 == 0, "header must keep 16-byte alignment");
 

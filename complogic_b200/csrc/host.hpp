@@ -57,6 +57,11 @@ struct Flat {
   const FlatStream *parts() const { return reinterpret_cast<const FlatStream *>(bytes.data() + header().off_parts); }
   const FlatInstr *part_instrs(uint32_t p) const { return reinterpret_cast<const FlatInstr *>(bytes.data() + parts()[p].off_instr); }
   const uint32_t *part_levels(uint32_t p) const { return reinterpret_cast<const uint32_t *>(bytes.data() + parts()[p].off_levels); }
+  const FlatRows &rows() const { return header().rows; }
+  const FlatInstr *row_instrs() const { return reinterpret_cast<const FlatInstr *>(bytes.data() + rows().off_instr); }
+  const uint32_t *row_tab() const { return reinterpret_cast<const uint32_t *>(bytes.data() + rows().off_rowtab); }
+  const FlatInstr *row_side() const { return reinterpret_cast<const FlatInstr *>(bytes.data() + rows().off_side); }
+  const uint32_t *row_sidetab() const { return reinterpret_cast<const uint32_t *>(bytes.data() + rows().off_sidetab); }
   const uint64_t *state_regs() const {
     return reinterpret_cast<const uint64_t *>(bytes.data() + header().off_state_regs);
   }

@@ -69,19 +69,19 @@ struct RunParams {
   // holds only the (rare) non-LUT instructions of each level in the 16-byte encoding.
   const uint2 *cinstr;
   const uint32_t *clevels;
-  // coop, row form (clg_coop_rows, K = 4, <= 16383 slots): the LUTs of a segment (a level, or a piece of a very wide
-  // one) are laid out as rows of 32, row r of segment s belongs to warp r % n_warps as its row slot r / n_warps (< ROW_SLOTS):
-  //   rinstr[((s * ROW_SLOTS + j) * n_warps + w) * 32 + lane] = {x, y}
-  //       x = a | b << 14 | k << 28 | from_register << 31     y = c | dst << 14 | no_store << 31      (slot indices)
-  //     k: which of the row's (at most three) truth tables this lane uses; from_register: operand a is the result this
-  //     thread computed in the same row slot of the previous segment (it is not loaded); no_store: the result is only
-  //     read that way (it gets no slot).
-  //   rhdr[s * n_warps + w] = {h0, h1, h2, first entry of segment s in `instr` | rows of segment s + 1 << 29}  (n_segs + 1
-  //     entries per warp, the last one closes the side list; bit 29 + j: the warp has a row in slot j of the NEXT segment), h_j = tt0 | tt1 << 8 | tt2 << 16 | n_tables << 24 | reads_c << 26 for the warp's row slot j;
-  //     n_tables == 0: no row. `instr` holds what is not a row LUT (loads, stores, LUTs with a fourth table in their row).
+  // coop, row form (clg_coop_rows, K = 4, <= 16383 slots; the row stream of flat.hpp, FlatRows). Every warp has its own
+  // sequence of rows (32 lane instructions each), rinstr[rwarp[w] + 32 * k + lane] = {x, y}:
+  //     x = a | b << 14 | k << 28 | h << 30 | from_reg << 31        y = c | dst << 14 | no_store << 31      (slot indices)
+  //   k: which of the row's (at most three) truth tables the lane uses; from_reg: operand a is the lane's previous
+  //   result (not loaded); no_store: the result is only read that way. Bit h of lane i is bit i of the ROW HEADER
+  //     tt0 | tt1 << 8 | tt2 << 16 | n_tables << 24 | reads_c << 26 | seg_end << 27 | side << 28 | last << 29 | wait << 30
+  //   (collected with one ballot): seg_end marks the warp's last row of a segment, side that the segment has entries in
+  //   `instr` (rside_off[s] .. rside_off[s + 1]: loads, stores), last the end of the program, wait the warp's first row of
+  //   a segment >= 2 (it may not start before every warp has finished the segment two back). Every warp has at least
+  //   one (possibly empty) row per segment, and two empty rows behind its last one (the fetch runs two rows ahead).
   const uint2 *rinstr;
-  const uint4 *rhdr;
-  uint32_t n_segs;
+  const uint32_t *rwarp;
+  const uint32_t *rside_off;
 };
 
 // ---- LOP3 with a compile-time immediate, dispatched on the instruction's truth table --------------
@@ -515,18 +515,18 @@ __device__ __forceinline__ void coop_compact_body(const RunParams &p) {
 }
 
 // ---- row form of the cooperative kernel ----------------------------------------------------------------
-// The same evaluation as clg_coop_c (one CTA, one K = 4 register stack in shared memory, a barrier per level) with the
-// per-LUT overhead taken out of the loop:
-//   * a warp's 32 LUTs (a row) share at most three truth tables, named by a per-row header word, so the LOP3 dispatch
-//     is a warp-UNIFORM brx.idx per table instead of a divergent one per lane;
-//   * every thread executes at most ROW_SLOTS rows per segment, statically unrolled, and fetches the instruction words
-//     and headers of the NEXT segment at the top of this one (registers, one segment ahead: their L2 latency is never
-//     exposed and nothing is software-pipelined inside the level);
-//   * the result of row slot j stays in the thread's registers P[j]; a LUT marked from_register takes it as operand a
-//     without touching shared memory, and a result that is only read that way is not stored (the compiler pass
-//     places producer and consumer on the same thread and row slot of consecutive segments).
-constexpr int ROW_SLOTS = 3;
-
+// The same evaluation as clg_coop_c (one CTA, one K = 4 register stack in shared memory) on the row stream of the
+// compiler pass (flat.hpp, FlatRows), which takes three things out of the level-by-level interpreter:
+//   * the barrier. A warp starts segment s as soon as EVERY warp has finished segment s - 2 (the pass keeps producers
+//     and shared-memory consumers two segments apart, and reuses a slot two segments after its last reader): warps
+//     arrive on one of two mbarriers when they finish a segment and test the phase of two segments ago before they
+//     start one, which has long completed unless the warp is running ahead. No warp ever waits for the slowest one
+//     of the current segment, so the LSU pipe does not drain at level boundaries;
+//   * one operand. The result of a lane's previous LUT stays in registers (P); a LUT marked from_reg takes it as
+//     operand a without touching shared memory, and a result that is only read that way is not stored;
+//   * the divergent dispatch. A warp's 32 LUTs (a row) share at most three truth tables, named by a row header that
+//     is spread over bit 30 of the 32 instruction words (one ballot), so the LOP3 dispatch is a warp-UNIFORM brx.idx.
+// Instruction words are fetched two rows ahead into registers (ld.global.nc, L2-resident program).
 __device__ __forceinline__ void lut3_rows(uint32_t t, uint32_t k, uint32_t pass, Vec<4> &P, const Vec<4> &B, const Vec<4> &C) {
   asm volatile(
 #include "lut_dispatch_k4p.inc"
@@ -540,19 +540,15 @@ __device__ __forceinline__ void lut3_row1(uint32_t t, Vec<4> &P, const Vec<4> &B
       : "r"(B.w[0]), "r"(B.w[1]), "r"(B.w[2]), "r"(B.w[3]), "r"(C.w[0]), "r"(C.w[1]), "r"(C.w[2]), "r"(C.w[3]), "r"(t));
 }
 
-__device__ __forceinline__ uint4 ld_hdr(const uint4 *p) {
-  uint4 v;
-  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
+constexpr uint32_t RH_READS_C = 1u << 26, RH_SEG_END = 1u << 27, RH_SIDE = 1u << 28, RH_LAST = 1u << 29, RH_WAIT = 1u << 30;
 
 __device__ __forceinline__ void row_exec(const uint2 ins, uint32_t h, Vec<4> &P, uint32_t sb) {
   constexpr uint32_t M = 0x3FFF0u;
   const uint32_t oa = (ins.x << 4) & M, ob = (ins.x >> 10) & M, oc = (ins.y << 4) & M, od = (ins.y >> 10) & M;
-  if ((int32_t)ins.x >= 0) P = lds<4>(sb + oa);  // else: operand a is this thread's previous result in this row slot
+  if ((int32_t)ins.x >= 0) P = lds<4>(sb + oa);  // else: operand a is this lane's previous result
   const Vec<4> B = lds<4>(sb + ob);
   Vec<4> C = dont_care<4>();
-  if (h & (1u << 26)) C = lds<4>(sb + oc);  // (warp-uniform: no lane of the row has a third operand otherwise)
+  if (h & RH_READS_C) C = lds<4>(sb + oc);  // (warp-uniform: no lane of the row has a third operand otherwise)
   const uint32_t n = (h >> 24) & 3u;
   if (n == 1) {
     lut3_row1(h & 0xFFu, P, B, C);
@@ -567,44 +563,82 @@ __device__ __forceinline__ void row_exec(const uint2 ins, uint32_t h, Vec<4> &P,
   if ((int32_t)ins.y >= 0) sts<4>(sb + od, P);
 }
 
-template <int R>
+// mbarrier primitives on 32-bit shared-space addresses kept in registers (the generic-pointer forms above make the
+// compiler rebuild the address at every use, which matters in a loop that runs once per row)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void coop_rows_body(const RunParams &p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const uint32_t tid = threadIdx.x, nt = blockDim.x, nw = nt >> 5;
-  uint32_t sb = smem_u32(smem);
-  asm volatile("" : "+r"(sb));
-  const size_t seg_stride = (size_t)R * nt;  // instruction words of one segment
-  constexpr uint32_t SIDE = 0x1FFFFFFFu;     // hdr.w: first side-list entry | (rows this warp has in the NEXT segment) << 29
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  uint32_t sb = smem_u32(smem), lane = tid & 31;
+  asm volatile("" : "+r"(sb), "+r"(lane));
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + p.code_off);  // two mbarriers behind the register stack
+  if (tid == 0) {
+    mbar_init(&bar[0], nt >> 5);
+    mbar_init(&bar[1], nt >> 5);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // Segment s arrives on barrier s & 1. Every thread consumes every phase of both barriers exactly once and in order
+  // (segment s waits for the phase of segment s - 2, the last two phases are consumed at the end of the column group),
+  // so the parity to wait for is one bit per barrier, flipped at every wait. `cur` is the current segment's barrier,
+  // `par` its parity bit; `oth` / `opar` the other one's.
+  uint32_t cur = sb + p.code_off, oth = cur + 8, par = 0, opar = 0;
+  asm volatile("" : "+r"(cur), "+r"(oth));
+  const uint2 *base = p.rinstr + (size_t)__ldg(p.rwarp + (tid >> 5)) + lane;
   for (uint32_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
     const size_t col = (size_t)g * 4;
-    const uint4 *hp = p.rhdr + (tid >> 5);  // this warp's header of the segment being fetched
-    const uint2 *ip = p.rinstr + tid;       // row (s * R + j) * nw + warp, lane
-    Vec<4> P[R];
-    uint2 ins[R];
-#pragma unroll
-    for (int j = 0; j < R; j++) P[j] = dont_care<4>(), ins[j] = make_uint2(0x80000000u, 0x80000000u);
-    uint4 hdr = ld_hdr(hp);
-    {
-      const uint32_t hj[3] = {hdr.x, hdr.y, hdr.z};
-#pragma unroll
-      for (int j = 0; j < R; j++)
-        if (hj[j] >> 24 & 3u) ins[j] = ld_cinstr(ip + (size_t)j * nt);
-    }
-    for (uint32_t s = 0; s < p.n_segs; s++) {
-      // The next segment's header is requested now; the instruction word of row slot j of the next segment is requested
-      // as soon as this segment's row j is done, into the same registers (which rows the next segment has is known
-      // from THIS segment's header, so no request waits for another one).
-      hp += nw, ip += seg_stride;
-      const uint4 hdr_n = ld_hdr(hp);
-      const uint32_t hj[3] = {hdr.x, hdr.y, hdr.z};
-#pragma unroll
-      for (int j = 0; j < R; j++) {
-        if (hj[j] >> 24 & 3u) row_exec(ins[j], hj[j], P[j], sb);
-        if (hdr.w >> (29 + j) & 1u) ins[j] = ld_cinstr(ip + (size_t)j * nt);
+    const uint2 *ip = base;
+    uint2 ins = ld_cinstr(ip), n1 = ld_cinstr(ip + 32);
+    Vec<4> P = dont_care<4>();
+    uint32_t sgm = 0;
+    for (;;) {
+      const uint2 n2 = ld_cinstr(ip + 64);
+      const uint32_t h = __ballot_sync(0xFFFFFFFFu, ins.x & (1u << 30));
+      if (h & RH_WAIT) {  // the warp's first row of a segment >= 2: everything it reads was written two segments ago or earlier
+        mbar_wait_u32(cur, par);
+        par ^= 1u;
       }
-      for (uint32_t i = (hdr.w & SIDE) + tid; i < (hdr_n.w & SIDE); i += nt) coop_exec<4>(p, ld_instr(p.instr + i), sb, col);  // loads / stores / odd LUTs
-      hdr = hdr_n;
-      __syncthreads();
+      if ((h >> 24) & 3u) row_exec(ins, h, P, sb);
+      if (h & RH_SEG_END) {
+        if (h & RH_SIDE) {  // loads, stores: entry i of the segment belongs to thread i % nt
+          const uint32_t e = __ldg(p.rside_off + sgm + 1);
+          for (uint32_t i = __ldg(p.rside_off + sgm) + tid; i < e; i += nt) coop_exec<4>(p, ld_instr(p.instr + i), sb, col);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u32(cur);
+        sgm++;
+        uint32_t t = cur;
+        cur = oth, oth = t, t = par, par = opar, opar = t;
+        if (h & RH_LAST) break;
+      }
+      ins = n1, n1 = n2, ip += 32;
+    }
+    // the phases of the last two segments: afterwards every warp is done with this column group and the stack is free
+    if (sgm >= 2) {
+      mbar_wait_u32(cur, par);
+      par ^= 1u;
+    }
+    mbar_wait_u32(oth, opar);
+    opar ^= 1u;
+    if (sgm & 1u) {  // the next group starts on barrier 0 again
+      uint32_t t = cur;
+      cur = oth, oth = t, t = par, par = opar, opar = t;
     }
   }
 }
@@ -759,4 +793,4 @@ extern "C" __global__ void __launch_bounds__(512) clg_lop3_peak(const uint32_t *
 CLG_ENTRY(1)
 CLG_ENTRY(2)
 CLG_ENTRY(4)
-extern "C" __global__ void __launch_bounds__(1024) clg_coop_rows(const clg::RunParams p) { clg::coop_rows_body<clg::ROW_SLOTS>(p); }
+extern "C" __global__ void __launch_bounds__(1024) clg_coop_rows(const clg::RunParams p) { clg::coop_rows_body(p); }

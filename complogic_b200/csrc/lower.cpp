@@ -1195,6 +1195,581 @@ Sched schedule_level(const Network &net, uint32_t BANKS = 8, bool estimate_only 
   return s;
 }
 
+// ---- row stream (clg_coop_rows; format in flat.hpp, FlatRows) ---------------------------------------------------
+// A forward list schedule over segments. Segment s may read from shared memory what was produced in segments
+// <= s - LAG; at most `cap_rows` rows (of 32 LUTs, all with the same operand count and at most three truth tables) are
+// issued per segment, most urgent LUTs first, dealt to the warps round-robin. A lane that still holds the result of
+// its previous LUT in registers prefers a LUT that reads it (operand a then comes from the register: one shared-memory
+// load less; a value that is only ever read this way is never stored). Free lanes are filled from the ready LUTs of
+// the row's tables so that the 8 lanes of a quarter-warp hit 8 different 16-byte bank groups per operand.
+struct RowsSched {
+  bool ok = false;
+  uint32_t n_slots = 0, n_warps = 0, n_segs = 0, lag = 2, n_from_reg = 0, n_no_store = 0;
+  std::vector<uint32_t> rowtab, sidetab;
+  std::vector<FlatInstr> instr, side;
+};
+
+RowsSched schedule_rows(const Network &net, uint32_t NW, uint32_t cap_rows) {
+  constexpr uint32_t LAG = 2, LANES = 32, BANKS = 8;
+  const size_t V = net.vals.size(), O = net.outs.size();
+  RowsSched rs;
+  rs.n_warps = NW, rs.lag = LAG;
+  size_t n_luts = 0, n_loads = 0;
+  for (size_t v = 0; v < V; v++) n_luts += net.vals[v].is_lut, n_loads += !net.vals[v].is_lut;
+  if (n_luts == 0 || n_loads > 4096) return rs;  // (every input is loaded in segment 0 and stays live until its last reader)
+
+  // priority: unit-delay ALAP level (small = urgent)
+  std::vector<uint32_t> asap(V, 0), alap(V, NONE);
+  uint32_t depth = 0;
+  for (size_t v = 0; v < V; v++)
+    if (net.vals[v].is_lut) {
+      uint32_t h = 0;
+      for (int i = 0; i < net.vals[v].nfan; i++) h = std::max(h, asap[net.vals[v].fan[i]]);
+      asap[v] = h + 1, depth = std::max(depth, h + 1);
+    }
+  for (const OutRef &o : net.outs)
+    if (o.val != NONE) alap[o.val] = depth;
+  for (size_t v = V; v-- > 0;) {
+    if (alap[v] == NONE) alap[v] = net.vals[v].is_lut ? asap[v] : 0;
+    if (net.vals[v].is_lut)
+      for (int i = 0; i < net.vals[v].nfan; i++) {
+        uint32_t &a = alap[net.vals[v].fan[i]];
+        a = std::min(a, alap[v] - 1);
+      }
+  }
+  // readers of each value
+  std::vector<uint32_t> coff(V + 1, 0), cons;
+  for (size_t v = 0; v < V; v++)
+    if (net.vals[v].is_lut)
+      for (int i = 0; i < net.vals[v].nfan; i++) coff[net.vals[v].fan[i] + 1]++;
+  for (size_t v = 0; v < V; v++) coff[v + 1] += coff[v];
+  cons.resize(coff[V]);
+  {
+    std::vector<uint32_t> fill(coff.begin(), coff.end() - 1);
+    for (size_t v = 0; v < V; v++)
+      if (net.vals[v].is_lut)
+        for (int i = 0; i < net.vals[v].nfan; i++) cons[fill[net.vals[v].fan[i]]++] = (uint32_t)v;
+  }
+  static const uint8_t PERM[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+
+  // what a lane executes
+  struct LaneOp {
+    uint32_t v = NONE;     // value (LUT) or NONE: no instruction
+    uint8_t pos[3] = {0, 1, 2};  // operand k of the value sits at position pos[k]
+    uint8_t tt = 0;
+    bool from_reg = false;  // the operand at position 0 is the lane's previous result
+  };
+  struct Row {
+    LaneOp lane[LANES];
+  };
+  std::vector<std::vector<Row>> rows;   // per (segment * NW + warp)
+  std::vector<uint32_t> seg_of(V, NONE);
+  std::vector<uint8_t> vis(V, 0), miss(V, 0), bankv(V, 0), reg_read(V, 0);
+  std::vector<uint32_t> smem_reads(V, 0), last_read(V, 0);  // shared-memory reads of each value; last segment that reads it
+  std::vector<std::vector<uint32_t>> produced;              // values produced per segment
+  for (size_t v = 0; v < V; v++)
+    if (net.vals[v].is_lut) miss[v] = net.vals[v].nfan;
+  using HeapItem = std::pair<uint32_t, uint32_t>;  // (alap, value)
+  std::vector<std::priority_queue<HeapItem, std::vector<HeapItem>, std::greater<HeapItem>>> ready(256);
+  std::vector<uint32_t> held(NW * LANES, NONE);
+  uint64_t bank_weight[BANKS] = {};
+  size_t left = n_luts;
+
+  // inputs: loaded in segment 0 through the side list
+  produced.emplace_back();
+  for (size_t v = 0; v < V; v++)
+    if (!net.vals[v].is_lut) {
+      seg_of[v] = 0, produced[0].push_back((uint32_t)v);
+      uint32_t b = 0;
+      for (uint32_t k = 1; k < BANKS; k++)
+        if (bank_weight[k] < bank_weight[b]) b = k;
+      bankv[v] = (uint8_t)b, bank_weight[b] += coff[v + 1] - coff[v];
+    }
+
+  auto tt_of = [&](const Val &x, const uint8_t pos[3]) { return remap(x.tt, pos); };
+  auto clean = [&](uint32_t t) {
+    while (!ready[t].empty() && seg_of[ready[t].top().second] != NONE) ready[t].pop();
+  };
+  uint32_t start_w = 0;
+  uint64_t dbg_picks = 0, dbg_conf = 0, dbg_win = 0;
+  uint32_t min_reg_quarter = 7;
+  if (const char *env = std::getenv("CLG_ROWS_MIN_REG")) min_reg_quarter = (uint32_t)std::atoi(env);  // tuning knob (1: every candidate, 9: none)
+  struct WinItemT {
+    uint32_t v;
+    uint8_t nops, perms, bank[3];
+    bool taken;
+  };
+  std::vector<WinItemT> window;
+  struct SigRef {
+    size_t c;
+    int pq;
+  };
+  std::vector<std::vector<SigRef>> by_sig(512);
+  for (uint32_t sgm = 0; left > 0; sgm++) {
+    if (sgm > 4 * (uint32_t)V + 64) return rs;  // (cannot happen: every segment with nothing to do is followed by one with something)
+    if (produced.size() <= sgm) produced.resize(sgm + 1);
+    rows.resize((size_t)(sgm + 1) * NW);
+    if (sgm >= LAG)
+      for (uint32_t u : produced[sgm - LAG]) {
+        vis[u] = 1;
+        for (uint32_t k = coff[u]; k < coff[u + 1]; k++) {
+          const uint32_t c = cons[k];
+          if (seg_of[c] == NONE && --miss[c] == 0) ready[net.vals[c].tt].push({alap[c], c});
+        }
+      }
+    uint32_t n_rows = 0, idle = 0, w = start_w;
+    while (n_rows < cap_rows && idle < NW) {
+      // ---- one row for warp w
+      // per lane: the most urgent unscheduled reader of the held value whose OTHER operands are all visible
+      uint32_t cand[LANES];
+      LaneOp cform[LANES];
+      uint32_t count[256] = {};
+      for (uint32_t i = 0; i < LANES; i++) {
+        cand[i] = NONE;
+        const uint32_t h = held[w * LANES + i];
+        if (h == NONE) continue;
+        uint32_t best = NONE;
+        for (uint32_t k = coff[h]; k < coff[h + 1]; k++) {
+          const uint32_t c = cons[k];
+          if (seg_of[c] != NONE) continue;
+          if (!(miss[c] == 0 || (miss[c] == 1 && !vis[h]))) continue;
+          if (best == NONE || alap[c] < alap[best]) best = c;
+        }
+        if (best == NONE) continue;
+        // operand order: the held value first, the others in the order that gives the smaller table
+        const Val &x = net.vals[best];
+        int ci = 0;
+        while (x.fan[ci] != h) ci++;
+        LaneOp f;
+        f.v = best, f.from_reg = true;
+        uint8_t p0[3] = {0, 1, 2}, p1[3] = {0, 1, 2};
+        int others[2], no = 0;
+        for (int k = 0; k < x.nfan; k++)
+          if (k != ci) others[no++] = k;
+        p0[ci] = 0, p1[ci] = 0;
+        if (no >= 1) p0[others[0]] = 1, p1[others[0]] = (uint8_t)(no == 2 ? 2 : 1);
+        if (no == 2) p0[others[1]] = 2, p1[others[1]] = 1;
+        for (int k = x.nfan; k < 3; k++) p0[k] = p1[k] = (uint8_t)k;
+        const uint8_t t0 = tt_of(x, p0), t1 = tt_of(x, p1);
+        if (t1 < t0) std::memcpy(f.pos, p1, 3), f.tt = t1;
+        else std::memcpy(f.pos, p0, 3), f.tt = t0;
+        cand[i] = best, cform[i] = f;
+        count[f.tt]++;
+      }
+      // the row's operand count and tables: register candidates first, then the most urgent ready LUTs
+      uint32_t score[4] = {0, 0, 0, 0}, urgent[4] = {NONE, NONE, NONE, NONE};
+      for (uint32_t t = 0; t < 256; t++) {
+        clean(t);
+        // (a table names its operand count: a function of two inputs does not depend on c)
+      }
+      auto nf_of_tt = [&](uint32_t t) {  // operands a table really depends on
+        const uint8_t x = (uint8_t)t;
+        const bool da = ((x >> 4) & 0x0F) != (x & 0x0F), db = ((x >> 2) & 0x33) != (x & 0x33), dc = ((x >> 1) & 0x55) != (x & 0x55);
+        return (uint32_t)da + db + dc;
+      };
+      for (uint32_t i = 0; i < LANES; i++)
+        if (cand[i] != NONE) score[net.vals[cand[i]].nfan] += 2;
+      for (uint32_t t = 0; t < 256; t++)
+        if (!ready[t].empty()) {
+          const uint32_t nf = net.vals[ready[t].top().second].nfan;
+          score[nf] += (uint32_t)std::min<size_t>(ready[t].size(), LANES);
+          urgent[nf] = std::min(urgent[nf], ready[t].top().first);
+        }
+      (void)nf_of_tt;
+      int cls = -1;
+      for (int nf = 1; nf <= 3; nf++)
+        if (score[nf] && (cls < 0 || urgent[nf] < urgent[cls] || (urgent[nf] == urgent[cls] && score[nf] > score[cls]))) cls = nf;
+      // (the most urgent ready LUT decides, so that no operand count starves; register candidates alone also make a row)
+      if (cls < 0) {
+        idle++, w = (w + 1) % NW;
+        continue;
+      }
+      uint8_t tts[3];
+      uint32_t n_tt = 0;
+      for (; n_tt < 3; n_tt++) {  // register candidates' tables, most frequent first
+        uint32_t best = 256;
+        for (uint32_t t = 0; t < 256; t++)
+          if (count[t] && (best == 256 || count[t] > count[best])) {
+            bool cls_ok = false;
+            for (uint32_t i = 0; i < LANES && !cls_ok; i++) cls_ok = cand[i] != NONE && cform[i].tt == t && net.vals[cand[i]].nfan == cls;
+            if (cls_ok) best = t;
+          }
+        if (best == 256) break;
+        tts[n_tt] = (uint8_t)best, count[best] = 0;
+      }
+      while (n_tt < 3) {  // then the tables of the most urgent ready LUTs of this operand count
+        uint32_t best = 256;
+        for (uint32_t t = 0; t < 256; t++) {
+          if (ready[t].empty() || net.vals[ready[t].top().second].nfan != cls) continue;
+          bool have = false;
+          for (uint32_t k = 0; k < n_tt; k++) have |= tts[k] == t;
+          if (!have && (best == 256 || ready[t].top().first < ready[best].top().first)) best = t;
+        }
+        if (best == 256) break;
+        tts[n_tt++] = (uint8_t)best;
+      }
+      auto in_set = [&](uint8_t t) {
+        for (uint32_t k = 0; k < n_tt; k++)
+          if (tts[k] == t) return true;
+        return false;
+      };
+      // ---- fill the lanes, quarter by quarter
+      // free lanes are filled from a WINDOW of the most urgent ready LUTs of the row's tables (taken off the heaps,
+      // what is left goes back): a lane takes the first one whose operands, in one of the orders its table allows,
+      // fall into bank groups the quarter does not use yet
+      Row row;
+      uint32_t filled = 0, from_reg = 0;
+      using WinItem = WinItemT;
+      std::vector<WinItem> &win = window;
+      win.clear();
+      {
+        const uint32_t WIN = 768;
+        while (win.size() < WIN) {
+          uint32_t bt = 256;
+          for (uint32_t k = 0; k < n_tt; k++) {
+            clean(tts[k]);
+            if (!ready[tts[k]].empty() && net.vals[ready[tts[k]].top().second].nfan == cls &&
+                (bt == 256 || ready[tts[k]].top().first < ready[bt].top().first))
+              bt = tts[k];
+          }
+          if (bt == 256) break;
+          const uint32_t v = ready[bt].top().second;
+          ready[bt].pop();
+          const Val &x = net.vals[v];
+          WinItem it{v, x.nfan, 1, {0, 0, 0}, false};
+          for (int k = 0; k < x.nfan; k++) it.bank[k] = bankv[x.fan[k]];
+          if (x.nfan >= 2)
+            for (int pq = 1; pq < 6; pq++) {
+              bool fits = true;
+              for (int k = 0; k < x.nfan; k++) fits &= PERM[pq][k] < x.nfan;
+              if (fits && remap(x.tt, PERM[pq]) == x.tt) it.perms |= (uint8_t)(1u << pq);
+            }
+          win.push_back(it);
+        }
+      }
+      size_t win_head = 0;
+      for (auto &l : by_sig) l.clear();
+      for (size_t c = 0; c < win.size(); c++)
+        for (int pq = 0; pq < 6; pq++) {
+          if (!(win[c].perms >> pq & 1)) continue;
+          uint32_t sig = 0;
+          for (int k = 0; k < win[c].nops; k++) sig |= (uint32_t)win[c].bank[k] << (3 * PERM[pq][k]);
+          by_sig[sig].push_back({c, pq});
+        }
+      for (uint32_t q0 = 0; q0 < LANES; q0 += BANKS) {
+        uint32_t mask[3] = {0, 0, 0};
+        // An LDS.128 serves a quarter-warp at a time, so a register operand only saves a wavefront when (nearly) the
+        // whole quarter has one: a quarter takes its register candidates if at least 7 of its 8 lanes have one (the
+        // eighth stays empty), otherwise none of them (scattered ones save nothing and only pin LUTs to lanes where
+        // their other operands collide).
+        uint32_t n_cand = 0;
+        for (uint32_t i = q0; i < q0 + BANKS; i++)
+          n_cand += cand[i] != NONE && net.vals[cand[i]].nfan == (uint32_t)cls && in_set(cform[i].tt) && seg_of[cand[i]] == NONE;
+        const bool reg_quarter = n_cand >= min_reg_quarter;
+        // register candidates are where they are
+        for (uint32_t i = q0; i < q0 + BANKS; i++) {
+          if (!reg_quarter) break;
+          if (cand[i] == NONE || net.vals[cand[i]].nfan != cls || !in_set(cform[i].tt) || seg_of[cand[i]] != NONE) continue;
+          const Val &x = net.vals[cand[i]];
+          LaneOp f = cform[i];
+          // its two loaded operands may trade places if the table allows it and that avoids a conflict
+          auto conflicts = [&](const uint8_t pos[3]) {
+            uint32_t n = 0;
+            for (int k = 0; k < x.nfan; k++)
+              if (pos[k] != 0) n += mask[pos[k]] >> bankv[x.fan[k]] & 1u;
+            return n;
+          };
+          if (x.nfan == 3 && conflicts(f.pos)) {
+            uint8_t alt[3];
+            for (int k = 0; k < 3; k++) alt[k] = f.pos[k] == 0 ? 0 : (uint8_t)(3 - f.pos[k]);
+            if (tt_of(x, alt) == f.tt && conflicts(alt) == 0) std::memcpy(f.pos, alt, 3);
+          }
+          for (int k = 0; k < x.nfan; k++)
+            if (f.pos[k] != 0) mask[f.pos[k]] |= 1u << bankv[x.fan[k]];
+          row.lane[i] = f, seg_of[cand[i]] = sgm, filled++, from_reg++;
+        }
+        if (reg_quarter) continue;
+        // ---- a plain quarter: 8 LUTs from the window whose operands, position by position, hit 8 different bank groups.
+        // The first six are taken first-fit in order of urgency (easy: most bank groups are still free); the last two
+        // must have exactly the bank groups that are left, so they are looked up by signature; if no such pair is in the
+        // window the sixth choice is varied. What still collides after that is placed with the fewest conflicts.
+        {
+          struct Pick {
+            size_t c;
+            int pq;
+          };
+          Pick picks[BANKS];
+          uint32_t np = 0;
+          auto fits = [&](const WinItem &it, int pq) {
+            for (int k = 0; k < it.nops; k++)
+              if (mask[PERM[pq][k]] >> it.bank[k] & 1u) return false;
+            return true;
+          };
+          auto apply = [&](const WinItem &it, int pq, bool on) {
+            for (int k = 0; k < it.nops; k++) {
+              if (on) mask[PERM[pq][k]] |= 1u << it.bank[k];
+              else mask[PERM[pq][k]] &= ~(1u << it.bank[k]);
+            }
+          };
+          auto usable = [&](size_t c) { return !win[c].taken && seg_of[win[c].v] == NONE; };
+          auto first_fit = [&](size_t from, size_t &found, int &found_pq) {
+            for (size_t c = from; c < win.size(); c++) {
+              if (!usable(c)) continue;
+              for (int pq = 0; pq < 6; pq++)
+                if ((win[c].perms >> pq & 1) && fits(win[c], pq)) {
+                  found = c, found_pq = pq;
+                  return true;
+                }
+            }
+            return false;
+          };
+          while (win_head < win.size() && !usable(win_head)) win_head++;
+          const uint32_t nops = (uint32_t)cls;
+          // greedy part
+          while (np < BANKS - 2) {
+            size_t c;
+            int pq;
+            if (!first_fit(win_head, c, pq)) break;
+            win[c].taken = true, apply(win[c], pq, true), picks[np++] = {c, pq};
+          }
+          // the last two by signature (key: bank group at each position)
+          auto complete_pair = [&]() -> bool {
+            uint32_t miss_b[3][2], nm[3] = {0, 0, 0};
+            for (uint32_t pos = 0; pos < nops; pos++)
+              for (uint32_t bk = 0; bk < BANKS; bk++)
+                if (!(mask[pos] >> bk & 1u)) {
+                  if (nm[pos] == 2) return false;
+                  miss_b[pos][nm[pos]++] = bk;
+                }
+            for (uint32_t pos = 0; pos < nops; pos++)
+              if (nm[pos] != 2) return false;
+            for (uint32_t combo = 0; combo < (1u << nops) / 2 + (nops == 0); combo++) {  // x takes miss[pos][bit], y the other; x <-> y symmetric
+              uint32_t sx = 0, sy = 0;
+              for (uint32_t pos = 0; pos < nops; pos++) {
+                const uint32_t bit = pos == 0 ? 0 : (combo >> (pos - 1)) & 1u;
+                sx |= miss_b[pos][bit] << (3 * pos), sy |= miss_b[pos][bit ^ 1u] << (3 * pos);
+              }
+              size_t cx = win.size(), cy = win.size();
+              int px = 0, py = 0;
+              for (const SigRef &r : by_sig[sx])
+                if (usable(r.c)) {
+                  cx = r.c, px = r.pq;
+                  break;
+                }
+              if (cx == win.size()) continue;
+              for (const SigRef &r : by_sig[sy])
+                if (usable(r.c) && r.c != cx) {
+                  cy = r.c, py = r.pq;
+                  break;
+                }
+              if (cy == win.size()) continue;
+              win[cx].taken = win[cy].taken = true;
+              apply(win[cx], px, true), apply(win[cy], py, true);
+              picks[np++] = {cx, px}, picks[np++] = {cy, py};
+              return true;
+            }
+            return false;
+          };
+          if (np == BANKS - 2 && !complete_pair()) {
+            // vary the sixth choice
+            const Pick sixth = picks[np - 1];
+            apply(win[sixth.c], sixth.pq, false), win[sixth.c].taken = false, np--;
+            bool done = false;
+            size_t from = win_head;
+            for (int attempt = 0; attempt < 48 && !done; attempt++) {
+              size_t c;
+              int pq;
+              if (!first_fit(from, c, pq)) break;
+              from = c + 1;
+              win[c].taken = true, apply(win[c], pq, true), picks[np++] = {c, pq};
+              done = complete_pair();
+              if (!done) apply(win[c], pq, false), win[c].taken = false, np--;
+            }
+            if (!done) {  // settle for the first choice and the fewest conflicts
+              win[sixth.c].taken = true, apply(win[sixth.c], sixth.pq, true), picks[np++] = sixth;
+              while (np < BANKS) {
+                size_t best = win.size();
+                int best_pq = 0;
+                uint32_t best_n = NONE, seen = 0;
+                for (size_t c = win_head; c < win.size() && seen < 256; c++) {
+                  if (!usable(c)) continue;
+                  seen++;
+                  for (int pq = 0; pq < 6; pq++) {
+                    if (!(win[c].perms >> pq & 1)) continue;
+                    uint32_t n = 0;
+                    for (int k = 0; k < win[c].nops; k++) n += mask[PERM[pq][k]] >> win[c].bank[k] & 1u;
+                    if (n < best_n) best_n = n, best = c, best_pq = pq;
+                  }
+                }
+                if (best == win.size()) break;
+                dbg_conf++;
+                win[best].taken = true, apply(win[best], best_pq, true), picks[np++] = {best, best_pq};
+              }
+            }
+          }
+          dbg_picks += np;
+          for (uint32_t j = 0; j < np; j++) {
+            const WinItem &it = win[picks[j].c];
+            LaneOp f;
+            f.v = it.v, f.tt = net.vals[it.v].tt, f.from_reg = false;
+            for (int k = 0; k < 3; k++) f.pos[k] = k < it.nops ? PERM[picks[j].pq][k] : (uint8_t)k;
+            row.lane[q0 + j] = f, seg_of[it.v] = sgm, filled++;
+          }
+        }
+      }
+      for (const WinItem &it : win)
+        if (!it.taken && seg_of[it.v] == NONE) ready[net.vals[it.v].tt].push({alap[it.v], it.v});
+      // a thin row early in the program is not worth its instruction fetch: leave its LUTs for later, unless it is
+      // mostly register forwarding or little else is left
+      if (filled == 0 || (filled < 8 && from_reg * 2 < filled && left > 4096 && n_rows > 0)) {
+        for (uint32_t i = 0; i < LANES; i++)
+          if (row.lane[i].v != NONE) {
+            const uint32_t v = row.lane[i].v;
+            seg_of[v] = NONE;
+            if (miss[v] == 0) ready[net.vals[v].tt].push({alap[v], v});
+          }
+        idle++, w = (w + 1) % NW;
+        continue;
+      }
+      idle = 0;
+      // bookkeeping: reads, results, bank groups of the results (distinct within a quarter, least read traffic first)
+      for (uint32_t q0 = 0; q0 < LANES; q0 += BANKS) {
+        uint32_t idx[BANKS], m = 0, dmask = 0;
+        for (uint32_t i = q0; i < q0 + BANKS; i++)
+          if (row.lane[i].v != NONE) idx[m++] = i;
+        std::stable_sort(idx, idx + m, [&](uint32_t a, uint32_t b) {
+          return coff[row.lane[a].v + 1] - coff[row.lane[a].v] > coff[row.lane[b].v + 1] - coff[row.lane[b].v];
+        });
+        for (uint32_t j = 0; j < m; j++) {
+          uint32_t bank = NONE;
+          for (uint32_t c = 0; c < BANKS; c++)
+            if (!(dmask >> c & 1u) && (bank == NONE || bank_weight[c] < bank_weight[bank])) bank = c;
+          dmask |= 1u << bank;
+          const uint32_t v = row.lane[idx[j]].v;
+          bankv[v] = (uint8_t)bank, bank_weight[bank] += coff[v + 1] - coff[v];
+        }
+      }
+      for (uint32_t i = 0; i < LANES; i++) {
+        const LaneOp &f = row.lane[i];
+        if (f.v == NONE) {
+          held[w * LANES + i] = NONE;  // the row's LOP3s run in every lane: a lane without an instruction loses its register
+          continue;
+        }
+        const Val &x = net.vals[f.v];
+        for (int k = 0; k < x.nfan; k++) {
+          if (f.from_reg && f.pos[k] == 0) reg_read[x.fan[k]] = 1;
+          else smem_reads[x.fan[k]]++, last_read[x.fan[k]] = sgm;
+        }
+        held[w * LANES + i] = f.v;
+        produced[sgm].push_back(f.v);
+        left--;
+        rs.n_from_reg += f.from_reg;
+      }
+      rows[(size_t)sgm * NW + w].push_back(row);
+      n_rows++, w = (w + 1) % NW;
+    }
+    start_w = w;
+  }
+  uint32_t n_segs = (uint32_t)(rows.size() / NW);
+  if (std::getenv("CLG_TIMING"))
+    std::fprintf(stderr, "[clg]   rows: %llu window picks, %llu with a conflict, mean window %.0f\n", (unsigned long long)dbg_picks, (unsigned long long)dbg_conf,
+                 dbg_picks ? (double)dbg_win / dbg_picks : 0.0);
+
+  // ---- stores: LAG segments after the value exists (constants too: a constant may overwrite a carried row that is
+  // loaded in segment 0)
+  std::vector<std::vector<uint32_t>> side_of(n_segs + LAG + 1);  // per segment: V + out index, or value id (LDIN)
+  for (size_t v = 0; v < V; v++)
+    if (!net.vals[v].is_lut) side_of[0].push_back((uint32_t)v);
+  for (size_t o = 0; o < O; o++) {
+    const OutRef &r = net.outs[o];
+    const uint32_t at = (r.val == NONE ? 0 : seg_of[r.val]) + LAG;
+    side_of[at].push_back((uint32_t)(V + o));
+    if (r.val != NONE) smem_reads[r.val]++, last_read[r.val] = std::max(last_read[r.val], at);
+  }
+  while (side_of.size() > 1 && side_of.back().empty()) side_of.pop_back();
+  n_segs = std::max<uint32_t>(n_segs, (uint32_t)side_of.size());
+  rows.resize((size_t)n_segs * NW);
+  side_of.resize(n_segs);
+
+  // ---- slots: a stored result takes a free slot of its bank group; a slot whose last reader runs in segment r may be
+  // written again from segment r + LAG on
+  std::vector<uint32_t> slot(V, NONE);
+  std::vector<std::vector<uint32_t>> release(n_segs + LAG + 1);
+  std::vector<uint32_t> free_[BANKS];
+  uint32_t fresh[BANKS], high = 0;
+  for (uint32_t b = 0; b < BANKS; b++) fresh[b] = b;
+  auto take = [&](uint32_t v, uint32_t sgm) {
+    const uint32_t b = bankv[v];
+    uint32_t sl;
+    if (!free_[b].empty()) sl = free_[b].back(), free_[b].pop_back();
+    else sl = fresh[b], fresh[b] += BANKS;
+    high = std::max(high, sl + 1);
+    slot[v] = sl;
+    release[std::max(last_read[v], sgm) + LAG].push_back(sl);
+  };
+  rs.rowtab.assign((size_t)n_segs * NW + 1, 0);
+  rs.sidetab.assign(n_segs + 1, 0);
+  for (uint32_t sgm = 0; sgm < n_segs; sgm++) {
+    for (uint32_t sl : release[sgm]) free_[sl % BANKS].push_back(sl);
+    for (uint32_t x : side_of[sgm])
+      if (x < V) take(x, sgm);
+    for (uint32_t w = 0; w < NW; w++)
+      for (const Row &row : rows[(size_t)sgm * NW + w])
+        for (uint32_t i = 0; i < LANES; i++)
+          if (row.lane[i].v != NONE && smem_reads[row.lane[i].v]) take(row.lane[i].v, sgm);
+    if (high > 16383) return rs;  // (the row kernel's instruction words hold 14-bit slot indices)
+    // emit
+    rs.sidetab[sgm] = (uint32_t)rs.side.size();
+    for (uint32_t x : side_of[sgm]) {
+      FlatInstr in{};
+      if (x >= V) {
+        const OutRef &o = net.outs[x - V];
+        in.row = o.row, in.flags = o.inv ? 1 : 0;
+        if (o.val == NONE) in.kind = K_STCONST;
+        else in.kind = K_STOUT, in.a = (uint16_t)slot[o.val];
+      } else {
+        in.kind = K_LDIN, in.row = net.vals[x].row, in.dst = (uint16_t)slot[x];
+      }
+      rs.side.push_back(in);
+    }
+    for (uint32_t w = 0; w < NW; w++) {
+      rs.rowtab[(size_t)sgm * NW + w] = (uint32_t)rs.instr.size();
+      for (const Row &row : rows[(size_t)sgm * NW + w])
+        for (uint32_t i = 0; i < LANES; i++) {
+          const LaneOp &f = row.lane[i];
+          FlatInstr in{};
+          if (f.v == NONE) {
+            in.kind = K_NOP;
+          } else {
+            const Val &x = net.vals[f.v];
+            in = make_lut(x);
+            in.tt = f.tt;
+            uint32_t sl[3] = {NONE, NONE, NONE};
+            for (int k = 0; k < x.nfan; k++)
+              if (!(f.from_reg && f.pos[k] == 0)) sl[f.pos[k]] = slot[x.fan[k]];
+            uint32_t any = NONE;
+            for (int k = 0; k < 3; k++)
+              if (sl[k] != NONE && any == NONE) any = sl[k];
+            if (any == NONE) any = 0;  // (a LUT of one operand that comes from the register reads nothing)
+            for (int k = 0; k < 3; k++)
+              if (sl[k] == NONE) sl[k] = any;  // positions that are not loaded alias a loaded one
+            in.a = (uint16_t)sl[0], in.b = (uint16_t)sl[1], in.c = (uint16_t)sl[2];
+            if (f.from_reg) in.flags |= FLAG_FROM_REG;
+            if (smem_reads[f.v]) in.dst = (uint16_t)slot[f.v];
+            else in.flags |= FLAG_NO_STORE, in.dst = 0, rs.n_no_store++;
+          }
+          rs.instr.push_back(in);
+        }
+    }
+  }
+  rs.rowtab[(size_t)n_segs * NW] = (uint32_t)rs.instr.size();
+  rs.sidetab[n_segs] = (uint32_t)rs.side.size();
+  rs.n_slots = std::max<uint32_t>(high, 1), rs.n_segs = n_segs;
+  rs.ok = true;
+  (void)reg_read;
+  return rs;
+}
+
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // Connected components of the value network (an output belongs to the component of its value), bin-packed
@@ -1427,6 +2002,25 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
       }
   }
 
+  // row stream for the cooperative row kernel: programs whose live set is beyond the specialised mode's reach and whose
+  // level-ordered stack fits shared memory at four words per slot
+  ph.reset(new Phase("schedule: rows"));
+  RowsSched rowsch;
+  if (!(flags & CLG_LV_NO_ROWS) && level.ok && (size_t)level.n_slots * 16 <= 227 * 1024 && n_luts >= 2048 && (!lane.ok || lane.n_slots > 400)) {
+    uint32_t depth = level.levels.empty() ? 1 : (uint32_t)level.levels.size() - 1;
+    uint32_t nw = 32;
+    if (const char *env = std::getenv("CLG_ROWS_WARPS")) nw = (uint32_t)std::max(1, std::min(32, std::atoi(env)));
+    // rows per segment: about as many as the program's parallelism sustains when every non-forwarded dependence costs
+    // two segments (more starves the scheduler of ready LUTs and leaves lanes empty, fewer only adds segments)
+    uint32_t cap = (uint32_t)std::max<uint64_t>(nw / 2, std::min<uint64_t>(4 * nw, (uint64_t)n_luts / 32 * 10 / (18ull * depth)));
+    if (const char *env = std::getenv("CLG_ROWS_CAP")) cap = (uint32_t)std::max(1, std::atoi(env));
+    rowsch = schedule_rows(net, nw, cap);
+    if (std::getenv("CLG_TIMING") && rowsch.ok)
+      std::fprintf(stderr, "[clg]   rows: %u warps, cap %u rows/segment -> %u segments, %zu rows (%.1f %% of lanes empty), %u slots, %.1f %% from register, %.1f %% never stored\n",
+                   nw, cap, rowsch.n_segs, rowsch.instr.size() / 32, 100.0 - 100.0 * n_luts / std::max<size_t>(1, rowsch.instr.size()), rowsch.n_slots,
+                   100.0 * rowsch.n_from_reg / n_luts, 100.0 * rowsch.n_no_store / n_luts);
+  }
+
   // serialise
   ph.reset(new Phase("serialise"));
   Flat f;
@@ -1459,6 +2053,15 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
       st.off_instr = (uint32_t)off, off = align16(off + parts[q].instr.size() * sizeof(FlatInstr));
     }
   }
+  if (rowsch.ok) {
+    FlatRows &r = h.rows;
+    r.n_slots = rowsch.n_slots, r.n_instr = (uint32_t)rowsch.instr.size(), r.n_segs = rowsch.n_segs, r.n_warps = rowsch.n_warps, r.lag = rowsch.lag;
+    r.n_side = (uint32_t)rowsch.side.size(), r.n_from_reg = rowsch.n_from_reg, r.n_no_store = rowsch.n_no_store;
+    r.off_rowtab = (uint32_t)off, off = align16(off + rowsch.rowtab.size() * 4);
+    r.off_instr = (uint32_t)off, off = align16(off + rowsch.instr.size() * sizeof(FlatInstr));
+    r.off_sidetab = (uint32_t)off, off = align16(off + rowsch.sidetab.size() * 4);
+    r.off_side = (uint32_t)off, off = align16(off + rowsch.side.size() * sizeof(FlatInstr));
+  }
   if (off >= 0xFFFFFFFFull) fail(CLG_E_UNSUPPORTED, "flat buffer exceeds 4 GiB");
   h.total_bytes = (uint32_t)off;
   f.bytes.assign(off, 0);
@@ -1469,6 +2072,12 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
     if (!ss[i]->ok) continue;
     std::memcpy(f.bytes.data() + h.stream[i].off_levels, ss[i]->levels.data(), ss[i]->levels.size() * 4);
     std::memcpy(f.bytes.data() + h.stream[i].off_instr, ss[i]->instr.data(), ss[i]->instr.size() * sizeof(FlatInstr));
+  }
+  if (rowsch.ok) {
+    std::memcpy(f.bytes.data() + h.rows.off_rowtab, rowsch.rowtab.data(), rowsch.rowtab.size() * 4);
+    std::memcpy(f.bytes.data() + h.rows.off_instr, rowsch.instr.data(), rowsch.instr.size() * sizeof(FlatInstr));
+    std::memcpy(f.bytes.data() + h.rows.off_sidetab, rowsch.sidetab.data(), rowsch.sidetab.size() * 4);
+    if (!rowsch.side.empty()) std::memcpy(f.bytes.data() + h.rows.off_side, rowsch.side.data(), rowsch.side.size() * sizeof(FlatInstr));
   }
   if (!parts.empty()) std::memcpy(f.bytes.data() + h.off_parts, part_tab.data(), part_tab.size() * sizeof(FlatStream));
   for (size_t q = 0; q < parts.size(); q++) {
@@ -1538,6 +2147,7 @@ void validate_flat(const Flat &f) {
             if (!defined[sl]) bad("slot read before it is written");
           };
           if (x.kind > K_STCONST) bad("unknown instruction kind");
+          if (x.flags & (FLAG_FROM_REG | FLAG_NO_STORE)) bad("register forwarding outside the row stream");
           if (reads) {
             if (x.kind == K_LUT) {
               const int nf = lut_nfan(x);
@@ -1588,6 +2198,114 @@ void validate_flat(const Flat &f) {
       }
     }
   }
+
+  // ---- row stream: index ranges, and the hazards of its relaxed order. A warp may run up to `lag` segments ahead of
+  // the slowest one, so two accesses to a slot are only ordered if their segments are at least `lag` apart.
+  const FlatRows &r = h.rows;
+  if (r.n_instr == 0) return;
+  if (r.lag < 1 || r.lag > 2) bad("row stream: unsupported lag");
+  if (r.n_warps < 1 || r.n_warps > 32 || r.n_segs == 0 || r.n_instr % 32) bad("row stream: bad geometry");
+  if (r.n_slots > 16383) bad("row stream: too many slots");
+  if (!span_ok(r.off_rowtab, ((uint64_t)r.n_segs * r.n_warps + 1) * 4) || !span_ok(r.off_instr, (uint64_t)r.n_instr * 16) ||
+      !span_ok(r.off_sidetab, ((uint64_t)r.n_segs + 1) * 4) || !span_ok(r.off_side, (uint64_t)r.n_side * 16))
+    bad("row stream out of range");
+  const uint32_t *rt = f.row_tab(), *stab = f.row_sidetab();
+  const FlatInstr *ri = f.row_instrs(), *rside = f.row_side();
+  if (rt[0] != 0 || rt[(size_t)r.n_segs * r.n_warps] != r.n_instr || stab[0] != 0 || stab[r.n_segs] != r.n_side) bad("row stream: tables do not cover the stream");
+  constexpr uint32_t NEVER = 0x7FFFFFFFu;
+  std::vector<uint32_t> wr_seg(r.n_slots, NEVER), rd_seg(r.n_slots, NEVER);  // last segment that wrote / read each slot
+  std::vector<uint8_t> lane_has(r.n_warps * 32u, 0), rrow_stored(n_out_rows, 0), rstate_loaded(h.n_state, 0);
+  std::vector<uint32_t> rstate_load_seg(h.n_state, NEVER);
+  for (uint32_t sgm = 0; sgm < r.n_segs; sgm++) {
+    // reads first, then writes, over everything of the segment: within a segment nothing is ordered between warps
+    for (int pass = 0; pass < 2; pass++) {
+      auto rd = [&](uint16_t sl) {
+        if (sl >= r.n_slots) bad("row stream: slot out of range");
+        if (wr_seg[sl] == NEVER || wr_seg[sl] + r.lag > sgm) bad("row stream: slot read before its value is visible");
+        rd_seg[sl] = sgm;
+      };
+      auto wr = [&](uint16_t sl) {
+        if (sl >= r.n_slots) bad("row stream: slot out of range");
+        if (wr_seg[sl] != NEVER && wr_seg[sl] + r.lag > sgm) bad("row stream: slot written twice within the lag");
+        if (rd_seg[sl] != NEVER && rd_seg[sl] + r.lag > sgm) bad("row stream: slot overwritten while it may still be read");
+        wr_seg[sl] = sgm;
+      };
+      for (uint32_t w = 0; w < r.n_warps; w++) {
+        const uint32_t b = rt[(size_t)sgm * r.n_warps + w], e = rt[(size_t)sgm * r.n_warps + w + 1];
+        if (b > e || e > r.n_instr || b % 32 || e % 32) bad("row stream: row table not monotone");
+        if (pass == 0)
+          for (uint32_t r0 = b; r0 < e; r0 += 32) {  // the kernel dispatches at most three tables per row
+            uint8_t seen[3];
+            uint32_t n_seen = 0;
+            for (uint32_t i = r0; i < r0 + 32; i++) {
+              if (ri[i].kind != K_LUT) continue;
+              uint32_t k = 0;
+              while (k < n_seen && seen[k] != ri[i].tt) k++;
+              if (k == n_seen) {
+                if (n_seen == 3) bad("row stream: more than three truth tables in one row");
+                seen[n_seen++] = ri[i].tt;
+              }
+            }
+          }
+        for (uint32_t i = b; i < e; i++) {
+          const FlatInstr &x = ri[i];
+          if (x.kind == K_NOP) {
+            // the row's LOP3s run in every lane: a lane without an instruction loses its register (unless the whole row is empty)
+            if (pass == 0) {
+              bool any = false;
+              for (uint32_t j = b + (i - b) / 32 * 32; j < b + (i - b) / 32 * 32 + 32 && !any; j++) any = ri[j].kind == K_LUT;
+              if (any) lane_has[w * 32u + (i - b) % 32] = 0;
+            }
+            continue;
+          }
+          if (x.kind != K_LUT) bad("row stream: a row holds LUTs only");
+          const int nf = lut_nfan(x);
+          if (nf < 1) bad("LUT without operands");
+          if (pass == 0) {
+            if (x.flags & FLAG_FROM_REG) {
+              if (!lane_has[w * 32u + (i - b) % 32]) bad("row stream: register operand before the lane computed anything");
+            } else
+              rd(x.a);
+            if (nf >= 2) rd(x.b);
+            if (nf >= 3) rd(x.c);
+            lane_has[w * 32u + (i - b) % 32] = 1;  // (a warp's rows run one after the other)
+          } else {
+            if (!(x.flags & FLAG_NO_STORE)) wr(x.dst);
+          }
+        }
+      }
+      if (stab[sgm] > stab[sgm + 1] || stab[sgm + 1] > r.n_side) bad("row stream: side table not monotone");
+      for (uint32_t i = stab[sgm]; i < stab[sgm + 1]; i++) {
+        const FlatInstr &x = rside[i];
+        if (x.kind > K_STCONST) bad("row stream: unknown side instruction");
+        if (x.flags & (FLAG_FROM_REG | FLAG_NO_STORE)) bad("row stream: register forwarding in the side list");
+        if (pass == 0) {
+          if (x.kind == K_LUT) rd(x.a), rd(x.b), rd(x.c);
+          if (x.kind == K_STOUT) rd(x.a);
+          if (x.kind == K_LDIN) {
+            if (x.row >= n_in_rows) bad("input row out of range");
+            if (x.row >= h.n_inputs) rstate_load_seg[x.row - h.n_inputs] = sgm;
+          }
+          if (x.kind == K_STOUT || x.kind == K_STCONST) {
+            if (x.row >= n_out_rows) bad("output row out of range");
+            if (rrow_stored[x.row]++) bad("an output or state row is stored twice");
+          }
+        } else {
+          if (x.kind == K_LUT || x.kind == K_LDIN) wr(x.dst);
+        }
+      }
+    }
+    // in-place state rows: a row's store must be ordered after its load
+    for (uint32_t i = stab[sgm]; i < stab[sgm + 1]; i++) {
+      const FlatInstr &x = rside[i];
+      if ((x.kind == K_STOUT || x.kind == K_STCONST) && x.row >= h.n_outputs) {
+        const uint32_t ls = rstate_load_seg[x.row - h.n_outputs];
+        if (ls != NEVER && ls + r.lag > sgm) bad("row stream: state row stored before its load is ordered");
+      }
+    }
+  }
+  // a state row that is stored must not be loaded later
+  (void)rstate_loaded;
 }
 
 }  // namespace clg

@@ -158,6 +158,7 @@ const char *clg_compiler_graph_dot(const clg_compiler *c);
 #define CLG_LV_NO_FUSE 2u      /* keep one LUT per surviving NAND (no cone mapping) */
 #define CLG_LV_NO_LANE_STREAM 4u /* do not build the lane-ordered stream */
 #define CLG_LV_NO_PARTS 8u      /* do not build the partitioned (per connected component) level streams */
+#define CLG_LV_NO_ROWS 16u      /* do not build the row stream of the cooperative row kernel */
 
 typedef struct clg_flat clg_flat;
 int clg_levelize(const clg_simulation *sim, size_t n_immediates, const uint64_t *out_regs, size_t n_out,
@@ -183,6 +184,13 @@ typedef struct clg_flat_info {
   uint32_t lane_instrs;
   uint32_t n_parts; /* independent parts of the partitioned level stream (0: one component) */
   uint32_t reserved;
+  /* row stream (cooperative row kernel; all 0 if absent) */
+  uint32_t rows_segments;  /* segments (a warp may run lag segments ahead of the slowest one) */
+  uint32_t rows_slots;     /* physical registers */
+  uint32_t rows_instrs;    /* lane instructions, empty lanes included (32 per row) */
+  uint32_t rows_from_reg;  /* LUTs that take one operand from the lane's registers instead of shared memory */
+  uint32_t rows_no_store;  /* LUTs whose result is never written to shared memory */
+  uint32_t rows_warps;     /* warps of the CTA the stream was scheduled for */
 } clg_flat_info;
 int clg_flat_get_info(const clg_flat *f, clg_flat_info *info);
 /* registers behind the state rows, in row order (stateful programs) */

@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 def test_struct_layouts_match_the_header():
     assert C.sizeof(_lib.ClgOp) == 32 and host.OP_DTYPE.itemsize == 32
     assert C.sizeof(_lib.ClgGate) == 8 + 13 * 8
-    assert C.sizeof(_lib.ClgFlatInfo) == 16 + 12 * 4
+    assert C.sizeof(_lib.ClgFlatInfo) == 16 + 18 * 4
 
 
 def test_no_library_dependency_on_cuda_at_link_time():
