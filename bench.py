@@ -246,6 +246,30 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def parity_sample(circ, imm_h, out_h, nv, n_groups=16, seed=12345):
+    """Compare sampled word columns of a benched output with the oracle VM (bit-sliced tier, validated against the
+    scalar VM in tests/): groups of 4 words -- the first, the last, and random ones -- of every output row."""
+    from oracle import oracle
+
+    oracle.build()
+    words = (nv + 31) // 32
+    groups = max(1, words // 4)
+    rng = np.random.default_rng(seed)
+    pick = sorted({0, groups - 1, *[int(x) for x in rng.integers(0, groups, size=max(0, n_groups - 2))]})
+    cols = np.concatenate([np.arange(4 * g, min(words, 4 * g + 4)) for g in pick])
+    sub = np.ascontiguousarray(imm_h[:, cols])
+    n_sub = len(cols) * 32
+    want = oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), sub, n_sub, circ.out_regs)
+    got = np.ascontiguousarray(out_h[:, cols])
+    if cols[-1] == words - 1 and nv % 32:  # lanes past the batch are not defined
+        m = np.uint32((1 << (nv % 32)) - 1)
+        want[:, -1] &= m
+        got[:, -1] &= m
+    bad = int((want != got).sum())
+    return {"words": int(len(cols)), "rows": int(got.shape[0]), "vectors": int(n_sub), "groups": [int(g) for g in pick], "mismatching_words": bad,
+            "ok": bad == 0, "oracle": "oracle.run_batch_sliced (C restatement of simulation.rs:16-30, bit-sliced tier)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -257,7 +281,9 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "lane", "coop", "spec"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time the other BASELINE configs (device-resident only)")
+    ap.add_argument("--extras", action="store_true", help="(default at N=1) also time the other BASELINE configs, device-resident")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs")
+    ap.add_argument("--no-parity-sample", action="store_true", help="skip the oracle check of sampled output columns")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -350,7 +376,7 @@ def main():
     cs = w["cs"]
     ms, clocks = timed_steps(w, args.steps, args.warmup, sample_clocks=True)
     # what the timed launches ran as (the host-buffer e2e leg below works on column chunks and may pick another mode)
-    run_mode, run_k, run_launches = cs.mode_name, cs.words_per_thread, cs.launches_per_run
+    run_mode, run_k, run_launches, run_kernel = cs.mode_name, cs.words_per_thread, cs.launches_per_run, cs.kernel_name
     total_vectors = w["nv"] * world
     value = w["gates"] * total_vectors / (ms * 1e-3)
 
@@ -375,7 +401,7 @@ def main():
     try:  # measured DRAM traffic of this kernel from the committed ncu capture, scaled to this batch size
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f).get(args.workload)
-        if tr and tr["kernel"].startswith("clg_" + run_mode) and run_k == 4:
+        if tr and tr["kernel"] == run_kernel:
             roofline["traffic"] = tr["dram_bytes"] * (w["nv"] / tr["profiled_vectors"])
             roofline["traffic_source"] = f"ncu capture at {tr['profiled_vectors']} vectors, scaled by batch size"
             if "lsu_data_pipe_pct_of_peak" in tr:  # the pipe that actually bounds the shared-memory interpreter
@@ -384,12 +410,14 @@ def main():
     except Exception:
         pass
     roofline.update({
-        "kernel": f"clg_{run_mode}" + (f"_k{run_k}" if run_mode != "spec" else f" (K={run_k})"),
+        "kernel": run_kernel,
         "algorithmic_lane_ops_per_launch": lane_ops, "issued_lop3_lane_ops_per_launch": issued_lane_ops,
         "frac_of_measured_lop3": (lane_ops / per_gpu_s / lop3_measured) if lop3_measured else None,
         "frac_issued_of_nominal_lop3": issued_lane_ops / per_gpu_s / lop3_nominal,
         "hbm_GBps": hbm_achieved, "hbm_frac": hbm_achieved / hbm_peak, "algorithmic_bytes_per_launch": w["io_bytes"],
         "gates_per_io_byte": gates_per_byte,
+        # an interpreter that keeps the register stack in shared memory moves (loads + stores) 16-byte slots through a
+        # 128 B/clk/SM data path (measured: tools/microbench.cu, profiles/r02_microbench_*.txt): LUTs/clk/SM <= 8 / accesses per LUT
         "smem_interpreter_bound_frac": None if run_mode == "spec" else 1.0 / 6.0,
     })
 
@@ -423,31 +451,96 @@ def main():
         barrier()
         e_ms = max_over_ranks(e_ms)
         checksum = int(h_out.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFFFFFF  # the result is really on the host
+        # ---- what was benched is verified: sampled word columns of the e2e output (first, last, random groups of 4
+        # words, every output row) against the oracle VM on the same input columns -- outside the timed region
+        parity = None
+        if rank == 0 and not args.no_parity_sample and not n_state:
+            parity = parity_sample(w["circ"], h_imm.numpy().view(np.uint32), h_out.numpy().view(np.uint32), nv, n_groups=16)
+            if not parity["ok"]:
+                print(json.dumps({"error": "benched output differs from the oracle VM", "parity_sample": parity}), flush=True)
+                raise SystemExit(3)
+        # ---- host-transfer ceiling: the same bytes over PCIe with plain copies and NO kernel, all ranks at once
+        # (H2D and D2H on their own streams, pinned buffers): what any host-buffer API could reach on this box
+        cp_in, cp_out = torch.cuda.Stream(), torch.cuda.Stream()
+        def copy_step():
+            with torch.cuda.stream(cp_in):
+                d_imm.copy_(h_imm, non_blocking=True)
+                if n_state:
+                    w["state"].copy_(h_state, non_blocking=True)
+            with torch.cuda.stream(cp_out):
+                h_out.copy_(d_out, non_blocking=True)
+                if n_state:
+                    h_state.copy_(w["state"], non_blocking=True)
+            cp_in.synchronize()
+            cp_out.synchronize()
+        copy_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copy_step()
+        c_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+        barrier()
+        c_ms = max_over_ranks(c_ms)
         e2e = {"value": w["gates"] * total_vectors / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (n_in + n_state) * stride * 4,
                "d2h_bytes_per_step": (n_out + n_state) * stride * 4, "ms_per_step": e_ms, "steps": e2e_steps,
                "api": "clg_exec_run_host (pinned host buffers; chunked H2D | kernel | D2H pipeline on three streams)",
-               "out_checksum": f"{checksum:016x}", "numa_binding": numa}
+               "out_checksum": f"{checksum:016x}", "numa_binding": numa, "parity_sample": parity,
+               "copy_ceiling": {"ms_per_step": c_ms, "note": "same H2D + D2H bytes with plain pinned-memory copies on two streams, no kernel, "
+                                "all ranks concurrently", "GBps_per_gpu": ((n_in + n_out + 2 * n_state) * stride * 4) / (c_ms * 1e-3) / 1e9},
+               "frac_of_copy_ceiling": c_ms / e_ms, "kernel_ms": ms, "bound": "kernel" if ms > c_ms else "host copies"}
         del h_imm, h_out
 
     main_gates, main_compile_s = w["gates"], w["compile_s"]
     l2_note = ("inputs larger than 2x L2 (no flush needed)" if len(w["bufs"]) == 1
                else f"rotating {len(w['bufs'])} buffer sets, together larger than 3x L2")
+    def config_record(w, ms_x):
+        """One BASELINE config, device-resident: its own roofline (HBM or ISSUED LOP3, whichever is closer to its peak;
+        gate-evals stay counted in reference NANDs, which for fused programs exceeds what is issued -- reported as a note)."""
+        cs_x = w["cs"]
+        nv_total = w["nv"] * world
+        hbm = w["io_bytes"] / (ms_x * 1e-3) / 1e9
+        issued = cs_x.info["n_luts"] * w["nv"] / 32 / (ms_x * 1e-3) / lop3_nominal
+        bound = "hbm" if hbm / hbm_peak >= issued else "lop3-issue"
+        rec = {"ms_per_step": ms_x, "value": w["gates"] * nv_total / (ms_x * 1e-3), "unit": UNIT, "vectors_per_gpu": w["nv"], "total_vectors": nv_total,
+               "mode": cs_x.mode_name, "kernel": cs_x.kernel_name, "K": cs_x.words_per_thread, "launches_per_step": cs_x.launches_per_run,
+               "gates": w["gates"], "n_luts": cs_x.info["n_luts"],
+               "roofline": {"bound": bound, "frac": hbm / hbm_peak if bound == "hbm" else issued,
+                            "achieved": hbm if bound == "hbm" else issued * lop3_nominal / 1e12, "peak": hbm_peak if bound == "hbm" else lop3_nominal / 1e12,
+                            "unit": "GB/s" if bound == "hbm" else "T lane-op/s (LOP3 actually issued)", "hbm_frac": hbm / hbm_peak, "lop3_issued_frac": issued,
+                            "note_nand_equivalent_lop3_frac": w["gates"] * w["nv"] / 32 / (ms_x * 1e-3) / lop3_nominal}}
+        return rec
+
     extras = None
-    if args.extras and rank == 0 and world == 1:
+    strong = None
+    if not args.no_extras and (world > 1 or args.extras or args.workload == "dag1m"):
         extras = {}
-        for name in ("adder32", "mul16", "mul64x12", "latch1500", "dag1m"):
+        if world == 1:
+            # every BASELINE config in the driver's line: configs[1] adder32 x 2^24, configs[2] mul16 x 2^26, the structured
+            # 1M-gate circuit, configs[4] one vector through 128 flattened multipliers, and configs[3] without its locality window
+            plan = [("adder32", None, 20), ("mul16", None, 20), ("mul64x12", None, 5), ("mul64x128", None, 20), ("dag1m_kinf", 22, 5)]
+        else:
+            # configs[2] "at 1/2/4/8 B200": 2^26 vectors in total, sharded over the ranks
+            plan = [("mul16", 26 - int(np.log2(world)), 20)]
+        for name, lg2, steps_x in plan:
             if name == args.workload:
                 continue
             del w
             torch.cuda.empty_cache()
-            w = prepare(name, None)
-            ms_x, _ = timed_steps(w, 10, 3)
-            extras[name] = {"ms_per_step": ms_x, "value": w["gates"] * w["nv"] / (ms_x * 1e-3), "vectors": w["nv"],
-                            "mode": w["cs"].mode_name, "K": w["cs"].words_per_thread, "n_luts": w["cs"].info["n_luts"],
-                            "gates": w["gates"], "hbm_GBps": w["io_bytes"] / (ms_x * 1e-3) / 1e9,
-                            "hbm_frac": w["io_bytes"] / (ms_x * 1e-3) / 1e9 / hbm_peak,
-                            "lop3_frac_algorithmic": w["gates"] * w["nv"] / 32 / (ms_x * 1e-3) / lop3_nominal,
-                            "lop3_frac_issued": w["cs"].info["n_luts"] * w["nv"] / 32 / (ms_x * 1e-3) / lop3_nominal}
+            try:
+                w = prepare(name, lg2)
+                ms_x, _ = timed_steps(w, steps_x, 3)
+                extras[name] = config_record(w, ms_x)
+            except Exception as e:  # a config that cannot run must not take the headline down with it
+                extras[name] = {"error": str(e)[:200]}
+                w = {"bufs": []}
+        if world > 1 and args.workload == "dag1m":
+            # strong scaling of the headline config: 2^24 vectors IN TOTAL, sharded over the ranks (configs[3])
+            del w
+            torch.cuda.empty_cache()
+            w = prepare("dag1m", 24 - int(np.log2(world)))
+            ms_s, _ = timed_steps(w, max(3, args.steps), 3)
+            strong = {"scaling": "strong", "total_vectors": w["nv"] * world, "vectors_per_gpu": w["nv"], "ms_per_step": ms_s,
+                      "value": w["gates"] * w["nv"] * world / (ms_s * 1e-3), "unit": UNIT, "kernel": w["cs"].kernel_name}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -489,6 +582,8 @@ def main():
         }
         if extras:
             line["other_configs"] = extras
+        if strong:
+            line["strong_scaling"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

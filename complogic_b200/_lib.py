@@ -85,6 +85,7 @@ PROTOTYPES = {
     "clg_exec_mode": (i32, [vp]),
     "clg_exec_words_per_thread": (i32, [vp]),
     "clg_exec_launches_per_run": (i32, [vp]),
+    "clg_exec_kernel_name": (C.c_char_p, [vp]),
     "clg_exec_ptx": (C.c_char_p, [vp]),
     "clg_exec_run": (i32, [vp, vp, vp, vp, sz, sz, vp]),
     "clg_exec_run_steps": (i32, [vp, vp, vp, vp, sz, sz, sz, vp]),
@@ -99,6 +100,11 @@ PROTOTYPES = {
     "clg_sim_runner_run": (i32, [vp, vp, sz]),
     "clg_shard_range": (i32, [sz, i32, i32, P(sz), P(sz)]),
     "clg_run_sharded_host": (i32, [vp, i32, P(i32), i32, vp, vp, sz, sz, P(C.c_double)]),
+    "clg_sharded_create": (i32, [vp, i32, P(i32), i32, P(vp)]),
+    "clg_sharded_destroy": (None, [vp]),
+    "clg_sharded_n_devices": (i32, [vp]),
+    "clg_sharded_run_host": (i32, [vp, vp, vp, vp, sz, sz, P(C.c_double)]),
+    "clg_sharded_run_steps_host": (i32, [vp, vp, vp, vp, sz, sz, sz, P(C.c_double)]),
     "clg_simulation_to_json": (i32, [vp, P(vp)]),
     "clg_simulation_from_json": (i32, [C.c_char_p, P(vp)]),
 }

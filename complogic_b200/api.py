@@ -472,6 +472,11 @@ class CudaSimulation:
         return lib().clg_exec_launches_per_run(self._h)
 
     @property
+    def kernel_name(self) -> str:
+        """Name of the kernel the most recent run launched ("" before any run)."""
+        return lib().clg_exec_kernel_name(self._h).decode()
+
+    @property
     def ptx(self) -> str:
         return lib().clg_exec_ptx(self._h).decode()
 
@@ -534,3 +539,41 @@ def run_sharded(flat: FlatProgram, imm: np.ndarray, n_vectors: int, devices: Seq
     secs = (C.c_double * len(devices))()
     check(lib().clg_run_sharded_host(flat._h, mode, dev, len(devices), imm.ctypes.data, out.ctypes.data, n_vectors, stride, secs))
     return out, list(secs)
+
+
+class ShardedSimulation:
+    """clg_sharded_*: the persistent single-process multi-GPU executor. Contexts, executors and staging buffers are made
+    once (one worker thread per device); every run starts the devices together. Stateful programs are allowed."""
+
+    def __init__(self, flat: FlatProgram, devices: Sequence[int], mode: int = MODE_AUTO):
+        self.flat, self.devices = flat, list(devices)
+        dev = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        check(lib().clg_sharded_create(flat._h, mode, dev, len(self.devices), C.byref(h)))
+        self._h = h
+        self.last_seconds: List[float] = []
+
+    def close(self):
+        if self._h:
+            lib().clg_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def run(self, imm: np.ndarray, n_vectors: int, state: Optional[np.ndarray] = None, steps: int = 1) -> np.ndarray:
+        """imm [n_inputs][stride] (steps == 1) or [steps][n_inputs][stride]; state [n_state][stride] is updated in place.
+        Returns out [n_outputs][stride] or [steps][n_outputs][stride]."""
+        imm = np.ascontiguousarray(imm, dtype=np.uint32)
+        stride = imm.shape[-1]
+        n_out = self.flat.info["n_outputs"]
+        out = np.zeros((steps, n_out, stride) if imm.ndim == 3 else (n_out, stride), dtype=np.uint32)
+        secs = (C.c_double * len(self.devices))()
+        sp = state.ctypes.data if state is not None else None
+        if imm.ndim == 3:
+            assert imm.shape[0] == steps
+            check(lib().clg_sharded_run_steps_host(self._h, imm.ctypes.data, out.ctypes.data, sp, n_vectors, stride, steps, secs))
+        else:
+            check(lib().clg_sharded_run_host(self._h, imm.ctypes.data, out.ctypes.data, sp, n_vectors, stride, secs))
+        self.last_seconds = list(secs)
+        return out

@@ -207,6 +207,7 @@ struct Exec {
   int mode;   // mode of the most recent (or, before any run, the preferred) plan
   int last_k = 0, last_parts = 0;
   bool last_rows = false;  // the most recent cooperative run used the row kernel
+  const char *last_kernel = "";
   // shape of the chunked specialised chain (computed on demand, for the mode choice): distinct kernels to assemble, and
   // per launch {instructions, instances side by side}
   struct ChainShape {
@@ -696,6 +697,7 @@ struct Exec {
     uint64_t imm_b = imm_step * 4, out_b = out_step * 4;
     void *args[] = {&imm, &out, &state, &stride32, &g, &steps32, &imm_b, &out_b};
     const uint32_t nt = spec_threads(g);
+    last_kernel = "clg_spec_steps";
     CU(cuLaunchKernel(P.steps_fn, (g + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, args, nullptr));
   }
 
@@ -718,7 +720,7 @@ struct Exec {
     // a batch that gives every SM a column group runs the row stream when the pass built one
     if (mode == CLG_MODE_COOP && !use_parts && has_rows() && (words + 3) / 4 >= (size_t)ctx->sm_count) {
       Plan &R = get_rows();
-      last_k = 4, last_parts = 0, last_rows = true;
+      last_k = 4, last_parts = 0, last_rows = true, last_kernel = "clg_coop_rows";
       launch_rows(R, params(R, imm, out, state, stride, (uint32_t)((words + 3) / 4)), stream);
       return;
     }
@@ -738,6 +740,7 @@ struct Exec {
           CU(cuMemAlloc(&P.scratch, std::max<size_t>(16, (size_t)lane_stream().n_slots * stride * 4)));
           P.scratch_stride = stride;
         }
+        last_kernel = "clg_spec_chunk";
         for (const Plan::ChunkLaunch &c : P.chunks) {
           const uint32_t ntc = spec_threads((uint32_t)std::min<uint64_t>((uint64_t)groups * c.count, 0xFFFFFFFFull));
           CUdeviceptr table = P.d_bases + (size_t)c.first * 16;
@@ -747,6 +750,7 @@ struct Exec {
         return;
       }
       void *args[] = {&imm, &out, &state, &stride32, &g};
+      last_kernel = "clg_spec";
       CU(cuLaunchKernel(P.spec_fn, (groups + nt - 1) / nt, 1, 1, nt, 1, 1, 0, stream, args, nullptr));
       return;
     }
@@ -754,6 +758,8 @@ struct Exec {
       RunParams p = params(P, imm, out, state, stride, groups);
       void *args[] = {&p};
       const uint32_t nc = P.coop_threads, grid = (groups + nc - 1) / nc;
+      static const char *lane_names[3] = {"clg_lane_k1", "clg_lane_k2", "clg_lane_k4"};
+      last_kernel = lane_names[kidx(K)];
       CU(cuLaunchKernel(ctx->lane[kidx(K)], grid, 1, 1, nc + 32, 1, 1, (unsigned)P.smem, stream, args, nullptr));
       return;
     }
@@ -777,6 +783,7 @@ struct Exec {
     ctx->bind();
     const FlatRows &r = flat.rows();
     const uint32_t nw = r.n_warps, S = r.n_segs;
+    if (r.lag != 2) fail(CLG_E_UNSUPPORTED, "row stream: the kernel synchronises two segments back (lag 2)");
     const FlatInstr *src = flat.row_instrs();
     const uint32_t *rt = flat.row_tab(), *stab = flat.row_sidetab();
     P.K = 4, P.n_slots = r.n_slots, P.rows_nt = nw * 32;
@@ -817,6 +824,19 @@ struct Exec {
               y[i] = c | (no_store ? 0u : (uint32_t)in.dst << 14) | (no_store ? 1u << 31 : 0u);
             }
             if (n_tt) hdr = tts[0] | (uint32_t)tts[1] << 8 | (uint32_t)tts[2] << 16 | n_tt << 24 | (reads_c ? 1u << 26 : 0u);
+            // The row's loads run in every lane. A lane without an instruction repeats the b and c addresses of a lane
+            // that has one, in its own quarter-warp if possible: equal addresses are served by the same wavefront, so
+            // the idle lane costs nothing (reading any fixed slot instead would collide with the lane that really
+            // reads that bank group).
+            for (uint32_t q0 = 0; q0 < 32 && n_tt; q0 += 8) {
+              int donor = -1;
+              for (uint32_t i = q0; i < q0 + 8 && donor < 0; i++)
+                if (row[i].kind == K_LUT) donor = (int)i;
+              for (uint32_t i = 0; i < 32 && donor < 0; i++)
+                if (row[i].kind == K_LUT) donor = (int)i;
+              for (uint32_t i = q0; i < q0 + 8; i++)
+                if (row[i].kind != K_LUT) x[i] = EMPTY_X | (x[donor] & (0x3FFFu << 14)), y[i] = EMPTY_Y | (y[donor] & 0x3FFFu);
+            }
           }
           if (q == 0 && sgm >= 2) hdr |= 1u << 30;
           if (q + 1 == n_rows) {
@@ -827,7 +847,7 @@ struct Exec {
           for (uint32_t i = 0; i < 32; i++) words.push_back(x[i] | ((hdr >> i & 1u) << 30)), words.push_back(y[i]);
         }
       }
-      for (uint32_t i = 0; i < 64; i++) words.push_back(EMPTY_X), words.push_back(EMPTY_Y);  // the fetch runs two rows ahead
+      for (uint32_t i = 0; i < 5 * 32; i++) words.push_back(EMPTY_X), words.push_back(EMPTY_Y);  // the fetch runs up to four rows ahead
     }
     if (words.size() / 2 >= (1ull << 32)) fail(CLG_E_UNSUPPORTED, "row stream too long");
     std::vector<uint32_t> side((size_t)std::max<uint32_t>(r.n_side, 1) * 4, 0);
@@ -877,6 +897,8 @@ struct Exec {
     }
     void *args[] = {&p};
     const int k = kidx(P.K);
+    static const char *names[3][3] = {{"clg_coop_res_k1", "clg_coop_res_k2", "clg_coop_res_k4"}, {"clg_coop_c_k1", "clg_coop_c_k2", "clg_coop_c_k4"}, {"clg_coop_k1", "clg_coop_k2", "clg_coop_k4"}};
+    last_kernel = names[P.resident ? 0 : P.d_cinstr ? 1 : 2][k];
     CU(cuLaunchKernel(P.resident ? ctx->coop_res[k] : P.d_cinstr ? ctx->coop_c[k] : ctx->coop[k], grid, 1, 1, nt, 1, 1, (unsigned)P.smem, stream, args, nullptr));
   }
   // Time the cooperative kernel of this plan on scratch buffers (zero inputs: the work does not depend on the data)
@@ -980,6 +1002,7 @@ int exec_k(const Exec *e) { return e->last_k; }
 int exec_launches(const Exec *e) {
   return e->mode == CLG_MODE_SPEC && !e->plan[CLG_MODE_SPEC].chunks.empty() ? (int)e->plan[CLG_MODE_SPEC].chunks.size() : 1;
 }
+const char *exec_kernel_name(const Exec *e) { return e->last_kernel; }
 const std::string &exec_ptx(const Exec *e) { return e->plan[CLG_MODE_SPEC].ptx; }
 const Flat &exec_flat(const Exec *e) { return e->flat; }
 Ctx *exec_ctx(const Exec *e) { return e->ctx; }

@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 #include "device.hpp"
@@ -29,6 +31,7 @@ void exec_destroy(Exec *);
 int exec_mode(const Exec *);
 int exec_k(const Exec *);
 int exec_launches(const Exec *);
+const char *exec_kernel_name(const Exec *);
 const std::string &exec_ptx(const Exec *);
 const Flat &exec_flat(const Exec *);
 Ctx *exec_ctx(const Exec *);
@@ -346,6 +349,7 @@ void clg_exec_destroy(clg_exec *ex) {
 int clg_exec_mode(const clg_exec *ex) { return ex ? exec_mode(ex->e) : 0; }
 int clg_exec_words_per_thread(const clg_exec *ex) { return ex ? exec_k(ex->e) : 0; }
 int clg_exec_launches_per_run(const clg_exec *ex) { return ex ? exec_launches(ex->e) : 0; }
+const char *clg_exec_kernel_name(const clg_exec *ex) { return ex ? exec_kernel_name(ex->e) : ""; }
 const char *clg_exec_ptx(const clg_exec *ex) { return ex ? exec_ptx(ex->e).c_str() : ""; }
 
 int clg_exec_run(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, void *stream) {
@@ -544,6 +548,162 @@ int clg_run_sharded_host(const clg_flat *flat, int mode, const int *devices, int
   for (auto &t : th) t.join();
   for (const Error &e : errs)
     if (e.code != CLG_OK) throw e;
+  CLG_CATCH
+}
+
+// ---- persistent single-process multi-GPU executor -----------------------------------------------------------------
+// One worker thread per device, each with its own context and executor created ONCE: resident programs, assembled
+// kernels, tuned launch shapes and the staging buffers of the host path live across calls. A run posts one job; the
+// workers meet at a start barrier (so the per-device times are comparable and no device idles while another one is still
+// setting up), run their shard of words through the pipelined host-buffer path, and report back.
+struct clg_sharded {
+  Flat flat;
+  int mode = CLG_MODE_AUTO;
+  struct Worker {
+    int device = 0;
+    Ctx *c = nullptr;
+    Exec *e = nullptr;
+    std::thread th;
+  };
+  std::vector<Worker> w;
+  std::mutex m;
+  std::condition_variable cv_job, cv_done, cv_start;
+  uint64_t gen = 0;
+  int pending = 0, at_start = 0;
+  bool quit = false;
+  // the job
+  const uint32_t *imm = nullptr;
+  uint32_t *out = nullptr, *state = nullptr;
+  size_t nv = 0, stride = 0, steps = 1;
+  std::vector<Error> errs;
+  std::vector<double> secs;
+
+  void worker(int d) {
+    uint64_t seen = 0;
+    try {
+      w[d].c = ctx_create(w[d].device);
+      w[d].e = exec_create(w[d].c, flat, mode);
+    } catch (const Error &e) {
+      errs[d] = e;
+    } catch (const std::exception &e) {
+      errs[d] = Error{CLG_E_INVALID, e.what()};
+    }
+    {
+      std::lock_guard<std::mutex> lk(m);
+      pending--;
+    }
+    cv_done.notify_all();
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv_job.wait(lk, [&] { return quit || gen != seen; });
+        if (quit) break;
+        seen = gen;
+        // start barrier: nobody begins before every worker has picked the job up
+        if (++at_start == (int)w.size()) cv_start.notify_all();
+        else cv_start.wait(lk, [&] { return at_start == (int)w.size(); });
+      }
+      try {
+        size_t w0, w1;  // contiguous ranges of 4-word quads: rows stay 16-byte aligned on every shard
+        shard_range(nv, (int)w.size(), d, w0, w1);
+        secs[d] = 0;
+        if (w1 > w0) {
+          const FlatHeader &h = flat.header();
+          const size_t n = std::min(nv, w1 * 32) - w0 * 32;
+          const size_t imm_step = (size_t)h.n_inputs * stride, out_step = (size_t)h.n_outputs * stride;
+          const auto t0 = std::chrono::steady_clock::now();
+          // this device's shard is words [w0, w1) of every row (immediates, outputs and carried state alike): same row
+          // stride, pointers moved by w0; consecutive steps carry the state through the caller's buffer
+          for (size_t st = 0; st < steps; st++)
+            exec_run_host(w[d].e, imm ? imm + st * imm_step + w0 : nullptr, out ? out + st * out_step + w0 : nullptr, state ? state + w0 : nullptr, n, stride);
+          secs[d] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
+      } catch (const Error &e) {
+        errs[d] = e;
+      } catch (const std::exception &e) {
+        errs[d] = Error{CLG_E_INVALID, e.what()};
+      }
+      {
+        std::lock_guard<std::mutex> lk(m);
+        pending--;
+      }
+      cv_done.notify_all();
+    }
+    if (w[d].e) exec_destroy(w[d].e);
+    if (w[d].c) ctx_destroy(w[d].c);
+  }
+  void wait_all() {
+    std::unique_lock<std::mutex> lk(m);
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  void throw_first_error() {
+    for (Error &e : errs)
+      if (e.code != CLG_OK) {
+        Error copy = e;
+        e = Error{CLG_OK, ""};
+        throw copy;
+      }
+  }
+  ~clg_sharded() {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      quit = true;
+    }
+    cv_job.notify_all();
+    for (Worker &x : w)
+      if (x.th.joinable()) x.th.join();
+  }
+};
+
+int clg_sharded_create(const clg_flat *flat, int mode, const int *devices, int n_devices, clg_sharded **out) {
+  CLG_TRY
+  NEED(flat), NEED(devices), NEED(out);
+  if (n_devices < 1 || n_devices > 64) fail(CLG_E_INVALID, "need between 1 and 64 devices");
+  std::unique_ptr<clg_sharded> s(new clg_sharded());
+  s->flat = flat->f, s->mode = mode;
+  s->w.resize(n_devices), s->errs.assign(n_devices, Error{CLG_OK, ""}), s->secs.assign(n_devices, 0.0);
+  s->pending = n_devices;
+  for (int d = 0; d < n_devices; d++) s->w[d].device = devices[d];
+  for (int d = 0; d < n_devices; d++) s->w[d].th = std::thread([p = s.get(), d] { p->worker(d); });
+  s->wait_all();  // contexts and executors exist (or an error is recorded)
+  s->throw_first_error();
+  *out = s.release();
+  CLG_CATCH
+}
+void clg_sharded_destroy(clg_sharded *s) { delete s; }
+int clg_sharded_n_devices(const clg_sharded *s) { return s ? (int)s->w.size() : 0; }
+
+static void sharded_run(clg_sharded *s, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, size_t n_steps,
+                        double *seconds_out) {
+  const FlatHeader &h = s->flat.header();
+  if (stride % 4) fail(CLG_E_INVALID, "stride must be a multiple of 4 words");
+  if ((n_vectors + 31) / 32 > stride) fail(CLG_E_INVALID, "n_vectors does not fit in stride words");
+  if (h.n_inputs && !imm) fail(CLG_E_INVALID, "imm is null");
+  if (h.n_outputs && !out) fail(CLG_E_INVALID, "out is null");
+  if (h.n_state && !state) fail(CLG_E_INVALID, "state is null for a stateful program");
+  {
+    std::lock_guard<std::mutex> lk(s->m);
+    s->imm = imm, s->out = out, s->state = state, s->nv = n_vectors, s->stride = stride, s->steps = n_steps;
+    s->pending = (int)s->w.size(), s->at_start = 0;
+    s->gen++;
+  }
+  s->cv_job.notify_all();
+  s->wait_all();
+  if (seconds_out)
+    for (size_t d = 0; d < s->w.size(); d++) seconds_out[d] = s->secs[d];
+  s->throw_first_error();
+}
+int clg_sharded_run_host(clg_sharded *s, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, double *seconds_out) {
+  CLG_TRY
+  NEED(s);
+  if (n_vectors) sharded_run(s, imm, out, state, n_vectors, stride, 1, seconds_out);
+  CLG_CATCH
+}
+int clg_sharded_run_steps_host(clg_sharded *s, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, size_t n_steps,
+                               double *seconds_out) {
+  CLG_TRY
+  NEED(s);
+  if (n_vectors && n_steps) sharded_run(s, imm, out, state, n_vectors, stride, n_steps, seconds_out);
   CLG_CATCH
 }
 

@@ -582,6 +582,22 @@ __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// the row header: bit 30 of the 32 lanes' first instruction words, collected with one ballot
+__device__ __forceinline__ uint32_t row_header(uint32_t x) {
+  uint32_t h;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t;\n"
+      "and.b32 t, %1, 0x40000000;\n"
+      "setp.ne.u32 p, t, 0;\n"
+      "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+      "}\n"
+      : "=r"(h)
+      : "r"(x));
+  return h;
+}
+
 __device__ __forceinline__ void coop_rows_body(const RunParams &p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t tid = threadIdx.x, nt = blockDim.x;
@@ -594,52 +610,47 @@ __device__ __forceinline__ void coop_rows_body(const RunParams &p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // Segment s arrives on barrier s & 1. Every thread consumes every phase of both barriers exactly once and in order
-  // (segment s waits for the phase of segment s - 2, the last two phases are consumed at the end of the column group),
-  // so the parity to wait for is one bit per barrier, flipped at every wait. `cur` is the current segment's barrier,
-  // `par` its parity bit; `oth` / `opar` the other one's.
-  uint32_t cur = sb + p.code_off, oth = cur + 8, par = 0, opar = 0;
-  asm volatile("" : "+r"(cur), "+r"(oth));
-  const uint2 *base = p.rinstr + (size_t)__ldg(p.rwarp + (tid >> 5)) + lane;
+  // Segment s arrives on barrier s & 1 (`cur`; the two are 8 bytes apart). Every thread consumes every phase of both
+  // barriers exactly once and in order (segment s waits for the phase of segment s - 2, the last two phases are
+  // consumed at the end of the column group), so the parity to wait for alternates per barrier: the k-th wait of a
+  // column group (k = s - 2) wants parity ((k >> 1) ^ start parity of barrier k & 1) & 1 -- kept as a two-bit counter
+  // per barrier pair: `par` holds the parities of (current, other) in bits 0 and 1 and is rotated with the barriers.
+  const uint32_t bar0 = sb + p.code_off;
+  uint32_t cur = bar0, par = 0;
+  asm volatile("" : "+r"(cur));
   for (uint32_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
-    const size_t col = (size_t)g * 4;
-    const uint2 *ip = base;
+    const uint2 *ip = p.rinstr + (size_t)__ldg(p.rwarp + (tid >> 5)) + lane;  // (re-derived per column group: registers are scarce)
     uint2 ins = ld_cinstr(ip), n1 = ld_cinstr(ip + 32);
     Vec<4> P = dont_care<4>();
     uint32_t sgm = 0;
     for (;;) {
-      const uint2 n2 = ld_cinstr(ip + 64);
-      const uint32_t h = __ballot_sync(0xFFFFFFFFu, ins.x & (1u << 30));
+      const uint2 n2 = ld_cinstr(ip + 64);  // instruction words are fetched two rows ahead
+      const uint32_t h = row_header(ins.x);
       if (h & RH_WAIT) {  // the warp's first row of a segment >= 2: everything it reads was written two segments ago or earlier
-        mbar_wait_u32(cur, par);
+        mbar_wait_u32(cur, par & 1u);
         par ^= 1u;
       }
       if ((h >> 24) & 3u) row_exec(ins, h, P, sb);
       if (h & RH_SEG_END) {
         if (h & RH_SIDE) {  // loads, stores: entry i of the segment belongs to thread i % nt
           const uint32_t e = __ldg(p.rside_off + sgm + 1);
-          for (uint32_t i = __ldg(p.rside_off + sgm) + tid; i < e; i += nt) coop_exec<4>(p, ld_instr(p.instr + i), sb, col);
+          for (uint32_t i = __ldg(p.rside_off + sgm) + tid; i < e; i += nt) coop_exec<4>(p, ld_instr(p.instr + i), sb, (size_t)g * 4);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_u32(cur);
-        sgm++;
-        uint32_t t = cur;
-        cur = oth, oth = t, t = par, par = opar, opar = t;
+        sgm++, cur ^= 8u, par = (par >> 1) | (par << 1 & 2u);
         if (h & RH_LAST) break;
       }
       ins = n1, n1 = n2, ip += 32;
     }
     // the phases of the last two segments: afterwards every warp is done with this column group and the stack is free
     if (sgm >= 2) {
-      mbar_wait_u32(cur, par);
+      mbar_wait_u32(cur, par & 1u);
       par ^= 1u;
     }
-    mbar_wait_u32(oth, opar);
-    opar ^= 1u;
-    if (sgm & 1u) {  // the next group starts on barrier 0 again
-      uint32_t t = cur;
-      cur = oth, oth = t, t = par, par = opar, opar = t;
-    }
+    mbar_wait_u32(cur ^ 8u, par >> 1 & 1u);
+    par ^= 2u;
+    if (sgm & 1u) cur ^= 8u, par = (par >> 1) | (par << 1 & 2u);  // the next group starts on barrier 0 again
   }
 }
 

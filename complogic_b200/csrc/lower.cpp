@@ -1423,7 +1423,7 @@ RowsSched schedule_rows(const Network &net, uint32_t NW, uint32_t cap_rows) {
       std::vector<WinItem> &win = window;
       win.clear();
       {
-        const uint32_t WIN = 768;
+        const uint32_t WIN = 1024;
         while (win.size() < WIN) {
           uint32_t bt = 256;
           for (uint32_t k = 0; k < n_tt; k++) {
@@ -1571,21 +1571,39 @@ RowsSched schedule_rows(const Network &net, uint32_t NW, uint32_t cap_rows) {
             return false;
           };
           if (np == BANKS - 2 && !complete_pair()) {
-            // vary the sixth choice
-            const Pick sixth = picks[np - 1];
+            // vary the sixth choice, then the fifth and the sixth
+            const Pick fifth = picks[np - 2], sixth = picks[np - 1];
             apply(win[sixth.c], sixth.pq, false), win[sixth.c].taken = false, np--;
             bool done = false;
-            size_t from = win_head;
-            for (int attempt = 0; attempt < 48 && !done; attempt++) {
-              size_t c;
-              int pq;
-              if (!first_fit(from, c, pq)) break;
-              from = c + 1;
-              win[c].taken = true, apply(win[c], pq, true), picks[np++] = {c, pq};
-              done = complete_pair();
-              if (!done) apply(win[c], pq, false), win[c].taken = false, np--;
+            auto vary_last = [&](int attempts) {
+              size_t from = win_head;
+              for (int attempt = 0; attempt < attempts && !done; attempt++) {
+                size_t c;
+                int pq;
+                if (!first_fit(from, c, pq)) break;
+                from = c + 1;
+                win[c].taken = true, apply(win[c], pq, true), picks[np++] = {c, pq};
+                done = complete_pair();
+                if (!done) apply(win[c], pq, false), win[c].taken = false, np--;
+              }
+            };
+            vary_last(64);
+            if (!done) {
+              apply(win[fifth.c], fifth.pq, false), win[fifth.c].taken = false, np--;
+              size_t from5 = win_head;
+              for (int a5 = 0; a5 < 24 && !done; a5++) {
+                size_t c;
+                int pq;
+                if (!first_fit(from5, c, pq)) break;
+                from5 = c + 1;
+                if (c == fifth.c) continue;
+                win[c].taken = true, apply(win[c], pq, true), picks[np++] = {c, pq};
+                vary_last(24);
+                if (!done) apply(win[c], pq, false), win[c].taken = false, np--;
+              }
+              if (!done) win[fifth.c].taken = true, apply(win[fifth.c], fifth.pq, true), picks[np++] = fifth;
             }
-            if (!done) {  // settle for the first choice and the fewest conflicts
+            if (!done) {  // settle for the first choices and the fewest conflicts
               win[sixth.c].taken = true, apply(win[sixth.c], sixth.pq, true), picks[np++] = sixth;
               while (np < BANKS) {
                 size_t best = win.size();
@@ -2006,9 +2024,12 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
   // level-ordered stack fits shared memory at four words per slot
   ph.reset(new Phase("schedule: rows"));
   RowsSched rowsch;
-  if (!(flags & CLG_LV_NO_ROWS) && level.ok && (size_t)level.n_slots * 16 <= 227 * 1024 && n_luts >= 2048 && (!lane.ok || lane.n_slots > 400)) {
+  const bool rows_forced = std::getenv("CLG_ROWS_FORCE") != nullptr;  // (tests: a row stream for any program)
+  if (!(flags & CLG_LV_NO_ROWS) && level.ok && (size_t)level.n_slots * 16 <= 227 * 1024 &&
+      (rows_forced || (n_luts >= 2048 && (!lane.ok || lane.n_slots > 400)))) {
     uint32_t depth = level.levels.empty() ? 1 : (uint32_t)level.levels.size() - 1;
-    uint32_t nw = 32;
+    // warps of the CTA: enough that a segment of average width gives each of them a row or two
+    uint32_t nw = (uint32_t)std::max<uint64_t>(2, std::min<uint64_t>(32, ((uint64_t)n_luts / depth + 47) / 48));
     if (const char *env = std::getenv("CLG_ROWS_WARPS")) nw = (uint32_t)std::max(1, std::min(32, std::atoi(env)));
     // rows per segment: about as many as the program's parallelism sustains when every non-forwarded dependence costs
     // two segments (more starves the scheduler of ready LUTs and leaves lanes empty, fewer only adds segments)

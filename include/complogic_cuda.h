@@ -247,6 +247,9 @@ int clg_exec_mode(const clg_exec *ex); /* the mode actually chosen */
 int clg_exec_words_per_thread(const clg_exec *ex); /* K: 32-bit words of each row one thread (lane/spec) or CTA (coop) owns */
 /* kernel launches one clg_exec_run issues in the mode last used (1, or the chain length of a chunked specialised program) */
 int clg_exec_launches_per_run(const clg_exec *ex);
+/* name of the kernel the most recent run launched ("clg_coop_rows", "clg_coop_c_k4", "clg_spec", ...; "" before any run);
+ * static storage, do not free */
+const char *clg_exec_kernel_name(const clg_exec *ex);
 /* specialised mode only: generated PTX text (NUL-terminated) for inspection */
 const char *clg_exec_ptx(const clg_exec *ex);
 
@@ -314,6 +317,21 @@ int clg_shard_range(size_t n_vectors, int n_shards, int shard, size_t *w0, size_
 int clg_run_sharded_host(const clg_flat *flat, int mode, const int *devices, int n_devices,
                          const uint32_t *imm, uint32_t *out, size_t n_vectors, size_t stride,
                          double *seconds_out);
+
+/* The same driver, persistent: contexts, executors (resident programs, assembled kernels, tuned launch shapes) and
+ * staging buffers are created once, one worker thread per device, and live across calls; every run starts the devices
+ * together behind a barrier. Stateful programs are allowed: a carried-state row shards by words like any other row.
+ * clg_sharded_run_steps_host runs n_steps consecutive run() calls per lane (imm is [n_steps][n_inputs][stride], out is
+ * [n_steps][n_outputs][stride], state is carried from step to step through the caller's buffer). One caller thread at a
+ * time per clg_sharded. */
+typedef struct clg_sharded clg_sharded;
+int clg_sharded_create(const clg_flat *flat, int mode, const int *devices, int n_devices, clg_sharded **out);
+void clg_sharded_destroy(clg_sharded *s);
+int clg_sharded_n_devices(const clg_sharded *s);
+int clg_sharded_run_host(clg_sharded *s, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors,
+                         size_t stride, double *seconds_out);
+int clg_sharded_run_steps_host(clg_sharded *s, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors,
+                               size_t stride, size_t n_steps, double *seconds_out);
 
 /* serde_json-shaped interchange of `Simulation` (the derives at simulation.rs:5, compile.rs:7):
  * {"ops":[{"Nand":[a,b,out]},{"Set":[id,val]},...],"registers":[false,...]} */

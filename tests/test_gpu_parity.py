@@ -598,6 +598,46 @@ def test_single_process_sharded_driver():
         assert len(secs) == len(devices)
 
 
+def test_persistent_sharded_executor_on_every_visible_device():
+    """clg_sharded_*: contexts / executors / staging buffers live across calls, a start barrier per run, every visible
+    device takes a shard (on a one-GPU box the same device is listed twice, so the shard arithmetic and the concurrent
+    workers are still exercised; the multi-device assertions need more than one GPU). Stateless and stateful programs,
+    single and multi-step runs, repeated calls on the same object."""
+    import torch
+
+    n_dev = torch.cuda.device_count()
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    circ = circuits.array_multiplier(16)
+    fp = host.FlatProgram.levelize(circ.sim, 32, circ.out_regs)
+    sh = host.ShardedSimulation(fp, devices)
+    for nv in (1 << 20, 100003, 33, 1 << 20):  # the same object again and again, batch sizes up and down
+        imm = random_sliced(32, stride_for(nv), seed=nv)
+        out = sh.run(imm, nv)
+        assert np.array_equal(mask_tail(out, nv), oracle_out(circ, imm, nv))
+        assert len(sh.last_seconds) == len(devices)
+        if nv >= 1 << 20:
+            assert all(t > 0 for t in sh.last_seconds)  # every device really had a shard
+    sh.close()
+    if n_dev > 1:  # each device's name / distinctness: the shards ran on different GPUs
+        assert len({host.Context(d).name + str(d) for d in devices}) == n_dev
+    # a sequential circuit: carried registers shard by words like any other row, state travels through the caller's buffer
+    latch = circuits.latch_chain(12)
+    fpl = host.FlatProgram.levelize(latch.sim, 2, latch.out_regs, flags=host.LV_STATEFUL)
+    nv, steps = 4099, 5
+    stride = stride_for(nv)
+    imms = np.stack([random_sliced(2, stride, seed=70 + s_) for s_ in range(steps)])
+    want = oracle.run_batch_sliced(latch.sim, len(latch.sim.registers), imms, nv, latch.out_regs, steps=steps, all_steps=True)
+    shl = host.ShardedSimulation(fpl, devices)
+    state = np.zeros((fpl.info["n_state"], stride), np.uint32)
+    got = shl.run(imms, nv, state=state, steps=steps)  # one call, five steps
+    assert np.array_equal(mask_tail(got, nv), mask_tail(want, nv))
+    state2 = np.zeros_like(state)
+    for s_ in range(steps):  # and step by step on the same object
+        assert np.array_equal(mask_tail(shl.run(imms[s_], nv, state=state2), nv), mask_tail(want[s_], nv))
+    assert np.array_equal(mask_tail(state, nv), mask_tail(state2, nv))
+    shl.close()
+
+
 def test_errors_are_status_codes():
     circ = circuits.ripple_adder(4)
     cs = host.CudaSimulation.from_simulation(circ.sim, 9, circ.out_regs)

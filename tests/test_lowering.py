@@ -362,3 +362,32 @@ def test_constant_store_over_a_carried_row_stays_with_its_load():
         got2 = mask_tail(flat_interp.run(flat, stream, imm, st, rng=np.random.default_rng(3)), nv)
         # X = !S: first run sees S = false -> X = 1 in every lane; second run sees S = true -> X = 0
         assert (got1[0, : nv // 32] == 0xFFFFFFFF).all() and (got2[0, : nv // 32] == 0).all()
+
+
+def _rows_vs_oracle(circ, nv=96):
+    """Row stream of the cooperative row kernel, run with the kernel's semantics (a register per lane, warps up to
+    lag - 1 segments apart) in all three skews against the oracle VM."""
+    fp = host.FlatProgram.levelize(circ.sim, circ.n_immediates, circ.out_regs)
+    flat = flat_interp.Flat(fp.to_bytes())
+    assert flat.rows is not None, "no row stream"
+    imm = random_sliced(circ.n_immediates, stride_for(nv), seed=11)
+    want = mask_tail(oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs), nv)
+    for ahead in (0, 1, 2):
+        got = mask_tail(flat_interp.run_rows(flat, imm, None, ahead=ahead), nv)
+        assert np.array_equal(got, want), f"row stream differs from the VM (skew {ahead})"
+    return fp
+
+
+@pytest.mark.parametrize("shape", [(40, 512, 128, 2, 5), (64, 1024, 256, 2, 3), (30, 300, 64, 0, 9)])
+def test_row_stream_random_dag(shape):
+    fp = _rows_vs_oracle(circuits.random_dag(*shape))
+    info = fp.info
+    assert info["rows_segments"] > 0 and info["rows_instrs"] % 32 == 0 and info["rows_slots"] <= 16383
+
+
+def test_row_stream_forced_on_small_and_structured_programs(monkeypatch):
+    """CLG_ROWS_FORCE builds the row stream for programs the pass would leave to the other modes: adders and
+    multipliers (narrow, deep), flattened instances."""
+    monkeypatch.setenv("CLG_ROWS_FORCE", "1")
+    for circ in (circuits.ripple_adder(8), circuits.array_multiplier(8), circuits.flatten_instances(circuits.array_multiplier(8), 5)):
+        _rows_vs_oracle(circ)

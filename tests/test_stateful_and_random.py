@@ -26,6 +26,11 @@ def run_steps_flat(fp, imm_steps, n_vectors, stream, seed=0):
     return np.stack(outs)
 
 
+@pytest.fixture(autouse=True)
+def _force_row_stream(monkeypatch):
+    monkeypatch.setenv("CLG_ROWS_FORCE", "1")
+
+
 def check_program(ops, n_regs, n_imm, steps, n_vectors, seed, flags=0):
     sim = host.Simulation(ops=ops, registers=[False] * n_regs)
     stride = stride_for(n_vectors)
@@ -36,7 +41,10 @@ def check_program(ops, n_regs, n_imm, steps, n_vectors, seed, flags=0):
     want_sliced = oracle.run_batch_sliced(ops, n_regs, imm, n_vectors, all_regs, steps=steps, all_steps=True)
     assert np.array_equal(mask_tail(want, n_vectors), mask_tail(want_sliced, n_vectors))
     fp = host.FlatProgram.levelize(sim, n_imm, None, flags=host.LV_STATEFUL | flags)
-    for stream in (flat_interp.STREAM_LEVEL, flat_interp.STREAM_LANE):
+    streams = [flat_interp.STREAM_LEVEL, flat_interp.STREAM_LANE]
+    if fp.info["rows_instrs"]:  # (CLG_ROWS_FORCE, set for this module: the row stream of the cooperative row kernel)
+        streams.append(flat_interp.STREAM_ROWS)
+    for stream in streams:
         got = run_steps_flat(fp, imm, n_vectors, stream, seed)
         assert np.array_equal(got, mask_tail(want, n_vectors)), f"stream {stream}"
     if steps == 1:  # stateless build must agree on a fresh simulation
