@@ -107,6 +107,10 @@ PROTOTYPES = {
     "clg_sharded_run_steps_host": (i32, [vp, vp, vp, vp, sz, sz, sz, P(C.c_double)]),
     "clg_simulation_to_json": (i32, [vp, P(vp)]),
     "clg_simulation_from_json": (i32, [C.c_char_p, P(vp)]),
+    "clg_compiler_to_json": (i32, [vp, P(vp)]),
+    "clg_compiler_from_json": (i32, [C.c_char_p, P(vp)]),
+    "clg_gate_to_json": (i32, [P(ClgGate), P(vp)]),
+    "clg_gate_from_json": (i32, [C.c_char_p, P(ClgGate)]),
 }
 
 _lib = None

@@ -92,6 +92,22 @@ class _Gate:
             g.f[i] = getattr(self, f.name)
         return g
 
+    def to_json(self) -> str:
+        """serde_json's text for `Gate` (gates.rs:103-117), e.g. {"And":{"a":0,"b":1,"out":2}}"""
+        g, out = self.to_c(), C.c_void_p()
+        check(lib().clg_gate_to_json(C.byref(g), C.byref(out)))
+        try:
+            return C.cast(out, C.c_char_p).value.decode()
+        finally:
+            lib().clg_free(out)
+
+    @staticmethod
+    def from_json(text: str) -> "_Gate":
+        g = ClgGate()
+        check(lib().clg_gate_from_json(text.encode(), C.byref(g)))
+        cls = _GATE_KINDS[g.kind]
+        return cls(*[int(g.f[i]) for i in range(len(fields(cls)))])
+
     def create(self, incrementer: Incrementer) -> List[Op]:
         """Gate::create(&self, &mut Incrementer) -> Ops (gates.rs:193)."""
         g = self.to_c()
@@ -121,6 +137,7 @@ HalfAdder = _gate("HalfAdder", 9, "a", "b", "s", "c")
 FullAdder = _gate("FullAdder", 10, "a", "b", "cin", "s", "cout")
 FourBitAdder = _gate("FourBitAdder", 11, "a1", "a2", "a3", "a4", "b1", "b2", "b3", "b4", "s1", "s2", "s3", "s4", "cout")
 Gate = _Gate
+_GATE_KINDS = {c.KIND: c for c in (Nand, Not, And, Or, Nor, Xor, RSLatch, RSLatchTest, DLatch, HalfAdder, FullAdder, FourBitAdder)}
 
 
 # ---- device context ------------------------------------------------------------------------------------------
@@ -321,6 +338,24 @@ class Compiler:
 
     def alloc(self) -> int:
         return lib().clg_compiler_alloc(self._h)
+
+    def to_json(self) -> str:
+        """serde_json's text for the derives at compile.rs:18,51: {"immediate_count":..,"ops":[..],"incrementer":{"val":..}}"""
+        out = C.c_void_p()
+        check(lib().clg_compiler_to_json(self._h, C.byref(out)))
+        try:
+            return C.cast(out, C.c_char_p).value.decode()
+        finally:
+            lib().clg_free(out)
+
+    @staticmethod
+    def from_json(text: str) -> "Compiler":
+        h = C.c_void_p()
+        check(lib().clg_compiler_from_json(text.encode(), C.byref(h)))
+        c = Compiler.__new__(Compiler)
+        c._h = h
+        c.incrementer = _IncrementerView(c)
+        return c
 
     def compile(self, gates: Sequence[_Gate]) -> Simulation:
         arr = (ClgGate * max(1, len(gates)))(*[g.to_c() for g in gates])

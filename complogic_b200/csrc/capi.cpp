@@ -732,4 +732,38 @@ int clg_simulation_from_json(const char *json, clg_simulation **out) {
   CLG_CATCH
 }
 
+static char *dup_string(const std::string &s) {
+  char *p = (char *)std::malloc(s.size() + 1);
+  if (!p) throw std::bad_alloc();
+  std::memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+int clg_compiler_to_json(const clg_compiler *c, char **json_out) {
+  CLG_TRY
+  NEED(c), NEED(json_out);
+  *json_out = dup_string(compiler_to_json(c->c));
+  CLG_CATCH
+}
+int clg_compiler_from_json(const char *json, clg_compiler **out) {
+  CLG_TRY
+  NEED(json), NEED(out);
+  Compiler parsed = compiler_from_json(json);
+  auto *c = new clg_compiler(parsed.immediate_count);
+  c->c = std::move(parsed);
+  *out = c;
+  CLG_CATCH
+}
+int clg_gate_to_json(const clg_gate *gate, char **json_out) {
+  CLG_TRY
+  NEED(gate), NEED(json_out);
+  *json_out = dup_string(gate_to_json(*gate));
+  CLG_CATCH
+}
+int clg_gate_from_json(const char *json, clg_gate *out) {
+  CLG_TRY
+  NEED(json), NEED(out);
+  *out = gate_from_json(json);
+  CLG_CATCH
+}
+
 }  // extern "C"

@@ -74,5 +74,9 @@ void validate_flat(const Flat &f);  // throws Error(CLG_E_FORMAT)
 // json.cpp
 std::string simulation_to_json(const Simulation &sim);
 Simulation simulation_from_json(const char *json);
+std::string compiler_to_json(const Compiler &c);
+Compiler compiler_from_json(const char *json);
+std::string gate_to_json(const clg_gate &g);
+clg_gate gate_from_json(const char *json);
 
 }  // namespace clg

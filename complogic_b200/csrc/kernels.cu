@@ -570,12 +570,13 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(1000000u)  // suspend-time hint (ns): the hardware wakes the warp when the phase completes, so a
+                                  // long limit only keeps a warp that is running ahead from re-issuing the test
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {

@@ -337,6 +337,14 @@ int clg_sharded_run_steps_host(clg_sharded *s, const uint32_t *imm, uint32_t *ou
  * {"ops":[{"Nand":[a,b,out]},{"Set":[id,val]},...],"registers":[false,...]} */
 int clg_simulation_to_json(const clg_simulation *sim, char **json_out);
 int clg_simulation_from_json(const char *json, clg_simulation **out);
+/* ... of `Compiler` (compile.rs:51-61; its Incrementer, compile.rs:18-21, as {"val":n}):
+ * {"immediate_count":2,"ops":[...],"incrementer":{"val":3}}
+ * and of `Gate` (gates.rs:5-117), serde's externally tagged enum around the variant's struct:
+ * {"FullAdder":{"a":0,"b":1,"cin":2,"s":3,"cout":4}}. JSON text is returned malloc'ed: free with clg_free. */
+int clg_compiler_to_json(const clg_compiler *c, char **json_out);
+int clg_compiler_from_json(const char *json, clg_compiler **out);
+int clg_gate_to_json(const clg_gate *gate, char **json_out);
+int clg_gate_from_json(const char *json, clg_gate *out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

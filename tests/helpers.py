@@ -54,3 +54,18 @@ def mask_tail(arr: np.ndarray, n_vectors: int) -> np.ndarray:
     if n_vectors & 31:
         arr[..., words - 1] &= np.uint32((1 << (n_vectors & 31)) - 1)
     return arr
+
+
+def sampled_word_columns(n_words: int, k: int = 4, n_ctas: int = 148, extra: int = 24, seed: int = 7) -> np.ndarray:
+    """Word columns to check against the oracle at full size: the first and the last column group (k words each), one
+    group for EVERY residue of the group index modulo the persistent grid (a CTA of a persistent kernel walks the groups
+    g = cta, cta + n_ctas, ...: an indexing error tied to the CTA, the pass number or the tail shows up), and `extra`
+    random ones."""
+    groups = (n_words + k - 1) // k
+    rng = np.random.default_rng(seed)
+    pick = {0, groups - 1}
+    for r in range(min(n_ctas, groups)):
+        pick.add(r + n_ctas * int(rng.integers(0, max(1, (groups - r + n_ctas - 1) // n_ctas))))
+    pick |= {int(x) for x in rng.integers(0, groups, size=extra)}
+    cols = np.concatenate([np.arange(k * g, min(n_words, k * g + k)) for g in sorted(pick)])
+    return cols

@@ -11,7 +11,7 @@ import complogic_b200 as host
 from complogic_b200 import circuits
 from oracle import oracle
 from tests.test_spec_ptx import feedback_dag
-from tests.helpers import exhaustive_sliced, mask_tail, random_sliced, stride_for, unslice_int
+from tests.helpers import sampled_word_columns, exhaustive_sliced, mask_tail, random_sliced, stride_for, unslice_int
 
 pytestmark = pytest.mark.gpu
 
@@ -282,7 +282,7 @@ def programs(draw):
     return ops, n_regs, draw(st.integers(0, n_regs + 1)), draw(st.sampled_from(MODES))
 
 
-@settings(max_examples=int(__import__("os").environ.get("CLG_HYPOTHESIS_EXAMPLES", "60")), deadline=None,
+@settings(max_examples=int(__import__("os").environ.get("CLG_HYPOTHESIS_EXAMPLES", "300")), deadline=None,
           suppress_health_check=[HealthCheck.too_slow])
 @given(programs(), st.integers(0, 2 ** 31))
 def test_random_programs(prog, seed):
@@ -300,7 +300,7 @@ def test_random_programs(prog, seed):
         assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv))
 
 
-@settings(max_examples=int(__import__("os").environ.get("CLG_HYPOTHESIS_EXAMPLES", "40")), deadline=None,
+@settings(max_examples=int(__import__("os").environ.get("CLG_HYPOTHESIS_EXAMPLES", "300")), deadline=None,
           suppress_health_check=[HealthCheck.too_slow])
 @given(programs(), st.integers(0, 2 ** 31), st.integers(2, 9))
 def test_random_programs_in_tiny_spec_chunks(prog, seed, chunk):
@@ -328,7 +328,7 @@ def test_random_programs_in_tiny_spec_chunks(prog, seed, chunk):
             os.environ["CLG_SPEC_CHUNK"] = old
 
 
-@settings(max_examples=int(__import__("os").environ.get("CLG_HYPOTHESIS_EXAMPLES", "40")), deadline=None,
+@settings(max_examples=int(__import__("os").environ.get("CLG_HYPOTHESIS_EXAMPLES", "300")), deadline=None,
           suppress_health_check=[HealthCheck.too_slow])
 @given(programs(), st.integers(0, 2 ** 31))
 def test_random_programs_streaming_cooperative_kernel(prog, seed):
@@ -448,27 +448,59 @@ def test_full_size_adder32_2p24():
     assert np.array_equal(unslice_int(out_h[:, sample], n), a + b + cin)
 
 
-def test_full_size_dag_1m_2p24_periodic_inputs():
-    """BASELINE config 4 at full size: the 1 048 576-gate DAG on 2^24 lanes. The inputs repeat with a period of 2^12
-    lanes, so every one of the 4096 blocks of output words must equal the first, and the first must equal the
-    oracle: all column groups of all CTAs are checked, not a prefix."""
+def _device_random(ctx, n_rows, stride, seed):
+    import torch
+    t = torch.empty((n_rows, stride), dtype=torch.int32, device="cuda:0")
+    ctx.fill_random(t.data_ptr(), n_rows, stride, seed, 0)
+    return t
+
+
+def _check_sampled_columns(circ, imm_dev, out_dev, nv, k=4):
+    """Full-size check without periodic inputs: sampled word columns (first, last, every CTA residue, random) of a
+    device-resident run against the oracle VM on the same input columns."""
+    import torch
+    cols = sampled_word_columns((nv + 31) // 32, k=k)
+    idx = torch.from_numpy(cols.astype(np.int64)).cuda()
+    imm_h = imm_dev.index_select(1, idx).cpu().numpy().view(np.uint32)
+    out_h = out_dev.index_select(1, idx).cpu().numpy().view(np.uint32)
+    want = oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), np.ascontiguousarray(imm_h), len(cols) * 32, circ.out_regs)
+    if nv % 32 and cols[-1] == (nv + 31) // 32 - 1:
+        m = np.uint32((1 << (nv % 32)) - 1)
+        want[:, -1] &= m
+        out_h[:, -1] &= m
+    assert np.array_equal(out_h, want)
+    return len(cols)
+
+
+def test_full_size_dag_1m_2p24():
+    """BASELINE config 4 at full size: the 1 048 576-gate DAG on 2^24 lanes of NON-periodic random inputs (generated on
+    the device, reproducible on the host); ~190 sampled column groups -- the first, the last, one for every residue of
+    the persistent grid, random ones -- of all 4096 output rows against the oracle VM. Runs the row kernel."""
     import torch
 
     circ = circuits.random_dag()
-    nv, period = 1 << 24, 1 << 12
-    stride, pw = stride_for(nv), period // 32
-    block = random_sliced(1024, pw, seed=0xD4A)
-    cs = host.CudaSimulation.from_simulation(circ.sim, 1024, circ.out_regs)
-    imm = torch.from_numpy(block.view(np.int32)).cuda().repeat(1, stride // pw).contiguous()
+    nv = 1 << 24
+    stride = stride_for(nv)
+    ctx = host.Context.default()
+    cs = host.CudaSimulation.from_simulation(circ.sim, 1024, circ.out_regs, ctx=ctx)
+    imm = _device_random(ctx, 1024, stride, 0xD4A)
     out = torch.zeros((4096, stride), dtype=torch.int32, device="cuda:0")
     cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
     torch.cuda.synchronize()
-    assert cs.mode == host.MODE_COOP
-    blocks = out.view(4096, stride // pw, pw)
-    assert bool((blocks == blocks[:, :1, :]).all())
-    first = blocks[:, 0, :].contiguous().cpu().numpy().view(np.uint32)
-    del imm, out, blocks
-    assert np.array_equal(first, oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), block, period, circ.out_regs))
+    assert cs.mode == host.MODE_COOP and cs.kernel_name == "clg_coop_rows"
+    assert _check_sampled_columns(circ, imm, out, nv) >= 4 * 150
+    # the previous generation of the cooperative kernel on the same inputs: identical buffers, word for word
+    import os
+    os.environ["CLG_COOP_NO_ROWS"] = "1"
+    try:
+        old = host.CudaSimulation.from_simulation(circ.sim, 1024, circ.out_regs, ctx=ctx, mode=host.MODE_COOP)
+        out2 = torch.zeros_like(out)
+        old.run_device(imm.data_ptr(), out2.data_ptr(), nv, stride)
+        torch.cuda.synchronize()
+        assert old.kernel_name.startswith("clg_coop_c")
+        assert bool((out == out2).all())
+    finally:
+        del os.environ["CLG_COOP_NO_ROWS"]
 
 
 def test_full_size_structured_1m_gate_circuit_2p24():
@@ -503,26 +535,34 @@ def test_full_size_structured_1m_gate_circuit_2p24():
     assert np.array_equal(got, want)
 
 
-def test_full_size_mul16_2p26_periodic_inputs():
-    """BASELINE config 3 at full size (2^26 lanes): inputs repeat every 2^16 lanes, so each of the 1024 output blocks
-    must equal the first, which must be a * b lane for lane."""
+def test_full_size_mul16_2p26():
+    """BASELINE config 3 at full size (2^26 lanes), non-periodic device-generated inputs: sampled column groups (first,
+    last, every residue of a 148-CTA grid, random) against a * b and against the oracle VM, and a checksum over the whole
+    buffer against a second run in another mode."""
     import torch
 
     circ = circuits.array_multiplier(16)
-    nv, period = 1 << 26, 1 << 16
-    stride, pw = stride_for(nv), period // 32
-    block = random_sliced(32, pw, seed=0x316)
-    cs = host.CudaSimulation.from_simulation(circ.sim, 32, circ.out_regs)
-    imm = torch.from_numpy(block.view(np.int32)).cuda().repeat(1, stride // pw).contiguous()
+    nv = 1 << 26
+    stride = stride_for(nv)
+    ctx = host.Context.default()
+    cs = host.CudaSimulation.from_simulation(circ.sim, 32, circ.out_regs, ctx=ctx)
+    imm = _device_random(ctx, 32, stride, 0x316)
     out = torch.zeros((32, stride), dtype=torch.int32, device="cuda:0")
     cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
     torch.cuda.synchronize()
     assert cs.mode == host.MODE_SPEC
-    blocks = out.view(32, stride // pw, pw)
-    assert bool((blocks == blocks[:, :1, :]).all())
-    first = blocks[:, 0, :].contiguous().cpu().numpy().view(np.uint32)
-    a, b = unslice_int(block[:16], period), unslice_int(block[16:], period)
-    assert np.array_equal(unslice_int(first, period), a * b)
+    _check_sampled_columns(circ, imm, out, nv, k=cs.words_per_thread)
+    cols = sampled_word_columns(nv // 32, k=cs.words_per_thread)
+    idx = torch.from_numpy(cols.astype(np.int64)).cuda()
+    imm_h = imm.index_select(1, idx).cpu().numpy().view(np.uint32)
+    out_h = out.index_select(1, idx).cpu().numpy().view(np.uint32)
+    n = len(cols) * 32
+    assert np.array_equal(unslice_int(out_h, n), unslice_int(imm_h[:16], n) * unslice_int(imm_h[16:], n))
+    lane = host.CudaSimulation.from_simulation(circ.sim, 32, circ.out_regs, ctx=ctx, mode=host.MODE_LANE)
+    out2 = torch.zeros_like(out)
+    lane.run_device(imm.data_ptr(), out2.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    assert bool((out == out2).all())
 
 
 def test_modes_agree_at_scale_mul16():
@@ -636,6 +676,94 @@ def test_persistent_sharded_executor_on_every_visible_device():
         assert np.array_equal(mask_tail(shl.run(imms[s_], nv, state=state2), nv), mask_tail(want[s_], nv))
     assert np.array_equal(mask_tail(state, nv), mask_tail(state2, nv))
     shl.close()
+
+
+def test_row_kernel_on_dags_and_forced_programs(monkeypatch):
+    """clg_coop_rows (row stream: lag-2 segments, no CTA barrier): random DAGs of several shapes, and -- with
+    CLG_ROWS_FORCE -- structured and sequential programs the pass would otherwise leave to the other modes, on batches
+    that give every SM a column group, word for word against the oracle VM."""
+    for shape, nv in (((64, 1024, 256, 2, 3), 1 << 16), ((40, 512, 128, 2, 5), 40000), ((30, 300, 64, 0, 9), 19001)):
+        circ = circuits.random_dag(*shape)
+        imm = random_sliced(circ.n_immediates, stride_for(nv), seed=4)
+        cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, mode=host.MODE_COOP)
+        got = mask_tail(cs.run_batch(imm, nv), nv)
+        assert cs.kernel_name == "clg_coop_rows" and cs.info["rows_segments"] > 0
+        assert np.array_equal(got, oracle_out(circ, imm, nv))
+        small = mask_tail(cs.run_batch(imm[:, :8], 200), 200)  # a batch too small for it goes to the older kernels
+        assert cs.kernel_name != "clg_coop_rows"
+        assert np.array_equal(small, oracle_out(circ, np.ascontiguousarray(imm[:, :8]), 200))
+    monkeypatch.setenv("CLG_ROWS_FORCE", "1")
+    nv = 19000
+    for circ in (circuits.array_multiplier(8), circuits.ripple_adder(16), circuits.flatten_instances(circuits.array_multiplier(8), 3)):
+        imm = random_sliced(circ.n_immediates, stride_for(nv), seed=5)
+        cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, mode=host.MODE_COOP)
+        got = mask_tail(cs.run_batch(imm, nv), nv)
+        assert cs.kernel_name == "clg_coop_rows"
+        assert np.array_equal(got, oracle_out(circ, imm, nv))
+    # a sequential circuit: carried registers through the row kernel, several steps
+    latch = circuits.latch_chain(10)
+    steps, stride = 4, stride_for(nv)
+    imms = np.stack([random_sliced(2, stride, seed=90 + s_) for s_ in range(steps)])
+    want = oracle.run_batch_sliced(latch.sim, len(latch.sim.registers), imms, nv, latch.out_regs, steps=steps, all_steps=True)
+    cs = host.CudaSimulation.from_simulation(latch.sim, 2, latch.out_regs, flags=host.LV_STATEFUL, mode=host.MODE_COOP)
+    state = np.zeros((cs.info["n_state"], stride), np.uint32)
+    for s_ in range(steps):
+        got = cs.run_batch(imms[s_], nv, state=state)
+        assert cs.kernel_name == "clg_coop_rows"
+        assert np.array_equal(mask_tail(got, nv), mask_tail(want[s_], nv))
+
+
+@settings(max_examples=int(__import__("os").environ.get("CLG_HYPOTHESIS_EXAMPLES", "300")), deadline=None,
+          suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(programs(), st.integers(0, 2 ** 31))
+def test_random_programs_row_kernel(prog, seed):
+    """Arbitrary stateful programs (multi-writer, read-before-write, short immediates) through the row kernel."""
+    import os
+    ops, n_regs, n_imm, _ = prog
+    sim = host.Simulation(ops=ops, registers=[False] * n_regs)
+    nv, steps = 19000, 2
+    stride = stride_for(nv)
+    imm = np.stack([random_sliced(n_imm, stride, seed + s) for s in range(steps)]) if n_imm else \
+        np.zeros((steps, 0, stride), np.uint32)
+    want = oracle.run_batch_sliced(ops, n_regs, imm, nv, list(range(n_regs)), steps=steps, all_steps=True)
+    os.environ["CLG_ROWS_FORCE"] = "1"
+    try:
+        cs = host.CudaSimulation.from_simulation(sim, n_imm, None, flags=host.LV_STATEFUL, mode=host.MODE_COOP)
+        state = np.zeros((cs.info["n_state"], stride), np.uint32)
+        for s in range(steps):
+            got = cs.run_batch(imm[s], nv, state=state)
+            assert cs.info["rows_instrs"] == 0 or cs.kernel_name == "clg_coop_rows"
+            assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv))
+    finally:
+        del os.environ["CLG_ROWS_FORCE"]
+
+
+def test_json_imported_program_runs_on_the_device():
+    """f3: a program that arrives as serde_json text (Simulation, and Compiler + gates) is levelized and evaluated on the
+    GPU, bit for bit like the oracle VM on the original."""
+    circ = circuits.array_multiplier(8)
+    sim2 = host.Simulation.from_json(circ.sim.to_json())
+    assert sim2.ops == circ.sim.ops and len(sim2.registers) == len(circ.sim.registers)
+    nv = 5000
+    imm = random_sliced(16, stride_for(nv), seed=21)
+    want = oracle_out(circ, imm, nv)
+    for mode in MODES:
+        cs = host.CudaSimulation.from_simulation(sim2, 16, circ.out_regs, mode=mode)
+        assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), want)
+    # the front end through JSON as well: compiler state and gate list, then compile + run
+    c = host.Compiler(3)
+    s_, k_ = c.alloc(), c.alloc()
+    gates = [host.FullAdder(0, 1, 2, s_, k_)]
+    c2 = host.Compiler.from_json(c.to_json())
+    g2 = [host.Gate.from_json(g.to_json()) for g in gates]
+    sim3 = c2.compile(g2)
+    assert sim3.ops == c.compile(gates).ops
+    cs = host.CudaSimulation.from_simulation(sim3, 3, [s_, k_])
+    imm = exhaustive_sliced(3)
+    got = cs.run_batch(imm, 8)
+    v = np.arange(8)
+    total = (v & 1) + (v >> 1 & 1) + (v >> 2 & 1)
+    assert list(unslice_int(got, 8)) == [int(t & 1) | int(t >> 1) << 1 for t in total]
 
 
 def test_errors_are_status_codes():

@@ -391,3 +391,30 @@ def test_row_stream_forced_on_small_and_structured_programs(monkeypatch):
     monkeypatch.setenv("CLG_ROWS_FORCE", "1")
     for circ in (circuits.ripple_adder(8), circuits.array_multiplier(8), circuits.flatten_instances(circuits.array_multiplier(8), 5)):
         _rows_vs_oracle(circ)
+
+
+def test_compiler_and_gate_json_in_serdes_shape():
+    """f3: Compiler / Incrementer / Gate as serde_json writes the derives at compile.rs:18,51 and gates.rs:5-117
+    (struct = object of its fields in declaration order, Gate = externally tagged enum)."""
+    c = host.Compiler(2)
+    q = c.alloc()
+    text = c.to_json()
+    assert text == '{"immediate_count":2,"ops":[],"incrementer":{"val":3}}'
+    sim = c.compile([host.And(0, 1, q)])
+    text = c.to_json()  # compile() leaves its op list in the public `ops` field (compile.rs:94-108)
+    assert text.startswith('{"immediate_count":2,"ops":[{"Set":[0,false]},{"Set":[1,false]},{"Nand":[0,1,3]},{"Nand":[3,3,2]}]')
+    again = host.Compiler.from_json(text)
+    assert again.immediate_count == 2 and again.incrementer.val == 3 and again.ops == c.ops
+    assert again.compile([host.And(0, 1, q)]).ops == sim.ops
+    assert host.Compiler.from_json(' { "incrementer" : {"val": 9}, "ops": [], "immediate_count": 4 } ').alloc() == 9  # any field order
+    gates = [host.Nand(0, 1, 2), host.Not(3, 4), host.Xor(1, 2, 3), host.RSLatch(0, 1, 2), host.DLatch(5, 6, 7), host.HalfAdder(0, 1, 2, 3),
+             host.FullAdder(0, 1, 2, 3, 4), host.FourBitAdder(*range(13))]
+    assert gates[6].to_json() == '{"FullAdder":{"a":0,"b":1,"cin":2,"s":3,"cout":4}}'
+    assert gates[3].to_json() == '{"RSLatch":{"s":0,"r":1,"q":2}}'
+    for g in gates:
+        back = host.Gate.from_json(g.to_json())
+        assert back == g and type(back) is type(g)
+    assert host.Gate.from_json('{"Or":{"out":7,"a":1,"b":2}}') == host.Or(1, 2, 7)
+    for bad in ('{"Nope":{"a":1}}', '{"And":{"a":1,"b":2}}', '{"And":{"a":1,"b":2,"out":3,"x":4}}', '{"immediate_count":1}', ''):
+        with pytest.raises(host.ClgError):
+            (host.Compiler.from_json if "immediate" in bad else host.Gate.from_json)(bad)
