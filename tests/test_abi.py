@@ -189,3 +189,25 @@ def test_product_never_touches_the_oracle():
     for pos in uses:  # each use sits inside a CPU-baseline / reference-arm block
         context = bench[max(0, pos - 1500):pos]
         assert "cpu" in context.lower() or "reference" in context.lower()
+
+
+def test_rust_ffi_is_generated_from_the_header():
+    """complogic-cuda/src/ffi.rs cannot be compiled here (no rustc), so it is GENERATED from include/complogic_cuda.h
+    (tools/gen_ffi.py) and checked: the committed text is what the generator produces from the current header, it declares
+    exactly the functions the header declares and the ctypes table binds, with the same number of arguments, and every
+    `clg_*` function the safe wrapper (lib.rs) calls is declared."""
+    import subprocess
+    import sys
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_ffi.py"), "--check"]).returncode == 0, \
+        "complogic-cuda/src/ffi.rs is stale: run python tools/gen_ffi.py"
+    text = open(os.path.join(ROOT, "complogic-cuda", "src", "ffi.rs")).read()
+    fns = dict(re.findall(r"pub fn (clg_\w+)\(([^)]*)\)", text))
+    assert set(fns) == set(_lib.PROTOTYPES), set(fns) ^ set(_lib.PROTOTYPES)
+    for name, args in fns.items():
+        n_args = 0 if not args.strip() else args.count(":")
+        assert n_args == len(_lib.PROTOTYPES[name][1]), name
+    used = set(re.findall(r"\b(clg_[a-z_0-9]+)\(", open(os.path.join(ROOT, "complogic-cuda", "src", "lib.rs")).read()))
+    assert used <= set(fns), used - set(fns)
+    for struct, ct in (("clg_op", _lib.ClgOp), ("clg_gate", _lib.ClgGate), ("clg_flat_info", _lib.ClgFlatInfo)):
+        body = re.search(r"pub struct %s \{(.*?)\}" % struct, text, flags=re.S).group(1)
+        assert [f for f in re.findall(r"pub (\w+):", body)] == [f[0] for f in ct._fields_], struct
