@@ -533,6 +533,61 @@ def main():
             except Exception as e:  # a config that cannot run must not take the headline down with it
                 extras[name] = {"error": str(e)[:200]}
                 w = {"bufs": []}
+        if world == 1:
+            # layout helpers (HBM-bound): vector-major `&[bool]` bytes <-> bit-sliced words, and the `&[bool]`-shaped entry
+            # point end to end (host bytes in, host bytes out: transposes + kernel + copies, PCIe moves a byte per bool)
+            try:
+                del w
+                torch.cuda.empty_cache()
+                tr = {}
+                for nv_t, rows_t in ((1 << 22, 64), (1 << 20, 1024)):
+                    stride_t = host.round_stride(nv_t)
+                    bools = torch.randint(0, 2, (nv_t, rows_t), dtype=torch.uint8, device=dev)
+                    sliced = torch.zeros((rows_t, stride_t), dtype=torch.int32, device=dev)
+                    st = torch.cuda.current_stream().cuda_stream
+                    for nm, fn in (("slice", lambda: ctx.slice_bools(bools.data_ptr(), sliced.data_ptr(), nv_t, rows_t, stride_t, st)),
+                                   ("unslice", lambda: ctx.unslice_bools(sliced.data_ptr(), bools.data_ptr(), nv_t, rows_t, stride_t, st))):
+                        for _ in range(3):
+                            fn()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(20):
+                            fn()
+                        e1.record()
+                        torch.cuda.synchronize()
+                        ms_t = e0.elapsed_time(e1) / 20
+                        gbs = (nv_t * rows_t + rows_t * stride_t * 4) / (ms_t * 1e-3) / 1e9
+                        tr[f"{nm}_{rows_t}rows"] = {"ms": ms_t, "GBps": gbs, "hbm_frac": gbs / hbm_peak, "vectors": nv_t}
+                    del bools, sliced
+                extras["transpose"] = dict(tr, roofline={"bound": "hbm", "unit": "GB/s", "peak": hbm_peak,
+                                                         "frac": min(v["hbm_frac"] for v in tr.values()), "note": "frac = the slowest of the four"})
+                circ_b, _, _ = build_workload("adder32")
+                cs_b = host.CudaSimulation.from_simulation(circ_b.sim, circ_b.n_immediates, circ_b.out_regs, ctx=ctx, mode=mode)
+                nv_b = 1 << 22
+                imm_b = torch.randint(0, 2, (nv_b, 65), dtype=torch.uint8).pin_memory()
+                out_b = torch.zeros((nv_b, 33), dtype=torch.uint8).pin_memory()
+                lib_b = host._lib.lib()
+                def bools_step():
+                    host._lib.check(lib_b.clg_exec_run_bools_host(cs_b._h, imm_b.data_ptr(), out_b.data_ptr(), nv_b))
+                bools_step()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    bools_step()
+                b_ms = 1e3 * (time.perf_counter() - t0) / 3
+                a = imm_b[:1000, :32].numpy().astype(np.uint64)
+                b = imm_b[:1000, 32:64].numpy().astype(np.uint64)
+                wts = (np.uint64(1) << np.arange(32, dtype=np.uint64))
+                want = (a * wts).sum(1) + (b * wts).sum(1) + imm_b[:1000, 64].numpy().astype(np.uint64)
+                got = (out_b[:1000].numpy().astype(np.uint64) * (np.uint64(1) << np.arange(33, dtype=np.uint64))).sum(1)
+                extras["bools_api"] = {"workload": "adder32 through clg_exec_run_bools_host (one &[bool] per vector, host bytes in and out)",
+                                       "vectors": nv_b, "ms_per_call": b_ms, "value": circ_b.sim.nand_count * nv_b / (b_ms * 1e-3), "unit": UNIT,
+                                       "host_bytes_per_call": nv_b * (65 + 33), "GBps_over_pcie": nv_b * 98 / (b_ms * 1e-3) / 1e9,
+                                       "checked": bool((want == got).all())}
+                del imm_b, out_b
+                w = {"bufs": []}
+            except Exception as e:
+                extras["transpose_error"] = str(e)[:200]
+                w = {"bufs": []}
         if world > 1 and args.workload == "dag1m":
             # strong scaling of the headline config: 2^24 vectors IN TOTAL, sharded over the ranks (configs[3])
             del w

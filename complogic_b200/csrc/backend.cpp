@@ -81,7 +81,7 @@ struct Ctx {
   CUcontext cu = nullptr;
   CUmodule mod = nullptr;
   int sm_count = 0;
-  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, slice_w[3] = {}, unslice_w[3] = {}, unslice_s64 = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
   std::string name;
 
   explicit Ctx(int device) {
@@ -121,6 +121,12 @@ struct Ctx {
     CU(cuModuleGetFunction(&unslice, mod, "clg_unslice"));
     CU(cuModuleGetFunction(&slice_v4, mod, "clg_slice_v4"));
     CU(cuModuleGetFunction(&unslice_v4, mod, "clg_unslice_v4"));
+    CU(cuModuleGetFunction(&unslice_s64, mod, "clg_unslice_s64"));
+    static const char *rt[3] = {"32", "64", "128"};
+    for (int i = 0; i < 3; i++) {
+      CU(cuModuleGetFunction(&slice_w[i], mod, (std::string("clg_slice_w") + rt[i]).c_str()));
+      CU(cuModuleGetFunction(&unslice_w[i], mod, (std::string("clg_unslice_w") + rt[i]).c_str()));
+    }
     CU(cuModuleGetFunction(&fill, mod, "clg_fill_random"));
     CU(cuModuleGetFunction(&lop3_peak, mod, "clg_lop3_peak"));
   }
@@ -1025,6 +1031,22 @@ void launch_slice(Ctx *c, bool unslice, const void *src, void *dst, size_t n_vec
   uint32_t nv = (uint32_t)n_vectors, nr = (uint32_t)n_rows, st = (uint32_t)stride;
   void *args[] = {&src, &dst, &nv, &nr, &st};
   const void *vec_side = unslice ? dst : src;
+  if (n_rows % 16 == 0 && ((uintptr_t)vec_side & 15) == 0 && !std::getenv("CLG_TRANSPOSE_NARROW")) {
+    // wide tiled kernels: a CTA owns 1024 vectors x 32 / 64 / 128 rows; up to 128 contiguous bytes per lane on the
+    // vector-major side, whole 128-byte lines on the sliced side
+    if (unslice && n_rows >= 64 && !std::getenv("CLG_TRANSPOSE_RT")) {  // staged 64-row tiles: 64 contiguous bytes per vector and store instruction
+      const uint64_t gx = ((n_vectors + 31) / 32 + 31) / 32, gy = (n_rows + 63) / 64;
+      if (gx * gy > 0x7FFFFFFFull) fail(CLG_E_INVALID, "transpose too large for one launch");
+      CU(cuLaunchKernel(c->unslice_s64, (unsigned)(gx * gy), 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr));
+      return;
+    }
+    int i = n_rows >= 64 ? 1 : 0;  // 64-row tiles (64 contiguous bytes per lane), 32-row tiles for narrow matrices
+    if (const char *env = std::getenv("CLG_TRANSPOSE_RT")) i = std::atoi(env) >= 128 ? 2 : std::atoi(env) >= 64 ? 1 : 0;  // tuning knob
+    const uint64_t rt = 32u << i, gx = ((n_vectors + 31) / 32 + 31) / 32, gy = (n_rows + rt - 1) / rt;
+    if (gx * gy > 0x7FFFFFFFull) fail(CLG_E_INVALID, "transpose too large for one launch");
+    CU(cuLaunchKernel(unslice ? c->unslice_w[i] : c->slice_w[i], (unsigned)(gx * gy), 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr));
+    return;
+  }
   if (n_rows % 16 == 0 && ((uintptr_t)vec_side & 15) == 0) {
     // tiled kernels: 128-bit accesses on the vector-major side, 32-byte segments on the sliced side
     const uint64_t gx = ((n_vectors + 31) / 32 + 7) / 8, gy = (n_rows + 31) / 32;

@@ -755,6 +755,142 @@ extern "C" __global__ void __launch_bounds__(256) clg_unslice_v4(const uint32_t 
   }
 }
 
+// ---- wide tiled transposes (n_rows % 16 == 0): full 128-byte lines on BOTH sides ---------------------------------
+// A CTA of 8 warps owns 1024 vectors (32 sliced words) x RT rows (RT = 32, 64 or 128). Warp w takes words 4w .. 4w + 3,
+// one after the other: lane k loads the RT row-bytes of vector 32 * word + k as RT / 16 uint4 (one contiguous run of up
+// to 128 bytes per lane, all requested before any is used), packs every 32 of them into a word (bit r = row r) and
+// transposes the 32 x 32 bit matrix "lane = vector" <-> "lane = row" with the five-stage butterfly (5 SHFL instead
+// of the 32 ballots of the narrow kernels). The words meet in a shared tile [RT][32 + 1]; on the sliced side a warp
+// then writes (reads) whole rows: 32 lanes x 4 bytes = one 128-byte line.
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
+  // lane i holds row i of a 32 x 32 bit matrix (bit j = column j); afterwards lane j holds column j (bit i = row i)
+#pragma unroll
+  for (int j = 16; j; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+    x = (lane & j) ? (x & ~m) | ((y >> j) & m) : (x & m) | ((y << j) & ~m);
+  }
+  return x;
+}
+__device__ __forceinline__ uint32_t pack16(const uint4 q) {  // 16 bytes (zero / non-zero) -> 16 bits
+  return pack4(q.x) | pack4(q.y) << 4 | pack4(q.z) << 8 | pack4(q.w) << 12;
+}
+
+template <int RT>
+__device__ __forceinline__ void slice_wide_body(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows, uint32_t stride) {
+  __shared__ uint32_t tile[RT][33];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_rt = (n_rows + RT - 1) / RT, wg = blockIdx.x / n_rt, r0 = (blockIdx.x % n_rt) * RT;
+  const uint32_t words = (n_vectors + 31) / 32;
+#pragma unroll 1
+  for (uint32_t it = 0; it < 4; it++) {
+    const uint32_t c = warp * 4 + it, v = (wg * 32 + c) * 32 + lane;
+    uint4 q[RT / 16];
+#pragma unroll
+    for (int j = 0; j < RT / 16; j++) {
+      q[j] = make_uint4(0, 0, 0, 0);
+      if (v < n_vectors && r0 + 16 * j < n_rows) q[j] = __ldcs(reinterpret_cast<const uint4 *>(bools + (size_t)v * n_rows + r0 + 16 * j));
+    }
+#pragma unroll
+    for (int sx = 0; sx < RT / 32; sx++) tile[32 * sx + lane][c] = transpose32(pack16(q[2 * sx]) | pack16(q[2 * sx + 1]) << 16, lane);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < RT / 8; k++) {
+    const uint32_t row = warp * (RT / 8) + k;
+    if (r0 + row < n_rows && wg * 32 + lane < words) __stcs(sliced + (size_t)(r0 + row) * stride + wg * 32 + lane, tile[row][lane]);
+  }
+}
+
+template <int RT>
+__device__ __forceinline__ void unslice_wide_body(const uint32_t *sliced, uint8_t *bools, uint32_t n_vectors, uint32_t n_rows, uint32_t stride) {
+  __shared__ uint32_t tile[RT][33];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_rt = (n_rows + RT - 1) / RT, wg = blockIdx.x / n_rt, r0 = (blockIdx.x % n_rt) * RT;
+  const uint32_t words = (n_vectors + 31) / 32;
+#pragma unroll
+  for (int k = 0; k < RT / 8; k++) {
+    const uint32_t row = warp * (RT / 8) + k;
+    uint32_t x = 0;
+    if (r0 + row < n_rows && wg * 32 + lane < words) x = __ldcs(sliced + (size_t)(r0 + row) * stride + wg * 32 + lane);
+    tile[row][lane] = x;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t it = 0; it < 4; it++) {
+    const uint32_t c = warp * 4 + it, v = (wg * 32 + c) * 32 + lane;
+    uint32_t bits[RT / 32];
+#pragma unroll
+    for (int sx = 0; sx < RT / 32; sx++) bits[sx] = transpose32(tile[32 * sx + lane][c], lane);  // lane = vector, bit r = row r0 + 32 sx + r
+    if (v >= n_vectors) continue;
+    uint8_t *dst = bools + (size_t)v * n_rows + r0;
+#pragma unroll
+    for (int j = 0; j < RT / 16; j++) {
+      const uint32_t b = bits[j / 2] >> (16 * (j & 1));
+      if (r0 + 16 * j < n_rows)
+        __stcs(reinterpret_cast<uint4 *>(dst + 16 * j), make_uint4(unpack4(b & 15), unpack4(b >> 4 & 15), unpack4(b >> 8 & 15), unpack4(b >> 12 & 15)));
+    }
+  }
+}
+
+// Staged form of clg_unslice for 64-row tiles: on the vector-major side a warp instruction covers 8 vectors x 64
+// contiguous bytes (lane l: vector l / 4 of the eight, bytes 16 (l % 4) ..), i.e. 8 fully written 64-byte pieces
+// instead of 32 separate 16-byte ones; the bytes change hands between "lane = vector" and "lane = piece" through
+// shared memory (80-byte rows). Scattered 16-byte stores capped the direct kernel near 2 TB/s on wide rows; staged it
+// writes 4.1-4.2 TB/s at every row count. (The same staging on the load side of clg_slice was measured too and is
+// slower than the direct 64-row tiles, 3.0-3.3 against 3.6-3.8 TB/s: loads do not suffer from partial sectors.)
+__device__ __forceinline__ void unslice_staged64(const uint32_t *sliced, uint8_t *bools, uint32_t n_vectors, uint32_t n_rows, uint32_t stride) {
+  __shared__ uint32_t tile[64][33];
+  __shared__ __align__(16) unsigned char raw[8][32 * 80];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_rt = (n_rows + 63) / 64, wg = blockIdx.x / n_rt, r0 = (blockIdx.x % n_rt) * 64;
+  const uint32_t words = (n_vectors + 31) / 32;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t row = warp * 8 + k;
+    uint32_t x = 0;
+    if (r0 + row < n_rows && wg * 32 + lane < words) x = __ldcs(sliced + (size_t)(r0 + row) * stride + wg * 32 + lane);
+    tile[row][lane] = x;
+  }
+  __syncthreads();
+  unsigned char *mine = raw[warp];
+#pragma unroll 1
+  for (uint32_t it = 0; it < 4; it++) {
+    const uint32_t c = warp * 4 + it, v0 = (wg * 32 + c) * 32;
+    const uint32_t b0 = transpose32(tile[lane][c], lane), b1 = transpose32(tile[32 + lane][c], lane);  // lane = vector
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t b = (j < 2 ? b0 : b1) >> (16 * (j & 1));
+      *reinterpret_cast<uint4 *>(mine + lane * 80 + 16 * j) = make_uint4(unpack4(b & 15), unpack4(b >> 4 & 15), unpack4(b >> 8 & 15), unpack4(b >> 12 & 15));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {  // 8 vectors per instruction, 64 contiguous bytes each
+      const uint32_t vv = 8 * i + lane / 4, piece = lane % 4;
+      if (v0 + vv < n_vectors && r0 + 16 * piece < n_rows)
+        __stcs(reinterpret_cast<uint4 *>(bools + (size_t)(v0 + vv) * n_rows + r0 + 16 * piece), *reinterpret_cast<const uint4 *>(mine + vv * 80 + 16 * piece));
+    }
+    __syncwarp();
+  }
+}
+extern "C" __global__ void __launch_bounds__(256) clg_unslice_s64(const uint32_t *sliced, uint8_t *bools, uint32_t n_vectors, uint32_t n_rows,
+                                                                 uint32_t stride) {
+  unslice_staged64(sliced, bools, n_vectors, n_rows, stride);
+}
+#define CLG_WIDE(RT)                                                                                                          \
+  extern "C" __global__ void __launch_bounds__(256) clg_slice_w##RT(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors, \
+                                                                    uint32_t n_rows, uint32_t stride) {                       \
+    slice_wide_body<RT>(bools, sliced, n_vectors, n_rows, stride);                                                            \
+  }                                                                                                                           \
+  extern "C" __global__ void __launch_bounds__(256) clg_unslice_w##RT(const uint32_t *sliced, uint8_t *bools, uint32_t n_vectors, \
+                                                                      uint32_t n_rows, uint32_t stride) {                     \
+    unslice_wide_body<RT>(sliced, bools, n_vectors, n_rows, stride);                                                          \
+  }
+CLG_WIDE(32)
+CLG_WIDE(64)
+CLG_WIDE(128)
+#undef CLG_WIDE
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ULL;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;

@@ -1353,6 +1353,9 @@ RowsSched schedule_rows(const Network &net, uint32_t NW, uint32_t cap_rows) {
         const uint8_t t0 = tt_of(x, p0), t1 = tt_of(x, p1);
         if (t1 < t0) std::memcpy(f.pos, p1, 3), f.tt = t1;
         else std::memcpy(f.pos, p0, 3), f.tt = t0;
+        // only forwardings that keep the LUT's own table (the held value is, or may trade places with, its operand a): a
+        // second table in the row costs a predicated LOP3 pass, more than the saved load is worth
+        if (f.tt != x.tt && !std::getenv("CLG_ROWS_ANY_TT")) continue;
         cand[i] = best, cform[i] = f;
         count[f.tt]++;
       }
@@ -1423,7 +1426,7 @@ RowsSched schedule_rows(const Network &net, uint32_t NW, uint32_t cap_rows) {
       std::vector<WinItem> &win = window;
       win.clear();
       {
-        const uint32_t WIN = 1024;
+        static const uint32_t WIN = std::getenv("CLG_ROWS_WIN") ? (uint32_t)std::atoi(std::getenv("CLG_ROWS_WIN")) : 1024;  // (knob)
         while (win.size() < WIN) {
           uint32_t bt = 256;
           for (uint32_t k = 0; k < n_tt; k++) {
@@ -2033,7 +2036,7 @@ Flat levelize(const Simulation &sim, size_t n_immediates, const uint64_t *out_re
     if (const char *env = std::getenv("CLG_ROWS_WARPS")) nw = (uint32_t)std::max(1, std::min(32, std::atoi(env)));
     // rows per segment: about as many as the program's parallelism sustains when every non-forwarded dependence costs
     // two segments (more starves the scheduler of ready LUTs and leaves lanes empty, fewer only adds segments)
-    uint32_t cap = (uint32_t)std::max<uint64_t>(nw / 2, std::min<uint64_t>(4 * nw, (uint64_t)n_luts / 32 * 10 / (18ull * depth)));
+    uint32_t cap = (uint32_t)std::max<uint64_t>(nw / 2, std::min<uint64_t>(4 * nw, (uint64_t)n_luts / 32 * 100 / (195ull * depth)));  // (dag1m: 44; 41..45 measured equal, 47+ slower)
     if (const char *env = std::getenv("CLG_ROWS_CAP")) cap = (uint32_t)std::max(1, std::atoi(env));
     rowsch = schedule_rows(net, nw, cap);
     if (std::getenv("CLG_TIMING") && rowsch.ok)

@@ -388,7 +388,14 @@ def test_transposes_tiled_and_fallback_paths():
 
     ctx = host.Context.default()
     rng = np.random.default_rng(8)
-    for nv, rows in ((1, 16), (33, 16), (300, 48), (5000, 64), (257, 1024), (1000, 17), (64, 33)):
+    import os
+    cases = [(1, 16), (33, 16), (300, 48), (5000, 64), (257, 1024), (1000, 17), (64, 33),
+             (1025, 80), (40000, 128), (3000, 144), (1024 * 3 + 7, 272), (70000, 32)]  # wide tiles: 32 / 64 / 128 rows, ragged edges
+    for nv, rows, narrow in [(a, b, False) for a, b in cases] + [(300, 48, True), (5000, 64, True), (257, 1024, True)]:
+        if narrow:  # the 32-byte-segment kernels stay in the library (CLG_TRANSPOSE_NARROW), keep them honest
+            os.environ["CLG_TRANSPOSE_NARROW"] = "1"
+        else:
+            os.environ.pop("CLG_TRANSPOSE_NARROW", None)
         stride = stride_for(nv)
         b = rng.integers(0, 2, size=(nv, rows), dtype=np.uint8) * rng.integers(1, 256, size=(nv, rows)).astype(np.uint8)
         bools = torch.from_numpy(b).cuda()
@@ -402,6 +409,7 @@ def test_transposes_tiled_and_fallback_paths():
         bits = ((got[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(rows, -1)[:, :nv].T.astype(bool)
         assert np.array_equal(bits, want_bits), (nv, rows)
         assert np.array_equal(back.cpu().numpy(), want_bits.astype(np.uint8)), (nv, rows)
+    os.environ.pop("CLG_TRANSPOSE_NARROW", None)
 
 
 def test_torch_buffers_and_stream_and_fill():

@@ -10,7 +10,7 @@ import torch
 import complogic_b200 as host
 
 ctx = host.Context(0)
-for nv, rows in ((1 << 22, 64), (1 << 20, 1024), (1 << 24, 17), (1 << 22, 33)):
+for nv, rows in ((1 << 24, 32), (1 << 22, 64), (1 << 22, 128), (1 << 20, 1024), (1 << 18, 4096), (1 << 24, 17), (1 << 22, 33)):
     stride = host.round_stride(nv)
     bools = torch.randint(0, 2, (nv, rows), dtype=torch.uint8, device="cuda")
     sliced = torch.zeros((rows, stride), dtype=torch.int32, device="cuda")
