@@ -788,7 +788,7 @@ struct Exec {
     if (P.ready) return P;
     ctx->bind();
     const FlatRows &r = flat.rows();
-    const uint32_t nw = r.n_warps, S = r.n_segs;
+    const uint32_t nw = r.n_warps, S0 = r.n_segs, S = std::max<uint32_t>(4, (S0 + 3) / 4 * 4);  // padded with empty segments (kernels.cu, rows_step)
     if (r.lag != 2) fail(CLG_E_UNSUPPORTED, "row stream: the kernel synchronises two segments back (lag 2)");
     const FlatInstr *src = flat.row_instrs();
     const uint32_t *rt = flat.row_tab(), *stab = flat.row_sidetab();
@@ -798,11 +798,11 @@ struct Exec {
     if (P.smem > SMEM_MAX) fail(CLG_E_UNSUPPORTED, "row stream: register stack exceeds one SM's shared memory");
     std::vector<uint32_t> words, wbase(nw);  // 2 words per lane instruction
     words.reserve(((size_t)r.n_instr + (size_t)(S + 3) * nw * 32) * 2);
-    constexpr uint32_t EMPTY_X = 0x80000000u, EMPTY_Y = 0x80000000u;  // no load of a, no store
+    constexpr uint32_t EMPTY_X = 0x40000000u, EMPTY_Y = 0x80000000u;  // no load of a, no store
     for (uint32_t w = 0; w < nw; w++) {
       wbase[w] = (uint32_t)(words.size() / 2);
       for (uint32_t sgm = 0; sgm < S; sgm++) {
-        const uint32_t b = rt[(size_t)sgm * nw + w], e = rt[(size_t)sgm * nw + w + 1];
+        const uint32_t b = sgm < S0 ? rt[(size_t)sgm * nw + w] : 0, e = sgm < S0 ? rt[(size_t)sgm * nw + w + 1] : 0;
         const uint32_t n_rows = std::max<uint32_t>(1, (e - b) / 32);  // at least one (empty) row: it carries the end-of-segment mark
         for (uint32_t q = 0; q < n_rows; q++) {
           uint32_t hdr = 0;
@@ -826,10 +826,11 @@ struct Exec {
               const bool from_reg = in.flags & FLAG_FROM_REG, no_store = in.flags & FLAG_NO_STORE;
               const uint32_t a = from_reg ? 0u : in.a, bb = nf >= 2 ? in.b : a, c = nf >= 3 ? in.c : bb;  // operands it does not read alias one it does
               reads_c |= nf >= 3;
-              x[i] = a | bb << 14 | k << 28 | (from_reg ? 1u << 31 : 0u);
+              x[i] = a | bb << 14 | k << 28 | (from_reg ? 1u << 30 : 0u);
               y[i] = c | (no_store ? 0u : (uint32_t)in.dst << 14) | (no_store ? 1u << 31 : 0u);
             }
             if (n_tt) hdr = tts[0] | (uint32_t)tts[1] << 8 | (uint32_t)tts[2] << 16 | n_tt << 24 | (reads_c ? 1u << 26 : 0u);
+            if (n_tt == 1 && ((tts[0] == 0x0E && reads_c) || (tts[0] == 0x03 && !reads_c))) hdr |= 1u << 31;  // the kernel's in-line tables
             // The row's loads run in every lane. A lane without an instruction repeats the b and c addresses of a lane
             // that has one, in its own quarter-warp if possible: equal addresses are served by the same wavefront, so
             // the idle lane costs nothing (reading any fixed slot instead would collide with the lane that really
@@ -847,13 +848,13 @@ struct Exec {
           if (q == 0 && sgm >= 2) hdr |= 1u << 30;
           if (q + 1 == n_rows) {
             hdr |= 1u << 27;
-            if (stab[sgm + 1] > stab[sgm]) hdr |= 1u << 28;
+            if (sgm < S0 && stab[sgm + 1] > stab[sgm]) hdr |= 1u << 28;
             if (sgm + 1 == S) hdr |= 1u << 29;
           }
-          for (uint32_t i = 0; i < 32; i++) words.push_back(x[i] | ((hdr >> i & 1u) << 30)), words.push_back(y[i]);
+          for (uint32_t i = 0; i < 32; i++) words.push_back(x[i] | ((hdr >> i & 1u) << 31)), words.push_back(y[i]);
         }
       }
-      for (uint32_t i = 0; i < 5 * 32; i++) words.push_back(EMPTY_X), words.push_back(EMPTY_Y);  // the fetch runs up to four rows ahead
+      for (uint32_t i = 0; i < 8 * 32; i++) words.push_back(EMPTY_X), words.push_back(EMPTY_Y);  // the fetch runs up to seven rows ahead
     }
     if (words.size() / 2 >= (1ull << 32)) fail(CLG_E_UNSUPPORTED, "row stream too long");
     std::vector<uint32_t> side((size_t)std::max<uint32_t>(r.n_side, 1) * 4, 0);
@@ -864,8 +865,10 @@ struct Exec {
     CU(cuMemcpyHtoDAsync(P.d_rwarp, wbase.data(), wbase.size() * 4, nullptr));
     CU(cuMemAlloc(&P.d_rside, side.size() * 4));
     CU(cuMemcpyHtoDAsync(P.d_rside, side.data(), side.size() * 4, nullptr));
-    CU(cuMemAlloc(&P.d_rside_off, ((size_t)S + 1) * 4));
-    CU(cuMemcpyHtoDAsync(P.d_rside_off, stab, ((size_t)S + 1) * 4, nullptr));
+    std::vector<uint32_t> soff(stab, stab + S0 + 1);
+    soff.resize((size_t)S + 1, stab[S0]);  // the padding segments have no side entries
+    CU(cuMemAlloc(&P.d_rside_off, soff.size() * 4));
+    CU(cuMemcpyHtoDAsync(P.d_rside_off, soff.data(), soff.size() * 4, nullptr));
     CU(cuStreamSynchronize(nullptr));
     P.ready = true;
     return P;

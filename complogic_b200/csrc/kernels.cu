@@ -71,14 +71,16 @@ struct RunParams {
   const uint32_t *clevels;
   // coop, row form (clg_coop_rows, K = 4, <= 16383 slots; the row stream of flat.hpp, FlatRows). Every warp has its own
   // sequence of rows (32 lane instructions each), rinstr[rwarp[w] + 32 * k + lane] = {x, y}:
-  //     x = a | b << 14 | k << 28 | h << 30 | from_reg << 31        y = c | dst << 14 | no_store << 31      (slot indices)
+  //     x = a | b << 14 | k << 28 | from_reg << 30 | h << 31        y = c | dst << 14 | no_store << 31      (slot indices)
   //   k: which of the row's (at most three) truth tables the lane uses; from_reg: operand a is the lane's previous
   //   result (not loaded); no_store: the result is only read that way. Bit h of lane i is bit i of the ROW HEADER
-  //     tt0 | tt1 << 8 | tt2 << 16 | n_tables << 24 | reads_c << 26 | seg_end << 27 | side << 28 | last << 29 | wait << 30
-  //   (collected with one ballot): seg_end marks the warp's last row of a segment, side that the segment has entries in
-  //   `instr` (rside_off[s] .. rside_off[s + 1]: loads, stores), last the end of the program, wait the warp's first row of
-  //   a segment >= 2 (it may not start before every warp has finished the segment two back). Every warp has at least
-  //   one (possibly empty) row per segment, and two empty rows behind its last one (the fetch runs two rows ahead).
+  //     tt0 | tt1 << 8 | tt2 << 16 | n_tables << 24 | reads_c << 26 | seg_end << 27 | side << 28 | last << 29 | wait << 30 | hot << 31
+  //   (the sign bits, collected with one ballot): seg_end marks the warp's last row of a segment, side that the segment
+  //   has entries in `instr` (rside_off[s] .. rside_off[s + 1]: loads, stores), last the end of the program, wait the
+  //   warp's first row of a segment >= 2 (it may not start before every warp has finished the segment two back). Every
+  //   warp has at least one (possibly empty) row per segment; the segment count is padded to a multiple of four with
+  //   empty segments (mbarrier parities then depend on the segment alone), and eight empty rows follow a warp's last
+  //   one (the fetch runs three rows ahead, in groups of four).
   const uint2 *rinstr;
   const uint32_t *rwarp;
   const uint32_t *rside_off;
@@ -540,15 +542,45 @@ __device__ __forceinline__ void lut3_row1(uint32_t t, Vec<4> &P, const Vec<4> &B
       : "r"(B.w[0]), "r"(B.w[1]), "r"(B.w[2]), "r"(B.w[3]), "r"(C.w[0]), "r"(C.w[1]), "r"(C.w[2]), "r"(C.w[3]), "r"(t));
 }
 
-constexpr uint32_t RH_READS_C = 1u << 26, RH_SEG_END = 1u << 27, RH_SIDE = 1u << 28, RH_LAST = 1u << 29, RH_WAIT = 1u << 30;
+constexpr uint32_t RH_TABLES = 3u << 24, RH_READS_C = 1u << 26, RH_SEG_END = 1u << 27, RH_SIDE = 1u << 28, RH_LAST = 1u << 29, RH_WAIT = 1u << 30;
+constexpr uint32_t RX_FROM_REG = 1u << 30;  // (bit 31 of x carries the lane's bit of the row header)
 
+__device__ __noinline__ uint4 rows_rare(uint2 ins, uint32_t h, uint4 p, uint32_t sb);
+// the row's table is ~a & (b | c) (0x0E) or ~a & ~b (0x03) -- the two a NAND network consists of after LUT3 mapping
+// (98.8 % of the 1M-gate DAG's LUTs) -- and no lane needs a second one: RH_HOT, and RH_HOT03 for the second
+constexpr uint32_t RH_HOT = 1u << 31;
 __device__ __forceinline__ void row_exec(const uint2 ins, uint32_t h, Vec<4> &P, uint32_t sb) {
   constexpr uint32_t M = 0x3FFF0u;
-  const uint32_t oa = (ins.x << 4) & M, ob = (ins.x >> 10) & M, oc = (ins.y << 4) & M, od = (ins.y >> 10) & M;
-  if ((int32_t)ins.x >= 0) P = lds<4>(sb + oa);  // else: operand a is this lane's previous result
+  if ((int32_t)h < 0) {
+    const uint32_t oa = (ins.x << 4) & M, ob = (ins.x >> 10) & M, oc = (ins.y << 4) & M;
+    if (!(ins.x & RX_FROM_REG)) P = lds<4>(sb + oa);  // else: operand a is this lane's previous result
+    const Vec<4> B = lds<4>(sb + ob);
+    if (h & RH_READS_C) {  // (warp-uniform: 0x0E reads three operands, 0x03 two)
+      const Vec<4> C = lds<4>(sb + oc);
+#pragma unroll
+      for (int k = 0; k < 4; k++) P.w[k] = lop3<0x0E>(P.w[k], B.w[k], C.w[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) P.w[k] = lop3<0x03>(P.w[k], B.w[k], B.w[k]);
+    }
+  } else {
+    // any other table, or up to three tables in one row (predicated passes): 1.2 % of the DAG's LUTs, out of line so the
+    // row loop stays small. (The barrier keeps the call's argument moves inside this branch.)
+    uint4 a = make_uint4(P.w[0], P.w[1], P.w[2], P.w[3]);
+    asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w));
+    const uint4 r = rows_rare(ins, h, a, sb);
+    P.w[0] = r.x, P.w[1] = r.y, P.w[2] = r.z, P.w[3] = r.w;
+  }
+  if ((int32_t)ins.y >= 0) sts<4>(sb + ((ins.y >> 10) & M), P);
+}
+__device__ __noinline__ uint4 rows_rare(uint2 ins, uint32_t h, uint4 p, uint32_t sb) {
+  constexpr uint32_t M = 0x3FFF0u;
+  Vec<4> P{{p.x, p.y, p.z, p.w}};
+  const uint32_t oa = (ins.x << 4) & M, ob = (ins.x >> 10) & M, oc = (ins.y << 4) & M;
+  if (!(ins.x & RX_FROM_REG)) P = lds<4>(sb + oa);
   const Vec<4> B = lds<4>(sb + ob);
   Vec<4> C = dont_care<4>();
-  if (h & RH_READS_C) C = lds<4>(sb + oc);  // (warp-uniform: no lane of the row has a third operand otherwise)
+  if (h & RH_READS_C) C = lds<4>(sb + oc);
   const uint32_t n = (h >> 24) & 3u;
   if (n == 1) {
     lut3_row1(h & 0xFFu, P, B, C);
@@ -560,7 +592,7 @@ __device__ __forceinline__ void row_exec(const uint2 ins, uint32_t h, Vec<4> &P,
       h >>= 8;
     }
   }
-  if ((int32_t)ins.y >= 0) sts<4>(sb + od, P);
+  return make_uint4(P.w[0], P.w[1], P.w[2], P.w[3]);
 }
 
 // mbarrier primitives on 32-bit shared-space addresses kept in registers (the generic-pointer forms above make the
@@ -583,15 +615,13 @@ __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// the row header: bit 30 of the 32 lanes' first instruction words, collected with one ballot
+// the row header: the sign bits of the 32 lanes' first instruction words, collected with one ballot
 __device__ __forceinline__ uint32_t row_header(uint32_t x) {
   uint32_t h;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      ".reg .b32 t;\n"
-      "and.b32 t, %1, 0x40000000;\n"
-      "setp.ne.u32 p, t, 0;\n"
+      "setp.lt.s32 p, %1, 0;\n"
       "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
       "}\n"
       : "=r"(h)
@@ -599,11 +629,40 @@ __device__ __forceinline__ uint32_t row_header(uint32_t x) {
   return h;
 }
 
+// the loads and stores of a segment: entry i belongs to thread i % nt (few segments have any: out of line)
+__device__ __noinline__ void rows_side(const RunParams &p, uint32_t sgm, uint32_t sb, uint32_t g) {
+  const uint32_t tid = threadIdx.x, nt = blockDim.x, e = __ldg(p.rside_off + sgm + 1);
+  for (uint32_t i = __ldg(p.rside_off + sgm) + tid; i < e; i += nt) coop_exec<4>(p, ld_instr(p.instr + i), sb, (size_t)g * 4);
+}
+// One row of the calling warp. The host pads the segment count to a multiple of four, so every column group moves
+// each of the two mbarriers through an even number of phases and the parity to test is a function of the segment
+// alone: segment s arrives on barrier s & 1 (the two are 8 bytes apart) as its phase s >> 1, and may start when
+// phase (s >> 1) - 1 of that barrier -- segment s - 2 -- is complete. Returns true behind the program's last row.
+__device__ __forceinline__ bool rows_step(const RunParams &p, const uint2 ins, Vec<4> &P, uint32_t &sgm, uint32_t &bcur, uint32_t sb, uint32_t g) {
+  const uint32_t h = row_header(ins.x);
+  if (h & RH_WAIT) mbar_wait_u32(bcur, ((sgm >> 1) & 1u) ^ 1u);  // the warp's first row of a segment >= 2
+  if (h & RH_TABLES) row_exec(ins, h, P, sb);
+  if (h & RH_SEG_END) {
+    if (h & RH_SIDE) rows_side(p, sgm, sb, g);
+    __syncwarp();
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(bcur)
+        : "memory");
+    sgm++, bcur ^= 8u;
+    return (h & RH_LAST) != 0;
+  }
+  return false;
+}
+
 __device__ __forceinline__ void coop_rows_body(const RunParams &p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t tid = threadIdx.x, nt = blockDim.x;
-  uint32_t sb = smem_u32(smem), lane = tid & 31;
-  asm volatile("" : "+r"(sb), "+r"(lane));
+  uint32_t sb = smem_u32(smem);
+  asm volatile("" : "+r"(sb));
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + p.code_off);  // two mbarriers behind the register stack
   if (tid == 0) {
     mbar_init(&bar[0], nt >> 5);
@@ -611,47 +670,28 @@ __device__ __forceinline__ void coop_rows_body(const RunParams &p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // Segment s arrives on barrier s & 1 (`cur`; the two are 8 bytes apart). Every thread consumes every phase of both
-  // barriers exactly once and in order (segment s waits for the phase of segment s - 2, the last two phases are
-  // consumed at the end of the column group), so the parity to wait for alternates per barrier: the k-th wait of a
-  // column group (k = s - 2) wants parity ((k >> 1) ^ start parity of barrier k & 1) & 1 -- kept as a two-bit counter
-  // per barrier pair: `par` holds the parities of (current, other) in bits 0 and 1 and is rotated with the barriers.
-  const uint32_t bar0 = sb + p.code_off;
-  uint32_t cur = bar0, par = 0;
-  asm volatile("" : "+r"(cur));
+  const uint32_t bar0 = sb + p.code_off;  // (16-byte aligned: bit 3 selects the barrier)
   for (uint32_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
-    const uint2 *ip = p.rinstr + (size_t)__ldg(p.rwarp + (tid >> 5)) + lane;  // (re-derived per column group: registers are scarce)
-    uint2 ins = ld_cinstr(ip), n1 = ld_cinstr(ip + 32);
+    const uint2 *ip = p.rinstr + (size_t)__ldg(p.rwarp + (tid >> 5)) + (tid & 31u);  // (re-derived per column group: registers are scarce)
+    // instruction words are fetched three rows ahead into four register pairs that take turns (no register moves)
+    uint2 A = ld_cinstr(ip), B = ld_cinstr(ip + 32), C = ld_cinstr(ip + 64), D;
     Vec<4> P = dont_care<4>();
-    uint32_t sgm = 0;
+    uint32_t sgm = 0, bcur = bar0;
     for (;;) {
-      const uint2 n2 = ld_cinstr(ip + 64);  // instruction words are fetched two rows ahead
-      const uint32_t h = row_header(ins.x);
-      if (h & RH_WAIT) {  // the warp's first row of a segment >= 2: everything it reads was written two segments ago or earlier
-        mbar_wait_u32(cur, par & 1u);
-        par ^= 1u;
-      }
-      if ((h >> 24) & 3u) row_exec(ins, h, P, sb);
-      if (h & RH_SEG_END) {
-        if (h & RH_SIDE) {  // loads, stores: entry i of the segment belongs to thread i % nt
-          const uint32_t e = __ldg(p.rside_off + sgm + 1);
-          for (uint32_t i = __ldg(p.rside_off + sgm) + tid; i < e; i += nt) coop_exec<4>(p, ld_instr(p.instr + i), sb, (size_t)g * 4);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_u32(cur);
-        sgm++, cur ^= 8u, par = (par >> 1) | (par << 1 & 2u);
-        if (h & RH_LAST) break;
-      }
-      ins = n1, n1 = n2, ip += 32;
+      D = ld_cinstr(ip + 96);
+      if (rows_step(p, A, P, sgm, bcur, sb, g)) break;
+      A = ld_cinstr(ip + 128);
+      if (rows_step(p, B, P, sgm, bcur, sb, g)) break;
+      B = ld_cinstr(ip + 160);
+      if (rows_step(p, C, P, sgm, bcur, sb, g)) break;
+      C = ld_cinstr(ip + 192);
+      if (rows_step(p, D, P, sgm, bcur, sb, g)) break;
+      ip += 128;
     }
-    // the phases of the last two segments: afterwards every warp is done with this column group and the stack is free
-    if (sgm >= 2) {
-      mbar_wait_u32(cur, par & 1u);
-      par ^= 1u;
-    }
-    mbar_wait_u32(cur ^ 8u, par >> 1 & 1u);
-    par ^= 2u;
-    if (sgm & 1u) cur ^= 8u, par = (par >> 1) | (par << 1 & 2u);  // the next group starts on barrier 0 again
+    // the last phase of either barrier (the segment count is a multiple of four: an even number of phases, the last one
+    // has parity 1): afterwards every warp is done with this column group and the stack is free
+    mbar_wait_u32(bar0, 1u);
+    mbar_wait_u32(bar0 + 8u, 1u);
   }
 }
 
@@ -941,4 +981,4 @@ extern "C" __global__ void __launch_bounds__(512) clg_lop3_peak(const uint32_t *
 CLG_ENTRY(1)
 CLG_ENTRY(2)
 CLG_ENTRY(4)
-extern "C" __global__ void __launch_bounds__(1024) clg_coop_rows(const clg::RunParams p) { clg::coop_rows_body(p); }
+extern "C" __global__ void __launch_bounds__(1024) clg_coop_rows(const __grid_constant__ clg::RunParams p) { clg::coop_rows_body(p); }
