@@ -24,7 +24,7 @@ namespace {
   X(cuModuleGetFunction) X(cuModuleUnload) X(cuFuncSetAttribute) X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree)          \
   X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuMemcpy2DAsync) X(cuStreamWaitEvent) X(cuMemsetD8Async) X(cuMemAllocHost) X(cuMemFreeHost) X(cuStreamSynchronize) \
   X(cuStreamCreate) X(cuStreamDestroy) X(cuEventCreate) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime)   \
-  X(cuEventDestroy) X(cuGetErrorString)
+  X(cuEventDestroy) X(cuGetErrorString) X(cuTensorMapEncodeTiled)
 
 struct Driver {
 #define X(name) decltype(&::name) name = nullptr;
@@ -81,8 +81,11 @@ struct Ctx {
   CUcontext cu = nullptr;
   CUmodule mod = nullptr;
   int sm_count = 0;
-  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, slice_w[3] = {}, unslice_w[3] = {}, unslice_s64 = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, slice_w[3] = {}, unslice_w[3] = {}, unslice_s64 = nullptr, slice_tma[7] = {}, unslice_tma[7] = {}, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
   std::string name;
+
+  static constexpr uint32_t TMA_RT[7] = {32, 64, 64, 128, 64, 128, 32}, TMA_VT[7] = {1024, 1024, 512, 512, 256, 256, 512};  // tile shapes of the TMA-tiled transposes (kernels.cu)
+  static size_t tma_smem(int i) { return (size_t)TMA_VT[i] * TMA_RT[i] + (size_t)TMA_RT[i] * (TMA_VT[i] / 32 + 1) * 4 + 16 + 1024; }  // (+ slack to align the base to 1024)
 
   explicit Ctx(int device) {
     Driver &d = driver();
@@ -126,6 +129,13 @@ struct Ctx {
     for (int i = 0; i < 3; i++) {
       CU(cuModuleGetFunction(&slice_w[i], mod, (std::string("clg_slice_w") + rt[i]).c_str()));
       CU(cuModuleGetFunction(&unslice_w[i], mod, (std::string("clg_unslice_w") + rt[i]).c_str()));
+    }
+    for (int i = 0; i < 7; i++) {  // TMA-tiled transposes: VT vectors x RT bytes staged per CTA + the word tile + one mbarrier
+      const std::string sfx = std::to_string(TMA_RT[i]) + "_" + std::to_string(TMA_VT[i]);
+      CU(cuModuleGetFunction(&slice_tma[i], mod, ("clg_slice_tma" + sfx).c_str()));
+      CU(cuModuleGetFunction(&unslice_tma[i], mod, ("clg_unslice_tma" + sfx).c_str()));
+      CU(cuFuncSetAttribute(slice_tma[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)tma_smem(i)));
+      CU(cuFuncSetAttribute(unslice_tma[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)tma_smem(i)));
     }
     CU(cuModuleGetFunction(&fill, mod, "clg_fill_random"));
     CU(cuModuleGetFunction(&lop3_peak, mod, "clg_lop3_peak"));
@@ -1034,6 +1044,25 @@ void launch_slice(Ctx *c, bool unslice, const void *src, void *dst, size_t n_vec
   uint32_t nv = (uint32_t)n_vectors, nr = (uint32_t)n_rows, st = (uint32_t)stride;
   void *args[] = {&src, &dst, &nv, &nr, &st};
   const void *vec_side = unslice ? dst : src;
+  if (n_rows % 16 == 0 && ((uintptr_t)vec_side & 15) == 0 && !std::getenv("CLG_TRANSPOSE_NARROW") && !std::getenv("CLG_TRANSPOSE_NO_TMA")) {
+    // TMA-tiled kernels: the vector-major side as a 2-D byte tensor [n_vectors][n_rows], boxes of 256 vectors x 32 / 64
+    // bytes, swizzled in shared memory by the same span (kernels.cu)
+    int i = n_rows >= 48 ? 2 : 0;  // 64 x 512 tiles; 32 x 1024 for narrow matrices
+    if (const char *env = std::getenv("CLG_TRANSPOSE_TMA")) i = std::max(0, std::min(6, std::atoi(env)));  // tuning knob: tile shape by index
+    const uint32_t rt = Ctx::TMA_RT[i], vt = Ctx::TMA_VT[i];
+    CUtensorMap tm;
+    const cuuint64_t dims[2] = {(cuuint64_t)n_rows, (cuuint64_t)n_vectors}, strides[1] = {(cuuint64_t)n_rows};
+    const cuuint32_t box[2] = {rt, 256}, estr[2] = {1, 1};
+    CU(cuTensorMapEncodeTiled(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(vec_side), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              rt == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rt == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+    const void *other = unslice ? src : dst;
+    void *targs[] = {&tm, &other, &nv, &nr, &st};
+    const uint64_t gx = (n_vectors + vt - 1) / vt, gy = (n_rows + rt - 1) / rt;
+    if (gx * gy > 0x7FFFFFFFull) fail(CLG_E_INVALID, "transpose too large for one launch");
+    CU(cuLaunchKernel(unslice ? c->unslice_tma[i] : c->slice_tma[i], (unsigned)(gx * gy), 1, 1, 256, 1, 1, (unsigned)Ctx::tma_smem(i), (CUstream)stream, targs, nullptr));
+    return;
+  }
   if (n_rows % 16 == 0 && ((uintptr_t)vec_side & 15) == 0 && !std::getenv("CLG_TRANSPOSE_NARROW")) {
     // wide tiled kernels: a CTA owns 1024 vectors x 32 / 64 / 128 rows; up to 128 contiguous bytes per lane on the
     // vector-major side, whole 128-byte lines on the sliced side

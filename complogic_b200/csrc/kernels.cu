@@ -732,12 +732,19 @@ extern "C" __global__ void __launch_bounds__(256) clg_unslice(const uint32_t *sl
 // sliced side. A CTA of 8 warps owns 256 vectors (8 words) x 32 rows; warp w owns word w. Lane k holds the 32
 // row-bytes of vector 32w+k as two uint4; bytes <-> bits with SWAR arithmetic, then 32 ballots transpose the
 // 32x32 bit matrix between "lane = vector" and "lane = row".
-__device__ __forceinline__ uint32_t pack4(uint32_t x) {  // 4 bytes (zero / non-zero) -> 4 bits
-  uint32_t y = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) >> 7 & 0x01010101u;
-  return (y | y >> 7 | y >> 14 | y >> 21) & 0xFu;
+// The transposes are bound by instruction issue before they are bound by HBM (ncu, first TMA version: 7.4 thread
+// instructions per `&[bool]` byte, issue slots 46 % busy at 2.4 TB/s), so the byte <-> bit arithmetic is what counts:
+// bytes are normalised to 0x80 / 0 in three instructions per word and gathered with dp4a (one instruction per four bytes:
+// weights 1, 2, 4, 8 or 16, 32, 64, 128 -- the sum is 128 x the packed bits), bits are spread into bytes with one
+// multiplication, and the 32 x 32 bit transpose exchanges pre-rotated words (3 instructions per butterfly stage).
+__device__ __forceinline__ uint32_t nz80(uint32_t x) {  // 4 bytes -> 0x80 where the byte is non-zero, 0 elsewhere
+  return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
 }
-__device__ __forceinline__ uint32_t unpack4(uint32_t b) {  // 4 bits -> 4 bytes of 0/1
-  return (b | b << 7 | b << 14 | b << 21) & 0x01010101u;
+__device__ __forceinline__ uint32_t pack4(uint32_t x) {  // 4 bytes (zero / non-zero) -> 4 bits
+  return __dp4a(nz80(x), 0x08040201u, 0u) >> 7;
+}
+__device__ __forceinline__ uint32_t unpack4(uint32_t b) {  // 4 bits -> 4 bytes of 0/1 (bit i lands at 8 i: i + 7 i)
+  return (b * 0x00204081u) & 0x01010101u;
 }
 
 extern "C" __global__ void __launch_bounds__(256) clg_slice_v4(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors,
@@ -802,18 +809,29 @@ extern "C" __global__ void __launch_bounds__(256) clg_unslice_v4(const uint32_t 
 // transposes the 32 x 32 bit matrix "lane = vector" <-> "lane = row" with the five-stage butterfly (5 SHFL instead
 // of the 32 ballots of the narrow kernels). The words meet in a shared tile [RT][32 + 1]; on the sliced side a warp
 // then writes (reads) whole rows: 32 lanes x 4 bytes = one 128-byte line.
+template <int J>
+__device__ __forceinline__ uint32_t transpose32_stage(uint32_t x, uint32_t lane) {
+  constexpr uint32_t m = J == 16 ? 0x0000FFFFu : J == 8 ? 0x00FF00FFu : J == 4 ? 0x0F0F0F0Fu : J == 2 ? 0x33333333u : 0x55555555u;
+  const bool up = lane & J;
+  const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, __funnelshift_l(x, x, up ? J : 32 - J), J), keep = up ? ~m : m;
+  return (x & keep) | (y & ~keep);
+}
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
-  // lane i holds row i of a 32 x 32 bit matrix (bit j = column j); afterwards lane j holds column j (bit i = row i)
-#pragma unroll
-  for (int j = 16; j; j >>= 1) {
-    const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
-    const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, j);
-    x = (lane & j) ? (x & ~m) | ((y >> j) & m) : (x & m) | ((y << j) & ~m);
-  }
-  return x;
+  // lane i holds row i of a 32 x 32 bit matrix (bit j = column j); afterwards lane j holds column j (bit i = row i).
+  // Stage J swaps the off-diagonal J x J blocks of lanes l and l ^ J: the upper lane keeps the high halves of its 2J-bit
+  // groups and needs the partner's high halves moved down, the lower lane the opposite -- so each lane sends its word
+  // already rotated towards where the partner needs it, and the receiver only selects (one LOP3).
+  // (Written out stage by stage: as a loop over J the compiler kept the loop and a jump table for the mask.)
+  x = transpose32_stage<16>(x, lane);
+  x = transpose32_stage<8>(x, lane);
+  x = transpose32_stage<4>(x, lane);
+  x = transpose32_stage<2>(x, lane);
+  return transpose32_stage<1>(x, lane);
 }
 __device__ __forceinline__ uint32_t pack16(const uint4 q) {  // 16 bytes (zero / non-zero) -> 16 bits
-  return pack4(q.x) | pack4(q.y) << 4 | pack4(q.z) << 8 | pack4(q.w) << 12;
+  const uint32_t lo = __dp4a(nz80(q.y), 0x80402010u, __dp4a(nz80(q.x), 0x08040201u, 0u));
+  const uint32_t hi = __dp4a(nz80(q.w), 0x80402010u, __dp4a(nz80(q.z), 0x08040201u, 0u));
+  return (lo >> 7) | (hi << 1);  // either sum is 128 x its eight bits
 }
 
 template <int RT>
@@ -930,6 +948,141 @@ CLG_WIDE(32)
 CLG_WIDE(64)
 CLG_WIDE(128)
 #undef CLG_WIDE
+
+// ---- TMA-tiled transposes (n_rows % 16 == 0, 16-byte aligned vector-major side) ------------------------------------
+// The vector-major side is eight times the sliced side, and a warp that gathers 16 bytes from each of 32 vectors touches
+// 32 lines per instruction. Here the tensor memory accelerator moves the bytes: the `&[bool]` matrix is a 2-D byte tensor
+// [n_vectors][n_rows], a CTA's tile of VT vectors x RT bytes is VT / 256 boxes, staged in shared memory with the 32-, 64-
+// or 128-byte swizzle (RT bytes per vector = the swizzle span), so that the eight lanes of a quarter-warp, each reading
+// or writing 16 bytes of its own vector, hit eight different bank groups. cp.async.bulk.tensor fills out-of-range parts
+// of a box with zeros on loads and clips them on stores, so ragged edges need no code. The sliced side moves whole rows
+// of the tile (64 or 128 bytes). One tile per CTA, several CTAs per SM. Measured (B200, tools/sweep_transpose.sh): with
+// the byte <-> bit arithmetic above, 64 x 512 tiles run at 6.0-6.6 TB/s in both directions (92-100 % of the measured copy
+// bandwidth; the LDG/STG kernels reach 3.3-6.1 slicing and 4.4-5.8 unslicing with the same arithmetic, everything was at
+// 2.9-4.4 TB/s before it). A persistent variant (one CTA per SM, twelve warps each looping over tiles with a private
+// stage buffer and mbarrier) was built as well and is slower, 5.6-6.0 / 3.9-4.9 TB/s: twelve warps do not cover the
+// arithmetic, which is still 2-3 instructions per byte.
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, uint32_t c0, uint32_t c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t c0, uint32_t c1, const void *src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(src))
+               : "memory");
+}
+struct alignas(64) TensorMap {  // CUtensorMap (cuda.h): 128 opaque bytes, built by the host with cuTensorMapEncodeTiled
+  unsigned long long opaque[16];
+};
+// physical 16-byte chunk of logical chunk j of vector `v` (tile-local) under the swizzle the tensor map was built with
+// (span = RT bytes: address bits 4.. are XORed with bits 7..)
+template <int RT>
+__device__ __forceinline__ uint32_t swz(uint32_t v, uint32_t j) {
+  return RT == 128 ? j ^ (v & 7u) : RT == 64 ? j ^ ((v >> 1) & 3u) : j ^ ((v >> 2) & 1u);
+}
+constexpr uint32_t TMA_BOX = 256;  // vectors per box (the largest a tensor map allows)
+
+// RT: bytes (rows) of a vector per tile; VT: vectors per tile (512 or 1024: 16 or 32 sliced words per row)
+template <int RT, int VT>
+__device__ __forceinline__ void slice_tma_body(const TensorMap &tm, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows, uint32_t stride) {
+  constexpr int WT = VT / 32;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *stage = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);              // [VT][RT] bytes, swizzled (the pattern is in address bits 4-9)
+  uint32_t(*tile)[WT + 1] = reinterpret_cast<uint32_t(*)[WT + 1]>(stage + VT * RT);        // [RT][WT + 1] words
+  uint64_t *bar = reinterpret_cast<uint64_t *>(stage + VT * RT + RT * (WT + 1) * 4);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_rt = (n_rows + RT - 1) / RT, wg = blockIdx.x / n_rt, r0 = (blockIdx.x % n_rt) * RT, v0 = wg * VT;
+  const uint32_t words = (n_vectors + 31) / 32;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint32_t boxes = 0;
+    for (uint32_t b = 0; b < VT / TMA_BOX; b++) boxes += v0 + b * TMA_BOX < n_vectors;
+    mbar_expect_tx(bar, boxes * TMA_BOX * RT);
+    for (uint32_t b = 0; b < boxes; b++) tma_load_2d(stage + b * TMA_BOX * RT, &tm, r0, v0 + b * TMA_BOX, bar);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  const uint32_t sbase = smem_u32(stage);
+#pragma unroll 1
+  for (uint32_t it = 0; it < WT / 8; it++) {
+    const uint32_t c = warp * (WT / 8) + it, vl = c * 32 + lane;
+    uint4 q[RT / 16];
+#pragma unroll
+    for (int j = 0; j < RT / 16; j++) {
+      q[j] = make_uint4(0, 0, 0, 0);
+      if (v0 + vl < n_vectors) {  // (a box that starts behind the last vector is not loaded at all)
+        const Vec<4> x = lds<4>(sbase + vl * RT + swz<RT>(vl, j) * 16);
+        q[j] = make_uint4(x.w[0], x.w[1], x.w[2], x.w[3]);
+      }
+    }
+#pragma unroll
+    for (int sx = 0; sx < RT / 32; sx++) tile[32 * sx + lane][c] = transpose32(pack16(q[2 * sx]) | pack16(q[2 * sx + 1]) << 16, lane);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < RT * WT / 256; k++) {  // 32 words per warp instruction: one row of a 1024-vector tile, two of a 512-vector one
+    const uint32_t idx = (warp * (RT * WT / 256) + k) * 32 + lane, row = idx / WT, w = idx % WT;
+    if (r0 + row < n_rows && wg * WT + w < words) __stcs(sliced + (size_t)(r0 + row) * stride + wg * WT + w, tile[row][w]);
+  }
+}
+
+template <int RT, int VT>
+__device__ __forceinline__ void unslice_tma_body(const TensorMap &tm, const uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows, uint32_t stride) {
+  constexpr int WT = VT / 32;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *stage = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  uint32_t(*tile)[WT + 1] = reinterpret_cast<uint32_t(*)[WT + 1]>(stage + VT * RT);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_rt = (n_rows + RT - 1) / RT, wg = blockIdx.x / n_rt, r0 = (blockIdx.x % n_rt) * RT, v0 = wg * VT;
+  const uint32_t words = (n_vectors + 31) / 32;
+#pragma unroll
+  for (int k = 0; k < RT * WT / 256; k++) {
+    const uint32_t idx = (warp * (RT * WT / 256) + k) * 32 + lane, row = idx / WT, w = idx % WT;
+    uint32_t x = 0;
+    if (r0 + row < n_rows && wg * WT + w < words) x = __ldcs(sliced + (size_t)(r0 + row) * stride + wg * WT + w);
+    tile[row][w] = x;
+  }
+  __syncthreads();
+  const uint32_t sbase = smem_u32(stage);
+#pragma unroll 1
+  for (uint32_t it = 0; it < WT / 8; it++) {
+    const uint32_t c = warp * (WT / 8) + it, vl = c * 32 + lane;
+    uint32_t bits[RT / 32];
+#pragma unroll
+    for (int sx = 0; sx < RT / 32; sx++) bits[sx] = transpose32(tile[32 * sx + lane][c], lane);  // lane = vector, bit r = row r0 + 32 sx + r
+#pragma unroll
+    for (int j = 0; j < RT / 16; j++) {
+      const uint32_t b = bits[j / 2] >> (16 * (j & 1));
+      sts<4>(sbase + vl * RT + swz<RT>(vl, j) * 16, Vec<4>{{unpack4(b & 15), unpack4(b >> 4 & 15), unpack4(b >> 8 & 15), unpack4(b >> 12 & 15)}});
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy writes above, before the bulk store reads them
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t b = 0; b < VT / TMA_BOX; b++)
+      if (v0 + b * TMA_BOX < n_vectors) tma_store_2d(&tm, r0, v0 + b * TMA_BOX, stage + b * TMA_BOX * RT);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+#define CLG_TMA(RT, VT)                                                                                                                   \
+  extern "C" __global__ void __launch_bounds__(256) clg_slice_tma##RT##_##VT(const __grid_constant__ TensorMap tm, uint32_t *sliced,      \
+                                                                             uint32_t n_vectors, uint32_t n_rows, uint32_t stride) {     \
+    slice_tma_body<RT, VT>(tm, sliced, n_vectors, n_rows, stride);                                                                        \
+  }                                                                                                                                       \
+  extern "C" __global__ void __launch_bounds__(256) clg_unslice_tma##RT##_##VT(const __grid_constant__ TensorMap tm, const uint32_t *sliced, \
+                                                                               uint32_t n_vectors, uint32_t n_rows, uint32_t stride) {   \
+    unslice_tma_body<RT, VT>(tm, sliced, n_vectors, n_rows, stride);                                                                      \
+  }
+CLG_TMA(32, 1024)
+CLG_TMA(32, 512)
+CLG_TMA(64, 1024)
+CLG_TMA(64, 512)
+CLG_TMA(128, 512)
+CLG_TMA(64, 256)
+CLG_TMA(128, 256)
+#undef CLG_TMA
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ULL;

@@ -391,11 +391,17 @@ def test_transposes_tiled_and_fallback_paths():
     import os
     cases = [(1, 16), (33, 16), (300, 48), (5000, 64), (257, 1024), (1000, 17), (64, 33),
              (1025, 80), (40000, 128), (3000, 144), (1024 * 3 + 7, 272), (70000, 32)]  # wide tiles: 32 / 64 / 128 rows, ragged edges
-    for nv, rows, narrow in [(a, b, False) for a, b in cases] + [(300, 48, True), (5000, 64, True), (257, 1024, True)]:
-        if narrow:  # the 32-byte-segment kernels stay in the library (CLG_TRANSPOSE_NARROW), keep them honest
-            os.environ["CLG_TRANSPOSE_NARROW"] = "1"
-        else:
-            os.environ.pop("CLG_TRANSPOSE_NARROW", None)
+    # default: the TMA-tiled kernels in their default tile shape; the other shapes (CLG_TRANSPOSE_TMA = shape index), the wide
+    # LDG/STG ones (CLG_TRANSPOSE_NO_TMA) and the 32-byte-segment ones (CLG_TRANSPOSE_NARROW) stay in the library, keep them honest
+    cases += [(256 * 12 + 1, 2048)]
+    variants = [(a, b, None) for a, b in cases] + [(a, b, "CLG_TRANSPOSE_NO_TMA=1") for a, b in cases if b % 16 == 0] + \
+               [(a, b, f"CLG_TRANSPOSE_TMA={t}") for t in range(7) for a, b in ((33, 16), (3000, 144), (1024 * 3 + 7, 272), (70000, 32))] + \
+               [(300, 48, "CLG_TRANSPOSE_NARROW=1"), (5000, 64, "CLG_TRANSPOSE_NARROW=1"), (257, 1024, "CLG_TRANSPOSE_NARROW=1")]
+    for nv, rows, env in variants:
+        for k in ("CLG_TRANSPOSE_NARROW", "CLG_TRANSPOSE_NO_TMA", "CLG_TRANSPOSE_TMA"):
+            os.environ.pop(k, None)
+        if env:
+            os.environ[env.split("=")[0]] = env.split("=")[1]
         stride = stride_for(nv)
         b = rng.integers(0, 2, size=(nv, rows), dtype=np.uint8) * rng.integers(1, 256, size=(nv, rows)).astype(np.uint8)
         bools = torch.from_numpy(b).cuda()
@@ -407,9 +413,10 @@ def test_transposes_tiled_and_fallback_paths():
         want_bits = (b != 0)
         got = sliced.cpu().numpy().view(np.uint32)
         bits = ((got[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(rows, -1)[:, :nv].T.astype(bool)
-        assert np.array_equal(bits, want_bits), (nv, rows)
-        assert np.array_equal(back.cpu().numpy(), want_bits.astype(np.uint8)), (nv, rows)
-    os.environ.pop("CLG_TRANSPOSE_NARROW", None)
+        assert np.array_equal(bits, want_bits), (nv, rows, env)
+        assert np.array_equal(back.cpu().numpy(), want_bits.astype(np.uint8)), (nv, rows, env)
+    for k in ("CLG_TRANSPOSE_NARROW", "CLG_TRANSPOSE_NO_TMA", "CLG_TRANSPOSE_TMA"):
+        os.environ.pop(k, None)
 
 
 def test_torch_buffers_and_stream_and_fill():
