@@ -116,6 +116,11 @@ impl CudaSimulation {
     Ok(out)
   }
 
+  /// Choose the mode for batches of `n_vectors`, build its plan and tune it now (otherwise the first run does it).
+  pub fn prepare(&self, n_vectors: usize) -> Result<(), Error> {
+    check(unsafe { clg_exec_prepare(self.exec, n_vectors) })
+  }
+
   /// Name of the kernel the most recent run launched (`clg_coop_rows`, `clg_spec`, ...).
   pub fn kernel_name(&self) -> String {
     unsafe { CStr::from_ptr(clg_exec_kernel_name(self.exec)) }.to_string_lossy().into_owned()

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "clg_exec_words_per_thread": (i32, [vp]),
     "clg_exec_launches_per_run": (i32, [vp]),
     "clg_exec_kernel_name": (C.c_char_p, [vp]),
+    "clg_exec_prepare": (C.c_int, [vp, C.c_size_t]),
     "clg_exec_ptx": (C.c_char_p, [vp]),
     "clg_exec_run": (i32, [vp, vp, vp, vp, sz, sz, vp]),
     "clg_exec_run_steps": (i32, [vp, vp, vp, vp, sz, sz, sz, vp]),

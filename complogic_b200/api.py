@@ -515,6 +515,10 @@ class CudaSimulation:
     def ptx(self) -> str:
         return lib().clg_exec_ptx(self._h).decode()
 
+    def prepare(self, n_vectors: int) -> None:
+        """clg_exec_prepare: choose the mode for this batch size, build its plan and tune it now instead of in the first run."""
+        check(lib().clg_exec_prepare(self._h, n_vectors))
+
     def run_device(self, imm_dptr: int, out_dptr: int, n_vectors: int, stride: int, state_dptr: int = 0, stream: int = 0) -> None:
         """clg_exec_run: device pointers, asynchronous on `stream`."""
         check(lib().clg_exec_run(self._h, imm_dptr, out_dptr, state_dptr or None, n_vectors, stride, stream or None))

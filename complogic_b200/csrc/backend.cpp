@@ -791,6 +791,24 @@ struct Exec {
     launch_coop(P, params(P, imm, out, state, stride, groups), nt, stream);
   }
 
+  // what run() does before its launch for a batch of this size: mode choice, plan, CTA-size timing (clg_exec_prepare)
+  void prepare(size_t n_vectors) {
+    if (n_vectors == 0) return;
+    const size_t words = (n_vectors + 31) / 32;
+    ctx->bind();
+    mode = choose(words);
+    const bool use_parts = mode == CLG_MODE_COOP && parts_k() && (words + parts_k() - 1) / parts_k() < (size_t)ctx->sm_count;
+    if (mode == CLG_MODE_COOP && !use_parts && has_rows() && (words + 3) / 4 >= (size_t)ctx->sm_count) {
+      get_rows();
+    } else {
+      Plan &P = use_parts ? get_parts() : get(mode);
+      const uint32_t groups = (uint32_t)std::min<size_t>((words + P.K - 1) / P.K, 0xFFFFFFFFu);
+      if (mode == CLG_MODE_COOP && !P.n_parts && groups > (uint32_t)ctx->sm_count * coop_ctas_per_sm(P, P.coop_threads) && !P.tuned_threads)
+        P.tuned_threads = tune_coop_threads(P);
+    }
+    CU(cuCtxSynchronize());
+  }
+
   // ---- row form of the cooperative mode (clg_coop_rows; device layout in kernels.cu, RunParams) -----------------
   bool has_rows() const { return flat.rows().n_instr != 0 && !std::getenv("CLG_COOP_NO_ROWS"); }
   Plan &get_rows() {
@@ -1032,6 +1050,7 @@ void exec_run_steps(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state
 void exec_run_host(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride) {
   e->run_host(imm, out, state, n_vectors, stride);
 }
+void exec_prepare(Exec *e, size_t n_vectors) { e->prepare(n_vectors); }
 void exec_run(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, void *stream) {
   e->run(imm, out, state, n_vectors, stride, (CUstream)stream);
 }

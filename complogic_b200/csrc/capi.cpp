@@ -36,6 +36,7 @@ const std::string &exec_ptx(const Exec *);
 const Flat &exec_flat(const Exec *);
 Ctx *exec_ctx(const Exec *);
 void exec_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t, void *);
+void exec_prepare(Exec *, size_t);
 void exec_run_host(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t);
 void exec_run_steps(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t, size_t, void *);
 void launch_slice(Ctx *, bool, const void *, void *, size_t, size_t, size_t, void *);
@@ -351,6 +352,13 @@ int clg_exec_words_per_thread(const clg_exec *ex) { return ex ? exec_k(ex->e) : 
 int clg_exec_launches_per_run(const clg_exec *ex) { return ex ? exec_launches(ex->e) : 0; }
 const char *clg_exec_kernel_name(const clg_exec *ex) { return ex ? exec_kernel_name(ex->e) : ""; }
 const char *clg_exec_ptx(const clg_exec *ex) { return ex ? exec_ptx(ex->e).c_str() : ""; }
+
+int clg_exec_prepare(clg_exec *ex, size_t n_vectors) {
+  CLG_TRY
+  NEED(ex);
+  exec_prepare(ex->e, n_vectors);
+  CLG_CATCH
+}
 
 int clg_exec_run(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, void *stream) {
   CLG_TRY

@@ -465,7 +465,7 @@ __device__ __forceinline__ void coop_body(const RunParams &p) {
 // Compact streaming form of the cooperative kernel: half the instruction bytes through the LSU pipe and L2.
 __device__ __forceinline__ uint2 ld_cinstr(const uint2 *p) {
   uint2 v;
-  asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
 

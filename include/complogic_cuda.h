@@ -252,6 +252,11 @@ int clg_exec_launches_per_run(const clg_exec *ex);
 const char *clg_exec_kernel_name(const clg_exec *ex);
 /* specialised mode only: generated PTX text (NUL-terminated) for inspection */
 const char *clg_exec_ptx(const clg_exec *ex);
+/* Everything a first clg_exec_run of `n_vectors` lanes would otherwise do before its launch, done now: the mode is
+ * chosen for that batch size (CLG_MODE_AUTO), its streams are encoded and uploaded, a specialised kernel or chain is
+ * assembled, and the cooperative CTA size is timed on scratch buffers (a few tens of ms, once per plan). Synchronous. A
+ * later run of a batch that selects another plan prepares that one on its own first call, as before. */
+int clg_exec_prepare(clg_exec *ex, size_t n_vectors);
 
 /* The hot path: `Simulation::run(&mut self, immediates: &[bool])`, simulation.rs:16-30, for
  * n_vectors independent lanes at once. All pointers are DEVICE pointers.

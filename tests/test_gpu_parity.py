@@ -693,6 +693,34 @@ def test_persistent_sharded_executor_on_every_visible_device():
     shl.close()
 
 
+def test_prepare_moves_the_first_run_cost_out_of_the_run():
+    """clg_exec_prepare: the mode choice, the plan (upload / JIT) and the cooperative CTA-size timing of a batch size,
+    ahead of the first run -- the prepared executor's first run is then an ordinary one, and the results are the oracle's."""
+    import time
+    circ = circuits.random_dag(64, 1024, 256, 2, 3)
+    nv = 1 << 16
+    imm = random_sliced(circ.n_immediates, stride_for(nv), seed=4)
+    want = oracle_out(circ, imm, nv)
+    for mode, small in ((host.MODE_AUTO, False), (host.MODE_COOP, False), (host.MODE_COOP, True), (host.MODE_SPEC, False)):
+        c2 = circuits.array_multiplier(8) if mode == host.MODE_SPEC else circ
+        n2 = 3000 if small else nv
+        i2 = random_sliced(c2.n_immediates, stride_for(n2), seed=6)
+        cs = host.CudaSimulation.from_simulation(c2.sim, c2.n_immediates, c2.out_regs, mode=mode)
+        cs.prepare(n2)
+        cs.prepare(0)  # nothing to do
+        t0 = time.perf_counter()
+        got = mask_tail(cs.run_batch(i2, n2), n2)
+        first = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        cs.run_batch(i2, n2)
+        second = time.perf_counter() - t0
+        assert np.array_equal(got, oracle_out(c2, i2, n2)), (mode, small, cs.kernel_name)
+        assert first < 5 * second + 0.05, (mode, small, first, second)  # no plan build, JIT or tuning left in the first run
+    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs)
+    cs.prepare(nv)
+    assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), want)
+
+
 def test_row_kernel_on_dags_and_forced_programs(monkeypatch):
     """clg_coop_rows (row stream: lag-2 segments, no CTA barrier): random DAGs of several shapes, and -- with
     CLG_ROWS_FORCE -- structured and sequential programs the pass would otherwise leave to the other modes, on batches
