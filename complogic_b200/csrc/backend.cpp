@@ -216,6 +216,8 @@ static void assemble(const std::string &text, const char *entry, const std::stri
   CU(cuModuleGetFunction(fn, *mod, entry));
 }
 
+void launch_slice(Ctx *c, bool unslice, const void *src, void *dst, size_t n_vectors, size_t n_rows, size_t stride, void *stream);
+
 struct Exec {
   Ctx *ctx;
   Flat flat;  // own copy: the caller may destroy its clg_flat
@@ -580,6 +582,9 @@ struct Exec {
       if (P.scratch) d.cuMemFree(P.scratch);
       if (P.d_bases) d.cuMemFree(P.d_bases);
     }
+    for (int b = 0; b < NBUF; b++)
+      for (CUdeviceptr q : bstage[b])
+        if (q) d.cuMemFree(q);
     for (int b = 0; b < NBUF; b++) {
       if (stage_in[b]) d.cuMemFree(stage_in[b]);
       if (stage_out[b]) d.cuMemFree(stage_out[b]);
@@ -599,6 +604,8 @@ struct Exec {
   CUevent ev_in[NBUF] = {}, ev_run[NBUF] = {}, ev_out[NBUF] = {};
   CUdeviceptr stage_in[NBUF] = {}, stage_out[NBUF] = {}, stage_state[NBUF] = {};
   size_t stage_words = 0;
+  CUdeviceptr bstage[NBUF][4] = {};  // run_bools_host: per staging set {bools in, sliced in, sliced out, bools out}
+  size_t bstage_vectors = 0;
 
   void copy2d(bool to_device, CUdeviceptr dev, size_t dev_pitch, const void *host, size_t host_pitch, size_t width, size_t rows,
               CUstream st) {
@@ -613,6 +620,69 @@ struct Exec {
     }
     c.WidthInBytes = width, c.Height = rows;
     CU(cuMemcpy2DAsync(&c, st));
+  }
+
+  void ensure_streams() {
+    if (s_in) return;
+    CU(cuStreamCreate(&s_in, CU_STREAM_NON_BLOCKING));
+    CU(cuStreamCreate(&s_run, CU_STREAM_NON_BLOCKING));
+    CU(cuStreamCreate(&s_out, CU_STREAM_NON_BLOCKING));
+    for (int b = 0; b < NBUF; b++) {
+      CU(cuEventCreate(&ev_in[b], CU_EVENT_DISABLE_TIMING));
+      CU(cuEventCreate(&ev_run[b], CU_EVENT_DISABLE_TIMING));
+      CU(cuEventCreate(&ev_out[b], CU_EVENT_DISABLE_TIMING));
+    }
+  }
+
+  // `&[bool]`-shaped batch on HOST buffers: imm is [n_vectors][n_inputs] bytes (one run()'s immediates per vector), out is
+  // [n_vectors][n_outputs] bytes. Chunks of vectors go through H2D | slice, kernel, unslice | D2H on three streams with
+  // staging buffers that live with the executor, so PCIe (one byte per bool each way) is what a big batch waits for.
+  void run_bools_host(const uint8_t *imm, uint8_t *out, size_t n_vectors) {
+    const FlatHeader &h = flat.header();
+    if (h.n_state) fail(CLG_E_UNSUPPORTED, "run_bools_host is for stateless programs; use clg_sim_runner for carried state");
+    if (n_vectors == 0) return;
+    if (h.n_inputs && !imm) fail(CLG_E_INVALID, "imm is null");
+    if (h.n_outputs && !out) fail(CLG_E_INVALID, "out is null");
+    ctx->bind();
+    ensure_streams();
+    const size_t per_vector = std::max<size_t>(1, (size_t)h.n_inputs + h.n_outputs);
+    size_t cv = ((size_t)64 << 20) / per_vector;  // ~64 MB of host bytes per chunk
+    if (const char *env = std::getenv("CLG_BOOLS_CHUNK_VECTORS")) cv = std::strtoull(env, nullptr, 10);  // tuning / tests
+    cv = std::max<size_t>(1024, cv / 1024 * 1024);
+    cv = std::min(cv, (n_vectors + 1023) / 1024 * 1024);
+    if (cv > bstage_vectors) {
+      CU(cuCtxSynchronize());
+      const size_t sizes[4] = {cv * h.n_inputs, (size_t)h.n_inputs * (cv / 32) * 4, (size_t)h.n_outputs * (cv / 32) * 4, cv * h.n_outputs};
+      for (int b = 0; b < NBUF; b++)
+        for (int k = 0; k < 4; k++) {
+          if (bstage[b][k]) driver().cuMemFree(bstage[b][k]);
+          bstage[b][k] = 0;
+          CU(cuMemAlloc(&bstage[b][k], std::max<size_t>(16, sizes[k])));
+          if (k == 1) CU(cuMemsetD8Async(bstage[b][k], 0, std::max<size_t>(16, sizes[k]), nullptr));  // (the words behind a short last chunk)
+        }
+      CU(cuCtxSynchronize());
+      bstage_vectors = cv;
+    }
+    const size_t cstride = bstage_vectors / 32, n_chunks = (n_vectors + cv - 1) / cv;
+    for (size_t c = 0; c < n_chunks; c++) {
+      const int b = (int)(c % NBUF);
+      const size_t v0 = c * cv, nv = std::min(n_vectors, v0 + cv) - v0;
+      if (c >= NBUF) CU(cuStreamWaitEvent(s_in, ev_run[b], 0));  // the bools of chunk c - NBUF have been sliced
+      if (h.n_inputs) CU(cuMemcpyHtoDAsync(bstage[b][0], imm + v0 * h.n_inputs, nv * h.n_inputs, s_in));
+      CU(cuEventRecord(ev_in[b], s_in));
+      CU(cuStreamWaitEvent(s_run, ev_in[b], 0));
+      if (c >= NBUF) CU(cuStreamWaitEvent(s_run, ev_out[b], 0));  // ... and its results have been copied out
+      if (h.n_inputs) launch_slice(ctx, false, (const void *)bstage[b][0], (void *)bstage[b][1], nv, h.n_inputs, cstride, s_run);
+      run((const uint32_t *)bstage[b][1], (uint32_t *)bstage[b][2], nullptr, nv, cstride, s_run);
+      if (h.n_outputs) launch_slice(ctx, true, (const void *)bstage[b][2], (void *)bstage[b][3], nv, h.n_outputs, cstride, s_run);
+      CU(cuEventRecord(ev_run[b], s_run));
+      CU(cuStreamWaitEvent(s_out, ev_run[b], 0));
+      if (h.n_outputs) CU(cuMemcpyDtoHAsync(out + v0 * h.n_outputs, bstage[b][3], nv * h.n_outputs, s_out));
+      CU(cuEventRecord(ev_out[b], s_out));
+    }
+    CU(cuStreamSynchronize(s_in));
+    CU(cuStreamSynchronize(s_run));
+    CU(cuStreamSynchronize(s_out));
   }
 
   void run_host(const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride) {
@@ -632,16 +702,7 @@ struct Exec {
     cw = std::max<size_t>(4, cw) / 4 * 4;
     const size_t padded = (words + 3) / 4 * 4;
     cw = std::min(cw, padded);
-    if (!s_in) {
-      CU(cuStreamCreate(&s_in, CU_STREAM_NON_BLOCKING));
-      CU(cuStreamCreate(&s_run, CU_STREAM_NON_BLOCKING));
-      CU(cuStreamCreate(&s_out, CU_STREAM_NON_BLOCKING));
-      for (int b = 0; b < NBUF; b++) {
-        CU(cuEventCreate(&ev_in[b], CU_EVENT_DISABLE_TIMING));
-        CU(cuEventCreate(&ev_run[b], CU_EVENT_DISABLE_TIMING));
-        CU(cuEventCreate(&ev_out[b], CU_EVENT_DISABLE_TIMING));
-      }
-    }
+    ensure_streams();
     if (cw > stage_words) {
       CU(cuCtxSynchronize());
       for (int b = 0; b < NBUF; b++) {
@@ -1051,6 +1112,7 @@ void exec_run_host(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state,
   e->run_host(imm, out, state, n_vectors, stride);
 }
 void exec_prepare(Exec *e, size_t n_vectors) { e->prepare(n_vectors); }
+void exec_run_bools_host(Exec *e, const uint8_t *imm, uint8_t *out, size_t n_vectors) { e->run_bools_host(imm, out, n_vectors); }
 void exec_run(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, void *stream) {
   e->run(imm, out, state, n_vectors, stride, (CUstream)stream);
 }

@@ -37,6 +37,7 @@ const Flat &exec_flat(const Exec *);
 Ctx *exec_ctx(const Exec *);
 void exec_run(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t, void *);
 void exec_prepare(Exec *, size_t);
+void exec_run_bools_host(Exec *, const uint8_t *, uint8_t *, size_t);
 void exec_run_host(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t);
 void exec_run_steps(Exec *, const uint32_t *, uint32_t *, uint32_t *, size_t, size_t, size_t, void *);
 void launch_slice(Ctx *, bool, const void *, void *, size_t, size_t, size_t, void *);
@@ -399,24 +400,7 @@ int clg_exec_run_host(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t
 int clg_exec_run_bools_host(clg_exec *ex, const uint8_t *imm, uint8_t *out, size_t n_vectors) {
   CLG_TRY
   NEED(ex);
-  Ctx *c = exec_ctx(ex->e);
-  const FlatHeader &h = exec_flat(ex->e).header();
-  if (h.n_state) fail(CLG_E_UNSUPPORTED, "run_bools_host is for stateless programs; use clg_sim_runner for carried state");
-  const size_t stride = ((n_vectors + 31) / 32 + 3) / 4 * 4, row = stride * 4;
-  DevBuf bi(c, n_vectors * h.n_inputs), bo(c, n_vectors * h.n_outputs), di(c, h.n_inputs * row), dout(c, h.n_outputs * row);
-  if (h.n_inputs && n_vectors) {
-    NEED(imm);
-    h2d(c, bi.p, imm, n_vectors * h.n_inputs, nullptr);
-    dev_memset(c, di.p, 0, h.n_inputs * row, nullptr);
-    launch_slice(c, false, bi.p, di.p, n_vectors, h.n_inputs, stride, nullptr);
-  }
-  exec_run(ex->e, (const uint32_t *)di.p, (uint32_t *)dout.p, nullptr, n_vectors, stride, nullptr);
-  if (h.n_outputs && n_vectors) {
-    NEED(out);
-    launch_slice(c, true, dout.p, bo.p, n_vectors, h.n_outputs, stride, nullptr);
-    d2h(c, out, bo.p, n_vectors * h.n_outputs, nullptr);
-  }
-  stream_sync(c, nullptr);
+  exec_run_bools_host(ex->e, imm, out, n_vectors);
   CLG_CATCH
 }
 

@@ -372,13 +372,28 @@ def test_bools_api_and_transposes():
     circ = circuits.array_multiplier(8)
     cs = host.CudaSimulation.from_simulation(circ.sim, 16, circ.out_regs)
     rng = np.random.default_rng(3)
-    for nv in (1, 33, 1000):
+    import os
+    for nv, chunk in ((1, None), (33, None), (1000, None), (5000, "1024"), (3 * 2048 + 5, "2048"), (7 * 1024, "1024")):
+        # (small CLG_BOOLS_CHUNK_VECTORS: the chunked H2D | slice, run, unslice | D2H pipeline wraps its three staging sets)
+        if chunk:
+            os.environ["CLG_BOOLS_CHUNK_VECTORS"] = chunk
         imm = rng.integers(0, 2, size=(nv, 16), dtype=np.uint8)
         out = cs.run_bools(imm)
+        os.environ.pop("CLG_BOOLS_CHUNK_VECTORS", None)
         a = (imm[:, :8].astype(np.uint64) << np.arange(8, dtype=np.uint64)).sum(axis=1)
         b = (imm[:, 8:].astype(np.uint64) << np.arange(8, dtype=np.uint64)).sum(axis=1)
         p = (out.astype(np.uint64) << np.arange(16, dtype=np.uint64)).sum(axis=1)
-        assert np.array_equal(p, a * b)
+        assert np.array_equal(p, a * b), (nv, chunk)
+    # an odd number of rows on either side (65 in, 33 out: the generic transposes)
+    add = circuits.ripple_adder(32)
+    ca = host.CudaSimulation.from_simulation(add.sim, 65, add.out_regs)
+    os.environ["CLG_BOOLS_CHUNK_VECTORS"] = "4096"
+    imm = rng.integers(0, 2, size=(20000, 65), dtype=np.uint8)
+    out = ca.run_bools(imm)
+    os.environ.pop("CLG_BOOLS_CHUNK_VECTORS", None)
+    w = np.uint64(1) << np.arange(32, dtype=np.uint64)
+    want = (imm[:, :32] * w).sum(1) + (imm[:, 32:64] * w).sum(1) + imm[:, 64]
+    assert np.array_equal((out.astype(np.uint64) * (np.uint64(1) << np.arange(33, dtype=np.uint64))).sum(1), want)
 
 
 def test_transposes_tiled_and_fallback_paths():
