@@ -278,10 +278,15 @@ struct Exec {
         }
       case CLG_MODE_LANE:
         if (ln.n_instr == 0) return 0;
-        // the kernel is latency bound: what counts is resident consumer warps x K, which shared memory fixes
-        // (stack bytes per thread = slots * K * 4). Prefer the widest vector that still leaves >= 16 consumer warps.
+        if (const char *env = std::getenv("CLG_LANE_K")) return std::atoi(env);  // tuning knob
+        // The kernel executes ~39 warp instructions per interpreted instruction whatever K is, and each is a long
+        // dependent chain (fetch, three LDS, table dispatch, STS): with many warps it is bound by instruction issue
+        // (K = 1, 31 warps: 81 % of the issue slots), with few by the chain's latency. Shared memory fixes warps x K
+        // (stack bytes per thread = slots * K * 4). Prefer the widest vector that still leaves >= 8 consumer warps
+        // (tools/sweep_lane_k.sh: mul16 K = 1 / 2 / 4: 0.63 / 0.49 / 0.47 ms at 2^24 vectors, a 77-slot DAG 5.8 / 4.7 / 4.7,
+        // adder32 0.17 / 0.12 / 0.08; below 8 warps it turns around: mul64, 222 slots, 1.48 / 2.79).
         for (int k : {4, 2, 1})
-          if (lane_resident(k) >= 512u) return k;
+          if (lane_resident(k) >= 256u) return k;
         {  // big stacks: whatever keeps the most words in flight per SM
           int best = 0;
           uint32_t best_words = 0;
