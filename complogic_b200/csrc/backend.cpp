@@ -81,7 +81,7 @@ struct Ctx {
   CUcontext cu = nullptr;
   CUmodule mod = nullptr;
   int sm_count = 0;
-  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, slice_w[3] = {}, unslice_w[3] = {}, unslice_s64 = nullptr, slice_tma[7] = {}, unslice_tma[7] = {}, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, coop_rows_t = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, slice_w[3] = {}, unslice_w[3] = {}, unslice_s64 = nullptr, slice_tma[7] = {}, unslice_tma[7] = {}, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
   std::string name;
 
   static constexpr uint32_t TMA_RT[7] = {32, 64, 64, 128, 64, 128, 32}, TMA_VT[7] = {1024, 1024, 512, 512, 256, 256, 512};  // tile shapes of the TMA-tiled transposes (kernels.cu)
@@ -120,6 +120,8 @@ struct Ctx {
     }
     CU(cuModuleGetFunction(&coop_rows, mod, "clg_coop_rows"));
     CU(cuFuncSetAttribute(coop_rows, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
+    CU(cuModuleGetFunction(&coop_rows_t, mod, "clg_coop_rows_t"));
+    CU(cuFuncSetAttribute(coop_rows_t, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
     CU(cuModuleGetFunction(&slice, mod, "clg_slice"));
     CU(cuModuleGetFunction(&unslice, mod, "clg_unslice"));
     CU(cuModuleGetFunction(&slice_v4, mod, "clg_slice_v4"));
@@ -181,7 +183,8 @@ struct Plan {
   bool ready = false;
   int K = 0;
   CUdeviceptr d_instr = 0, d_levels = 0, d_parts = 0, d_cinstr = 0, d_clevels = 0;  // (compact cooperative form)
-  uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0, n_parts = 0, code_off = 0;
+  uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0, n_parts = 0, code_off = 0, ring_off = 0;
+  bool rows_tma = false;  // row form: instruction stream staged through shared memory (clg_coop_rows_t)
   size_t smem = 0;
   uint32_t tuned_threads = 0;  // cooperative, big batches: CTA size found by timing candidates on this device (0: not tuned yet)
   bool resident = false;  // cooperative: the (largest part's) instruction stream is staged in shared memory
@@ -802,7 +805,7 @@ struct Exec {
     // a batch that gives every SM a column group runs the row stream when the pass built one
     if (mode == CLG_MODE_COOP && !use_parts && has_rows() && (words + 3) / 4 >= (size_t)ctx->sm_count) {
       Plan &R = get_rows();
-      last_k = 4, last_parts = 0, last_rows = true, last_kernel = "clg_coop_rows";
+      last_k = 4, last_parts = 0, last_rows = true, last_kernel = R.rows_tma ? "clg_coop_rows_t" : "clg_coop_rows";
       launch_rows(R, params(R, imm, out, state, stride, (uint32_t)((words + 3) / 4)), stream);
       return;
     }
@@ -890,11 +893,20 @@ struct Exec {
     P.code_off = (uint32_t)(((size_t)r.n_slots * 16 + 15) / 16 * 16);
     P.smem = P.code_off + 16;  // register stack + two mbarriers
     if (P.smem > SMEM_MAX) fail(CLG_E_UNSUPPORTED, "row stream: register stack exceeds one SM's shared memory");
-    std::vector<uint32_t> words, wbase(nw);  // 2 words per lane instruction
+    // clg_coop_rows_t: + per warp a ring of two stages of four rows (2 KB) and two mbarriers, if there is room
+    P.ring_off = (uint32_t)((P.smem + 127) / 128 * 128);
+    const size_t with_ring = (size_t)P.ring_off + (size_t)nw * (2 * 4 * 256 + 2 * 8);
+    // (measured slower: dag1m x 2^22 52.4 ms against 42.4 ms with the ld.global fetch -- 32 warps x one 1 KB bulk copy every
+    // four rows is more requests than the copy engine turns around, and bigger stages do not fit next to the stack. Kept
+    // as an option, CLG_ROWS_TMA=1, and in the parity tests.)
+    P.rows_tma = with_ring <= SMEM_MAX && std::getenv("CLG_ROWS_TMA");
+    if (P.rows_tma) P.smem = with_ring;
+    std::vector<uint32_t> words, wbase(2 * (size_t)nw);  // 2 words per lane instruction; wbase: nw offsets, then nw row counts
     words.reserve(((size_t)r.n_instr + (size_t)(S + 3) * nw * 32) * 2);
     constexpr uint32_t EMPTY_X = 0x40000000u, EMPTY_Y = 0x80000000u;  // no load of a, no store
     for (uint32_t w = 0; w < nw; w++) {
       wbase[w] = (uint32_t)(words.size() / 2);
+      const size_t first_word = words.size();
       for (uint32_t sgm = 0; sgm < S; sgm++) {
         const uint32_t b = sgm < S0 ? rt[(size_t)sgm * nw + w] : 0, e = sgm < S0 ? rt[(size_t)sgm * nw + w + 1] : 0;
         const uint32_t n_rows = std::max<uint32_t>(1, (e - b) / 32);  // at least one (empty) row: it carries the end-of-segment mark
@@ -948,7 +960,16 @@ struct Exec {
           for (uint32_t i = 0; i < 32; i++) words.push_back(x[i] | ((hdr >> i & 1u) << 31)), words.push_back(y[i]);
         }
       }
-      for (uint32_t i = 0; i < 8 * 32; i++) words.push_back(EMPTY_X), words.push_back(EMPTY_Y);  // the fetch runs up to seven rows ahead
+      // a multiple of four rows per warp (clg_coop_rows_t stages them four at a time): empty rows before the last one
+      {
+        const size_t n_rows_w = (words.size() - first_word) / 64, pad = (4 - n_rows_w % 4) % 4;
+        std::vector<uint32_t> last(words.end() - 64, words.end());
+        words.resize(words.size() - 64);
+        for (size_t i = 0; i < pad * 32; i++) words.push_back(EMPTY_X), words.push_back(EMPTY_Y);
+        words.insert(words.end(), last.begin(), last.end());
+        wbase[nw + w] = (uint32_t)(n_rows_w + pad);
+      }
+      for (uint32_t i = 0; i < 8 * 32; i++) words.push_back(EMPTY_X), words.push_back(EMPTY_Y);  // clg_coop_rows fetches up to seven rows ahead
     }
     if (words.size() / 2 >= (1ull << 32)) fail(CLG_E_UNSUPPORTED, "row stream too long");
     std::vector<uint32_t> side((size_t)std::max<uint32_t>(r.n_side, 1) * 4, 0);
@@ -969,11 +990,11 @@ struct Exec {
   }
   void launch_rows(Plan &P, RunParams p, CUstream stream) {
     p.instr = (const void *)P.d_rside, p.rinstr = (const void *)P.d_rinstr, p.rwarp = (const uint32_t *)P.d_rwarp;
-    p.rside_off = (const uint32_t *)P.d_rside_off, p.code_off = P.code_off;
+    p.rside_off = (const uint32_t *)P.d_rside_off, p.code_off = P.code_off, p.ring_off = P.ring_off;
     const uint32_t per_sm = coop_ctas_per_sm(P, P.rows_nt);
     const uint32_t grid = std::min<uint32_t>(p.n_groups, (uint32_t)ctx->sm_count * per_sm);
     void *args[] = {&p};
-    CU(cuLaunchKernel(ctx->coop_rows, grid, 1, 1, P.rows_nt, 1, 1, (unsigned)P.smem, stream, args, nullptr));
+    CU(cuLaunchKernel(P.rows_tma ? ctx->coop_rows_t : ctx->coop_rows, grid, 1, 1, P.rows_nt, 1, 1, (unsigned)P.smem, stream, args, nullptr));
   }
 
   RunParams params(const Plan &P, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t stride, uint32_t groups) const {

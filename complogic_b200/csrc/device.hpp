@@ -57,6 +57,7 @@ struct RunParams {
   const void *rinstr;  // row form (clg_coop_rows)
   const uint32_t *rwarp;
   const uint32_t *rside_off;
+  uint32_t ring_off;  // clg_coop_rows_t: byte offset of the per-warp instruction rings in shared memory
 };
 
 constexpr int LANE_MIN_THREADS = 64, LANE_MAX_THREADS = 992;  // consumer threads of a lane-kernel CTA (+ 32 producer)

@@ -81,9 +81,14 @@ struct RunParams {
   //   warp has at least one (possibly empty) row per segment; the segment count is padded to a multiple of four with
   //   empty segments (mbarrier parities then depend on the segment alone), and eight empty rows follow a warp's last
   //   one (the fetch runs three rows ahead, in groups of four).
+  //   A warp's row count is a multiple of four (empty rows are inserted before its last one); rwarp holds the n_warps
+  //   offsets and then the n_warps row counts.
+  //   clg_coop_rows_t stages the rows through shared memory instead of fetching them with ld.global: ring_off is the byte
+  //   offset of the per-warp rings (two stages of four rows, 2 KB per warp) and their mbarriers behind them.
   const uint2 *rinstr;
   const uint32_t *rwarp;
   const uint32_t *rside_off;
+  uint32_t ring_off;
 };
 
 // ---- LOP3 with a compile-time immediate, dispatched on the instruction's truth table --------------
@@ -696,6 +701,101 @@ __device__ __forceinline__ void coop_rows_body(const RunParams &p) {
   }
 }
 
+// The same kernel with the instruction stream staged through shared memory by the bulk-copy engine (what the level and
+// lane interpreters do with their streams): every warp owns a ring of two stages of four rows (2 x 1 KB) and one
+// mbarrier per stage. The warp's elected lane issues `cp.async.bulk` for the stage two ahead as soon as the four rows of
+// the current one are in registers (four conflict-free LDS.64 per lane, whose headers are balloted at once, so the
+// buffer is provably read before it is refilled); the program is the same for every column group, so the ring simply
+// wraps from a group's last stage to the next group's first and never drains. No ld.global of instruction words, no L1
+// tags, no four-deep register prefetch.
+constexpr uint32_t RING_ROWS = 4, RING_NS = 2, RING_STAGE_BYTES = RING_ROWS * 256, RING_WARP_BYTES = RING_NS * RING_STAGE_BYTES;
+
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void ring_issue(uint32_t dst, const uint2 *src, uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%2], %3;\n"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %3, [%2];\n"
+      "}\n" ::"r"(dst),
+      "l"(src), "r"(bar), "r"(RING_STAGE_BYTES)
+      : "memory");
+}
+// rows_step with the header already balloted and no fetch of its own
+__device__ __forceinline__ bool rows_step_h(const RunParams &p, const uint2 ins, const uint32_t h, Vec<4> &P, uint32_t &sgm, uint32_t &bcur, uint32_t sb, uint32_t g) {
+  if (h & RH_WAIT) mbar_wait_u32(bcur, ((sgm >> 1) & 1u) ^ 1u);
+  if (h & RH_TABLES) row_exec(ins, h, P, sb);
+  if (h & RH_SEG_END) {
+    if (h & RH_SIDE) rows_side(p, sgm, sb, g);
+    __syncwarp();
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(bcur)
+        : "memory");
+    sgm++, bcur ^= 8u;
+    return (h & RH_LAST) != 0;
+  }
+  return false;
+}
+
+__device__ __forceinline__ void coop_rows_t_body(const RunParams &p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31u;
+  uint32_t sb = smem_u32(smem);
+  asm volatile("" : "+r"(sb));
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + p.code_off);  // two mbarriers behind the register stack
+  const uint32_t ring = sb + p.ring_off + warp * RING_WARP_BYTES;   // this warp's two stages ...
+  const uint32_t full = sb + p.ring_off + (nt >> 5) * RING_WARP_BYTES + warp * (RING_NS * 8);  // ... and their mbarriers
+  if (tid == 0) {
+    mbar_init(&bar[0], nt >> 5);
+    mbar_init(&bar[1], nt >> 5);
+  }
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full + 8u));
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const uint32_t bar0 = sb + p.code_off;
+  const uint32_t w0 = __ldg(p.rwarp + warp), n_stages = __ldg(p.rwarp + (nt >> 5) + warp) / RING_ROWS;
+  const uint2 *src = p.rinstr + w0;
+  // stage j counted from a column group's first stage belongs to the group j / n_stages launches of this CTA further
+  // on (the program is the same for every group, so the ring wraps and never drains)
+  auto refill = [&](uint32_t g, uint32_t j, uint32_t b) {
+    if ((uint64_t)g + (uint64_t)(j / n_stages) * gridDim.x < p.n_groups)
+      ring_issue(ring + b * RING_STAGE_BYTES, src + (size_t)(j % n_stages) * (RING_ROWS * 32), full + b * 8u);
+  };
+  refill(blockIdx.x, 0, 0);
+  refill(blockIdx.x, 1, 1);
+  uint32_t t = 0;  // stages consumed so far, over all column groups: stage t sits in buffer t & 1, its barrier is in phase (t >> 1) & 1
+  for (uint32_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+    Vec<4> P = dont_care<4>();
+    uint32_t sgm = 0, bcur = bar0;
+    for (uint32_t tg = 0; tg < n_stages; tg++, t++) {
+      const uint32_t b = t & 1u, buf = ring + b * RING_STAGE_BYTES + lane * 8u;
+      mbar_wait_u32(full + b * 8u, (t >> 1) & 1u);
+      const uint2 A = lds64(buf), B = lds64(buf + 256u), C = lds64(buf + 512u), D = lds64(buf + 768u);
+      const uint32_t hA = row_header(A.x), hB = row_header(B.x), hC = row_header(C.x), hD = row_header(D.x);
+      // (every lane's four loads have delivered: the ballots consumed them.) Refill this buffer with the stage two ahead.
+      refill(g, tg + RING_NS, b);
+      rows_step_h(p, A, hA, P, sgm, bcur, sb, g);
+      rows_step_h(p, B, hB, P, sgm, bcur, sb, g);
+      rows_step_h(p, C, hC, P, sgm, bcur, sb, g);
+      rows_step_h(p, D, hD, P, sgm, bcur, sb, g);  // (the warp's last row is the fourth of its last stage)
+    }
+    mbar_wait_u32(bar0, 1u);
+    mbar_wait_u32(bar0 + 8u, 1u);
+  }
+}
+
 // ---- layout helpers ----------------------------------------------------------------------------------
 // bools [n_vectors][n_rows] bytes (one run()'s `&[bool]` per vector)  ->  sliced [n_rows][stride] words
 extern "C" __global__ void __launch_bounds__(256) clg_slice(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows,
@@ -1136,3 +1236,4 @@ CLG_ENTRY(1)
 CLG_ENTRY(2)
 CLG_ENTRY(4)
 extern "C" __global__ void __launch_bounds__(1024) clg_coop_rows(const __grid_constant__ clg::RunParams p) { clg::coop_rows_body(p); }
+extern "C" __global__ void __launch_bounds__(1024) clg_coop_rows_t(const __grid_constant__ clg::RunParams p) { clg::coop_rows_t_body(p); }

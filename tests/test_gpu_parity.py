@@ -517,7 +517,7 @@ def test_full_size_dag_1m_2p24():
     out = torch.zeros((4096, stride), dtype=torch.int32, device="cuda:0")
     cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
     torch.cuda.synchronize()
-    assert cs.mode == host.MODE_COOP and cs.kernel_name == "clg_coop_rows"
+    assert cs.mode == host.MODE_COOP and cs.kernel_name.startswith("clg_coop_rows")
     assert _check_sampled_columns(circ, imm, out, nv) >= 4 * 150
     # the previous generation of the cooperative kernel on the same inputs: identical buffers, word for word
     import os
@@ -740,23 +740,29 @@ def test_row_kernel_on_dags_and_forced_programs(monkeypatch):
     """clg_coop_rows (row stream: lag-2 segments, no CTA barrier): random DAGs of several shapes, and -- with
     CLG_ROWS_FORCE -- structured and sequential programs the pass would otherwise leave to the other modes, on batches
     that give every SM a column group, word for word against the oracle VM."""
-    for shape, nv in (((64, 1024, 256, 2, 3), 1 << 16), ((40, 512, 128, 2, 5), 40000), ((30, 300, 64, 0, 9), 19001)):
+    for shape, nv in (((64, 1024, 256, 2, 3), 1 << 16), ((40, 512, 128, 2, 5), 40000), ((30, 300, 64, 0, 9), 19001),
+                      ((40, 512, 128, 2, 5), 50000)):
+        # the last one through clg_coop_rows_t (instruction stream staged through shared memory with cp.async.bulk)
+        if nv == 50000:
+            monkeypatch.setenv("CLG_ROWS_TMA", "1")
         circ = circuits.random_dag(*shape)
         imm = random_sliced(circ.n_immediates, stride_for(nv), seed=4)
         cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, mode=host.MODE_COOP)
         got = mask_tail(cs.run_batch(imm, nv), nv)
-        assert cs.kernel_name == "clg_coop_rows" and cs.info["rows_segments"] > 0
+        assert cs.kernel_name.startswith("clg_coop_rows") and cs.info["rows_segments"] > 0
         assert np.array_equal(got, oracle_out(circ, imm, nv))
+        assert (cs.kernel_name == "clg_coop_rows_t") == (nv == 50000)
         small = mask_tail(cs.run_batch(imm[:, :8], 200), 200)  # a batch too small for it goes to the older kernels
-        assert cs.kernel_name != "clg_coop_rows"
+        assert not cs.kernel_name.startswith("clg_coop_rows")
         assert np.array_equal(small, oracle_out(circ, np.ascontiguousarray(imm[:, :8]), 200))
+    monkeypatch.delenv("CLG_ROWS_TMA")
     monkeypatch.setenv("CLG_ROWS_FORCE", "1")
     nv = 19000
     for circ in (circuits.array_multiplier(8), circuits.ripple_adder(16), circuits.flatten_instances(circuits.array_multiplier(8), 3)):
         imm = random_sliced(circ.n_immediates, stride_for(nv), seed=5)
         cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, mode=host.MODE_COOP)
         got = mask_tail(cs.run_batch(imm, nv), nv)
-        assert cs.kernel_name == "clg_coop_rows"
+        assert cs.kernel_name.startswith("clg_coop_rows")
         assert np.array_equal(got, oracle_out(circ, imm, nv))
     # a sequential circuit: carried registers through the row kernel, several steps
     latch = circuits.latch_chain(10)
@@ -767,7 +773,7 @@ def test_row_kernel_on_dags_and_forced_programs(monkeypatch):
     state = np.zeros((cs.info["n_state"], stride), np.uint32)
     for s_ in range(steps):
         got = cs.run_batch(imms[s_], nv, state=state)
-        assert cs.kernel_name == "clg_coop_rows"
+        assert cs.kernel_name.startswith("clg_coop_rows")
         assert np.array_equal(mask_tail(got, nv), mask_tail(want[s_], nv))
 
 
@@ -790,7 +796,7 @@ def test_random_programs_row_kernel(prog, seed):
         state = np.zeros((cs.info["n_state"], stride), np.uint32)
         for s in range(steps):
             got = cs.run_batch(imm[s], nv, state=state)
-            assert cs.info["rows_instrs"] == 0 or cs.kernel_name == "clg_coop_rows"
+            assert cs.info["rows_instrs"] == 0 or cs.kernel_name.startswith("clg_coop_rows")
             assert np.array_equal(mask_tail(got, nv), mask_tail(want[s], nv))
     finally:
         del os.environ["CLG_ROWS_FORCE"]
