@@ -224,8 +224,9 @@ struct Mapper {
     return remap_table().t[p[0] * 9 + p[1] * 3 + p[2]][c.tt];
   }
 
+  float leaf_w = 0.f;  // cost of a cut = 1 + leaf_w * leaves (0: count LUTs; > 0: also count operand loads, what the cooperative kernels pay per LUT)
   void eval_cut(Cut &c, uint32_t node) const {
-    float f = 1.0f;
+    float f = 1.0f + leaf_w * (float)c.n;
     uint16_t d = 0;
     for (int i = 0; i < c.n; i++) f += flow[c.leaf[i]], d = std::max(d, depth[c.leaf[i]]);
     c.flow = f / (float)std::max<uint32_t>(1u, refs[node]);
@@ -324,8 +325,9 @@ struct Mapper {
     Mapper &m;
     std::vector<uint32_t> r;
     explicit Exact(Mapper &m_) : m(m_), r(m_.cover_refs()) {}
+    uint32_t cost(uint32_t n) const { return 256u + (uint32_t)(256.f * m.leaf_w) * m.best[n].n; }
     uint32_t deref(uint32_t n) {
-      uint32_t a = 1;
+      uint32_t a = cost(n);
       for (int i = 0; i < m.best[n].n; i++) {
         uint32_t l = m.best[n].leaf[i];
         if (--r[l] == 0 && m.g.is_and(l)) a += deref(l);
@@ -333,7 +335,7 @@ struct Mapper {
       return a;
     }
     uint32_t ref(uint32_t n) {
-      uint32_t a = 1;
+      uint32_t a = cost(n);
       for (int i = 0; i < m.best[n].n; i++) {
         uint32_t l = m.best[n].leaf[i];
         if (r[l]++ == 0 && m.g.is_and(l)) a += ref(l);
@@ -362,6 +364,7 @@ struct Mapper {
   };
 
   void run() {
+    if (const char *env = std::getenv("CLG_MAP_LEAF_WEIGHT")) leaf_w = (float)std::atof(env);  // (experiment knob)
     {
       Phase ph("map: cut enumeration");
       mark_live();
