@@ -81,9 +81,10 @@ struct Ctx {
   CUcontext cu = nullptr;
   CUmodule mod = nullptr;
   int sm_count = 0;
-  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, coop_rows_t = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, slice_w[3] = {}, unslice_w[3] = {}, unslice_s64 = nullptr, slice_tma[7] = {}, unslice_tma[7] = {}, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, coop_rows_t = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, slice_w[3] = {}, unslice_w[3] = {}, unslice_s64 = nullptr, slice_tma[7] = {}, unslice_tma[7] = {}, slice_gen = nullptr, unslice_gen = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
   std::string name;
 
+  static constexpr uint32_t GEN_MAX_BYTES = 96 * 1024;  // staged transposes for any row count (kernels.cu, clg_slice_gen)
   static constexpr uint32_t TMA_RT[7] = {32, 64, 64, 128, 64, 128, 32}, TMA_VT[7] = {1024, 1024, 512, 512, 256, 256, 512};  // tile shapes of the TMA-tiled transposes (kernels.cu)
   static size_t tma_smem(int i) { return (size_t)TMA_VT[i] * TMA_RT[i] + (size_t)TMA_RT[i] * (TMA_VT[i] / 32 + 1) * 4 + 16 + 1024; }  // (+ slack to align the base to 1024)
 
@@ -139,6 +140,10 @@ struct Ctx {
       CU(cuFuncSetAttribute(slice_tma[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)tma_smem(i)));
       CU(cuFuncSetAttribute(unslice_tma[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)tma_smem(i)));
     }
+    CU(cuModuleGetFunction(&slice_gen, mod, "clg_slice_gen"));
+    CU(cuModuleGetFunction(&unslice_gen, mod, "clg_unslice_gen"));
+    CU(cuFuncSetAttribute(slice_gen, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)(GEN_MAX_BYTES + 256)));
+    CU(cuFuncSetAttribute(unslice_gen, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)(GEN_MAX_BYTES + 256)));
     CU(cuModuleGetFunction(&fill, mod, "clg_fill_random"));
     CU(cuModuleGetFunction(&lop3_peak, mod, "clg_lop3_peak"));
   }
@@ -1191,6 +1196,18 @@ void launch_slice(Ctx *c, bool unslice, const void *src, void *dst, size_t n_vec
     const uint64_t gx = ((n_vectors + 31) / 32 + 7) / 8, gy = (n_rows + 31) / 32;
     if (gx * gy > 0x7FFFFFFFull) fail(CLG_E_INVALID, "transpose too large for one launch");
     CU(cuLaunchKernel(unslice ? c->unslice_v4 : c->slice_v4, (unsigned)(gx * gy), 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr));
+    return;
+  }
+  if (((uintptr_t)vec_side & 15) == 0 && n_rows * 32 <= Ctx::GEN_MAX_BYTES && !std::getenv("CLG_TRANSPOSE_NARROW") && !std::getenv("CLG_TRANSPOSE_BYTEWISE")) {
+    // any row count: VT consecutive vectors are one contiguous, 32-byte aligned run of VT * n_rows bytes, staged in shared
+    // memory by a 1-D bulk copy (kernels.cu, clg_slice_gen)
+    uint32_t vt = (uint32_t)std::min<size_t>(256, Ctx::GEN_MAX_BYTES / n_rows / 32 * 32);
+    vt = (uint32_t)std::min<size_t>(vt, (n_vectors + 31) / 32 * 32);
+    const uint64_t grid = (n_vectors + vt - 1) / vt;
+    if (grid > 0x7FFFFFFFull) fail(CLG_E_INVALID, "transpose too large for one launch");
+    const void *other = unslice ? src : dst, *vec = vec_side;
+    void *gargs[] = {unslice ? (void *)&other : (void *)&vec, unslice ? (void *)&vec : (void *)&other, &nv, &nr, &st, &vt};
+    CU(cuLaunchKernel(unslice ? c->unslice_gen : c->slice_gen, (unsigned)grid, 1, 1, 256, 1, 1, (unsigned)((size_t)vt * n_rows + 256), (CUstream)stream, gargs, nullptr));
     return;
   }
   uint64_t warps = (uint64_t)((n_rows + 31) / 32) * ((n_vectors + 31) / 32);

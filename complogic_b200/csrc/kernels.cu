@@ -1185,6 +1185,146 @@ CLG_TMA(64, 256)
 CLG_TMA(128, 256)
 #undef CLG_TMA
 
+// ---- staged transposes for ANY row count (16-byte aligned matrix) ------------------------------------------------------
+// With n_rows % 16 != 0 (an n-bit adder has 2n + 1 inputs and n + 1 outputs) a vector's bytes start at any alignment and
+// no 2-D tensor map describes the matrix -- but VT consecutive vectors are still ONE contiguous run of VT * n_rows bytes
+// that starts 32-byte aligned when VT is a multiple of 32. A CTA moves that run between global and shared memory with one
+// 1-D bulk copy (cp.async.bulk; the last few bytes of the matrix, which need not be a multiple of 16, with plain byte
+// accesses) and does the byte-granular work in shared memory: lane = vector reads the 32 bytes of a row tile as nine
+// aligned words and funnel-shifts them into place (writes: aligned words in the middle, single bytes at the two ragged
+// ends, because the neighbouring bytes belong to another warp's row tile). Packing, unpacking and the 32 x 32 bit
+// transpose are the ones above. A warp keeps the VT / 32 (up to 8) words of its row in registers, lane = row, so the
+// sliced side moves 32 bytes per row. The generic kernels before these read one byte per load (1.2-1.4 TB/s).
+constexpr uint32_t GEN_MAX_BYTES = 96 * 1024;  // of vector-major bytes staged per CTA
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+extern "C" __global__ void __launch_bounds__(256) clg_slice_gen(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows, uint32_t stride,
+                                                                uint32_t vt) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  unsigned char *stage = smem + 128;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, R = n_rows;
+  const uint32_t v0 = blockIdx.x * vt, nvt = min(vt, n_vectors - v0), words = (n_vectors + 31) / 32;
+  const size_t g0 = (size_t)v0 * R;
+  const uint32_t bytes = nvt * R, bulk = bytes & ~15u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (bulk) {
+      mbar_expect_tx(bar, bulk);
+      bulk_g2s(stage, bools + g0, bulk, bar);
+    }
+  }
+  if (threadIdx.x < bytes - bulk) stage[bulk + threadIdx.x] = bools[g0 + bulk + threadIdx.x];
+  __syncthreads();
+  if (bulk) mbar_wait(bar, 0);
+  const uint32_t sbase = smem_u32(stage), n_rt = (R + 31) / 32, n_c = (nvt + 31) / 32;
+  for (uint32_t rt = warp; rt < n_rt; rt += 8) {
+    const uint32_t nr = min(32u, R - rt * 32), row_mask = nr == 32 ? 0xFFFFFFFFu : (1u << nr) - 1u;
+    uint32_t acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      acc[c] = 0;
+      if ((uint32_t)c >= n_c) continue;  // (warp-uniform)
+      const uint32_t vl = c * 32 + lane, o = vl * R + rt * 32, sh = (o & 3u) * 8u, wa = sbase + (o & ~3u);
+      uint32_t bits = 0;
+      if (vl < nvt) {
+        uint32_t W[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) W[k] = lds32(wa + 4 * k);  // (up to 36 bytes from o: the stage has slack behind the last vector)
+        uint32_t B[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) B[k] = __funnelshift_r(W[k], W[k + 1], sh);
+        bits = (pack16(make_uint4(B[0], B[1], B[2], B[3])) | pack16(make_uint4(B[4], B[5], B[6], B[7])) << 16) & row_mask;
+      }
+      acc[c] = transpose32(bits, lane);  // lane = row rt * 32 + lane, bit k = vector v0 + 32 c + k
+    }
+    const uint32_t row = rt * 32 + lane;
+    if (row < R) {
+      uint32_t *dst = sliced + (size_t)row * stride + v0 / 32;
+      if (n_c == 8 && v0 / 32 + 8 <= words && ((v0 / 32) & 7u) == 0) {
+        __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(acc[0], acc[1], acc[2], acc[3]));
+        __stcs(reinterpret_cast<uint4 *>(dst) + 1, make_uint4(acc[4], acc[5], acc[6], acc[7]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+          if ((uint32_t)c < n_c && v0 / 32 + c < words) dst[c] = acc[c];
+      }
+    }
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(256) clg_unslice_gen(const uint32_t *sliced, uint8_t *bools, uint32_t n_vectors, uint32_t n_rows, uint32_t stride,
+                                                                  uint32_t vt) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char *stage = smem + 128;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, R = n_rows;
+  const uint32_t v0 = blockIdx.x * vt, nvt = min(vt, n_vectors - v0), words = (n_vectors + 31) / 32;
+  const size_t g0 = (size_t)v0 * R;
+  const uint32_t bytes = nvt * R, bulk = bytes & ~15u;
+  const uint32_t sbase = smem_u32(stage), n_rt = (R + 31) / 32, n_c = (nvt + 31) / 32;
+  for (uint32_t rt = warp; rt < n_rt; rt += 8) {
+    const uint32_t nr = min(32u, R - rt * 32), row = rt * 32 + lane;
+    uint32_t acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) acc[c] = 0;
+    if (row < R) {
+      const uint32_t *src = sliced + (size_t)row * stride + v0 / 32;
+      if (n_c == 8 && v0 / 32 + 8 <= words && ((v0 / 32) & 7u) == 0) {
+        const uint4 lo = __ldcs(reinterpret_cast<const uint4 *>(src)), hi = __ldcs(reinterpret_cast<const uint4 *>(src) + 1);
+        acc[0] = lo.x, acc[1] = lo.y, acc[2] = lo.z, acc[3] = lo.w, acc[4] = hi.x, acc[5] = hi.y, acc[6] = hi.z, acc[7] = hi.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+          if ((uint32_t)c < n_c && v0 / 32 + c < words) acc[c] = src[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      if ((uint32_t)c >= n_c) continue;  // (warp-uniform)
+      const uint32_t bits = transpose32(acc[c], lane);  // lane = vector v0 + 32 c + lane, bit r = row rt * 32 + r
+      const uint32_t vl = c * 32 + lane;
+      if (vl >= nvt) continue;
+      uint32_t B[9];
+#pragma unroll
+      for (int k = 0; k < 8; k++) B[k] = unpack4((bits >> (4 * k)) & 15u);
+      B[8] = 0;
+      // bytes [o, o + nr) of the stage: `lead` single bytes up to the next word boundary, whole words, single bytes at the end
+      const uint32_t o = vl * R + rt * 32, lead = min((4u - (o & 3u)) & 3u, nr), nw = (nr - lead) / 4, tail = nr - lead - 4 * nw;
+      const uint32_t a0 = sbase + o + lead;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        if ((uint32_t)i < lead) asm volatile("st.shared.u8 [%0], %1;" ::"r"(sbase + o + i), "r"(B[0] >> (8 * i)) : "memory");
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t w = __funnelshift_r(B[j], B[j + 1], lead * 8u);  // bytes lead + 4 j .. of this lane's 32
+        if ((uint32_t)j < nw) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a0 + 4 * j), "r"(w) : "memory");
+        if ((uint32_t)j == nw) {
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+            if ((uint32_t)i < tail) asm volatile("st.shared.u8 [%0], %1;" ::"r"(a0 + 4 * j + i), "r"(w >> (8 * i)) : "memory");
+        }
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy writes above, before the bulk store reads them
+  __syncthreads();
+  if (threadIdx.x == 0 && bulk) {
+    bulk_s2g(bools + g0, sbase, bulk);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  if (threadIdx.x < bytes - bulk) bools[g0 + bulk + threadIdx.x] = stage[bulk + threadIdx.x];
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ULL;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;

@@ -273,11 +273,35 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
     for (uint32_t i = begin; i < end; i++)
       if ((in[i].kind == K_LUT || in[i].kind == K_LDIN) && out_live[in[i].dst]) store_at[in[i].dst] = i;
   }
+  // A live-in register's slot belongs to it from the top of the chunk (that is what live across the cut means), so
+  // loading it early costs no register: reloads are issued `ahead` instructions before the first use -- far enough to
+  // cover a DRAM round trip at two warps per scheduler, not all at the top, where the whole chunk would wait for them.
+  // Scratch words this chunk does not write itself are read-only for the kernel (.nc: the assembler may keep the load
+  // where it is put instead of ordering it against the chunk's stores).
+  std::vector<std::pair<uint32_t, uint32_t>> first_use;  // (instruction, slot), ascending
+  size_t next_reload = 0;
+  static const uint32_t ahead = std::getenv("CLG_SPEC_PREFETCH") ? (uint32_t)std::atoi(std::getenv("CLG_SPEC_PREFETCH")) : 768u;
+  if (chunk) {
+    std::vector<uint8_t> seen(n_slots, 0);
+    for (uint32_t i = begin; i < end; i++) {
+      const FlatInstr &x = in[i];
+      auto use = [&](uint32_t sl) {
+        if (sl < n_slots && need_load[sl] && !seen[sl]) seen[sl] = 1, first_use.push_back({i, sl});
+      };
+      if (x.kind == K_LUT) use(x.a), use(x.b), use(x.c);
+      else if (x.kind == K_STOUT) use(x.a);
+      if ((x.kind == K_LUT || x.kind == K_LDIN) && x.dst < n_slots) seen[x.dst] = 1;  // (defined here before any use: not a reload)
+    }
+  }
   auto reload = [&](uint32_t sl) {
     if (!chunk || !need_load[sl]) return;
     need_load[sl] = 0;
-    std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  ld.global%s.u32 %s, [%%addr];\n", sl, vt, vec(sl).c_str());
+    std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  ld.global%s%s.u32 %s, [%%addr];\n", sl,
+                  store_at[sl] == UINT32_MAX ? ".nc.L1::no_allocate" : "", vt, vec(sl).c_str());
     s += buf;
+  };
+  auto reload_ahead = [&](uint32_t i) {
+    while (next_reload < first_use.size() && first_use[next_reload].first <= i + ahead) reload(first_use[next_reload++].second);
   };
   auto hand_over = [&](uint32_t i, uint32_t sl) {
     if (!chunk) return;
@@ -303,6 +327,7 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
   }
   for (uint32_t i = begin; i < end; i++) {
     const FlatInstr &x = in[i];
+    if (chunk) reload_ahead(i);
     switch (x.kind) {
       case K_LUT:
         reload(x.a), reload(x.b), reload(x.c);  // operands a LUT does not read alias one it does

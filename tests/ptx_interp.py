@@ -31,6 +31,7 @@ def run_kernel(ptx: str, k: int, groups: int, mem: dict):
             return np.full(groups, int(name) & 0xFFFFFFFF, np.uint32)
         return reg[name]
 
+    scr_nc, scr_stored = set(), set()
     for l in lines[start:]:
         if not l or l.startswith("//") or l.startswith(".reg") or l in ("DONE:", "ret;", "}"):
             continue
@@ -44,8 +45,11 @@ def run_kernel(ptx: str, k: int, groups: int, mem: dict):
             assert m, l
             dst = _regs(m.group(1))
             assert len(dst) == k and (("v%d" % k) in op or k == 1), l
-            if addr[0] in ("state", "scr"):
+            if addr[0] == "state":
                 assert ".nc" not in op, "rows rewritten during the run must use coherent loads: " + l
+            if addr[0] == "scr" and ".nc" in op:  # legal only for scratch rows this kernel never writes
+                assert addr[1] not in scr_stored, "read-only load of a scratch row this chunk has written: " + l
+                scr_nc.add(addr[1])
             row = mem[addr[0]][addr[1]]
             for j, r in enumerate(dst):
                 reg[r] = row[cols[:, j]].copy()
@@ -54,6 +58,9 @@ def run_kernel(ptx: str, k: int, groups: int, mem: dict):
             assert m, l
             src = _regs(m.group(1))
             assert len(src) == k, l
+            if addr[0] == "scr":
+                assert addr[1] not in scr_nc, "store to a scratch row this chunk reads through the read-only path: " + l
+                scr_stored.add(addr[1])
             row = mem[addr[0]][addr[1]]
             for j, r in enumerate(src):
                 row[cols[:, j]] = val(r)

@@ -409,11 +409,16 @@ def test_transposes_tiled_and_fallback_paths():
     # default: the TMA-tiled kernels in their default tile shape; the other shapes (CLG_TRANSPOSE_TMA = shape index), the wide
     # LDG/STG ones (CLG_TRANSPOSE_NO_TMA) and the 32-byte-segment ones (CLG_TRANSPOSE_NARROW) stay in the library, keep them honest
     cases += [(256 * 12 + 1, 2048)]
+    # any other row count: the staged kernels (one bulk copy of VT x rows contiguous bytes per CTA); rows * 32 > 96 KB and
+    # CLG_TRANSPOSE_BYTEWISE: the byte-wise kernels
+    odd = [(1, 1), (100, 1), (31, 3), (5000, 65), (777, 33), (300, 3000), (40, 3071), (20, 3073), (1 << 16, 9), (257, 255)]
+    cases += odd
     variants = [(a, b, None) for a, b in cases] + [(a, b, "CLG_TRANSPOSE_NO_TMA=1") for a, b in cases if b % 16 == 0] + \
                [(a, b, f"CLG_TRANSPOSE_TMA={t}") for t in range(7) for a, b in ((33, 16), (3000, 144), (1024 * 3 + 7, 272), (70000, 32))] + \
-               [(300, 48, "CLG_TRANSPOSE_NARROW=1"), (5000, 64, "CLG_TRANSPOSE_NARROW=1"), (257, 1024, "CLG_TRANSPOSE_NARROW=1")]
+               [(300, 48, "CLG_TRANSPOSE_NARROW=1"), (5000, 64, "CLG_TRANSPOSE_NARROW=1"), (257, 1024, "CLG_TRANSPOSE_NARROW=1")] + \
+               [(a, b, "CLG_TRANSPOSE_BYTEWISE=1") for a, b in ((5000, 65), (777, 33), (31, 3))]
     for nv, rows, env in variants:
-        for k in ("CLG_TRANSPOSE_NARROW", "CLG_TRANSPOSE_NO_TMA", "CLG_TRANSPOSE_TMA"):
+        for k in ("CLG_TRANSPOSE_NARROW", "CLG_TRANSPOSE_NO_TMA", "CLG_TRANSPOSE_TMA", "CLG_TRANSPOSE_BYTEWISE"):
             os.environ.pop(k, None)
         if env:
             os.environ[env.split("=")[0]] = env.split("=")[1]
@@ -430,8 +435,20 @@ def test_transposes_tiled_and_fallback_paths():
         bits = ((got[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(rows, -1)[:, :nv].T.astype(bool)
         assert np.array_equal(bits, want_bits), (nv, rows, env)
         assert np.array_equal(back.cpu().numpy(), want_bits.astype(np.uint8)), (nv, rows, env)
-    for k in ("CLG_TRANSPOSE_NARROW", "CLG_TRANSPOSE_NO_TMA", "CLG_TRANSPOSE_TMA"):
+    for k in ("CLG_TRANSPOSE_NARROW", "CLG_TRANSPOSE_NO_TMA", "CLG_TRANSPOSE_TMA", "CLG_TRANSPOSE_BYTEWISE"):
         os.environ.pop(k, None)
+    # a vector-major matrix that is not 16-byte aligned (a view one byte into a buffer): the byte-wise kernels
+    nv, rows = 3000, 48
+    b = rng.integers(0, 2, size=(nv, rows), dtype=np.uint8)
+    buf = torch.zeros(nv * rows + 16, dtype=torch.uint8, device="cuda")
+    buf[1:1 + nv * rows] = torch.from_numpy(b.reshape(-1)).cuda()
+    sliced = torch.zeros((rows, stride_for(nv)), dtype=torch.int32, device="cuda")
+    back = torch.full((nv * rows + 16,), 7, dtype=torch.uint8, device="cuda")
+    ctx.slice_bools(buf.data_ptr() + 1, sliced.data_ptr(), nv, rows, stride_for(nv))
+    ctx.unslice_bools(sliced.data_ptr(), back.data_ptr() + 1, nv, rows, stride_for(nv))
+    torch.cuda.synchronize()
+    got = back.cpu().numpy()
+    assert np.array_equal(got[1:1 + nv * rows].reshape(nv, rows), b) and got[0] == 7 and got[1 + nv * rows] == 7
 
 
 def test_torch_buffers_and_stream_and_fill():
