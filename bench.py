@@ -540,7 +540,7 @@ def main():
                 del w
                 torch.cuda.empty_cache()
                 tr = {}
-                for nv_t, rows_t in ((1 << 22, 64), (1 << 20, 1024)):
+                for nv_t, rows_t in ((1 << 22, 64), (1 << 20, 1024), (1 << 22, 33)):
                     stride_t = host.round_stride(nv_t)
                     bools = torch.randint(0, 2, (nv_t, rows_t), dtype=torch.uint8, device=dev)
                     sliced = torch.zeros((rows_t, stride_t), dtype=torch.int32, device=dev)
@@ -557,10 +557,12 @@ def main():
                         torch.cuda.synchronize()
                         ms_t = e0.elapsed_time(e1) / 20
                         gbs = (nv_t * rows_t + rows_t * stride_t * 4) / (ms_t * 1e-3) / 1e9
-                        tr[f"{nm}_{rows_t}rows"] = {"ms": ms_t, "GBps": gbs, "hbm_frac": gbs / hbm_peak, "vectors": nv_t}
+                        tr[f"{nm}_{rows_t}rows"] = {"ms": ms_t, "GBps": gbs, "hbm_frac": gbs / hbm_peak, "vectors": nv_t, "rows": rows_t}
                     del bools, sliced
                 extras["transpose"] = dict(tr, roofline={"bound": "hbm", "unit": "GB/s", "peak": hbm_peak,
-                                                         "frac": min(v["hbm_frac"] for v in tr.values()), "note": "frac = the slowest of the four"})
+                                                         "frac": min(v["hbm_frac"] for v in tr.values() if v["rows"] % 16 == 0),
+                                                         "note": "frac = the slowest of the four shapes with rows % 16 == 0 (TMA-tiled kernels); the "
+                                                                 "*_33rows entries are the staged kernels for any row count"})
                 circ_b, _, _ = build_workload("adder32")
                 cs_b = host.CudaSimulation.from_simulation(circ_b.sim, circ_b.n_immediates, circ_b.out_regs, ctx=ctx, mode=mode)
                 nv_b = 1 << 22

@@ -1201,7 +1201,10 @@ void launch_slice(Ctx *c, bool unslice, const void *src, void *dst, size_t n_vec
   if (((uintptr_t)vec_side & 15) == 0 && n_rows * 32 <= Ctx::GEN_MAX_BYTES && !std::getenv("CLG_TRANSPOSE_NARROW") && !std::getenv("CLG_TRANSPOSE_BYTEWISE")) {
     // any row count: VT consecutive vectors are one contiguous, 32-byte aligned run of VT * n_rows bytes, staged in shared
     // memory by a 1-D bulk copy (kernels.cu, clg_slice_gen)
-    uint32_t vt = (uint32_t)std::min<size_t>(256, Ctx::GEN_MAX_BYTES / n_rows / 32 * 32);
+    // vectors per CTA: up to 2048 (eight groups of 256, so that a narrow matrix still has a unit of work for every warp),
+    // in whole groups while more than one fits, else a multiple of 32
+    size_t fit = Ctx::GEN_MAX_BYTES / n_rows;
+    uint32_t vt = (uint32_t)(fit >= 512 ? std::min<size_t>(2048, fit / 256 * 256) : std::min<size_t>(256, fit / 32 * 32));
     vt = (uint32_t)std::min<size_t>(vt, (n_vectors + 31) / 32 * 32);
     const uint64_t grid = (n_vectors + vt - 1) / vt;
     if (grid > 0x7FFFFFFFull) fail(CLG_E_INVALID, "transpose too large for one launch");

@@ -1226,15 +1226,18 @@ extern "C" __global__ void __launch_bounds__(256) clg_slice_gen(const uint8_t *b
   if (threadIdx.x < bytes - bulk) stage[bulk + threadIdx.x] = bools[g0 + bulk + threadIdx.x];
   __syncthreads();
   if (bulk) mbar_wait(bar, 0);
-  const uint32_t sbase = smem_u32(stage), n_rt = (R + 31) / 32, n_c = (nvt + 31) / 32;
-  for (uint32_t rt = warp; rt < n_rt; rt += 8) {
+  // work units: (row tile of 32 rows, group of 256 vectors = 8 sliced words); vt is a multiple of 256 (or the whole,
+  // smaller, matrix), chosen by the host so that narrow matrices still give all eight warps something to do
+  const uint32_t sbase = smem_u32(stage), n_rt = (R + 31) / 32, n_g = (nvt + 255) / 256;
+  for (uint32_t u = warp; u < n_rt * n_g; u += 8) {
+    const uint32_t rt = u / n_g, vb = (u % n_g) * 256, n_c = (min(256u, nvt - vb) + 31) / 32;
     const uint32_t nr = min(32u, R - rt * 32), row_mask = nr == 32 ? 0xFFFFFFFFu : (1u << nr) - 1u;
     uint32_t acc[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) {
       acc[c] = 0;
       if ((uint32_t)c >= n_c) continue;  // (warp-uniform)
-      const uint32_t vl = c * 32 + lane, o = vl * R + rt * 32, sh = (o & 3u) * 8u, wa = sbase + (o & ~3u);
+      const uint32_t vl = vb + c * 32 + lane, o = vl * R + rt * 32, sh = (o & 3u) * 8u, wa = sbase + (o & ~3u);
       uint32_t bits = 0;
       if (vl < nvt) {
         uint32_t W[9];
@@ -1247,16 +1250,16 @@ extern "C" __global__ void __launch_bounds__(256) clg_slice_gen(const uint8_t *b
       }
       acc[c] = transpose32(bits, lane);  // lane = row rt * 32 + lane, bit k = vector v0 + 32 c + k
     }
-    const uint32_t row = rt * 32 + lane;
+    const uint32_t row = rt * 32 + lane, w0 = (v0 + vb) / 32;
     if (row < R) {
-      uint32_t *dst = sliced + (size_t)row * stride + v0 / 32;
-      if (n_c == 8 && v0 / 32 + 8 <= words && ((v0 / 32) & 7u) == 0) {
+      uint32_t *dst = sliced + (size_t)row * stride + w0;
+      if (n_c == 8 && w0 + 8 <= words && (w0 & 7u) == 0) {
         __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(acc[0], acc[1], acc[2], acc[3]));
         __stcs(reinterpret_cast<uint4 *>(dst) + 1, make_uint4(acc[4], acc[5], acc[6], acc[7]));
       } else {
 #pragma unroll
         for (int c = 0; c < 8; c++)
-          if ((uint32_t)c < n_c && v0 / 32 + c < words) dst[c] = acc[c];
+          if ((uint32_t)c < n_c && w0 + c < words) dst[c] = acc[c];
       }
     }
   }
@@ -1270,28 +1273,29 @@ extern "C" __global__ void __launch_bounds__(256) clg_unslice_gen(const uint32_t
   const uint32_t v0 = blockIdx.x * vt, nvt = min(vt, n_vectors - v0), words = (n_vectors + 31) / 32;
   const size_t g0 = (size_t)v0 * R;
   const uint32_t bytes = nvt * R, bulk = bytes & ~15u;
-  const uint32_t sbase = smem_u32(stage), n_rt = (R + 31) / 32, n_c = (nvt + 31) / 32;
-  for (uint32_t rt = warp; rt < n_rt; rt += 8) {
+  const uint32_t sbase = smem_u32(stage), n_rt = (R + 31) / 32, n_g = (nvt + 255) / 256;
+  for (uint32_t u = warp; u < n_rt * n_g; u += 8) {
+    const uint32_t rt = u / n_g, vb = (u % n_g) * 256, n_c = (min(256u, nvt - vb) + 31) / 32, w0 = (v0 + vb) / 32;
     const uint32_t nr = min(32u, R - rt * 32), row = rt * 32 + lane;
     uint32_t acc[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) acc[c] = 0;
     if (row < R) {
-      const uint32_t *src = sliced + (size_t)row * stride + v0 / 32;
-      if (n_c == 8 && v0 / 32 + 8 <= words && ((v0 / 32) & 7u) == 0) {
+      const uint32_t *src = sliced + (size_t)row * stride + w0;
+      if (n_c == 8 && w0 + 8 <= words && (w0 & 7u) == 0) {
         const uint4 lo = __ldcs(reinterpret_cast<const uint4 *>(src)), hi = __ldcs(reinterpret_cast<const uint4 *>(src) + 1);
         acc[0] = lo.x, acc[1] = lo.y, acc[2] = lo.z, acc[3] = lo.w, acc[4] = hi.x, acc[5] = hi.y, acc[6] = hi.z, acc[7] = hi.w;
       } else {
 #pragma unroll
         for (int c = 0; c < 8; c++)
-          if ((uint32_t)c < n_c && v0 / 32 + c < words) acc[c] = src[c];
+          if ((uint32_t)c < n_c && w0 + c < words) acc[c] = src[c];
       }
     }
 #pragma unroll
     for (int c = 0; c < 8; c++) {
       if ((uint32_t)c >= n_c) continue;  // (warp-uniform)
-      const uint32_t bits = transpose32(acc[c], lane);  // lane = vector v0 + 32 c + lane, bit r = row rt * 32 + r
-      const uint32_t vl = c * 32 + lane;
+      const uint32_t bits = transpose32(acc[c], lane);  // lane = vector v0 + vb + 32 c + lane, bit r = row rt * 32 + r
+      const uint32_t vl = vb + c * 32 + lane;
       if (vl >= nvt) continue;
       uint32_t B[9];
 #pragma unroll
