@@ -263,7 +263,10 @@ int clg_exec_prepare(clg_exec *ex, size_t n_vectors);
  *   imm    [n_inputs][stride]  bit-sliced immediates
  *   out    [n_outputs][stride] bit-sliced values of the named output registers after the run
  *   state  [n_state][stride]   carried registers, updated in place (NULL unless stateful)
- * Asynchronous on `stream` (a CUstream / cudaStream_t; NULL = the legacy default stream). */
+ * Asynchronous on `stream` (a CUstream / cudaStream_t; NULL = the legacy default stream). Runs of ONE executor must not
+ * overlap on the device: issue them on one stream, or order the streams with events -- a chunked specialised program
+ * hands registers from kernel to kernel through a scratch buffer that belongs to the executor (growing it synchronises
+ * the context), and the first big cooperative run times CTA sizes on the legacy stream unless clg_exec_prepare was called. */
 int clg_exec_run(clg_exec *ex, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors,
                  size_t stride, void *stream);
 
