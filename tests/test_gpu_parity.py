@@ -451,6 +451,35 @@ def test_transposes_tiled_and_fallback_paths():
     assert np.array_equal(got[1:1 + nv * rows].reshape(nv, rows), b) and got[0] == 7 and got[1 + nv * rows] == 7
 
 
+def test_transposes_random_shapes():
+    """200 random (vectors, rows, offset) shapes through whichever transpose kernels the library picks -- TMA-tiled, staged,
+    byte-wise (odd offsets) -- against numpy, with guard bytes around the vector-major result."""
+    import torch
+
+    ctx = host.Context.default()
+    rng = np.random.default_rng(2024)
+    for case in range(200):
+        rows = int(rng.choice([rng.integers(1, 40), rng.integers(1, 400), 16 * rng.integers(1, 40)]))
+        nv = int(rng.choice([rng.integers(1, 70), rng.integers(1, 3000), rng.integers(1, 40000)]))
+        off = int(rng.choice([0, 0, 16, 48, 1, 5]))
+        stride = stride_for(nv)
+        b = (rng.random((nv, rows)) < 0.5).astype(np.uint8) * rng.integers(1, 256, size=(nv, rows)).astype(np.uint8)
+        buf = torch.zeros(nv * rows + 128, dtype=torch.uint8, device="cuda")
+        buf[off:off + nv * rows] = torch.from_numpy(b.reshape(-1)).cuda()
+        sliced = torch.zeros((rows, stride), dtype=torch.int32, device="cuda")
+        back = torch.full((nv * rows + 128,), 0xA5, dtype=torch.uint8, device="cuda")
+        ctx.slice_bools(buf.data_ptr() + off, sliced.data_ptr(), nv, rows, stride)
+        ctx.unslice_bools(sliced.data_ptr(), back.data_ptr() + off, nv, rows, stride)
+        torch.cuda.synchronize()
+        want = b != 0
+        got = sliced.cpu().numpy().view(np.uint32)
+        bits = ((got[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(rows, -1)[:, :nv].T.astype(bool)
+        assert np.array_equal(bits, want), (case, nv, rows, off)
+        out = back.cpu().numpy()
+        assert np.array_equal(out[off:off + nv * rows].reshape(nv, rows), want.astype(np.uint8)), (case, nv, rows, off)
+        assert (out[:off] == 0xA5).all() and (out[off + nv * rows:] == 0xA5).all(), (case, nv, rows, off)
+
+
 def test_torch_buffers_and_stream_and_fill():
     """Device pointers from torch, torch's current stream, and the on-device input generator."""
     import torch
