@@ -599,6 +599,57 @@ def main():
             strong = {"scaling": "strong", "total_vectors": w["nv"] * world, "vectors_per_gpu": w["nv"], "ms_per_step": ms_s,
                       "value": w["gates"] * w["nv"] * world / (ms_s * 1e-3), "unit": UNIT, "kernel": w["cs"].kernel_name}
 
+    # ---- the product's own multi-GPU call: ONE process (rank 0) drives all N GPUs through clg_sharded_* (a worker
+    # thread, context, executor and staging buffers per device, made once; per-GPU result buffers copied back by the
+    # host). 2^24 vectors in total, host buffers in and out; the other ranks wait at the barrier with idle GPUs.
+    sharded = None
+    if world > 1 and args.workload == "dag1m" and not args.no_e2e:
+        del w
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            try:
+                circ_s, _, seed_s = build_workload("dag1m")
+                flat_s = host.FlatProgram.levelize(circ_s.sim, circ_s.n_immediates, circ_s.out_regs)
+                sh = host.ShardedSimulation(flat_s, list(range(world)), mode)
+                nv_s = 1 << 24
+                stride_s = host.round_stride(nv_s)
+                n_in_s, n_out_s = flat_s.info["n_inputs"], flat_s.info["n_outputs"]
+                hs_imm = torch.empty((n_in_s, stride_s), dtype=torch.int32, pin_memory=True)
+                hs_out = torch.empty((n_out_s, stride_s), dtype=torch.int32, pin_memory=True)
+                d_tmp = torch.empty((n_in_s, stride_s), dtype=torch.int32, device=dev)
+                ctx.fill_random(d_tmp.data_ptr(), n_in_s, stride_s, seed_s + 77, torch.cuda.current_stream().cuda_stream)
+                hs_imm.copy_(d_tmp)
+                torch.cuda.synchronize()
+                del d_tmp
+                lib_s = host._lib.lib()
+                secs = (__import__("ctypes").c_double * world)()
+
+                def sharded_call():
+                    host._lib.check(lib_s.clg_sharded_run_host(sh._h, hs_imm.data_ptr(), hs_out.data_ptr(), None, nv_s, stride_s, secs))
+
+                sharded_call()  # (first call: plans, staging buffers)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    sharded_call()
+                s_ms = 1e3 * (time.perf_counter() - t0) / 3
+                par_s = parity_sample(circ_s, hs_imm.numpy().view(np.uint32), hs_out.numpy().view(np.uint32), nv_s, n_groups=2 * world)
+                sharded = {"api": "clg_sharded_run_host (one process, one worker thread + context + executor per device, no collective)",
+                           "devices": world, "total_vectors": nv_s, "ms_per_call": s_ms, "value": circ_s.sim.nand_count * nv_s / (s_ms * 1e-3),
+                           "unit": UNIT, "per_device_seconds": [round(x, 4) for x in secs], "host_bytes_per_call": (n_in_s + n_out_s) * stride_s * 4,
+                           "parity_sample": {k: par_s[k] for k in ("words", "rows", "mismatching_words", "ok")}}
+                sh.close()
+                del hs_imm, hs_out
+                if not par_s["ok"]:
+                    print(json.dumps({"error": "sharded output differs from the oracle VM", "parity_sample": par_s}), flush=True)
+                    raise SystemExit(3)
+            except SystemExit:
+                raise
+            except Exception as e:
+                sharded = {"error": str(e)[:200]}
+        barrier()
+        w = {"bufs": []}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
@@ -637,6 +688,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * run_launches,
             "roofline": roofline, "cpu_baseline": cpu,
         }
+        if sharded:
+            line["sharded_single_process"] = sharded
         if extras:
             line["other_configs"] = extras
         if strong:
