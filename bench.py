@@ -605,6 +605,12 @@ def main():
     sharded = None
     if world > 1 and args.workload == "dag1m" and not args.no_e2e:
         del w
+        try:  # the e2e leg's pinned host buffers (10.7 GB per rank) are no longer needed
+            del h_imm, h_out, d_imm, d_out
+        except NameError:
+            pass
+        import gc
+        gc.collect()
         torch.cuda.empty_cache()
         barrier()
         if rank == 0:
