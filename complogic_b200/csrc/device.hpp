@@ -20,7 +20,8 @@ std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K);  // n_chunks + 1 in
 constexpr uint16_t FLAG_STATE_ROW = 0x10;  // chunk-local code only: `row` indexes the state buffer
 struct SpecChunk {
   std::vector<FlatInstr> code;              // rows relative to the bases below
-  std::vector<uint32_t> live_in, live_out;  // registers handed over through the scratch buffer
+  std::vector<uint32_t> live_in, live_out;  // registers handed over through the scratch buffer (chunk-local names)
+  std::vector<uint32_t> scr_row;            // chunk-local register -> its row of the scratch buffer (empty: the same number)
   uint32_t n_slots = 0;
   uint32_t imm_base = 0, out_base = 0, state_base = 0;  // rows the kernel's pointers are advanced by at launch
   bool same_kernel(const SpecChunk &o) const;           // equal code: the two chunks can share one assembled kernel

@@ -92,9 +92,12 @@ std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K) {
   return cuts;
 }
 
-// Instructions [begin, end) of the lane stream in chunk-local terms. An isolated chunk (nothing live across either
-// of its cuts) has its registers renumbered by first appearance and its rows made relative to the lowest row it
-// touches in each buffer, so that two instances of the same sub-circuit produce EQUAL chunks and share one kernel.
+// Instructions [begin, end) of the lane stream in chunk-local terms: registers renumbered by first appearance and
+// rows made relative to the lowest row the chunk touches in each buffer, so that two instances of the same sub-circuit
+// produce EQUAL chunks and share one assembled kernel. A register that crosses a cut keeps its place in the scratch
+// buffer (scr_row: its number in the whole program), so chunks that hand registers over can be shared as well when the
+// instances' registers were allocated alike -- the two halves of every 64 x 64 multiplier of a flattened program are
+// two kernels, not two per instance.
 static SpecChunk local_code(const Flat &f, uint32_t begin, uint32_t end, std::vector<uint32_t> live_in, std::vector<uint32_t> live_out,
                             bool may_rebase) {
   const FlatHeader &h = f.header();
@@ -107,7 +110,7 @@ static SpecChunk local_code(const Flat &f, uint32_t begin, uint32_t end, std::ve
     if (x.kind == K_LDIN && x.row >= h.n_inputs) x.row -= h.n_inputs, x.flags |= FLAG_STATE_ROW;
     if ((x.kind == K_STOUT || x.kind == K_STCONST) && x.row >= h.n_outputs) x.row -= h.n_outputs, x.flags |= FLAG_STATE_ROW;
   }
-  if (!may_rebase || !c.live_in.empty() || !c.live_out.empty()) return c;
+  if (!may_rebase) return c;
   uint32_t lo[3] = {UINT32_MAX, UINT32_MAX, UINT32_MAX};  // imm, out, state
   std::vector<uint16_t> name(c.n_slots, UINT16_MAX);
   uint16_t next = 0;
@@ -127,12 +130,21 @@ static SpecChunk local_code(const Flat &f, uint32_t begin, uint32_t end, std::ve
   c.imm_base = lo[0] == UINT32_MAX ? 0 : lo[0], c.out_base = lo[1] == UINT32_MAX ? 0 : lo[1], c.state_base = lo[2] == UINT32_MAX ? 0 : lo[2];
   for (FlatInstr &x : c.code)
     if (x.kind != K_LUT) x.row -= (x.flags & FLAG_STATE_ROW) ? c.state_base : x.kind == K_LDIN ? c.imm_base : c.out_base;
+  // the live sets in local names (a register that crosses the whole chunk untouched has none: it stays in the scratch buffer)
+  c.scr_row.assign(next, UINT32_MAX);
+  for (std::vector<uint32_t> *lv : {&c.live_in, &c.live_out}) {
+    std::vector<uint32_t> local;
+    for (uint32_t sl : *lv)
+      if (name[sl] != UINT16_MAX) local.push_back(name[sl]), c.scr_row[name[sl]] = sl;
+    std::sort(local.begin(), local.end());
+    lv->swap(local);
+  }
   c.n_slots = next;
   return c;
 }
 
 bool SpecChunk::same_kernel(const SpecChunk &o) const {
-  return n_slots == o.n_slots && code.size() == o.code.size() && live_in == o.live_in && live_out == o.live_out &&
+  return n_slots == o.n_slots && code.size() == o.code.size() && live_in == o.live_in && live_out == o.live_out && scr_row == o.scr_row &&
          std::memcmp(code.data(), o.code.data(), code.size() * sizeof(FlatInstr)) == 0;
 }
 
@@ -278,6 +290,7 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
   // cover a DRAM round trip at two warps per scheduler, not all at the top, where the whole chunk would wait for them.
   // Scratch words this chunk does not write itself are read-only for the kernel (.nc: the assembler may keep the load
   // where it is put instead of ordering it against the chunk's stores).
+  auto scr = [&](uint32_t sl) { return cc.scr_row.empty() ? sl : cc.scr_row[sl]; };  // a register's row of the scratch buffer
   std::vector<std::pair<uint32_t, uint32_t>> first_use;  // (instruction, slot), ascending
   size_t next_reload = 0;
   static const uint32_t ahead = std::getenv("CLG_SPEC_PREFETCH") ? (uint32_t)std::atoi(std::getenv("CLG_SPEC_PREFETCH")) : 768u;
@@ -296,7 +309,7 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
   auto reload = [&](uint32_t sl) {
     if (!chunk || !need_load[sl]) return;
     need_load[sl] = 0;
-    std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  ld.global%s%s.u32 %s, [%%addr];\n", sl,
+    std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  ld.global%s%s.u32 %s, [%%addr];\n", scr(sl),
                   store_at[sl] == UINT32_MAX ? ".nc.L1::no_allocate" : "", vt, vec(sl).c_str());
     s += buf;
   };
@@ -307,7 +320,7 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
     if (!chunk) return;
     need_load[sl] = 0;
     if (store_at[sl] != i) return;
-    std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  st.global%s.u32 [%%addr], %s;\n", sl, vt, vec(sl).c_str());
+    std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  st.global%s.u32 [%%addr], %s;\n", scr(sl), vt, vec(sl).c_str());
     s += buf;
   };
   const char *cvt = K == 4 ? ".v4" : K == 2 ? ".v2" : "";
