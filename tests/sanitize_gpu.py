@@ -28,8 +28,8 @@ def check(circ, nv, mode, flags=0, expect=None):
     print(f"{circ.name:14s} {nv:6d} vectors  {cs.kernel_name:16s} ok", flush=True)
 
 
-dag = circuits.random_dag(24, 256, 64, 2, 5)
-check(dag, 148 * 128, host.MODE_COOP, expect="clg_coop_rows")  # row kernel: mbarrier-ordered shared-memory traffic
+dag = circuits.random_dag(40, 512, 128, 2, 5)
+check(dag, 148 * 256, host.MODE_COOP, expect="clg_coop_rows")  # row kernel: mbarrier-ordered shared-memory traffic
 check(dag, 300, host.MODE_COOP)                                 # resident cooperative kernel (bulk copy + barrier per level)
 os.environ["CLG_COOP_NO_ROWS"] = "1"
 os.environ["CLG_COOP_NO_RESIDENT"] = "1"
