@@ -876,6 +876,14 @@ def test_json_imported_program_runs_on_the_device():
     assert list(unslice_int(got, 8)) == [int(t & 1) | int(t >> 1) << 1 for t in total]
 
 
+def test_driver_smoke_entry_point():
+    """__graft_entry__.smoke(): what the driver runs on a B200 before the bench -- every mode on a small multiplier, the row
+    kernel on a DAG, the reference's and_gate test through the device path, each against the oracle."""
+    import __graft_entry__ as entry
+
+    entry.smoke()
+
+
 def test_errors_are_status_codes():
     circ = circuits.ripple_adder(4)
     cs = host.CudaSimulation.from_simulation(circ.sim, 9, circ.out_regs)
