@@ -776,7 +776,7 @@ def test_prepare_moves_the_first_run_cost_out_of_the_run():
         cs.run_batch(i2, n2)
         second = time.perf_counter() - t0
         assert np.array_equal(got, oracle_out(c2, i2, n2)), (mode, small, cs.kernel_name)
-        assert first < 5 * second + 0.05, (mode, small, first, second)  # no plan build, JIT or tuning left in the first run
+        assert first < 5 * second + 0.25, (mode, small, first, second)  # no plan build, JIT or tuning left in the first run
     cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs)
     cs.prepare(nv)
     assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), want)
