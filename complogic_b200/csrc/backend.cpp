@@ -708,11 +708,16 @@ struct Exec {
     if (h.n_state && !state) fail(CLG_E_INVALID, "state is null for a stateful program");
     if (n_vectors == 0) return;
     ctx->bind();
-    // chunk = a contiguous range of words of every row, ~192 MB of I/O, so copies and kernels overlap
+    // chunk = a contiguous range of words of every row, ~128 MB of I/O, so copies and kernels overlap
     const size_t rows = (size_t)h.n_inputs + h.n_outputs + 2 * (size_t)h.n_state;
-    size_t cw = ((size_t)192 << 20) / (std::max<size_t>(rows, 1) * 4);
+    size_t cw = ((size_t)128 << 20) / (std::max<size_t>(rows, 1) * 4);
     if (const char *env = std::getenv("CLG_HOST_CHUNK_WORDS")) cw = std::strtoull(env, nullptr, 10);  // tuning / tests
     cw = std::max<size_t>(4, cw) / 4 * 4;
+    // whole rounds of the persistent cooperative grid (one 4-word column group per CTA and round): a chunk of 16.6 groups
+    // per SM costs 17 rounds (1M-gate DAG x 2^24 vectors, same box: 193 ms per call with 9 828-word chunks, 174-182 ms with
+    // any whole number of rounds between 2 and 32)
+    const size_t round_words = 4 * (size_t)ctx->sm_count;
+    if (cw >= 4 * round_words && !std::getenv("CLG_HOST_CHUNK_WORDS")) cw = cw / round_words * round_words;
     const size_t padded = (words + 3) / 4 * 4;
     cw = std::min(cw, padded);
     ensure_streams();
