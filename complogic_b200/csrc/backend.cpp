@@ -231,7 +231,7 @@ struct Exec {
   Flat flat;  // own copy: the caller may destroy its clg_flat
   int want;   // CLG_MODE_AUTO or the mode the caller pinned
   int mode;   // mode of the most recent (or, before any run, the preferred) plan
-  int last_k = 0, last_parts = 0;
+  int last_k = 0, last_parts = 0, last_launches = 0;  // (last_launches: 0 before any run)
   bool last_rows = false;  // the most recent cooperative run used the row kernel
   const char *last_kernel = "";
   // shape of the chunked specialised chain (computed on demand, for the mode choice): distinct kernels to assemble, and
@@ -249,8 +249,9 @@ struct Exec {
     }
     return shape_;
   }
-  Plan plan[6];  // indexed by clg_mode; [PLAN_PARTS] = cooperative mode over the partitioned level stream, [PLAN_ROWS] = over the row stream
-  static constexpr int PLAN_PARTS = 4, PLAN_ROWS = 5;
+  Plan plan[7];  // indexed by clg_mode; [PLAN_PARTS] = cooperative mode over the partitioned level stream, [PLAN_ROWS] = over the row
+                 // stream, [PLAN_SPEC_TP] = the specialised chain in chunks below the instruction-cache cliff (big batches)
+  static constexpr int PLAN_PARTS = 4, PLAN_ROWS = 5, PLAN_SPEC_TP = 6;
 
   const FlatStream &level_stream() const { return flat.header().stream[STREAM_LEVEL]; }
   const FlatStream &lane_stream() const { return flat.header().stream[STREAM_LANE]; }
@@ -473,6 +474,68 @@ struct Exec {
     return P;
   }
 
+  // chunked specialisation: cut where few registers are live; equal chunks (the instances of a flattened program)
+  // share one assembled kernel and differ only in the rows their pointers are advanced by
+  void build_chain(Plan &P, uint32_t limit) {
+    const SpecChain chain = spec_chain(flat, P.K, limit);
+    const std::vector<SpecChunk> &chunks = chain.chunks;
+    const std::vector<uint32_t> &unique = chain.unique;
+    P.chunk_mods.assign(unique.size(), nullptr);
+    std::vector<CUfunction> fns(unique.size(), nullptr);
+    try {
+      for (uint32_t u = 0; u < unique.size(); u++) {
+        const std::string text = emit_spec_chunk_ptx(flat, P.K, chunks[unique[u]]);
+        if (u == 0) P.ptx = text;
+        assemble(text, "clg_spec_chunk", "chunk " + std::to_string(unique[u]) + " of the specialised program", &P.chunk_mods[u], &fns[u]);
+      }
+    } catch (...) {  // leave no half-built chain behind: a later run() would build it again from scratch
+      for (CUmodule m : P.chunk_mods)
+        if (m) driver().cuModuleUnload(m);
+      P.chunk_mods.clear();
+      throw;
+    }
+    std::vector<uint32_t> bases(chunks.size() * 4, 0);
+    for (uint32_t c = 0; c < chunks.size(); c++)
+      bases[4 * c] = chunks[c].imm_base, bases[4 * c + 1] = chunks[c].out_base, bases[4 * c + 2] = chunks[c].state_base;
+    for (const SpecChain::Launch &l : chain.launches) P.chunks.push_back({fns[chain.kernel_of[l.first]], l.first, l.count});
+    CU(cuMemAlloc(&P.d_bases, bases.size() * 4));
+    CU(cuMemcpyHtoDAsync(P.d_bases, bases.data(), bases.size() * 4, nullptr));
+    CU(cuStreamSynchronize(nullptr));
+  }
+
+  // ---- the specialised chain for big batches of register-heavy programs ------------------------------------------
+  // Straight-line code is executed once per warp, so what it costs to fetch depends on whether the kernel still sits in
+  // the SM's instruction cache when the next wave of CTAs starts: up to 128 KB of SASS it does (89-92 % of LOP3 peak at two
+  // warps per scheduler), beyond it does not (65 %; tools/microbench_ifetch.cu). Programs with few live registers run four
+  // or more warps per scheduler and do not care; a program that needs the whole register file (mul64: 222 live values)
+  // does. For those, a batch big enough that every launch fills the machine several times over runs a second chain whose
+  // chunks stay below the cliff: more launches and a register hand-over through the scratch buffer, 10 % less time
+  // (12 x mul64 x 2^24 vectors: 7.3 -> 6.5-6.8 ms). Small batches (config 5's single vector: one launch for all instances)
+  // keep the chain with the fewest launches.
+  static constexpr uint32_t TP_CHUNK = 6800;  // lane-order instructions at K = 1 (~110 KB of SASS with the hand-over code)
+  mutable int tp_state_ = 0;                  // 0: not decided, 1: the program has a throughput chain, -1: it has none
+  bool wants_tp_chain(size_t words) const {
+    if (std::getenv("CLG_SPEC_CHUNK") || std::getenv("CLG_SPEC_NO_TP")) return false;
+    const int k = fit_k(CLG_MODE_SPEC);
+    const FlatStream &ln = lane_stream();
+    if (!k || ln.n_slots * (uint32_t)k < 160 || (uint64_t)ln.n_instr * k <= 8192 || ln.n_instr * (uint64_t)k > 4000000u) return false;
+    if ((words + k - 1) / k < (size_t)ctx->sm_count * 128 * 8) return false;  // every launch: eight waves of 128-thread CTAs or more
+    if (tp_state_ == 0) {  // at most four kernels to assemble, else the default chain's tiering rules apply
+      const SpecChain ch = spec_chain(flat, k, std::max(2u, TP_CHUNK / (uint32_t)k));
+      tp_state_ = ch.unique.size() <= 4 && ch.chunks.size() > 1 ? 1 : -1;
+    }
+    return tp_state_ == 1;
+  }
+  Plan &get_spec_tp() {
+    Plan &P = plan[PLAN_SPEC_TP];
+    if (P.ready) return P;
+    ctx->bind();
+    P.K = fit_k(CLG_MODE_SPEC);
+    build_chain(P, std::max(2u, TP_CHUNK / (uint32_t)P.K));
+    P.ready = true;
+    return P;
+  }
+
   Plan &get(int m) {
     Plan &P = plan[m];
     if (P.ready) return P;
@@ -542,32 +605,7 @@ struct Exec {
       CU(cuMemcpyHtoDAsync(P.d_levels, flat.levels(sidx), ((size_t)P.n_levels + 1) * 4, nullptr));
       CU(cuStreamSynchronize(nullptr));
     } else if (ln.n_instr > spec_chunk_limit(P.K)) {
-      // chunked specialisation: cut where few registers are live; equal chunks (the instances of a flattened program)
-      // share one assembled kernel and differ only in the rows their pointers are advanced by
-      const SpecChain chain = spec_chain(flat, P.K);
-      const std::vector<SpecChunk> &chunks = chain.chunks;
-      const std::vector<uint32_t> &unique = chain.unique;
-      P.chunk_mods.assign(unique.size(), nullptr);
-      std::vector<CUfunction> fns(unique.size(), nullptr);
-      try {
-        for (uint32_t u = 0; u < unique.size(); u++) {
-          const std::string text = emit_spec_chunk_ptx(flat, P.K, chunks[unique[u]]);
-          if (u == 0) P.ptx = text;
-          assemble(text, "clg_spec_chunk", "chunk " + std::to_string(unique[u]) + " of the specialised program", &P.chunk_mods[u], &fns[u]);
-        }
-      } catch (...) {  // leave no half-built chain behind: a later run() would build it again from scratch
-        for (CUmodule m : P.chunk_mods)
-          if (m) driver().cuModuleUnload(m);
-        P.chunk_mods.clear();
-        throw;
-      }
-      std::vector<uint32_t> bases(chunks.size() * 4, 0);
-      for (uint32_t c = 0; c < chunks.size(); c++)
-        bases[4 * c] = chunks[c].imm_base, bases[4 * c + 1] = chunks[c].out_base, bases[4 * c + 2] = chunks[c].state_base;
-      for (const SpecChain::Launch &l : chain.launches) P.chunks.push_back({fns[chain.kernel_of[l.first]], l.first, l.count});
-      CU(cuMemAlloc(&P.d_bases, bases.size() * 4));
-      CU(cuMemcpyHtoDAsync(P.d_bases, bases.data(), bases.size() * 4, nullptr));
-      CU(cuStreamSynchronize(nullptr));
+      build_chain(P, 0);
     } else {
       P.ptx = emit_spec_ptx(flat, P.K);
       assemble(P.ptx, "clg_spec", "the specialised kernel", &P.spec_mod, &P.spec_fn);
@@ -815,12 +853,13 @@ struct Exec {
     // a batch that gives every SM a column group runs the row stream when the pass built one
     if (mode == CLG_MODE_COOP && !use_parts && has_rows() && (words + 3) / 4 >= (size_t)ctx->sm_count) {
       Plan &R = get_rows();
-      last_k = 4, last_parts = 0, last_rows = true, last_kernel = R.rows_tma ? "clg_coop_rows_t" : "clg_coop_rows";
+      last_k = 4, last_parts = 0, last_rows = true, last_launches = 1, last_kernel = R.rows_tma ? "clg_coop_rows_t" : "clg_coop_rows";
       launch_rows(R, params(R, imm, out, state, stride, (uint32_t)((words + 3) / 4)), stream);
       return;
     }
     last_rows = false;
-    Plan &P = use_parts ? get_parts() : get(mode);
+    Plan &P = use_parts ? get_parts() : mode == CLG_MODE_SPEC && wants_tp_chain(words) ? get_spec_tp() : get(mode);
+    last_launches = mode == CLG_MODE_SPEC && !P.chunks.empty() ? (int)P.chunks.size() : 1;
     const int K = P.K;
     last_k = K, last_parts = (int)P.n_parts;
     const uint32_t groups = (uint32_t)((words + K - 1) / K);
@@ -880,7 +919,7 @@ struct Exec {
     if (mode == CLG_MODE_COOP && !use_parts && has_rows() && (words + 3) / 4 >= (size_t)ctx->sm_count) {
       get_rows();
     } else {
-      Plan &P = use_parts ? get_parts() : get(mode);
+      Plan &P = use_parts ? get_parts() : mode == CLG_MODE_SPEC && wants_tp_chain(words) ? get_spec_tp() : get(mode);
       const uint32_t groups = (uint32_t)std::min<size_t>((words + P.K - 1) / P.K, 0xFFFFFFFFu);
       if (mode == CLG_MODE_COOP && !P.n_parts && groups > (uint32_t)ctx->sm_count * coop_ctas_per_sm(P, P.coop_threads) && !P.tuned_threads)
         P.tuned_threads = tune_coop_threads(P);
@@ -1134,6 +1173,7 @@ void exec_destroy(Exec *e) { delete e; }
 int exec_mode(const Exec *e) { return e->mode; }
 int exec_k(const Exec *e) { return e->last_k; }
 int exec_launches(const Exec *e) {
+  if (e->last_launches) return e->last_launches;  // what the most recent run issued
   return e->mode == CLG_MODE_SPEC && !e->plan[CLG_MODE_SPEC].chunks.empty() ? (int)e->plan[CLG_MODE_SPEC].chunks.size() : 1;
 }
 const char *exec_kernel_name(const Exec *e) { return e->last_kernel; }

@@ -57,10 +57,10 @@ uint32_t spec_chunk_limit(int K) {
   return std::max(2u, K == 1 ? n : K == 2 ? n / 2 : (uint32_t)((uint64_t)n * 3 / 8));
 }
 
-std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K) {
+std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K, uint32_t limit_or_0) {
   const FlatStream &st = f.header().stream[STREAM_LANE];
   const FlatInstr *in = f.instrs(STREAM_LANE);
-  const uint32_t n = st.n_instr, limit = spec_chunk_limit(K);
+  const uint32_t n = st.n_instr, limit = limit_or_0 ? std::max(2u, limit_or_0) : spec_chunk_limit(K);
   std::vector<uint32_t> cuts{0};
   if (n > limit) {
     std::vector<uint32_t> live_at(n + 1, 0);  // registers live at the boundary before instruction i
@@ -149,8 +149,8 @@ bool SpecChunk::same_kernel(const SpecChunk &o) const {
 }
 
 // The chain a long program runs as: cuts where few registers are live, the live sets at the cuts, chunk-local code.
-std::vector<SpecChunk> spec_chunks(const Flat &f, int K) {
-  const std::vector<uint32_t> cuts = spec_chunk_cuts(f, K);
+std::vector<SpecChunk> spec_chunks(const Flat &f, int K, uint32_t limit) {
+  const std::vector<uint32_t> cuts = spec_chunk_cuts(f, K, limit);
   const size_t n = cuts.size() - 1;
   std::vector<std::vector<uint32_t>> live(n + 1);
   for (size_t c = 1; c < n; c++) live[c] = spec_live_slots(f, cuts[c]);
@@ -162,9 +162,9 @@ std::vector<SpecChunk> spec_chunks(const Flat &f, int K) {
 // The launches of the chain: which chunks get assembled (one per distinct kernel) and which consecutive chunks run
 // side by side in one launch. Consecutive chunks that share a kernel, hand nothing over and touch disjoint
 // carried-state rows are independent of each other; blockIdx.y then selects the instance's row bases.
-SpecChain spec_chain(const Flat &f, int K) {
+SpecChain spec_chain(const Flat &f, int K, uint32_t limit) {
   SpecChain ch;
-  ch.chunks = spec_chunks(f, K);
+  ch.chunks = spec_chunks(f, K, limit);
   const std::vector<SpecChunk> &chunks = ch.chunks;
   ch.kernel_of.resize(chunks.size());
   for (uint32_t c = 0; c < chunks.size(); c++) {

@@ -597,7 +597,9 @@ def test_full_size_structured_1m_gate_circuit_2p24():
     out = torch.zeros((12 * 128, stride), dtype=torch.int32, device="cuda:0")
     cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
     torch.cuda.synchronize()
-    assert cs.mode == host.MODE_SPEC and cs.launches_per_run == 1
+    # a batch this big runs the chain whose chunks stay below the instruction-cache cliff: two chunks per instance that
+    # hand ~200 registers over through the scratch buffer, two shared kernels, 24 launches
+    assert cs.mode == host.MODE_SPEC and cs.launches_per_run == 24 and cs.kernel_name == "clg_spec_chunk"
     blocks = out.view(12, 128, stride)
     assert bool((blocks == blocks[:1]).all())
     n = 1 << 12
@@ -609,6 +611,22 @@ def test_full_size_structured_1m_gate_circuit_2p24():
     assert [int(l) | int(h) << 64 for l, h in zip(lo, hi)] == [x * y for x, y in zip(a, b)]
     want = oracle.run_batch_sliced(base.sim, len(base.sim.registers), imm_h, n, base.out_regs)
     assert np.array_equal(got, want)
+    # a small batch on the same executor keeps the instance-parallel single launch; same words
+    out2 = torch.zeros((12 * 128, stride), dtype=torch.int32, device="cuda:0")
+    cs.run_device(imm.data_ptr(), out2.data_ptr(), n, stride)
+    torch.cuda.synchronize()
+    assert cs.launches_per_run == 1
+    assert bool((out2[:, :n // 32] == out[:, :n // 32]).all())
+    # ... and so does the big batch when the second chain is switched off
+    import os
+    os.environ["CLG_SPEC_NO_TP"] = "1"
+    try:
+        out3 = torch.zeros_like(out2)
+        cs.run_device(imm.data_ptr(), out3.data_ptr(), nv, stride)
+        torch.cuda.synchronize()
+        assert cs.launches_per_run == 1 and bool((out3 == out).all())
+    finally:
+        del os.environ["CLG_SPEC_NO_TP"]
 
 
 def test_full_size_mul16_2p26():
@@ -756,30 +774,30 @@ def test_persistent_sharded_executor_on_every_visible_device():
 
 def test_prepare_moves_the_first_run_cost_out_of_the_run():
     """clg_exec_prepare: the mode choice, the plan (upload / JIT) and the cooperative CTA-size timing of a batch size,
-    ahead of the first run -- the prepared executor's first run is then an ordinary one, and the results are the oracle's."""
-    import time
+    ahead of the first run; the results are the oracle's. (No wall-clock assertion: what can be observed without one is
+    that the specialised kernel's text exists after prepare and before any run, and that prepare is idempotent.)"""
     circ = circuits.random_dag(64, 1024, 256, 2, 3)
     nv = 1 << 16
-    imm = random_sliced(circ.n_immediates, stride_for(nv), seed=4)
-    want = oracle_out(circ, imm, nv)
     for mode, small in ((host.MODE_AUTO, False), (host.MODE_COOP, False), (host.MODE_COOP, True), (host.MODE_SPEC, False)):
         c2 = circuits.array_multiplier(8) if mode == host.MODE_SPEC else circ
         n2 = 3000 if small else nv
         i2 = random_sliced(c2.n_immediates, stride_for(n2), seed=6)
         cs = host.CudaSimulation.from_simulation(c2.sim, c2.n_immediates, c2.out_regs, mode=mode)
         cs.prepare(n2)
+        cs.prepare(n2)
         cs.prepare(0)  # nothing to do
-        t0 = time.perf_counter()
+        if mode == host.MODE_SPEC:
+            assert "lop3.b32" in cs.ptx
         got = mask_tail(cs.run_batch(i2, n2), n2)
-        first = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        cs.run_batch(i2, n2)
-        second = time.perf_counter() - t0
         assert np.array_equal(got, oracle_out(c2, i2, n2)), (mode, small, cs.kernel_name)
-        assert first < 5 * second + 0.25, (mode, small, first, second)  # no plan build, JIT or tuning left in the first run
-    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs)
-    cs.prepare(nv)
-    assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), want)
+    # a big batch of a register-heavy program: prepare builds the chain the run will use (chunks below the instruction-cache cliff)
+    mul = circuits.array_multiplier(64)
+    big = 148 * 128 * 8 * 32
+    cs = host.CudaSimulation.from_simulation(mul.sim, mul.n_immediates, mul.out_regs)
+    cs.prepare(big)
+    imm = random_sliced(128, stride_for(4096), seed=9)
+    got = mask_tail(cs.run_batch(imm, 4096), 4096)  # (a small batch on the same executor: the single kernel)
+    assert cs.launches_per_run == 1 and np.array_equal(got, oracle_out(mul, imm, 4096))
 
 
 def test_row_kernel_on_dags_and_forced_programs(monkeypatch):
