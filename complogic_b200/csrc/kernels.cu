@@ -556,7 +556,7 @@ __device__ __noinline__ uint4 rows_rare(uint2 ins, uint32_t h, uint4 p, uint32_t
 constexpr uint32_t RH_HOT = 1u << 31;
 __device__ __forceinline__ void row_exec(const uint2 ins, uint32_t h, Vec<4> &P, uint32_t sb) {
   constexpr uint32_t M = 0x3FFF0u;
-  if ((int32_t)h < 0) {
+  if (h & RH_HOT) {
     const uint32_t oa = (ins.x << 4) & M, ob = (ins.x >> 10) & M, oc = (ins.y << 4) & M;
     if (!(ins.x & RX_FROM_REG)) P = lds<4>(sb + oa);  // else: operand a is this lane's previous result
     const Vec<4> B = lds<4>(sb + ob);
@@ -1087,7 +1087,7 @@ constexpr uint32_t TMA_BOX = 256;  // vectors per box (the largest a tensor map 
 template <int RT, int VT>
 __device__ __forceinline__ void slice_tma_body(const TensorMap &tm, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows, uint32_t stride) {
   constexpr int WT = VT / 32;
-  extern __shared__ __align__(1024) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];  // (aligned to 1024 by hand below: the swizzle pattern is in address bits 4-9)
   unsigned char *stage = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);              // [VT][RT] bytes, swizzled (the pattern is in address bits 4-9)
   uint32_t(*tile)[WT + 1] = reinterpret_cast<uint32_t(*)[WT + 1]>(stage + VT * RT);        // [RT][WT + 1] words
   uint64_t *bar = reinterpret_cast<uint64_t *>(stage + VT * RT + RT * (WT + 1) * 4);
@@ -1131,7 +1131,7 @@ __device__ __forceinline__ void slice_tma_body(const TensorMap &tm, uint32_t *sl
 template <int RT, int VT>
 __device__ __forceinline__ void unslice_tma_body(const TensorMap &tm, const uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows, uint32_t stride) {
   constexpr int WT = VT / 32;
-  extern __shared__ __align__(1024) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];  // (aligned to 1024 by hand below: the swizzle pattern is in address bits 4-9)
   unsigned char *stage = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   uint32_t(*tile)[WT + 1] = reinterpret_cast<uint32_t(*)[WT + 1]>(stage + VT * RT);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1195,7 +1195,6 @@ CLG_TMA(128, 256)
 // ends, because the neighbouring bytes belong to another warp's row tile). Packing, unpacking and the 32 x 32 bit
 // transpose are the ones above. A warp keeps the VT / 32 (up to 8) words of its row in registers, lane = row, so the
 // sliced side moves 32 bytes per row. The generic kernels before these read one byte per load (1.2-1.4 TB/s).
-constexpr uint32_t GEN_MAX_BYTES = 96 * 1024;  // of vector-major bytes staged per CTA
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
@@ -1206,8 +1205,7 @@ __device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
-extern "C" __global__ void __launch_bounds__(256) clg_slice_gen(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows, uint32_t stride,
-                                                                uint32_t vt) {
+__device__ __forceinline__ void slice_gen_body(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows, uint32_t stride, uint32_t vt) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
   unsigned char *stage = smem + 128;
@@ -1265,8 +1263,7 @@ extern "C" __global__ void __launch_bounds__(256) clg_slice_gen(const uint8_t *b
   }
 }
 
-extern "C" __global__ void __launch_bounds__(256) clg_unslice_gen(const uint32_t *sliced, uint8_t *bools, uint32_t n_vectors, uint32_t n_rows, uint32_t stride,
-                                                                  uint32_t vt) {
+__device__ __forceinline__ void unslice_gen_body(const uint32_t *sliced, uint8_t *bools, uint32_t n_vectors, uint32_t n_rows, uint32_t stride, uint32_t vt) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *stage = smem + 128;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, R = n_rows;
@@ -1327,6 +1324,15 @@ extern "C" __global__ void __launch_bounds__(256) clg_unslice_gen(const uint32_t
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   if (threadIdx.x < bytes - bulk) bools[g0 + bulk + threadIdx.x] = stage[bulk + threadIdx.x];
+}
+
+extern "C" __global__ void __launch_bounds__(256) clg_slice_gen(const uint8_t *bools, uint32_t *sliced, uint32_t n_vectors, uint32_t n_rows, uint32_t stride,
+                                                                uint32_t vt) {
+  slice_gen_body(bools, sliced, n_vectors, n_rows, stride, vt);
+}
+extern "C" __global__ void __launch_bounds__(256) clg_unslice_gen(const uint32_t *sliced, uint8_t *bools, uint32_t n_vectors, uint32_t n_rows, uint32_t stride,
+                                                                  uint32_t vt) {
+  unslice_gen_body(sliced, bools, n_vectors, n_rows, stride, vt);
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
