@@ -508,6 +508,13 @@ def main():
                             "achieved": hbm if bound == "hbm" else issued * lop3_nominal / 1e12, "peak": hbm_peak if bound == "hbm" else lop3_nominal / 1e12,
                             "unit": "GB/s" if bound == "hbm" else "T lane-op/s (LOP3 actually issued)", "hbm_frac": hbm / hbm_peak, "lop3_issued_frac": issued,
                             "note_nand_equivalent_lop3_frac": w["gates"] * w["nv"] / 32 / (ms_x * 1e-3) / lop3_nominal}}
+        if cs_x.mode_name != "spec":
+            # an interpreter keeps the register stack in shared memory: what bounds it is the LSU data pipe (3-4 slot
+            # accesses per LUT through 128 B/clk/SM), not LOP3 issue; the issued-LOP3 fraction is reported for comparison only
+            rec["roofline"]["note"] = (f"interpreted ({cs_x.kernel_name}, {cs_x.words_per_thread} word(s) per slot): bound by shared-memory "
+                                       "gathers (DESIGN.md 5), not by LOP3 issue or HBM")
+        if w["nv"] == 1:
+            rec["roofline"]["note"] = "ONE input vector: a latency measurement (a dependent chain per instance), no roofline applies"
         return rec
 
     extras = None
