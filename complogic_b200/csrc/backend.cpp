@@ -508,9 +508,9 @@ struct Exec {
   // the SM's instruction cache when the next wave of CTAs starts: up to 128 KB of SASS it does (89-92 % of LOP3 peak at two
   // warps per scheduler), beyond it does not (65 %; tools/microbench_ifetch.cu). Programs with few live registers run four
   // or more warps per scheduler and do not care; a program that needs the whole register file (mul64: 222 live values)
-  // does. For those, a batch big enough that every launch fills the machine several times over runs a second chain whose
-  // chunks stay below the cliff: more launches and a register hand-over through the scratch buffer, 10 % less time
-  // (12 x mul64 x 2^24 vectors: 7.3 -> 6.5-6.8 ms). Small batches (config 5's single vector: one launch for all instances)
+  // does. For those -- if their default chain hands nothing over -- a batch big enough that every launch fills the machine
+  // several times over runs a second chain whose chunks stay below the cliff: more launches and a register hand-over
+  // through the scratch buffer, 7-10 % less time (12 x mul64 x 2^24 vectors: 7.3 -> 6.8 ms; mul64 x 2^24: 0.61 -> 0.57 ms). Small batches (config 5's single vector: one launch for all instances)
   // keep the chain with the fewest launches.
   static constexpr uint32_t TP_CHUNK = 6800;  // lane-order instructions at K = 1 (~110 KB of SASS with the hand-over code)
   mutable int tp_state_ = 0;                  // 0: not decided, 1: the program has a throughput chain, -1: it has none
@@ -520,9 +520,16 @@ struct Exec {
     const FlatStream &ln = lane_stream();
     if (!k || ln.n_slots * (uint32_t)k < 160 || (uint64_t)ln.n_instr * k <= 8192 || ln.n_instr * (uint64_t)k > 4000000u) return false;
     if ((words + k - 1) / k < (size_t)ctx->sm_count * 128 * 8) return false;  // every launch: eight waves of 128-thread CTAs or more
-    if (tp_state_ == 0) {  // at most four kernels to assemble, else the default chain's tiering rules apply
+    if (tp_state_ == 0) {
+      // Only for programs whose default chain hands nothing over (one kernel, or the isolated instances of a flattened
+      // program): there the cliff is paid in full and one extra cut per instance is cheap next to it. A chain that
+      // already hands ~200 registers over at every cut gets slower with more cuts (a 19 k-instruction random DAG with
+      // 225 live values: 0.86 ms in four chunks against 0.52 ms in two; tools/bench_tp_chain.py). And at most four kernels
+      // to assemble, else the default chain's tiering rules would have to apply.
+      bool isolated = true;
+      for (const SpecChunk &c : spec_chain(flat, k).chunks) isolated &= c.live_in.empty() && c.live_out.empty();
       const SpecChain ch = spec_chain(flat, k, std::max(2u, TP_CHUNK / (uint32_t)k));
-      tp_state_ = ch.unique.size() <= 4 && ch.chunks.size() > 1 ? 1 : -1;
+      tp_state_ = isolated && ch.unique.size() <= 4 && ch.chunks.size() > 1 ? 1 : -1;
     }
     return tp_state_ == 1;
   }

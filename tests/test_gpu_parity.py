@@ -629,40 +629,41 @@ def test_full_size_structured_1m_gate_circuit_2p24():
         del os.environ["CLG_SPEC_NO_TP"]
 
 
-def test_throughput_chain_of_a_register_heavy_dag():
-    """A random DAG with 225 live values and 19 k instructions: a big batch runs it as the second specialised chain (four
-    chunks below the instruction-cache cliff, every one its own kernel, ~200 registers handed over at each cut), a small
-    batch and CLG_SPEC_NO_TP as the default chain of two. Sampled columns against the oracle VM, and the two chains
-    against each other over the whole buffer."""
+def test_throughput_chain_only_where_it_pays():
+    """The second specialised chain (chunks below the instruction-cache cliff) is for programs whose default chain hands
+    nothing over: a single 64 x 64 multiplier on a big batch runs as two chunks with ~200 registers handed over; a random
+    DAG with 225 live values, whose default chain already hands registers over, keeps its two chunks (more cuts make it
+    slower). Sampled columns against the oracle VM / a * b, and the two chains against each other over the whole buffer."""
     import os
     import torch
 
-    circ = circuits.random_dag(210, 160, 64, 2, 7)
+    ctx = host.Context.default()
     nv = 1 << 23
     stride = stride_for(nv)
-    ctx = host.Context.default()
-    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=host.MODE_SPEC)
-    assert cs.info["lane_slots"] >= 160 and cs.info["lane_instrs"] > 16384
-    imm = _device_random(ctx, circ.n_immediates, stride, 0x7C4)
-    out = torch.zeros((len(circ.out_regs), stride), dtype=torch.int32, device="cuda:0")
-    cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
-    torch.cuda.synchronize()
-    assert cs.launches_per_run == 4 and cs.kernel_name == "clg_spec_chunk"
-    assert _check_sampled_columns(circ, imm, out, nv) >= 100
-    os.environ["CLG_SPEC_NO_TP"] = "1"
-    try:
-        out2 = torch.zeros_like(out)
-        cs.run_device(imm.data_ptr(), out2.data_ptr(), nv, stride)
+    for circ, want_launches in ((circuits.array_multiplier(64), 2), (circuits.random_dag(210, 160, 64, 2, 7), 2)):
+        is_mul = circ.name.startswith("mul")
+        cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=host.MODE_SPEC)
+        assert cs.info["lane_slots"] >= 160
+        imm = _device_random(ctx, circ.n_immediates, stride, 0x7C4)
+        out = torch.zeros((len(circ.out_regs), stride), dtype=torch.int32, device="cuda:0")
+        cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
         torch.cuda.synchronize()
-        assert cs.launches_per_run == 2 and bool((out2 == out).all())
-    finally:
-        del os.environ["CLG_SPEC_NO_TP"]
-    small = 5000
-    out3 = torch.zeros_like(out)
-    cs.run_device(imm.data_ptr(), out3.data_ptr(), small, stride)
-    torch.cuda.synchronize()
-    w = (small + 31) // 32
-    assert cs.launches_per_run == 2 and bool((out3[:, :w - 1] == out[:, :w - 1]).all())
+        assert cs.launches_per_run == want_launches and cs.kernel_name.startswith("clg_spec"), (circ.name, cs.launches_per_run)
+        assert _check_sampled_columns(circ, imm, out, nv) >= 100
+        os.environ["CLG_SPEC_NO_TP"] = "1"
+        try:
+            out2 = torch.zeros_like(out)
+            cs.run_device(imm.data_ptr(), out2.data_ptr(), nv, stride)
+            torch.cuda.synchronize()
+            assert cs.launches_per_run == (1 if is_mul else 2) and bool((out2 == out).all())
+        finally:
+            del os.environ["CLG_SPEC_NO_TP"]
+        small = 5000
+        out3 = torch.zeros_like(out)
+        cs.run_device(imm.data_ptr(), out3.data_ptr(), small, stride)
+        torch.cuda.synchronize()
+        w = (small + 31) // 32
+        assert cs.launches_per_run == (1 if is_mul else 2) and bool((out3[:, :w - 1] == out[:, :w - 1]).all())
 
 
 def test_full_size_mul16_2p26():
