@@ -81,7 +81,7 @@ struct Ctx {
   CUcontext cu = nullptr;
   CUmodule mod = nullptr;
   int sm_count = 0;
-  CUfunction lane[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, coop_rows_t = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, slice_w[3] = {}, unslice_w[3] = {}, unslice_s64 = nullptr, slice_tma[7] = {}, unslice_tma[7] = {}, slice_gen = nullptr, unslice_gen = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
+  CUfunction lane[3] = {}, lane_n[3] = {}, coop[3] = {}, coop_res[3] = {}, coop_c[3] = {}, coop_rows = nullptr, coop_rows_t = nullptr, slice = nullptr, unslice = nullptr, slice_v4 = nullptr, unslice_v4 = nullptr, slice_w[3] = {}, unslice_w[3] = {}, unslice_s64 = nullptr, slice_tma[7] = {}, unslice_tma[7] = {}, slice_gen = nullptr, unslice_gen = nullptr, fill = nullptr, lop3_peak = nullptr;  // index: K = 1,2,4 -> 0,1,2
   std::string name;
 
   static constexpr uint32_t GEN_MAX_BYTES = 96 * 1024;  // staged transposes for any row count (kernels.cu, clg_slice_gen)
@@ -113,6 +113,8 @@ struct Ctx {
       CU(cuModuleGetFunction(&lane[i], mod, (std::string("clg_lane_k") + ks[i]).c_str()));
       CU(cuModuleGetFunction(&coop[i], mod, (std::string("clg_coop_k") + ks[i]).c_str()));
       CU(cuFuncSetAttribute(lane[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
+      CU(cuModuleGetFunction(&lane_n[i], mod, (std::string("clg_lane_n_k") + ks[i]).c_str()));
+      CU(cuFuncSetAttribute(lane_n[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
       CU(cuFuncSetAttribute(coop[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
       CU(cuModuleGetFunction(&coop_c[i], mod, (std::string("clg_coop_c_k") + ks[i]).c_str()));
       CU(cuFuncSetAttribute(coop_c[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)SMEM_MAX));
@@ -189,6 +191,7 @@ struct Plan {
   int K = 0;
   CUdeviceptr d_instr = 0, d_levels = 0, d_parts = 0, d_cinstr = 0, d_clevels = 0;  // (compact cooperative form)
   uint32_t n_instr = 0, n_levels = 0, n_slots = 0, coop_threads = 0, n_parts = 0, code_off = 0, ring_off = 0;
+  bool nandish = false;   // lane mode: most LUTs are the NAND network's two tables (clg_lane_n_k*)
   bool rows_tma = false;  // row form: instruction stream staged through shared memory (clg_coop_rows_t)
   size_t smem = 0;
   uint32_t tuned_threads = 0;  // cooperative, big batches: CTA size found by timing candidates on this device (0: not tuned yet)
@@ -560,6 +563,13 @@ struct Exec {
         st = &ln;
         P.coop_threads = lane_consumers(P.K);  // (consumer threads of the lane kernel)
         P.smem = LANE_RING_BYTES + (size_t)ln.n_slots * P.coop_threads * P.K * 4;
+        {
+          const FlatInstr *src = flat.instrs(STREAM_LANE);
+          size_t luts = 0, hot = 0;
+          for (uint32_t i = 0; i < ln.n_instr; i++)
+            if (src[i].kind == K_LUT) luts++, hot += src[i].tt == 0x0E || src[i].tt == 0x03;
+          P.nandish = !std::getenv("CLG_LANE_PLAIN") && hot * 2 > luts;  // (knob: A/B runs)
+        }
         break;
       case CLG_MODE_COOP:
         if (!P.K) fail(CLG_E_UNSUPPORTED, "live register set exceeds one SM's shared memory even at one word per register");
@@ -899,9 +909,9 @@ struct Exec {
       RunParams p = params(P, imm, out, state, stride, groups);
       void *args[] = {&p};
       const uint32_t nc = P.coop_threads, grid = (groups + nc - 1) / nc;
-      static const char *lane_names[3] = {"clg_lane_k1", "clg_lane_k2", "clg_lane_k4"};
-      last_kernel = lane_names[kidx(K)];
-      CU(cuLaunchKernel(ctx->lane[kidx(K)], grid, 1, 1, nc + 32, 1, 1, (unsigned)P.smem, stream, args, nullptr));
+      static const char *lane_names[2][3] = {{"clg_lane_k1", "clg_lane_k2", "clg_lane_k4"}, {"clg_lane_n_k1", "clg_lane_n_k2", "clg_lane_n_k4"}};
+      last_kernel = lane_names[P.nandish][kidx(K)];
+      CU(cuLaunchKernel((P.nandish ? ctx->lane_n : ctx->lane)[kidx(K)], grid, 1, 1, nc + 32, 1, 1, (unsigned)P.smem, stream, args, nullptr));
       return;
     }
     // Cooperative CTA size. One wave of column groups or less is a latency problem: as many threads as the widest

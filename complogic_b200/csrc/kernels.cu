@@ -274,7 +274,10 @@ constexpr int LANE_MAX_THREADS = 1024;  // consumers (blockDim.x - 32, chosen by
 constexpr int RING_STAGES = 4;
 constexpr int RING_CHUNK = 256;  // instructions per stage (4 KiB)
 
-template <int K>
+// NANDISH: most LUTs of the program are the two tables a NAND network maps to (the host counts them), so those are
+// tested for in line before the jump table; arithmetic programs (XOR3 / MAJ tables) keep the plain dispatch, where
+// the two extra compares sit on the critical path of every instruction (mul16: 12 % slower with them).
+template <int K, bool NANDISH>
 __device__ __forceinline__ void lane_body(const RunParams &p) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint4 *ring = reinterpret_cast<uint4 *>(smem);
@@ -330,7 +333,18 @@ __device__ __forceinline__ void lane_body(const RunParams &p) {
         Vec<K> b = dont_care<K>(), cc = dont_care<K>();
         if (kind <= D_LUT2) b = lds<K>(my + (ins.y & 0xFFFFFFu));
         if (kind == D_LUT3) cc = lds<K>(my + ins.z);
-        sts<K>(my + ins.w, lut3<K, true>(ins.x >> 24, a, b, cc));
+        const uint32_t tt = ins.x >> 24;
+        Vec<K> r;
+        if (NANDISH && tt == 0x0Eu) {
+#pragma unroll
+          for (int k = 0; k < K; k++) r.w[k] = lop3<0x0E>(a.w[k], b.w[k], cc.w[k]);
+        } else if (NANDISH && tt == 0x03u) {
+#pragma unroll
+          for (int k = 0; k < K; k++) r.w[k] = lop3<0x03>(a.w[k], b.w[k], b.w[k]);
+        } else {
+          r = lut3<K, true>(tt, a, b, cc);
+        }
+        sts<K>(my + ins.w, r);
       } else if (kind == D_LDIN) {
         Vec<K> v;
 #pragma unroll
@@ -1377,7 +1391,10 @@ extern "C" __global__ void __launch_bounds__(512) clg_lop3_peak(const uint32_t *
 // C-named entry points the host looks up in the cubin (one per words-per-thread variant)
 #define CLG_ENTRY(K)                                                                                           \
   extern "C" __global__ void __launch_bounds__(clg::LANE_MAX_THREADS) clg_lane_k##K(const clg::RunParams p) { \
-    clg::lane_body<K>(p);                                                                                      \
+    clg::lane_body<K, false>(p);                                                                               \
+  }                                                                                                            \
+  extern "C" __global__ void __launch_bounds__(clg::LANE_MAX_THREADS) clg_lane_n_k##K(const clg::RunParams p) { \
+    clg::lane_body<K, true>(p);                                                                                \
   }                                                                                                            \
   extern "C" __global__ void __launch_bounds__(1024) clg_coop_k##K(const clg::RunParams p) { clg::coop_body<K, false>(p); } \
   extern "C" __global__ void __launch_bounds__(1024) clg_coop_res_k##K(const clg::RunParams p) { clg::coop_body<K, true>(p); } \

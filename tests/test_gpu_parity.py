@@ -220,6 +220,27 @@ def test_latch_chain_needs_few_registers_in_lane_order():
             assert np.array_equal(mask_tail(got, nv), mask_tail(want[t], nv)), (host.MODE_NAMES[mode], t)
 
 
+def test_lane_interpreter_variant_follows_the_table_mix(monkeypatch):
+    """The lane interpreter tests for the NAND network's two tables in line (clg_lane_n_k*) only where they are the
+    majority of the program's LUTs; arithmetic keeps the plain jump table. Both are bit-exact, and so is the plain
+    kernel forced onto the NAND network."""
+    dag = circuits.random_dag(24, 96, 64, 2, 9)
+    mul = circuits.array_multiplier(8)
+    nv = 3000
+    for circ, prefix in ((dag, "clg_lane_n_k"), (mul, "clg_lane_k")):
+        imm = random_sliced(circ.n_immediates, stride_for(nv), seed=3)
+        want = mask_tail(oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs), nv)
+        cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, mode=host.MODE_LANE)
+        assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), want)
+        assert cs.kernel_name.startswith(prefix), cs.kernel_name
+    monkeypatch.setenv("CLG_LANE_PLAIN", "1")
+    imm = random_sliced(dag.n_immediates, stride_for(nv), seed=3)
+    want = mask_tail(oracle.run_batch_sliced(dag.sim, len(dag.sim.registers), imm, nv, dag.out_regs), nv)
+    cs = host.CudaSimulation.from_simulation(dag.sim, dag.n_immediates, dag.out_regs, mode=host.MODE_LANE)
+    assert np.array_equal(mask_tail(cs.run_batch(imm, nv), nv), want)
+    assert cs.kernel_name.startswith("clg_lane_k"), cs.kernel_name
+
+
 def test_lane_only_program_when_level_order_needs_too_many_registers():
     """20 000 latches side by side need > 65 536 registers in level order: the flat buffer then carries the lane stream
     alone and AUTO runs the lane interpreter."""
