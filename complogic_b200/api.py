@@ -451,6 +451,12 @@ class FlatProgram:
         check(lib().clg_flat_spec_chain_info(self._h, k, C.byref(a), C.byref(b), C.byref(c)))
         return {"chunks": a.value, "kernels": b.value, "launches": c.value}
 
+    def spec_batch_chain_info(self, k: int = 1) -> dict:
+        """Shape of the second specialised chain (the one big batches run): chunks, kernels, launches, registers handed over."""
+        a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().clg_flat_spec_batch_chain_info(self._h, k, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"chunks": a.value, "kernels": b.value, "launches": c.value, "handed_over": d.value}
+
     def spec_chunk_ptx(self, k: int, chunk: int, with_bases: bool = False):
         """PTX of one kernel of the chunked specialised form and the length of the chain (and, with_bases, the rows
         (imm, out, state) the kernel's pointers are advanced by)."""

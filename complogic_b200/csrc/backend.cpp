@@ -479,8 +479,8 @@ struct Exec {
 
   // chunked specialisation: cut where few registers are live; equal chunks (the instances of a flattened program)
   // share one assembled kernel and differ only in the rows their pointers are advanced by
-  void build_chain(Plan &P, uint32_t limit) {
-    const SpecChain chain = spec_chain(flat, P.K, limit);
+  void build_chain(Plan &P, uint32_t limit, bool fine = false) {
+    const SpecChain chain = spec_chain(flat, P.K, limit, fine);
     const std::vector<SpecChunk> &chunks = chain.chunks;
     const std::vector<uint32_t> &unique = chain.unique;
     P.chunk_mods.assign(unique.size(), nullptr);
@@ -515,13 +515,17 @@ struct Exec {
   // several times over runs a second chain whose chunks stay below the cliff: more launches and a register hand-over
   // through the scratch buffer, 7-10 % less time (12 x mul64 x 2^24 vectors: 7.3 -> 6.8 ms; mul64 x 2^24: 0.61 -> 0.57 ms). Small batches (config 5's single vector: one launch for all instances)
   // keep the chain with the fewest launches.
-  static constexpr uint32_t TP_CHUNK = 6800;  // lane-order instructions at K = 1 (~110 KB of SASS with the hand-over code)
+  static uint32_t tp_chunk() { return spec_tp_chunk_limit(); }
+  static uint32_t tp_min_regs() {  // live registers x words per thread from which a program takes the second chain
+    const char *e = std::getenv("CLG_SPEC_TP_MIN_REGS");
+    return e ? (uint32_t)std::atol(e) : 160u;
+  }
   mutable int tp_state_ = 0;                  // 0: not decided, 1: the program has a throughput chain, -1: it has none
   bool wants_tp_chain(size_t words) const {
     if (std::getenv("CLG_SPEC_CHUNK") || std::getenv("CLG_SPEC_NO_TP")) return false;
     const int k = fit_k(CLG_MODE_SPEC);
     const FlatStream &ln = lane_stream();
-    if (!k || ln.n_slots * (uint32_t)k < 160 || (uint64_t)ln.n_instr * k <= 8192 || ln.n_instr * (uint64_t)k > 4000000u) return false;
+    if (!k || (uint64_t)ln.n_instr * k <= 8192 || ln.n_instr * (uint64_t)k > 4000000u) return false;
     if ((words + k - 1) / k < (size_t)ctx->sm_count * 128 * 8) return false;  // every launch: eight waves of 128-thread CTAs or more
     if (tp_state_ == 0) {
       // Only for programs whose default chain hands nothing over (one kernel, or the isolated instances of a flattened
@@ -529,10 +533,15 @@ struct Exec {
       // already hands ~200 registers over at every cut gets slower with more cuts (a 19 k-instruction random DAG with
       // 225 live values: 0.86 ms in four chunks against 0.52 ms in two; tools/bench_tp_chain.py). And at most four kernels
       // to assemble, else the default chain's tiering rules would have to apply.
-      bool isolated = true;
+      // A second chain that itself hands nothing over (every cut falls between two instances) is taken whatever the
+      // register count: 12 x mul32 (110 live) 2.12 -> 1.24 ms, 8 x mul40 2.20 -> 1.44 ms, 16 x mul16 0.55 -> 0.48 ms.
+      // One that cuts inside the instances pays for the hand-over and is only for programs that run two warps per
+      // scheduler anyway (160 registers or more).
+      bool isolated = true, tp_isolated = true;
       for (const SpecChunk &c : spec_chain(flat, k).chunks) isolated &= c.live_in.empty() && c.live_out.empty();
-      const SpecChain ch = spec_chain(flat, k, std::max(2u, TP_CHUNK / (uint32_t)k));
-      tp_state_ = isolated && ch.unique.size() <= 4 && ch.chunks.size() > 1 ? 1 : -1;
+      const SpecChain ch = spec_chain(flat, k, std::max(2u, tp_chunk() / (uint32_t)k), true);
+      for (const SpecChunk &c : ch.chunks) tp_isolated &= c.live_in.empty() && c.live_out.empty();
+      tp_state_ = isolated && ch.unique.size() <= 4 && ch.chunks.size() > 1 && (tp_isolated || ln.n_slots * (uint32_t)k >= tp_min_regs()) ? 1 : -1;
     }
     return tp_state_ == 1;
   }
@@ -541,7 +550,7 @@ struct Exec {
     if (P.ready) return P;
     ctx->bind();
     P.K = fit_k(CLG_MODE_SPEC);
-    build_chain(P, std::max(2u, TP_CHUNK / (uint32_t)P.K));
+    build_chain(P, std::max(2u, tp_chunk() / (uint32_t)P.K), true);
     P.ready = true;
     return P;
   }

@@ -262,6 +262,21 @@ int clg_flat_spec_chain_info(const clg_flat *f, int k, uint32_t *n_chunks, uint3
   if (n_launches) *n_launches = (uint32_t)ch.launches.size();
   CLG_CATCH
 }
+int clg_flat_spec_batch_chain_info(const clg_flat *f, int k, uint32_t *n_chunks, uint32_t *n_kernels, uint32_t *n_launches, uint32_t *n_handed_over) {
+  CLG_TRY
+  NEED(f);
+  if (k != 1 && k != 2 && k != 4) fail(CLG_E_INVALID, "K must be 1, 2 or 4");
+  if (f->f.header().stream[STREAM_LANE].n_instr == 0) fail(CLG_E_UNSUPPORTED, "no lane-ordered stream in this flat buffer");
+  const SpecChain ch = spec_chain(f->f, k, std::max(2u, spec_tp_chunk_limit() / (uint32_t)k), true);
+  if (n_chunks) *n_chunks = (uint32_t)ch.chunks.size();
+  if (n_kernels) *n_kernels = (uint32_t)ch.unique.size();
+  if (n_launches) *n_launches = (uint32_t)ch.launches.size();
+  if (n_handed_over) {
+    *n_handed_over = 0;
+    for (const SpecChunk &c : ch.chunks) *n_handed_over += (uint32_t)c.live_out.size();
+  }
+  CLG_CATCH
+}
 
 // ---- device -------------------------------------------------------------------------------------------------
 int clg_ctx_create(int device, clg_ctx **out) {

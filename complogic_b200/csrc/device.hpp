@@ -15,7 +15,7 @@ namespace clg {
 std::string emit_spec_ptx(const Flat &f, int K, bool multi_step = false);
 std::vector<uint32_t> spec_live_slots(const Flat &f, uint32_t at);
 uint32_t spec_chunk_limit(int K);                        // longest chunk, in lane-order instructions
-std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K, uint32_t limit = 0);  // n_chunks + 1 instruction indices
+std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K, uint32_t limit = 0, bool fine = false);  // n_chunks + 1 instruction indices
 // One kernel of the chunked specialised form, in chunk-local terms (spec.cpp)
 constexpr uint16_t FLAG_STATE_ROW = 0x10;  // chunk-local code only: `row` indexes the state buffer
 struct SpecChunk {
@@ -26,7 +26,7 @@ struct SpecChunk {
   uint32_t imm_base = 0, out_base = 0, state_base = 0;  // rows the kernel's pointers are advanced by at launch
   bool same_kernel(const SpecChunk &o) const;           // equal code: the two chunks can share one assembled kernel
 };
-std::vector<SpecChunk> spec_chunks(const Flat &f, int K, uint32_t limit = 0);  // limit: longest chunk in lane-order instructions (0: spec_chunk_limit(K))
+std::vector<SpecChunk> spec_chunks(const Flat &f, int K, uint32_t limit = 0, bool fine = false);  // limit: longest chunk in lane-order instructions (0: spec_chunk_limit(K))
 struct SpecChain {
   std::vector<SpecChunk> chunks;
   std::vector<uint32_t> unique;     // chunks that get assembled (one per distinct kernel)
@@ -36,7 +36,7 @@ struct SpecChain {
   };
   std::vector<Launch> launches;
 };
-SpecChain spec_chain(const Flat &f, int K, uint32_t limit = 0);
+SpecChain spec_chain(const Flat &f, int K, uint32_t limit = 0, bool fine = false);  // fine: cut at the FIRST point no register crosses (one instance of a flattened program per kernel)
 std::string emit_spec_chunk_ptx(const Flat &f, int K, const SpecChunk &c);
 
 // mirrors kernels.cu
@@ -71,6 +71,13 @@ inline uint32_t spec_chunk_limit() {    // ... unless CLG_SPEC_CHUNK says otherw
   const char *e = std::getenv("CLG_SPEC_CHUNK");
   const long n = e ? std::atol(e) : 0;
   return n >= 2 ? (uint32_t)n : SPEC_CHUNK;
+}
+
+// The second chain, for big batches (backend.cpp, wants_tp_chain): chunks short enough to stay in the instruction cache.
+inline uint32_t spec_tp_chunk_limit() {  // lane-order instructions at K = 1 (6 800: ~110 KB of SASS with the hand-over code)
+  const char *e = std::getenv("CLG_SPEC_TP_CHUNK");
+  const long n = e ? std::atol(e) : 0;
+  return n >= 2 ? (uint32_t)n : 6800u;
 }
 
 }  // namespace clg

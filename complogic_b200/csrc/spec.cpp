@@ -57,7 +57,7 @@ uint32_t spec_chunk_limit(int K) {
   return std::max(2u, K == 1 ? n : K == 2 ? n / 2 : (uint32_t)((uint64_t)n * 3 / 8));
 }
 
-std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K, uint32_t limit_or_0) {
+std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K, uint32_t limit_or_0, bool fine) {
   const FlatStream &st = f.header().stream[STREAM_LANE];
   const FlatInstr *in = f.instrs(STREAM_LANE);
   const uint32_t n = st.n_instr, limit = limit_or_0 ? std::max(2u, limit_or_0) : spec_chunk_limit(K);
@@ -80,8 +80,32 @@ std::vector<uint32_t> spec_chunk_cuts(const Flat &f, int K, uint32_t limit_or_0)
         rd(x.a);
       live_at[i] = count;
     }
-    while (n - cuts.back() > limit) {
-      const uint32_t lo = cuts.back() + limit / 2 + 1, hi = cuts.back() + limit;
+    // fine: the first boundary no register crosses, if one is in reach -- the instances of a flattened program then
+    // get a kernel each (run side by side, blockIdx.y) instead of one kernel for as many as fit the limit: the
+    // shorter the straight-line code, the better it sits in the instruction cache (12 x mul32 at 2^24 vectors: 81 %
+    // of the LOP3 pipe with one instance per kernel, 71 % with two, 47 % with five; tools/sweep_tp_chunk.py)
+    // An instance longer than the limit is cut into equal parts at the cheapest boundary near each split point, so
+    // that the parts of every instance come out alike and share their kernels too.
+    const uint32_t min_len = std::min(limit / 2, 1024u);
+    for (;;) {
+      const uint32_t last = cuts.back();
+      uint32_t lo, hi;
+      if (fine) {
+        uint32_t z = last + min_len + 1;
+        while (z < n && live_at[z] != 0) z++;
+        if (z >= n || n - z <= min_len) z = n;
+        const uint32_t len = z - last;
+        if (len <= limit) {
+          if (z == n) break;
+          cuts.push_back(z);
+          continue;
+        }
+        const uint32_t parts = (len + limit - 1) / limit, target = last + len / parts, slack = len / parts / 8;
+        lo = target - slack, hi = std::min(last + limit, target + slack);
+      } else {
+        if (n - last <= limit) break;
+        lo = last + limit / 2 + 1, hi = last + limit;
+      }
       uint32_t best = hi;
       for (uint32_t i = hi; i >= lo; i--)
         if (live_at[i] < live_at[best]) best = i;
@@ -149,8 +173,8 @@ bool SpecChunk::same_kernel(const SpecChunk &o) const {
 }
 
 // The chain a long program runs as: cuts where few registers are live, the live sets at the cuts, chunk-local code.
-std::vector<SpecChunk> spec_chunks(const Flat &f, int K, uint32_t limit) {
-  const std::vector<uint32_t> cuts = spec_chunk_cuts(f, K, limit);
+std::vector<SpecChunk> spec_chunks(const Flat &f, int K, uint32_t limit, bool fine) {
+  const std::vector<uint32_t> cuts = spec_chunk_cuts(f, K, limit, fine);
   const size_t n = cuts.size() - 1;
   std::vector<std::vector<uint32_t>> live(n + 1);
   for (size_t c = 1; c < n; c++) live[c] = spec_live_slots(f, cuts[c]);
@@ -162,9 +186,9 @@ std::vector<SpecChunk> spec_chunks(const Flat &f, int K, uint32_t limit) {
 // The launches of the chain: which chunks get assembled (one per distinct kernel) and which consecutive chunks run
 // side by side in one launch. Consecutive chunks that share a kernel, hand nothing over and touch disjoint
 // carried-state rows are independent of each other; blockIdx.y then selects the instance's row bases.
-SpecChain spec_chain(const Flat &f, int K, uint32_t limit) {
+SpecChain spec_chain(const Flat &f, int K, uint32_t limit, bool fine) {
   SpecChain ch;
-  ch.chunks = spec_chunks(f, K, limit);
+  ch.chunks = spec_chunks(f, K, limit, fine);
   const std::vector<SpecChunk> &chunks = ch.chunks;
   ch.kernel_of.resize(chunks.size());
   for (uint32_t c = 0; c < chunks.size(); c++) {
@@ -414,6 +438,15 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
     }
   }
   s += "DONE:\n  ret;\n}\n";
+  if (std::getenv("CLG_SPEC_ADDR32")) {
+    // experiment: row addresses as ONE 32 x 32 + 64 multiply-add (IMAD.WIDE.U32) instead of the 64-bit product's three
+    // instructions; needs stride * 4 < 2^32
+    const std::string from = "mad.lo.u64 %addr, %sb, ", to = "mad.wide.u32 %addr, %sw, ";
+    for (size_t at = 0; (at = s.find(from, at)) != std::string::npos; at += to.size()) s.replace(at, from.size(), to);
+    const std::string anchor = "  mul.wide.u32 %sb, %stride, 4;\n";
+    const size_t at = s.find(anchor);
+    s.insert(at + anchor.size(), "  .reg .b32 %sw;\n  shl.b32 %sw, %stride, 2;\n");
+  }
   return s;
 }
 

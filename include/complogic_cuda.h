@@ -210,6 +210,12 @@ int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *
 /* Shape of that chain without generating any code: chunks, distinct kernels that would have to be assembled (about a
  * second each on the first run), and launches per run (equal independent chunks share one launch). Any may be NULL. */
 int clg_flat_spec_chain_info(const clg_flat *f, int k, uint32_t *n_chunks, uint32_t *n_kernels, uint32_t *n_launches);
+/* The same for the SECOND chain, the one big batches run (a launch that fills the machine many times over): chunks short
+ * enough to stay in the SM's instruction cache (CLG_SPEC_TP_CHUNK lane-order instructions, 6 800 / k by default), cut at
+ * the first boundary no register crosses -- one instance of a flattened program per kernel, all instances side by side
+ * in one launch -- and, where an instance is longer than that, into equal parts. *n_handed_over (optional): registers
+ * that cross a cut, summed over the chain (0: the chain is taken whatever the program's register count). */
+int clg_flat_spec_batch_chain_info(const clg_flat *f, int k, uint32_t *n_chunks, uint32_t *n_kernels, uint32_t *n_launches, uint32_t *n_handed_over);
 
 /* ---------------------------------------------------------------------------------------------
  * Device side. Raw CUDA driver API underneath (libcuda.so.1 is dlopen'ed when the first context

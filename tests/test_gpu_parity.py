@@ -665,6 +665,8 @@ def test_throughput_chain_only_where_it_pays():
         is_mul = circ.name.startswith("mul")
         cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=host.MODE_SPEC)
         assert cs.info["lane_slots"] >= 160
+        if is_mul:
+            assert cs.flat.spec_batch_chain_info(1) == {"chunks": 2, "kernels": 2, "launches": 2, "handed_over": 203}
         imm = _device_random(ctx, circ.n_immediates, stride, 0x7C4)
         out = torch.zeros((len(circ.out_regs), stride), dtype=torch.int32, device="cuda:0")
         cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
@@ -685,6 +687,38 @@ def test_throughput_chain_only_where_it_pays():
         torch.cuda.synchronize()
         w = (small + 31) // 32
         assert cs.launches_per_run == (1 if is_mul else 2) and bool((out3[:, :w - 1] == out[:, :w - 1]).all())
+
+
+def test_throughput_chain_one_instance_per_kernel():
+    """A flattened program whose instances are short (6 x mul32, 110 live registers): a big batch runs ONE launch of a
+    kernel that holds one instance (side by side over blockIdx.y) instead of the default chain's two kernels of three
+    instances each -- no register crosses a cut, so the chain is taken whatever the register count. Sampled columns
+    against the oracle VM, the two chains against each other over the whole buffer."""
+    import os
+    import torch
+
+    ctx = host.Context.default()
+    nv = 1 << 23
+    stride = stride_for(nv)
+    circ = circuits.flatten_instances(circuits.array_multiplier(32), 6)
+    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=host.MODE_SPEC)
+    assert cs.info["lane_slots"] < 160
+    assert cs.flat.spec_chain_info(1) == {"chunks": 2, "kernels": 2, "launches": 2}
+    assert cs.flat.spec_batch_chain_info(1) == {"chunks": 6, "kernels": 1, "launches": 1, "handed_over": 0}
+    imm = _device_random(ctx, circ.n_immediates, stride, 0x7C5)
+    out = torch.zeros((len(circ.out_regs), stride), dtype=torch.int32, device="cuda:0")
+    cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    assert cs.launches_per_run == 1 and cs.kernel_name == "clg_spec_chunk"
+    assert _check_sampled_columns(circ, imm, out, nv) >= 100
+    os.environ["CLG_SPEC_NO_TP"] = "1"
+    try:
+        out2 = torch.zeros_like(out)
+        cs.run_device(imm.data_ptr(), out2.data_ptr(), nv, stride)
+        torch.cuda.synchronize()
+        assert cs.launches_per_run == 2 and bool((out2 == out).all())
+    finally:
+        del os.environ["CLG_SPEC_NO_TP"]
 
 
 def test_full_size_mul16_2p26():

@@ -54,6 +54,31 @@ def test_chunked_chain_hands_registers_over(k):
         fp.spec_chunk_ptx(k, n)
 
 
+def test_batch_chain_cuts_between_instances_and_in_equal_parts():
+    """The second chain (big batches): one instance of a flattened program per kernel where an instance fits the limit
+    -- all instances then share ONE kernel and ONE launch and nothing is handed over; an instance longer than the limit
+    is cut into equal parts, so the parts of every instance share their kernels as well."""
+    for n, m, first, second in (
+        (32, 6, {"chunks": 2, "kernels": 2, "launches": 2}, {"chunks": 6, "kernels": 1, "launches": 1, "handed_over": 0}),
+        (40, 4, {"chunks": 2, "kernels": 2, "launches": 2}, {"chunks": 4, "kernels": 1, "launches": 1, "handed_over": 0}),
+        (16, 16, {"chunks": 1, "kernels": 1, "launches": 1}, {"chunks": 8, "kernels": 1, "launches": 1, "handed_over": 0}),  # (two 784-instruction instances per kernel)
+        (48, 3, {"chunks": 2, "kernels": 2, "launches": 2}, {"chunks": 6, "kernels": 2, "launches": 6}),
+        (64, 2, {"chunks": 2, "kernels": 1, "launches": 1}, {"chunks": 4, "kernels": 2, "launches": 4}),
+    ):
+        circ = circuits.flatten_instances(circuits.array_multiplier(n), m)
+        fp = host.FlatProgram.levelize(circ.sim, circ.n_immediates, circ.out_regs)
+        assert fp.spec_chain_info(1) == first, (n, m)
+        got = fp.spec_batch_chain_info(1)
+        if "handed_over" not in second:
+            assert got.pop("handed_over") > 0
+        assert got == second, (n, m)
+    # a DAG is cut where few registers are live, as in the first chain, only shorter
+    dag = circuits.random_dag(210, 160, 64, 2, 7)
+    fp = host.FlatProgram.levelize(dag.sim, 64, dag.out_regs)
+    info = fp.spec_batch_chain_info(1)
+    assert info["chunks"] == info["kernels"] == info["launches"] == 4 and info["handed_over"] > 300
+
+
 def test_chunked_chain_stateful_steps():
     sim, outs = feedback_dag()
     fp = host.FlatProgram.levelize(sim, 64, outs, flags=host.LV_STATEFUL)
