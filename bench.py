@@ -69,6 +69,8 @@ def build_workload(name: str, api=None):
     if name in ("mul64x4", "mul64x8", "mul64x12"):
         m = int(name[6:])
         return circuits.flatten_instances(circuits.array_multiplier(64, api=api), m, api=api), 24 if m == 12 else 21, 0xC0FFF1
+    if name == "mul32x48":
+        return circuits.flatten_instances(circuits.array_multiplier(32, api=api), 48, api=api), 24, 0xC0FFF2
     if name == "adder8":
         return circuits.ripple_adder(8, api=api), 17, 0xC0FFED
     if name == "latch1500":
@@ -92,9 +94,11 @@ WORKLOAD_DESC = {
     "latch1500": "a SEQUENTIAL circuit: 1 500 D latches in a row (24 000 NANDs), 6 000 carried registers per lane rewritten "
                  "in place every step; one step per launch on 2^24 lanes: bound by HBM (13 502 rows of 2 MB per step)",
     "mul64x12": "a STRUCTURED 1M-gate circuit: 64x64 array multiplier x 12 instances flattened = 1 009 152 NANDs, 2^24 vectors; "
-                "runs as a chain of 12 launches of one specialised kernel",
+                "runs as a chain of 24 launches of two specialised kernels (the halves of an instance, each below the instruction-cache cliff)",
     "mul64x8": "64x64 array multiplier x 8 instances flattened = 672 768 NANDs, batched: a program too long for one "
                "specialised kernel (98 816 instructions), run as a chain of chunk kernels",
+    "mul32x48": "a STRUCTURED 1M-gate circuit of narrower parts: 32x32 array multiplier x 48 instances flattened = 986 112 NANDs, "
+                "2^24 vectors; one instance per kernel (50 KB of SASS: it stays in the instruction cache), all 48 side by side in one launch",
     "mul64x128": "64x64 array multiplier (84 096 NANDs) x 128 instances flattened into one program = 10 764 288 gates, "
                  "ONE input vector (BASELINE configs[4]; M = 128 instances gives the ~10M gates the config names, see SURVEY "
                  "8d). --mode coop: the warp-cooperative intra-level mode, one CTA per part; auto: the instances are equal "
@@ -524,7 +528,7 @@ def main():
         if world == 1:
             # every BASELINE config in the driver's line: configs[1] adder32 x 2^24, configs[2] mul16 x 2^26, the structured
             # 1M-gate circuit, configs[4] one vector through 128 flattened multipliers, and configs[3] without its locality window
-            plan = [("adder32", None, 20), ("mul16", None, 20), ("mul64x12", None, 5), ("mul64x128", None, 20), ("dag1m_kinf", 22, 5)]
+            plan = [("adder32", None, 20), ("mul16", None, 20), ("mul64x12", None, 5), ("mul32x48", None, 5), ("mul64x128", None, 20), ("dag1m_kinf", 22, 5)]
         else:
             # configs[2] "at 1/2/4/8 B200": 2^26 vectors in total, sharded over the ranks
             # (strong: a 20-microsecond kernel per GPU at N = 8) and, as "mul16_weak", 2^26 vectors per GPU

@@ -438,15 +438,6 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
     }
   }
   s += "DONE:\n  ret;\n}\n";
-  if (std::getenv("CLG_SPEC_ADDR32")) {
-    // experiment: row addresses as ONE 32 x 32 + 64 multiply-add (IMAD.WIDE.U32) instead of the 64-bit product's three
-    // instructions; needs stride * 4 < 2^32
-    const std::string from = "mad.lo.u64 %addr, %sb, ", to = "mad.wide.u32 %addr, %sw, ";
-    for (size_t at = 0; (at = s.find(from, at)) != std::string::npos; at += to.size()) s.replace(at, from.size(), to);
-    const std::string anchor = "  mul.wide.u32 %sb, %stride, 4;\n";
-    const size_t at = s.find(anchor);
-    s.insert(at + anchor.size(), "  .reg .b32 %sw;\n  shl.b32 %sw, %stride, 2;\n");
-  }
   return s;
 }
 

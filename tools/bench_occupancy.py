@@ -13,7 +13,7 @@ from complogic_b200 import circuits
 
 ctx = host.Context(0)
 clock_hz = 1.965e9
-peak = ctx.sm_count * 64 * clock_hz  # LOP3 lane-ops / s
+peak = ctx.sm_count * 64 * clock_hz  # LOP3 / s
 for n, m, lg in ((16, 16, 24), (24, 16, 24), (32, 12, 24), (40, 8, 24), (48, 8, 23), (64, 4, 23)):
     circ = circuits.flatten_instances(circuits.array_multiplier(n), m)
     nv = 1 << lg
@@ -37,6 +37,6 @@ for n, m, lg in ((16, 16, 24), (24, 16, 24), (32, 12, 24), (40, 8, 24), (48, 8, 
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        lop3 = cs.info["n_luts"] * (nv / 32) * 32 / (ms * 1e-3)
+        lop3 = cs.info["n_luts"] * (nv / 32) / (ms * 1e-3)  # a LOP3 = one thread, one 32-bit word
         print(f"mul{n} x {m:2d}  2^{lg}  K={k}  live {cs.info['lane_slots']:3d} ({cs.info['lane_slots'] * k:3d} registers)  launches {cs.launches_per_run:2d}  "
               f"{ms:7.3f} ms  LOP3 issued {lop3 / peak * 100:5.1f} % of peak  kernel {cs.kernel_name}", flush=True)
