@@ -208,7 +208,7 @@ struct Plan {
   std::vector<ChunkLaunch> chunks;   // the chain, in order
   CUdeviceptr d_bases = 0;           // uint32[chunks of the program][4]: imm / out / state row base of each chunk
   CUdeviceptr scratch = 0;
-  size_t scratch_stride = 0;
+  size_t scratch_bytes = 0;
   CUmodule spec_mod = nullptr, steps_mod = nullptr;
   CUfunction spec_fn = nullptr, steps_fn = nullptr;  // steps_fn: the fused multi-step form, assembled on first use
   std::string ptx;
@@ -893,12 +893,14 @@ struct Exec {
       uint32_t stride32 = (uint32_t)stride, g = groups;
       const uint32_t nt = spec_threads(groups);
       if (!P.chunks.empty()) {
-        if (stride > P.scratch_stride) {  // registers that are live across chunk cuts: [slot][stride] words
+        // registers that are live across chunk cuts: [column group / 32][slot][32 lanes][K words] (spec.cpp)
+        const size_t scratch_bytes = (size_t)lane_stream().n_slots * (((size_t)groups + 31) / 32 * 32) * K * 4;
+        if (scratch_bytes > P.scratch_bytes) {
           CU(cuCtxSynchronize());
           if (P.scratch) driver().cuMemFree(P.scratch);
-          P.scratch = 0, P.scratch_stride = 0;
-          CU(cuMemAlloc(&P.scratch, std::max<size_t>(16, (size_t)lane_stream().n_slots * stride * 4)));
-          P.scratch_stride = stride;
+          P.scratch = 0, P.scratch_bytes = 0;
+          CU(cuMemAlloc(&P.scratch, std::max<size_t>(16, scratch_bytes)));
+          P.scratch_bytes = scratch_bytes;
         }
         last_kernel = "clg_spec_chunk";
         for (const Plan::ChunkLaunch &c : P.chunks) {

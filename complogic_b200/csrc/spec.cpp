@@ -292,7 +292,17 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
                 K * 4);
   s += buf;
   if (chunk) {
-    s += "  .reg .b64 %scr;\n  ld.param.u64 %scr, [p_scratch];\n  cvta.to.global.u64 %scr, %scr;\n  add.u64 %scr, %scr, %off;\n";
+    // The scratch buffer is the library's own, so its layout is chosen for cheap addresses: blocked by warp,
+    // [column group / 32][register][32 lanes][K words]. A register's row is then a compile-time offset from one base per
+    // thread ([%scr+imm]: no address arithmetic per access, against three instructions for a row of the caller's
+    // [row][stride] buffers), a warp's access is one contiguous 128 K bytes, and a warp's whole hand-over is one
+    // contiguous block of the buffer.
+    std::snprintf(buf, sizeof buf,
+                  "  .reg .b64 %%scr, %%scrw;\n  .reg .b32 %%wid, %%lid;\n  ld.param.u64 %%scr, [p_scratch];\n  cvta.to.global.u64 %%scr, %%scr;\n"
+                  "  shr.u32 %%wid, %%gid, 5;\n  and.b32 %%lid, %%gid, 31;\n  mul.wide.u32 %%scrw, %%wid, %u;\n"
+                  "  mad.wide.u32 %%scrw, %%lid, %d, %%scrw;\n  add.u64 %%scr, %%scr, %%scrw;\n",
+                  h.stream[STREAM_LANE].n_slots * 128u * (uint32_t)K, K * 4);
+    s += buf;
     // Row bases: blockIdx.y picks one entry {imm, out, state, -} of the launch's table, so that equal chunks (the
     // instances of a flattened program) run side by side in ONE launch, each on its own rows.
     s += "  .reg .b64 %bases, %row;\n  .reg .b32 %inst, %b<4>;\n  ld.param.u64 %bases, [p_bases];\n  cvta.to.global.u64 %bases, %bases;\n"
@@ -333,8 +343,8 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
   auto reload = [&](uint32_t sl) {
     if (!chunk || !need_load[sl]) return;
     need_load[sl] = 0;
-    std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  ld.global%s%s.u32 %s, [%%addr];\n", scr(sl),
-                  store_at[sl] == UINT32_MAX ? ".nc.L1::no_allocate" : "", vt, vec(sl).c_str());
+    std::snprintf(buf, sizeof buf, "  ld.global%s%s.u32 %s, [%%scr+%u];\n", store_at[sl] == UINT32_MAX ? ".nc.L1::no_allocate" : "", vt,
+                  vec(sl).c_str(), scr(sl) * 128u * (uint32_t)K);
     s += buf;
   };
   auto reload_ahead = [&](uint32_t i) {
@@ -344,7 +354,7 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
     if (!chunk) return;
     need_load[sl] = 0;
     if (store_at[sl] != i) return;
-    std::snprintf(buf, sizeof buf, "  mad.lo.u64 %%addr, %%sb, %u, %%scr;\n  st.global%s.u32 [%%addr], %s;\n", scr(sl), vt, vec(sl).c_str());
+    std::snprintf(buf, sizeof buf, "  st.global%s.u32 [%%scr+%u], %s;\n", vt, scr(sl) * 128u * (uint32_t)K, vec(sl).c_str());
     s += buf;
   };
   const char *cvt = K == 4 ? ".v4" : K == 2 ? ".v2" : "";

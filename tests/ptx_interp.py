@@ -41,8 +41,12 @@ def run_kernel(ptx: str, k: int, groups: int, mem: dict):
             assert d == "%addr" and sb == "%sb" and base[1:] in _BASES, l
             addr = (base[1:], int(n))
         elif op.startswith("ld.global"):
-            m = re.fullmatch(r"(\{[^}]*\}|%\w+), \[%addr\]", rest)
+            m = re.fullmatch(r"(\{[^}]*\}|%\w+), \[(%addr|%scr\+\d+)\]", rest)
             assert m, l
+            if m.group(2) != "%addr":  # a scratch row: a compile-time offset of 128 k bytes per row from the thread's base
+                off = int(m.group(2)[5:])
+                assert off % (128 * k) == 0, l
+                addr = ("scr", off // (128 * k))
             dst = _regs(m.group(1))
             assert len(dst) == k and (("v%d" % k) in op or k == 1), l
             if addr[0] == "state":
@@ -54,9 +58,13 @@ def run_kernel(ptx: str, k: int, groups: int, mem: dict):
             for j, r in enumerate(dst):
                 reg[r] = row[cols[:, j]].copy()
         elif op.startswith("st.global"):
-            m = re.fullmatch(r"\[%addr\], (\{[^}]*\}|%\w+)", rest)
+            m = re.fullmatch(r"\[(%addr|%scr\+\d+)\], (\{[^}]*\}|%\w+)", rest)
             assert m, l
-            src = _regs(m.group(1))
+            if m.group(1) != "%addr":
+                off = int(m.group(1)[5:])
+                assert off % (128 * k) == 0, l
+                addr = ("scr", off // (128 * k))
+            src = _regs(m.group(2))
             assert len(src) == k, l
             if addr[0] == "scr":
                 assert addr[1] not in scr_nc, "store to a scratch row this chunk reads through the read-only path: " + l
