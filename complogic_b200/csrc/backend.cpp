@@ -203,6 +203,7 @@ struct Plan {
   struct ChunkLaunch {
     CUfunction fn;
     uint32_t first, count;  // entries of the row-base table: `count` equal, independent chunks run side by side (grid.y)
+    uint32_t group;         // > 1: this and the next group - 1 launches run `count` groups of `group` chunks each, position by position
   };
   std::vector<CUmodule> chunk_mods;  // one per DISTINCT chunk
   std::vector<ChunkLaunch> chunks;   // the chain, in order
@@ -497,10 +498,15 @@ struct Exec {
       P.chunk_mods.clear();
       throw;
     }
-    std::vector<uint32_t> bases(chunks.size() * 4, 0);
-    for (uint32_t c = 0; c < chunks.size(); c++)
-      bases[4 * c] = chunks[c].imm_base, bases[4 * c + 1] = chunks[c].out_base, bases[4 * c + 2] = chunks[c].state_base;
-    for (const SpecChain::Launch &l : chain.launches) P.chunks.push_back({fns[chain.kernel_of[l.first]], l.first, l.count});
+    // the row-base table in launch order: {imm, out, state row, part of the scratch buffer} of every member of every launch
+    std::vector<uint32_t> bases;
+    for (const SpecChain::Launch &l : chain.launches) {
+      P.chunks.push_back({fns[chain.kernel_of[l.first]], (uint32_t)(bases.size() / 4), l.count, l.stride});
+      for (uint32_t i = 0; i < l.count; i++) {
+        const SpecChunk &c = chunks[l.first + (size_t)i * l.stride];
+        bases.insert(bases.end(), {c.imm_base, c.out_base, c.state_base, l.stride > 1 ? i : 0u});
+      }
+    }
     CU(cuMemAlloc(&P.d_bases, bases.size() * 4));
     CU(cuMemcpyHtoDAsync(P.d_bases, bases.data(), bases.size() * 4, nullptr));
     CU(cuStreamSynchronize(nullptr));
@@ -516,6 +522,10 @@ struct Exec {
   // through the scratch buffer, 7-10 % less time (12 x mul64 x 2^24 vectors: 7.3 -> 6.8 ms; mul64 x 2^24: 0.61 -> 0.57 ms). Small batches (config 5's single vector: one launch for all instances)
   // keep the chain with the fewest launches.
   static uint32_t tp_chunk() { return spec_tp_chunk_limit(); }
+  static size_t scratch_budget() {  // bytes of hand-over scratch a plan may hold (side-by-side groups share it)
+    const char *e = std::getenv("CLG_SPEC_SCRATCH_MB");
+    return (size_t)(e ? std::max(1L, std::atol(e)) : 8192L) << 20;
+  }
   static uint32_t tp_min_regs() {  // live registers x words per thread from which a program takes the second chain
     const char *e = std::getenv("CLG_SPEC_TP_MIN_REGS");
     return e ? (uint32_t)std::atol(e) : 160u;
@@ -893,21 +903,40 @@ struct Exec {
       uint32_t stride32 = (uint32_t)stride, g = groups;
       const uint32_t nt = spec_threads(groups);
       if (!P.chunks.empty()) {
-        // registers that are live across chunk cuts: [column group / 32][slot][32 lanes][K words] (spec.cpp)
-        const size_t scratch_bytes = (size_t)lane_stream().n_slots * (((size_t)groups + 31) / 32 * 32) * K * 4;
-        if (scratch_bytes > P.scratch_bytes) {
+        // registers that are live across chunk cuts: [part][column group / 32][slot][32 lanes][K words] (spec.cpp). Groups
+        // of chunks that run side by side hand over in a part each: as many at a time as the scratch budget holds.
+        const size_t part_bytes = (size_t)lane_stream().n_slots * (((size_t)groups + 31) / 32 * 32) * K * 4;
+        uint32_t widest = 1;
+        for (const Plan::ChunkLaunch &c : P.chunks)
+          if (c.group > 1) widest = std::max(widest, c.count);
+        const uint32_t at_once = (uint32_t)std::min<size_t>(widest, std::max<size_t>(1, scratch_budget() / std::max<size_t>(part_bytes, 1)));
+        if (part_bytes * at_once > P.scratch_bytes) {
           CU(cuCtxSynchronize());
           if (P.scratch) driver().cuMemFree(P.scratch);
           P.scratch = 0, P.scratch_bytes = 0;
-          CU(cuMemAlloc(&P.scratch, std::max<size_t>(16, scratch_bytes)));
-          P.scratch_bytes = scratch_bytes;
+          CU(cuMemAlloc(&P.scratch, std::max<size_t>(16, part_bytes * at_once)));
+          P.scratch_bytes = part_bytes * at_once;
         }
         last_kernel = "clg_spec_chunk";
-        for (const Plan::ChunkLaunch &c : P.chunks) {
-          const uint32_t ntc = spec_threads((uint32_t)std::min<uint64_t>((uint64_t)groups * c.count, 0xFFFFFFFFull));
-          CUdeviceptr table = P.d_bases + (size_t)c.first * 16;
-          void *cargs[] = {&imm, &out, &state, &stride32, &g, &P.scratch, &table};
-          CU(cuLaunchKernel(c.fn, (groups + ntc - 1) / ntc, c.count, 1, ntc, 1, 1, 0, stream, cargs, nullptr));
+        last_launches = 0;
+        auto launch = [&](const Plan::ChunkLaunch &c, uint32_t first, uint32_t count) {
+          const uint32_t ntc = spec_threads((uint32_t)std::min<uint64_t>((uint64_t)groups * count, 0xFFFFFFFFull));
+          CUdeviceptr table = P.d_bases + ((size_t)c.first + first) * 16;
+          CUdeviceptr scratch = P.scratch - (size_t)first * part_bytes;  // (the kernel adds the member's number x part_bytes)
+          void *cargs[] = {&imm, &out, &state, &stride32, &g, &scratch, &table};
+          CU(cuLaunchKernel(c.fn, (groups + ntc - 1) / ntc, count, 1, ntc, 1, 1, 0, stream, cargs, nullptr));
+          last_launches++;
+        };
+        for (size_t i = 0; i < P.chunks.size();) {
+          const Plan::ChunkLaunch &c = P.chunks[i];
+          if (c.group <= 1) {
+            launch(c, 0, c.count);
+            i++;
+            continue;
+          }
+          for (uint32_t first = 0; first < c.count; first += at_once)
+            for (uint32_t p = 0; p < c.group; p++) launch(P.chunks[i + p], first, std::min(at_once, c.count - first));
+          i += c.group;
         }
         return;
       }

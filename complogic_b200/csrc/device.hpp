@@ -24,6 +24,7 @@ struct SpecChunk {
   std::vector<uint32_t> scr_row;            // chunk-local register -> its row of the scratch buffer (empty: the same number)
   uint32_t n_slots = 0;
   uint32_t imm_base = 0, out_base = 0, state_base = 0;  // rows the kernel's pointers are advanced by at launch
+  bool crosses_in = false, crosses_out = false;         // some register is live across the cut before / after the chunk (whether or not the chunk touches it)
   bool same_kernel(const SpecChunk &o) const;           // equal code: the two chunks can share one assembled kernel
 };
 std::vector<SpecChunk> spec_chunks(const Flat &f, int K, uint32_t limit = 0, bool fine = false);  // limit: longest chunk in lane-order instructions (0: spec_chunk_limit(K))
@@ -32,7 +33,11 @@ struct SpecChain {
   std::vector<uint32_t> unique;     // chunks that get assembled (one per distinct kernel)
   std::vector<uint32_t> kernel_of;  // chunk -> index into `unique`
   struct Launch {
-    uint32_t first, count;  // chunks [first, first + count) run side by side in one launch (grid.y = count)
+    // chunks first, first + stride, ... (count of them) run side by side in one launch (grid.y = count). stride 1: equal
+    // chunks that hand nothing over. stride G > 1: the launch is one of G consecutive launches that together run `count`
+    // equal groups of G chunks (a group hands registers over inside but not across its ends: the instances of a flattened
+    // program whose instance is longer than a chunk) -- position by position, every group on its own part of the scratch buffer.
+    uint32_t first, count, stride;
   };
   std::vector<Launch> launches;
 };

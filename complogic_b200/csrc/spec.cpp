@@ -179,13 +179,15 @@ std::vector<SpecChunk> spec_chunks(const Flat &f, int K, uint32_t limit, bool fi
   std::vector<std::vector<uint32_t>> live(n + 1);
   for (size_t c = 1; c < n; c++) live[c] = spec_live_slots(f, cuts[c]);
   std::vector<SpecChunk> out;
-  for (size_t c = 0; c < n; c++) out.push_back(local_code(f, cuts[c], cuts[c + 1], live[c], live[c + 1], true));
+  for (size_t c = 0; c < n; c++) {
+    out.push_back(local_code(f, cuts[c], cuts[c + 1], live[c], live[c + 1], true));
+    out.back().crosses_in = !live[c].empty(), out.back().crosses_out = !live[c + 1].empty();
+  }
   return out;
 }
 
-// The launches of the chain: which chunks get assembled (one per distinct kernel) and which consecutive chunks run
-// side by side in one launch. Consecutive chunks that share a kernel, hand nothing over and touch disjoint
-// carried-state rows are independent of each other; blockIdx.y then selects the instance's row bases.
+// The launches of the chain: which chunks get assembled (one per distinct kernel) and which chunks run side by side in
+// one launch; blockIdx.y then selects the instance's row bases and its part of the scratch buffer.
 SpecChain spec_chain(const Flat &f, int K, uint32_t limit, bool fine) {
   SpecChain ch;
   ch.chunks = spec_chunks(f, K, limit, fine);
@@ -205,24 +207,45 @@ SpecChain spec_chain(const Flat &f, int K, uint32_t limit, bool fine) {
     r.erase(std::unique(r.begin(), r.end()), r.end());
     return r;
   };
-  std::vector<uint32_t> rows_of_run;  // absolute state rows touched by the chunks of the current launch
-  for (uint32_t c = 0; c < chunks.size(); c++) {
-    auto isolated = [&](uint32_t i) { return chunks[i].live_in.empty() && chunks[i].live_out.empty(); };
-    std::vector<uint32_t> rows = state_rows(chunks[c]), both;
-    bool merge = c > 0 && isolated(c) && isolated(c - 1) && ch.kernel_of[c] == ch.kernel_of[c - 1] && ch.launches.back().count < 65535;
-    if (merge) {
-      std::set_intersection(rows.begin(), rows.end(), rows_of_run.begin(), rows_of_run.end(), std::back_inserter(both));
-      merge = both.empty();
+  // Groups: from a cut nothing crosses to the next such cut. Consecutive groups of the same kernels (position by
+  // position) that touch disjoint carried-state rows are independent of each other and run side by side.
+  const uint32_t n = (uint32_t)chunks.size();
+  std::vector<uint32_t> gstart;  // first chunk of every group, then n
+  for (uint32_t c = 0; c < n; c++)
+    if (c == 0 || !chunks[c].crosses_in) gstart.push_back(c);
+  gstart.push_back(n);
+  auto group_rows = [&](uint32_t g) {
+    std::vector<uint32_t> r;
+    for (uint32_t c = gstart[g]; c < gstart[g + 1]; c++) {
+      const std::vector<uint32_t> rc = state_rows(chunks[c]);
+      r.insert(r.end(), rc.begin(), rc.end());
     }
-    if (merge) {
-      ch.launches.back().count++;
-      std::vector<uint32_t> all;
+    std::sort(r.begin(), r.end());
+    r.erase(std::unique(r.begin(), r.end()), r.end());
+    return r;
+  };
+  auto same_group = [&](uint32_t a, uint32_t b) {
+    const uint32_t len = gstart[a + 1] - gstart[a];
+    if (gstart[b + 1] - gstart[b] != len) return false;
+    for (uint32_t i = 0; i < len; i++)
+      if (ch.kernel_of[gstart[a] + i] != ch.kernel_of[gstart[b] + i]) return false;
+    return true;
+  };
+  const uint32_t n_groups = (uint32_t)gstart.size() - 1;
+  for (uint32_t g = 0; g < n_groups;) {
+    const uint32_t len = gstart[g + 1] - gstart[g];
+    std::vector<uint32_t> rows_of_run = group_rows(g);  // absolute state rows touched by the groups of the current run
+    uint32_t run = 1;
+    while (g + run < n_groups && run < 65535 && same_group(g, g + run)) {
+      std::vector<uint32_t> rows = group_rows(g + run), both, all;
+      std::set_intersection(rows.begin(), rows.end(), rows_of_run.begin(), rows_of_run.end(), std::back_inserter(both));
+      if (!both.empty()) break;
       std::merge(rows.begin(), rows.end(), rows_of_run.begin(), rows_of_run.end(), std::back_inserter(all));
       rows_of_run.swap(all);
-    } else {
-      ch.launches.push_back({c, 1});
-      rows_of_run.swap(rows);
+      run++;
     }
+    for (uint32_t p = 0; p < len; p++) ch.launches.push_back({gstart[g] + p, run, run > 1 ? len : 1});
+    g += run;
   }
   return ch;
 }
@@ -309,6 +332,13 @@ static std::string emit_spec(const Flat &f, int K, bool multi_step, const SpecCh
          "  mov.u32 %inst, %ctaid.y;\n  mad.wide.u32 %bases, %inst, 16, %bases;\n  ld.global.nc.v4.u32 {%b0,%b1,%b2,%b3}, [%bases];\n"
          "  cvt.u64.u32 %row, %b0;\n  mad.lo.u64 %imm, %sb, %row, %imm;\n  cvt.u64.u32 %row, %b1;\n  mad.lo.u64 %out, %sb, %row, %out;\n"
          "  cvt.u64.u32 %row, %b2;\n  mad.lo.u64 %state, %sb, %row, %state;\n";
+    // the launch's fourth table word: which part of the scratch buffer this instance hands its registers over in
+    // (groups of chunks that run side by side, position by position; a part holds every register of every column group)
+    std::snprintf(buf, sizeof buf,
+                  "  add.u32 %%wid, %%groups, 31;\n  shr.u32 %%wid, %%wid, 5;\n  mul.wide.u32 %%scrw, %%wid, %u;\n"
+                  "  cvt.u64.u32 %%row, %%b3;\n  mad.lo.u64 %%scr, %%scrw, %%row, %%scr;\n",
+                  h.stream[STREAM_LANE].n_slots * 128u * (uint32_t)K);
+    s += buf;
     // Hand-over: a live-in register is reloaded from the scratch buffer right before its first use here (not at
     // the top, where hundreds of reloads would all be live at once), a live-out one is stored right after its last
     // definition here. A register that is live across the whole chunk untouched is already in the scratch buffer.

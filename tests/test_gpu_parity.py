@@ -600,10 +600,11 @@ def test_full_size_dag_1m_2p24():
         del os.environ["CLG_COOP_NO_ROWS"]
 
 
-def test_full_size_structured_1m_gate_circuit_2p24():
-    """Twelve flattened 64x64 multipliers (1 009 152 gates) on 2^24 lanes through the instance-parallel specialised
-    launch: every instance gets the same inputs, so all twelve output blocks must be equal, block 0 must be a * b on a
-    sample of lanes, and a prefix must equal the oracle."""
+def test_full_size_structured_1m_gate_circuit_2p24(monkeypatch):
+    """Twelve flattened 64x64 multipliers (1 009 152 gates) on 2^24 lanes, every instance on its OWN random inputs:
+    sampled column groups of all 1 536 output rows against the oracle VM, and two instances' blocks must be a * b on a
+    sample of lanes. The halves of the instances run side by side (two launches of twelve), each instance handing its
+    registers over in its own part of the scratch buffer -- also when the scratch budget only holds five parts at a time."""
     import torch
 
     base = circuits.array_multiplier(64)
@@ -612,26 +613,32 @@ def test_full_size_structured_1m_gate_circuit_2p24():
     stride = stride_for(nv)
     ctx = host.Context.default()
     cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx)
-    one = torch.empty((128, stride), dtype=torch.int32, device="cuda:0")
-    ctx.fill_random(one.data_ptr(), 128, stride, 0x12A, 0)
-    imm = one.repeat(12, 1).contiguous()
+    imm = _device_random(ctx, 12 * 128, stride, 0x12A)
     out = torch.zeros((12 * 128, stride), dtype=torch.int32, device="cuda:0")
     cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
     torch.cuda.synchronize()
     # a batch this big runs the chain whose chunks stay below the instruction-cache cliff: two chunks per instance that
-    # hand ~200 registers over through the scratch buffer, two shared kernels, 24 launches
-    assert cs.mode == host.MODE_SPEC and cs.launches_per_run == 24 and cs.kernel_name == "clg_spec_chunk"
-    blocks = out.view(12, 128, stride)
-    assert bool((blocks == blocks[:1]).all())
+    # hand ~200 registers over through the scratch buffer, two shared kernels, first halves in one launch, second halves in the next
+    assert cs.mode == host.MODE_SPEC and cs.launches_per_run == 2 and cs.kernel_name == "clg_spec_chunk"
+    assert cs.flat.spec_batch_chain_info(1) == {"chunks": 24, "kernels": 2, "launches": 2, "handed_over": 12 * 203}
+    assert _check_sampled_columns(circ, imm, out, nv, k=1) >= 100
     n = 1 << 12
-    imm_h = one[:, :n // 32].contiguous().cpu().numpy().view(np.uint32)
-    got = blocks[0, :, :n // 32].contiguous().cpu().numpy().view(np.uint32)
-    a = [int(x) for x in unslice_int(imm_h[:64], n)]
-    b = [int(x) for x in unslice_int(imm_h[64:], n)]
-    lo, hi = unslice_int(got[:64], n), unslice_int(got[64:], n)
-    assert [int(l) | int(h) << 64 for l, h in zip(lo, hi)] == [x * y for x, y in zip(a, b)]
-    want = oracle.run_batch_sliced(base.sim, len(base.sim.registers), imm_h, n, base.out_regs)
-    assert np.array_equal(got, want)
+    for inst in (0, 7):
+        imm_h = imm[inst * 128:(inst + 1) * 128, :n // 32].contiguous().cpu().numpy().view(np.uint32)
+        got = out[inst * 128:(inst + 1) * 128, :n // 32].contiguous().cpu().numpy().view(np.uint32)
+        a = [int(x) for x in unslice_int(imm_h[:64], n)]
+        b = [int(x) for x in unslice_int(imm_h[64:], n)]
+        lo, hi = unslice_int(got[:64], n), unslice_int(got[64:], n)
+        assert [int(l) | int(h) << 64 for l, h in zip(lo, hi)] == [x * y for x, y in zip(a, b)]
+    # five instances at a time (a part is 222 registers x 2 MB): 5 + 5 + 2, two launches each
+    monkeypatch.setenv("CLG_SPEC_SCRATCH_MB", "2400")
+    cs5 = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx)
+    out5 = torch.zeros_like(out)
+    cs5.run_device(imm.data_ptr(), out5.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    assert cs5.launches_per_run == 6 and bool((out5 == out).all())
+    monkeypatch.delenv("CLG_SPEC_SCRATCH_MB")
+    del cs5, out5
     # a small batch on the same executor keeps the instance-parallel single launch; same words
     out2 = torch.zeros((12 * 128, stride), dtype=torch.int32, device="cuda:0")
     cs.run_device(imm.data_ptr(), out2.data_ptr(), n, stride)

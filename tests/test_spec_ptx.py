@@ -57,13 +57,14 @@ def test_chunked_chain_hands_registers_over(k):
 def test_batch_chain_cuts_between_instances_and_in_equal_parts():
     """The second chain (big batches): one instance of a flattened program per kernel where an instance fits the limit
     -- all instances then share ONE kernel and ONE launch and nothing is handed over; an instance longer than the limit
-    is cut into equal parts, so the parts of every instance share their kernels as well."""
+    is cut into equal parts, so the parts of every instance share their kernels as well and run side by side, part by part."""
     for n, m, first, second in (
         (32, 6, {"chunks": 2, "kernels": 2, "launches": 2}, {"chunks": 6, "kernels": 1, "launches": 1, "handed_over": 0}),
         (40, 4, {"chunks": 2, "kernels": 2, "launches": 2}, {"chunks": 4, "kernels": 1, "launches": 1, "handed_over": 0}),
         (16, 16, {"chunks": 1, "kernels": 1, "launches": 1}, {"chunks": 8, "kernels": 1, "launches": 1, "handed_over": 0}),  # (two 784-instruction instances per kernel)
-        (48, 3, {"chunks": 2, "kernels": 2, "launches": 2}, {"chunks": 6, "kernels": 2, "launches": 6}),
-        (64, 2, {"chunks": 2, "kernels": 1, "launches": 1}, {"chunks": 4, "kernels": 2, "launches": 4}),
+        # (the halves of all instances side by side, position by position: first halves in one launch, second halves in the next)
+        (48, 3, {"chunks": 2, "kernels": 2, "launches": 2}, {"chunks": 6, "kernels": 2, "launches": 2}),
+        (64, 2, {"chunks": 2, "kernels": 1, "launches": 1}, {"chunks": 4, "kernels": 2, "launches": 2}),
     ):
         circ = circuits.flatten_instances(circuits.array_multiplier(n), m)
         fp = host.FlatProgram.levelize(circ.sim, circ.n_immediates, circ.out_regs)
