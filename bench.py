@@ -94,7 +94,7 @@ WORKLOAD_DESC = {
     "latch1500": "a SEQUENTIAL circuit: 1 500 D latches in a row (24 000 NANDs), 6 000 carried registers per lane rewritten "
                  "in place every step; one step per launch on 2^24 lanes: bound by HBM (13 502 rows of 2 MB per step)",
     "mul64x12": "a STRUCTURED 1M-gate circuit: 64x64 array multiplier x 12 instances flattened = 1 009 152 NANDs, 2^24 vectors; "
-                "runs as a chain of 24 launches of two specialised kernels (the halves of an instance, each below the instruction-cache cliff)",
+                "runs as 2 launches of two specialised kernels (the halves of an instance, each below the instruction-cache cliff; the twelve instances side by side)",
     "mul64x8": "64x64 array multiplier x 8 instances flattened = 672 768 NANDs, batched: a program too long for one "
                "specialised kernel (98 816 instructions), run as a chain of chunk kernels",
     "mul32x48": "a STRUCTURED 1M-gate circuit of narrower parts: 32x32 array multiplier x 48 instances flattened = 986 112 NANDs, "

@@ -12,8 +12,8 @@ from complogic_b200 import circuits
 
 ctx = host.Context(0)
 peak = ctx.sm_count * 64 * 1.965e9  # LOP3 per second (one thread, one 32-bit word)
-for n, m, lg, chunks in ((64, 12, 24, (0, 2600, 3100, 4200, 5000, 6200, -1)), (32, 12, 24, (0, 1600, 3200, -1)), (40, 8, 24, (0, 2500, -1)),
-                         (48, 8, 23, (0, 3500, -1)), (24, 16, 24, (0, -1)), (16, 16, 24, (0, -1)), (8, 256, 23, (0, -1))):
+for n, m, lg, chunks in ((64, 12, 24, (0, 3200, 4200, 5000, 6200, -1)), (32, 12, 24, (0, 1600, -1)), (40, 8, 24, (0, 2500, -1)),
+                         (48, 8, 23, (0, 2400, -1)), (24, 16, 24, (0, -1)), (16, 16, 24, (0, -1)), (8, 256, 23, (0, -1))):
     circ = circuits.flatten_instances(circuits.array_multiplier(n), m)
     nv = 1 << lg
     stride = host.round_stride(nv)
