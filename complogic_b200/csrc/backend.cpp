@@ -244,14 +244,15 @@ struct Exec {
     int k = 0, distinct = 0;
     std::vector<std::pair<uint32_t, uint32_t>> launches;
   };
-  mutable ChainShape shape_;
-  const ChainShape &chain_shape(int k) const {
-    if (shape_.k != k) {
-      const SpecChain ch = spec_chain(flat, k);
-      shape_ = ChainShape{k, (int)ch.unique.size(), {}};
-      for (const SpecChain::Launch &l : ch.launches) shape_.launches.push_back({(uint32_t)ch.chunks[l.first].code.size(), l.count});
+  mutable ChainShape shape_[2];  // [0] the first chain, [1] the second (wants_tp_chain)
+  const ChainShape &chain_shape(int k, bool second = false) const {
+    ChainShape &sh = shape_[second];
+    if (sh.k != k) {
+      const SpecChain ch = second ? spec_chain(flat, k, std::max(2u, tp_chunk() / (uint32_t)k), true) : spec_chain(flat, k);
+      sh = ChainShape{k, (int)ch.unique.size(), {}};
+      for (const SpecChain::Launch &l : ch.launches) sh.launches.push_back({(uint32_t)ch.chunks[l.first].code.size(), l.count});
     }
-    return shape_;
+    return sh;
   }
   Plan plan[7];  // indexed by clg_mode; [PLAN_PARTS] = cooperative mode over the partitioned level stream, [PLAN_ROWS] = over the row
                  // stream, [PLAN_SPEC_TP] = the specialised chain in chunks below the instruction-cache cliff (big batches)
@@ -372,9 +373,10 @@ struct Exec {
       const double threads = groups * instances, warps = std::min(resident, std::ceil(threads / ctx->sm_count / 32.0) * 32.0) / 32.0;
       return std::ceil(threads / (resident * ctx->sm_count)) * n_instr * k * std::max(4.0, 0.85 * warps) + 5000.0;
     };
-    if (ln.n_instr <= spec_chunk_limit(k)) return launch(ln.n_instr, 1);
+    const bool second = wants_tp_chain(words);
+    if (!second && ln.n_instr <= spec_chunk_limit(k)) return launch(ln.n_instr, 1);
     double cycles = 0;
-    for (const auto &l : chain_shape(k).launches) cycles += launch(l.first, l.second);
+    for (const auto &l : chain_shape(k, second).launches) cycles += launch(l.first, l.second);
     return cycles;
   }
   // CTA size of the specialised kernels: 128 threads, narrower when the batch would otherwise leave SMs without a CTA
@@ -403,8 +405,9 @@ struct Exec {
         // Tiered specialisation: every distinct kernel of the chain costs about a second of assembly. Up to 4 of them
         // are paid at once; beyond that the program runs in an interpreter until that has cost as much GPU time as
         // the assembly will (run() keeps the tally), and is specialised then.
-        const int distinct = chain_shape(spec_k).distinct;
-        if (distinct <= 4 || plan[CLG_MODE_SPEC].ready || interp_seconds >= distinct * tier_seconds_per_kernel()) return CLG_MODE_SPEC;
+        const bool second = wants_tp_chain(words);
+        const int distinct = chain_shape(spec_k, second).distinct;
+        if (distinct <= 4 || plan[second ? PLAN_SPEC_TP : CLG_MODE_SPEC].ready || interp_seconds >= distinct * tier_seconds_per_kernel()) return CLG_MODE_SPEC;
         tier_pending = lane_ok || coop_ok;
         if (!tier_pending) return CLG_MODE_SPEC;  // nothing else can run it
       }
@@ -416,7 +419,7 @@ struct Exec {
   Exec(Ctx *c, const Flat &f, int want_) : ctx(c), flat(f), want(want_) {
     if (want < CLG_MODE_AUTO || want > CLG_MODE_SPEC) fail(CLG_E_INVALID, "unknown execution mode");
     mode = choose((size_t)1 << 20);  // the plan a large batch would use; small batches may pick another (auto)
-    last_k = get(mode).K;
+    last_k = (mode == CLG_MODE_SPEC && wants_tp_chain(1) ? get_spec_tp() : get(mode)).K;  // (a program that runs its second chain at every batch size never builds the first)
   }
 
   // K the partitioned cooperative plan would use (stack sized for the largest part); 0 = no partitioned form
@@ -530,13 +533,12 @@ struct Exec {
     const char *e = std::getenv("CLG_SPEC_TP_MIN_REGS");
     return e ? (uint32_t)std::atol(e) : 160u;
   }
-  mutable int tp_state_ = 0;                  // 0: not decided, 1: the program has a throughput chain, -1: it has none
+  mutable int tp_state_ = 0;                  // 0: not decided, 1: the program has a second chain for big batches, 2: for every batch, -1: it has none
   bool wants_tp_chain(size_t words) const {
     if (std::getenv("CLG_SPEC_CHUNK") || std::getenv("CLG_SPEC_NO_TP")) return false;
     const int k = fit_k(CLG_MODE_SPEC);
     const FlatStream &ln = lane_stream();
     if (!k || (uint64_t)ln.n_instr * k <= 8192 || ln.n_instr * (uint64_t)k > 4000000u) return false;
-    if ((words + k - 1) / k < (size_t)ctx->sm_count * 128 * 8) return false;  // every launch: eight waves of 128-thread CTAs or more
     if (tp_state_ == 0) {
       // Only for programs whose default chain hands nothing over (one kernel, or the isolated instances of a flattened
       // program): there the cliff is paid in full and one extra cut per instance is cheap next to it. A chain that
@@ -544,16 +546,22 @@ struct Exec {
       // 225 live values: 0.86 ms in four chunks against 0.52 ms in two; tools/bench_tp_chain.py). And at most four kernels
       // to assemble, else the default chain's tiering rules would have to apply.
       // A second chain that itself hands nothing over (every cut falls between two instances) is taken whatever the
-      // register count: 12 x mul32 (110 live) 2.12 -> 1.24 ms, 8 x mul40 2.20 -> 1.44 ms, 16 x mul16 0.55 -> 0.48 ms.
-      // One that cuts inside the instances pays for the hand-over and is only for programs that run two warps per
-      // scheduler anyway (160 registers or more).
+      // register count: 12 x mul32 (110 live) 2.12 -> 1.24 ms, 8 x mul40 2.20 -> 1.44 ms, 16 x mul16 0.55 -> 0.48 ms --
+      // and, if it does not take more launches than the first, whatever the batch: its kernels are shorter and its
+      // launches wider (16 x mul16: one thread per column group runs all sixteen instances in the first chain, eight
+      // threads two each in the second). One that cuts inside the instances pays for the hand-over and is only for
+      // programs that run two warps per scheduler anyway (160 registers or more), on big batches.
       bool isolated = true, tp_isolated = true;
-      for (const SpecChunk &c : spec_chain(flat, k).chunks) isolated &= c.live_in.empty() && c.live_out.empty();
+      const SpecChain first = spec_chain(flat, k);
+      for (const SpecChunk &c : first.chunks) isolated &= !c.crosses_in && !c.crosses_out;
       const SpecChain ch = spec_chain(flat, k, std::max(2u, tp_chunk() / (uint32_t)k), true);
-      for (const SpecChunk &c : ch.chunks) tp_isolated &= c.live_in.empty() && c.live_out.empty();
-      tp_state_ = isolated && ch.unique.size() <= 4 && ch.chunks.size() > 1 && (tp_isolated || ln.n_slots * (uint32_t)k >= tp_min_regs()) ? 1 : -1;
+      for (const SpecChunk &c : ch.chunks) tp_isolated &= !c.crosses_in && !c.crosses_out;
+      if (!isolated || ch.unique.size() > 4 || ch.chunks.size() <= 1) tp_state_ = -1;
+      else if (tp_isolated) tp_state_ = ch.launches.size() <= first.launches.size() && !std::getenv("CLG_SPEC_TP_BIG_ONLY") ? 2 : 1;
+      else tp_state_ = ln.n_slots * (uint32_t)k >= tp_min_regs() ? 1 : -1;
     }
-    return tp_state_ == 1;
+    if (tp_state_ == 2) return true;
+    return tp_state_ == 1 && (words + k - 1) / k >= (size_t)ctx->sm_count * 128 * 8;  // every launch: eight waves of 128-thread CTAs or more
   }
   Plan &get_spec_tp() {
     Plan &P = plan[PLAN_SPEC_TP];
@@ -1231,10 +1239,12 @@ int exec_mode(const Exec *e) { return e->mode; }
 int exec_k(const Exec *e) { return e->last_k; }
 int exec_launches(const Exec *e) {
   if (e->last_launches) return e->last_launches;  // what the most recent run issued
-  return e->mode == CLG_MODE_SPEC && !e->plan[CLG_MODE_SPEC].chunks.empty() ? (int)e->plan[CLG_MODE_SPEC].chunks.size() : 1;
+  if (e->mode != CLG_MODE_SPEC) return 1;
+  const Plan &P = e->plan[e->plan[CLG_MODE_SPEC].ready ? CLG_MODE_SPEC : Exec::PLAN_SPEC_TP];
+  return P.chunks.empty() ? 1 : (int)P.chunks.size();
 }
 const char *exec_kernel_name(const Exec *e) { return e->last_kernel; }
-const std::string &exec_ptx(const Exec *e) { return e->plan[CLG_MODE_SPEC].ptx; }
+const std::string &exec_ptx(const Exec *e) { return e->plan[e->plan[CLG_MODE_SPEC].ptx.empty() ? Exec::PLAN_SPEC_TP : CLG_MODE_SPEC].ptx; }
 const Flat &exec_flat(const Exec *e) { return e->flat; }
 Ctx *exec_ctx(const Exec *e) { return e->ctx; }
 void exec_run_steps(Exec *e, const uint32_t *imm, uint32_t *out, uint32_t *state, size_t n_vectors, size_t stride, size_t n_steps,

@@ -718,6 +718,14 @@ def test_throughput_chain_one_instance_per_kernel():
     torch.cuda.synchronize()
     assert cs.launches_per_run == 1 and cs.kernel_name == "clg_spec_chunk"
     assert _check_sampled_columns(circ, imm, out, nv) >= 100
+    # the chain takes no more launches than the first, so a small batch runs it too (six threads per column group
+    # instead of one that runs three instances back to back, twice)
+    small = 5000
+    out3 = torch.zeros_like(out)
+    cs.run_device(imm.data_ptr(), out3.data_ptr(), small, stride)
+    torch.cuda.synchronize()
+    w = (small + 31) // 32
+    assert cs.launches_per_run == 1 and bool((out3[:, :w - 1] == out[:, :w - 1]).all())
     os.environ["CLG_SPEC_NO_TP"] = "1"
     try:
         out2 = torch.zeros_like(out)
