@@ -736,6 +736,44 @@ def test_throughput_chain_one_instance_per_kernel():
         del os.environ["CLG_SPEC_NO_TP"]
 
 
+@pytest.mark.parametrize("k,seed,want", [(1, 11, (12, 2, 2)), (2, 12, (18, 3, 3))])
+def test_groups_of_chunks_side_by_side(monkeypatch, k, seed, want):
+    """Six flattened instances of a random DAG, every instance cut into two or three chunks that hand ~70 registers over
+    (a 1 000-instruction limit): the chunks of all instances run position by position -- as many launches as an instance
+    has chunks -- each instance in its own part of the scratch buffer. Every instance on its own random inputs, sampled
+    columns against the oracle VM; the same with a scratch budget that holds two parts at a time, and against the
+    first chain over the whole buffer."""
+    import torch
+
+    monkeypatch.setenv("CLG_SPEC_TP_CHUNK", "1000")
+    monkeypatch.setenv("CLG_SPEC_TP_MIN_REGS", "0")
+    monkeypatch.setenv("CLG_SPEC_K", str(k))
+    ctx = host.Context.default()
+    circ = circuits.flatten_instances(circuits.random_dag(40, 64, 32, 2, seed), 6)
+    nv = 1 << 24
+    stride = stride_for(nv)
+    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=host.MODE_SPEC)
+    info = cs.flat.spec_batch_chain_info(k)
+    assert (info["chunks"], info["kernels"], info["launches"]) == want and info["handed_over"] > 300
+    imm = _device_random(ctx, circ.n_immediates, stride, 0x6A0 + seed)
+    out = torch.zeros((len(circ.out_regs), stride), dtype=torch.int32, device="cuda:0")
+    cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    assert cs.words_per_thread == k and cs.launches_per_run == want[2] and cs.kernel_name == "clg_spec_chunk"
+    assert _check_sampled_columns(circ, imm, out, nv) >= 100
+    monkeypatch.setenv("CLG_SPEC_SCRATCH_MB", str(2 * cs.info["lane_slots"] * (stride * 4 >> 20) + 1))  # two parts and a bit
+    cs2 = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=host.MODE_SPEC)
+    out2 = torch.zeros_like(out)
+    cs2.run_device(imm.data_ptr(), out2.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    assert cs2.launches_per_run == 3 * want[2] and bool((out2 == out).all())
+    monkeypatch.setenv("CLG_SPEC_NO_TP", "1")
+    out3 = torch.zeros_like(out)
+    cs2.run_device(imm.data_ptr(), out3.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    assert cs2.launches_per_run <= 2 and bool((out3 == out).all())
+
+
 def test_full_size_mul16_2p26():
     """BASELINE config 3 at full size (2^26 lanes), non-periodic device-generated inputs: sampled column groups (first,
     last, every residue of a 148-CTA grid, random) against a * b and against the oracle VM, and a checksum over the whole
