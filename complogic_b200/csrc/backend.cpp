@@ -851,7 +851,8 @@ struct Exec {
     const size_t imm_step = (size_t)h.n_inputs * stride, out_step = (size_t)h.n_outputs * stride;
     // the fused form is ONE kernel of n_instr * K instructions: a program that needs a chunk chain runs step by step
     // (building the fused kernel would first assemble the whole unused chain and then minutes of straight-line code)
-    if (choose(words) != CLG_MODE_SPEC || n_steps == 1 || lane_stream().n_instr > spec_chunk_limit(fit_k(CLG_MODE_SPEC))) {
+    // (... and so does one whose second chain runs this batch: an instance per thread beats one thread for all instances)
+    if (choose(words) != CLG_MODE_SPEC || n_steps == 1 || lane_stream().n_instr > spec_chunk_limit(fit_k(CLG_MODE_SPEC)) || wants_tp_chain(words)) {
       for (size_t s_ = 0; s_ < n_steps; s_++) run(imm ? imm + s_ * imm_step : nullptr, out ? out + s_ * out_step : nullptr, state, n_vectors, stride, stream);
       return;
     }
