@@ -210,6 +210,7 @@ struct Plan {
   CUdeviceptr d_bases = 0;           // uint32[chunks of the program][4]: imm / out / state row base of each chunk
   CUdeviceptr scratch = 0;
   size_t scratch_bytes = 0;
+  uint32_t scratch_parts_max = UINT32_MAX;  // lowered when the device had no room for as many parts as the budget allows
   CUmodule spec_mod = nullptr, steps_mod = nullptr;
   CUfunction spec_fn = nullptr, steps_fn = nullptr;  // steps_fn: the fused multi-step form, assembled on first use
   std::string ptx;
@@ -918,12 +919,14 @@ struct Exec {
         uint32_t widest = 1;
         for (const Plan::ChunkLaunch &c : P.chunks)
           if (c.group > 1) widest = std::max(widest, c.count);
-        const uint32_t at_once = (uint32_t)std::min<size_t>(widest, std::max<size_t>(1, scratch_budget() / std::max<size_t>(part_bytes, 1)));
+        uint32_t at_once = (uint32_t)std::min<size_t>(std::min(widest, P.scratch_parts_max), std::max<size_t>(1, scratch_budget() / std::max<size_t>(part_bytes, 1)));
         if (part_bytes * at_once > P.scratch_bytes) {
           CU(cuCtxSynchronize());
           if (P.scratch) driver().cuMemFree(P.scratch);
           P.scratch = 0, P.scratch_bytes = 0;
-          CU(cuMemAlloc(&P.scratch, std::max<size_t>(16, part_bytes * at_once)));
+          // a device too full for that many parts runs fewer groups at a time (one part is what the chain needs at least)
+          while (at_once > 1 && driver().cuMemAlloc(&P.scratch, part_bytes * at_once) != CUDA_SUCCESS) P.scratch = 0, at_once /= 2, P.scratch_parts_max = at_once;
+          if (!P.scratch) CU(cuMemAlloc(&P.scratch, std::max<size_t>(16, part_bytes * at_once)));
           P.scratch_bytes = part_bytes * at_once;
         }
         last_kernel = "clg_spec_chunk";

@@ -774,6 +774,36 @@ def test_groups_of_chunks_side_by_side(monkeypatch, k, seed, want):
     assert cs2.launches_per_run <= 2 and bool((out3 == out).all())
 
 
+def test_side_by_side_groups_on_a_full_device():
+    """When the device has no room for a scratch part per instance, fewer groups run at a time: same words, more launches."""
+    import torch
+
+    ctx = host.Context.default()
+    circ = circuits.flatten_instances(circuits.array_multiplier(64), 12)
+    nv = 1 << 23
+    stride = stride_for(nv)
+    imm = _device_random(ctx, circ.n_immediates, stride, 0x51D)
+    out = torch.zeros((len(circ.out_regs), stride), dtype=torch.int32, device="cuda:0")
+    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=host.MODE_SPEC)
+    cs.run_device(imm.data_ptr(), out.data_ptr(), nv, stride)
+    torch.cuda.synchronize()
+    assert cs.launches_per_run == 2
+    part = cs.info["lane_slots"] * stride * 4  # 222 registers x 1 MB
+    del cs
+    torch.cuda.empty_cache()
+    cs = host.CudaSimulation.from_simulation(circ.sim, circ.n_immediates, circ.out_regs, ctx=ctx, mode=host.MODE_SPEC)
+    out2 = torch.zeros_like(out)
+    free, _ = torch.cuda.mem_get_info()
+    filler = torch.empty(free - 5 * part, dtype=torch.uint8, device="cuda:0")  # room for five parts, not for twelve
+    try:
+        cs.run_device(imm.data_ptr(), out2.data_ptr(), nv, stride)
+        torch.cuda.synchronize()
+    finally:
+        del filler
+        torch.cuda.empty_cache()
+    assert cs.launches_per_run > 2 and bool((out2 == out).all()), cs.launches_per_run
+
+
 def test_full_size_mul16_2p26():
     """BASELINE config 3 at full size (2^26 lanes), non-periodic device-generated inputs: sampled column groups (first,
     last, every residue of a 148-CTA grid, random) against a * b and against the oracle VM, and a checksum over the whole
