@@ -67,6 +67,7 @@ PROTOTYPES = {
     "clg_flat_spec_ptx": (i32, [vp, i32, P(vp)]),
     "clg_flat_spec_steps_ptx": (i32, [vp, i32, P(vp)]),
     "clg_flat_spec_chunk_ptx": (i32, [vp, i32, u32, P(u32), P(u32), P(vp)]),
+    "clg_flat_spec_batch_chunk_ptx": (i32, [vp, i32, u32, P(u32), P(u32), P(vp)]),
     "clg_flat_spec_chain_info": (i32, [vp, i32, P(u32), P(u32), P(u32)]),
     "clg_flat_spec_batch_chain_info": (i32, [vp, i32, P(u32), P(u32), P(u32), P(u32)]),
     "clg_ctx_create": (i32, [i32, P(vp)]),

@@ -457,11 +457,12 @@ class FlatProgram:
         check(lib().clg_flat_spec_batch_chain_info(self._h, k, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return {"chunks": a.value, "kernels": b.value, "launches": c.value, "handed_over": d.value}
 
-    def spec_chunk_ptx(self, k: int, chunk: int, with_bases: bool = False):
+    def spec_chunk_ptx(self, k: int, chunk: int, with_bases: bool = False, second: bool = False):
         """PTX of one kernel of the chunked specialised form and the length of the chain (and, with_bases, the rows
-        (imm, out, state) the kernel's pointers are advanced by)."""
+        (imm, out, state) the kernel's pointers are advanced by). second: of the chain big batches run."""
         out, n, bases = C.c_void_p(), C.c_uint32(), (C.c_uint32 * 3)()
-        check(lib().clg_flat_spec_chunk_ptx(self._h, k, chunk, C.byref(n), bases, C.byref(out)))
+        fn = lib().clg_flat_spec_batch_chunk_ptx if second else lib().clg_flat_spec_chunk_ptx
+        check(fn(self._h, k, chunk, C.byref(n), bases, C.byref(out)))
         s = C.string_at(out).decode()
         lib().clg_free(out)
         return (s, n.value, tuple(bases)) if with_bases else (s, n.value)

@@ -234,12 +234,11 @@ static int spec_ptx_text(const clg_flat *f, int k, bool steps, char **ptx_out) {
   *ptx_out = p;
   CLG_CATCH
 }
-int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, uint32_t *row_bases, char **ptx_out) {
-  CLG_TRY
+static void chunk_ptx(const clg_flat *f, int k, bool second, uint32_t chunk, uint32_t *n_chunks, uint32_t *row_bases, char **ptx_out) {
   NEED(f), NEED(ptx_out);
   if (k != 1 && k != 2 && k != 4) fail(CLG_E_INVALID, "K must be 1, 2 or 4");
   if (f->f.header().stream[STREAM_LANE].n_instr == 0) fail(CLG_E_UNSUPPORTED, "no lane-ordered stream in this flat buffer");
-  const std::vector<SpecChunk> chunks = spec_chunks(f->f, k);
+  const std::vector<SpecChunk> chunks = second ? spec_chunks(f->f, k, std::max(2u, spec_tp_chunk_limit() / (uint32_t)k), true) : spec_chunks(f->f, k);
   if (n_chunks) *n_chunks = (uint32_t)chunks.size();
   if (chunk >= chunks.size()) fail(CLG_E_INVALID, "chunk index out of range");
   const SpecChunk &c = chunks[chunk];
@@ -249,6 +248,15 @@ int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *
   if (!p) throw std::bad_alloc();
   std::memcpy(p, s.c_str(), s.size() + 1);
   *ptx_out = p;
+}
+int clg_flat_spec_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, uint32_t *row_bases, char **ptx_out) {
+  CLG_TRY
+  chunk_ptx(f, k, false, chunk, n_chunks, row_bases, ptx_out);
+  CLG_CATCH
+}
+int clg_flat_spec_batch_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, uint32_t *row_bases, char **ptx_out) {
+  CLG_TRY
+  chunk_ptx(f, k, true, chunk, n_chunks, row_bases, ptx_out);
   CLG_CATCH
 }
 int clg_flat_spec_chain_info(const clg_flat *f, int k, uint32_t *n_chunks, uint32_t *n_kernels, uint32_t *n_launches) {

@@ -216,6 +216,8 @@ int clg_flat_spec_chain_info(const clg_flat *f, int k, uint32_t *n_chunks, uint3
  * in one launch -- and, where an instance is longer than that, into equal parts. *n_handed_over (optional): registers
  * that cross a cut, summed over the chain (0: the chain is taken whatever the program's register count). */
 int clg_flat_spec_batch_chain_info(const clg_flat *f, int k, uint32_t *n_chunks, uint32_t *n_kernels, uint32_t *n_launches, uint32_t *n_handed_over);
+/* Text of chunk `chunk` of that second chain (arguments as for clg_flat_spec_chunk_ptx). */
+int clg_flat_spec_batch_chunk_ptx(const clg_flat *f, int k, uint32_t chunk, uint32_t *n_chunks, uint32_t *row_bases, char **ptx_out);
 
 /* ---------------------------------------------------------------------------------------------
  * Device side. Raw CUDA driver API underneath (libcuda.so.1 is dlopen'ed when the first context

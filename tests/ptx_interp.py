@@ -90,17 +90,18 @@ def run_kernel(ptx: str, k: int, groups: int, mem: dict):
             raise AssertionError("unexpected instruction in generated PTX: " + l)
 
 
-def run_program(flat_program, k: int, imm: np.ndarray, state: np.ndarray, n_outputs: int, n_slots: int):
+def run_program(flat_program, k: int, imm: np.ndarray, state: np.ndarray, n_outputs: int, n_slots: int, second: bool = False):
     """Run the whole (possibly chunked) specialised program over imm [n_inputs][stride]; state is updated in place.
+    second: the chain big batches run (in chunk order, which is one of the orders its launches allow).
     The scratch buffer starts poisoned so that a register a chunk forgot to hand over shows up as a mismatch."""
     stride = imm.shape[1]
     assert stride % k == 0
     out = np.zeros((max(1, n_outputs), stride), np.uint32)
     scr = np.full((max(1, n_slots), stride), 0xDEADBEEF, np.uint32)
     mem = {"imm": imm, "out": out, "state": state if state is not None else np.zeros((1, stride), np.uint32), "scr": scr}
-    _, n = flat_program.spec_chunk_ptx(k, 0)
+    _, n = flat_program.spec_chunk_ptx(k, 0, second=second)
     for c in range(n):
-        text, _, (bi, bo, bs) = flat_program.spec_chunk_ptx(k, c, with_bases=True)
+        text, _, (bi, bo, bs) = flat_program.spec_chunk_ptx(k, c, with_bases=True, second=second)
         view = {"imm": mem["imm"][bi:], "out": mem["out"][bo:], "state": mem["state"][bs:], "scr": scr}
         run_kernel(text, k, stride // k, view)
     return out[:n_outputs]

@@ -73,6 +73,22 @@ def test_batch_chain_cuts_between_instances_and_in_equal_parts():
         if "handed_over" not in second:
             assert got.pop("handed_over") > 0
         assert got == second, (n, m)
+    # the generated kernels of such a chain, run by the PTX interpreter: an instance per kernel (mul16, two per kernel),
+    # and instances cut in two equal parts that hand ~100 registers over (a 1 000-instruction limit)
+    for circ, k, limit in ((circuits.flatten_instances(circuits.array_multiplier(16), 10), 1, None),
+                           (circuits.flatten_instances(circuits.random_dag(40, 64, 32, 2, 11), 3), 2, "1000")):
+        if limit:
+            os.environ["CLG_SPEC_TP_CHUNK"] = limit
+        try:
+            fp = host.FlatProgram.levelize(circ.sim, circ.n_immediates, circ.out_regs)
+            assert fp.spec_chunk_ptx(k, 0, second=True)[1] == fp.spec_batch_chain_info(k)["chunks"] >= 5
+            nv, stride = 32 * 4, 4
+            imm = random_sliced(circ.n_immediates, stride, seed=5)
+            want = oracle.run_batch_sliced(circ.sim, len(circ.sim.registers), imm, nv, circ.out_regs)
+            got = ptx_interp.run_program(fp, k, imm, None, len(circ.out_regs), fp.info["lane_slots"], second=True)
+            assert np.array_equal(got, want)
+        finally:
+            os.environ.pop("CLG_SPEC_TP_CHUNK", None)
     # a DAG is cut where few registers are live, as in the first chain, only shorter
     dag = circuits.random_dag(210, 160, 64, 2, 7)
     fp = host.FlatProgram.levelize(dag.sim, 64, dag.out_regs)
