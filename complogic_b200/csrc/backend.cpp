@@ -534,6 +534,7 @@ struct Exec {
     const char *e = std::getenv("CLG_SPEC_TP_MIN_REGS");
     return e ? (uint32_t)std::atol(e) : 160u;
   }
+  mutable uint32_t tp_narrowest_ = 1;         // fewest instances side by side in a launch of the second chain
   mutable int tp_state_ = 0;                  // 0: not decided, 1: the program has a second chain for big batches, 2: for every batch, -1: it has none
   bool wants_tp_chain(size_t words) const {
     if (std::getenv("CLG_SPEC_CHUNK") || std::getenv("CLG_SPEC_NO_TP")) return false;
@@ -557,12 +558,15 @@ struct Exec {
       for (const SpecChunk &c : first.chunks) isolated &= !c.crosses_in && !c.crosses_out;
       const SpecChain ch = spec_chain(flat, k, std::max(2u, tp_chunk() / (uint32_t)k), true);
       for (const SpecChunk &c : ch.chunks) tp_isolated &= !c.crosses_in && !c.crosses_out;
+      tp_narrowest_ = UINT32_MAX;
+      for (const SpecChain::Launch &l : ch.launches) tp_narrowest_ = std::min(tp_narrowest_, l.count);
       if (!isolated || ch.unique.size() > 4 || ch.chunks.size() <= 1) tp_state_ = -1;
       else if (tp_isolated) tp_state_ = ch.launches.size() <= first.launches.size() && !std::getenv("CLG_SPEC_TP_BIG_ONLY") ? 2 : 1;
       else tp_state_ = ln.n_slots * (uint32_t)k >= tp_min_regs() ? 1 : -1;
     }
     if (tp_state_ == 2) return true;
-    return tp_state_ == 1 && (words + k - 1) / k >= (size_t)ctx->sm_count * 128 * 8;  // every launch: eight waves of 128-thread CTAs or more
+    // every launch (column groups x the instances it runs side by side): eight waves of 128-thread CTAs or more
+    return tp_state_ == 1 && (words + k - 1) / k * tp_narrowest_ >= (size_t)ctx->sm_count * 128 * 8;
   }
   Plan &get_spec_tp() {
     Plan &P = plan[PLAN_SPEC_TP];
