@@ -633,8 +633,10 @@ Sched schedule_lane(const Network &net) {
     if (s.ok && s.n_slots > 3000) break;
     // The on-demand order is the tightest (it finishes a multiplier row before it starts the next) and for that very
     // reason the slowest to run when both fit the register file: one dependent carry chain per warp, no second row to
-    // overlap with (mul64 x 12: 7.9 ms against 7.2 ms). It is only tried when everything else would spill.
-    if (on_demand && s.ok && s.n_slots <= 230) break;
+    // overlap with (mul64 x 12: 7.9 ms against 7.2 ms as one kernel per instance; 5.57 against 5.46-5.56 ms in the
+    // second chain, where it hands 128 registers over instead of 203 and runs three warps per scheduler: no gain
+    // either). It is only tried when everything else would spill.
+    if (on_demand && s.ok && s.n_slots <= 230 && !std::getenv("CLG_LANE_ON_DEMAND")) break;  // (knob: measure the tight order anyway)
     std::vector<uint32_t> coff(V + 1, 0), cons;  // readers (LUTs) of each value
     auto each_operand = [&](uint32_t v, auto &&fn) {
       const Val &x = net.vals[v];
